@@ -1,0 +1,107 @@
+"""ctypes binding of libhfc.so (the C ABI declared in include/hfc.h).
+
+There is no fallback: if the shared library is missing the import fails, and every compute entry
+point returns an error (raised here as RuntimeError) on a machine without an sm_100 GPU.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhfc.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+
+class ActGeom(ctypes.Structure):
+    """Mirror of ``hfc_act_geom``."""
+    _fields_ = [(k, ctypes.c_int32) for k in ("n", "h", "w", "c", "cpad", "pt", "pl", "pb", "pr")]
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of ``hfc_conv_desc``."""
+    _fields_ = [
+        ("inp", ActGeom),
+        ("kh", ctypes.c_int32), ("kw", ctypes.c_int32),
+        ("stride", ctypes.c_int32), ("transposed", ctypes.c_int32),
+        ("pad_mode", ctypes.c_int32),
+        ("pad_t", ctypes.c_int32), ("pad_l", ctypes.c_int32),
+        ("pad_b", ctypes.c_int32), ("pad_r", ctypes.c_int32),
+        ("cout", ctypes.c_int32), ("window", ctypes.c_int32),
+        ("out_mode", ctypes.c_int32),
+        ("out", ActGeom),
+        ("out_reflect", ctypes.c_int32),
+        ("act", ctypes.c_int32), ("norm", ctypes.c_int32),
+        ("eps", ctypes.c_float),
+        ("block_n", ctypes.c_int32), ("precision", ctypes.c_int32),
+    ]
+
+
+class ConvInfo(ctypes.Structure):
+    """Mirror of ``hfc_conv_info``."""
+    _fields_ = [
+        ("packed_weight_bytes", ctypes.c_size_t),
+        ("out_h", ctypes.c_int32), ("out_w", ctypes.c_int32), ("phases", ctypes.c_int32),
+        ("block_n", ctypes.c_int32), ("n_tiles", ctypes.c_int32), ("m_tiles", ctypes.c_int32),
+        ("stages", ctypes.c_int32), ("k_total", ctypes.c_int32),
+        ("flops", ctypes.c_double),
+    ]
+
+
+PAD_ZERO, PAD_REFLECT = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY02 = 0, 1, 2
+OUT_NHWC_F16, OUT_NHWC_F32, OUT_NCHW_F32 = 0, 1, 2
+PREC_F16, PREC_BF16X3 = 0, 1
+
+# name -> (restype, argtypes); doubles as the list of symbols the ABI test checks.
+_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+SIGNATURES = {
+    "hfc_abi_version": (ctypes.c_int, []),
+    "hfc_last_error": (ctypes.c_char_p, []),
+    "hfc_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
+    "hfc_launch_count": (ctypes.c_ulonglong, []),
+    "hfc_conv_query": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvInfo)]),
+    "hfc_conv_pack_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "hfc_conv_forward": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hfc_nchw_to_act": (ctypes.c_int, [_vp, ctypes.POINTER(ActGeom), _i32, _i32, _vp, _vp, _f32, _vp, _vp]),
+    "hfc_channelnorm": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _vp, _f32, _i32,
+                                       _vp, _vp, _vp, _vp, _vp]),
+    "hfc_latent_likelihood": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp]),
+    "hfc_hyperlatent_likelihood": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+}
+
+
+def build(verbose=False):
+    """Compile libhfc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR, "-j4"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("libhfc build failed")
+    return LIB_PATH
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"libhfc.so not found at {LIB_PATH}: build it with `make -C {CSRC_DIR}` or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError = ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class HfcError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.hfc_last_error().decode("utf-8", "replace")
+        raise HfcError(f"libhfc {what} failed (status {rc}): {msg}")

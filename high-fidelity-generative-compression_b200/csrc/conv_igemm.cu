@@ -1,0 +1,756 @@
+// Implicit-GEMM convolution / transposed convolution for sm_100a.
+//
+//   D[M = batch*grid_h*grid_w pixels, N = cout] = sum over taps, cin  A[pixel + tap, cin] * W[cout, tap, cin]
+//
+// * A tiles (128 pixels x 64 channels, fp16) are fetched by 4-D TMA boxes straight from the NHWC
+//   activation buffer: one box per (filter tap, 64-channel chunk).  Zero padding is TMA's
+//   out-of-bounds fill; reflection padding was materialised by the producer of the buffer;
+//   stride-2 convolutions use the tensor map's element strides; stride-2 transposed convolutions
+//   are decomposed into 4 sub-pixel phases (one launch each).
+// * W tiles (block_n x 64) come from a pre-packed K-major matrix via a 2-D TMA box.
+// * tcgen05.mma (cta_group::1, kind::f16, M=128, N=block_n, K=16) accumulates into TMEM; two
+//   accumulator stages of 256 columns let the epilogue of tile i overlap the main loop of i+1.
+// * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer,
+//   warps 2..5 = epilogue (one TMEM lane quadrant each; thread == output pixel, so the per-pixel
+//   ChannelNorm over channels is an in-thread reduction with no shuffles).
+// * Epilogue: + bias, optional fused ChannelNorm2D (unbiased variance, eps), ReLU / LeakyReLU,
+//   then one of: NHWC fp16 with reflected border (input of the next conv), NHWC fp32 rows (input
+//   of the stand-alone ChannelNorm for 480/960 channels), NCHW fp32 (module boundary).
+//
+// Reference call sites this replaces are listed in include/hfc.h (hfc_conv_desc).
+#include "hfc_internal.h"
+#include "hfc_ptx.cuh"
+
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace hfc {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;                       // 64 x 16-bit = one 128 B swizzle row
+static constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+static constexpr int kThreads = 192;                     // 6 warps
+static constexpr int kMaxTaps = 64;
+static constexpr int kAccStride = 256;                   // TMEM columns per accumulator stage
+static constexpr int kTmemCols = 512;
+static constexpr int kMaxStages = 8;
+
+struct ConvKernelParams {
+  int32_t tw, th, tn;                 // tile extents, tw*th*tn == 128
+  int32_t tiles_w, tiles_h, tiles_n;  // M tiles per dimension
+  int32_t n_tiles;                    // N tiles
+  int32_t block_n;
+  int32_t num_kb, c_chunks, ntaps;
+  int32_t stages;
+  int32_t grid_h, grid_w, batch;
+  int32_t sh, sw;                     // input coordinate scale
+  int32_t ih0, iw0;                   // input coordinate offset (materialised border)
+  int32_t out_mode, osh, osw, ooh, oow;
+  int32_t out_h, out_w;
+  int32_t out_cpad;
+  int32_t out_pt, out_pl, out_pb, out_pr;
+  int32_t out_reflect;
+  int32_t cout;
+  int32_t act, norm;
+  float eps;
+  uint32_t fmt;                       // 0 fp16, 1 bf16
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  void* out;
+  int8_t tap_dh[kMaxTaps];
+  int8_t tap_dw[kMaxTaps];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == HFC_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == HFC_ACT_LEAKY02) return v > 0.f ? v : 0.2f * v;
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ ConvKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024 B alignment for the 128B-swizzled tiles.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int b_bytes = p.block_n * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = bars;                     // [stages]
+  uint64_t* empty_bar = bars + kMaxStages;       // [stages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = tiles_m * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int twi = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int thi = mt % p.tiles_h;
+        const int tni = mt / p.tiles_h;
+        const int w_base = twi * p.tw * p.sw + p.iw0;
+        const int h_base = thi * p.th * p.sh + p.ih0;
+        const int n_base = tni * p.tn;
+        int tap = 0, chunk = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+          tma_load_4d(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
+                      h_base + p.tap_dh[tap], n_base);
+          tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, nt * p.block_n);
+          if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_f16(p.fmt, kBlockM, static_cast<uint32_t>(p.block_n));
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kAccStride;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4)
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;
+    const int twi_in = m % p.tw;
+    const int thi_in = (m / p.tw) % p.th;
+    const int tni_in = m / (p.tw * p.th);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int twi = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int thi = mt % p.tiles_h;
+      const int tni = mt / p.tiles_h;
+      const int gw = twi * p.tw + twi_in;
+      const int gh = thi * p.th + thi_in;
+      const int n = tni * p.tn + tni_in;
+      const int oh = gh * p.osh + p.ooh;
+      const int ow = gw * p.osw + p.oow;
+      const bool valid = (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
+                         (ow < p.out_w);
+      const int c_base = nt * p.block_n;
+      const bool last_nt = (nt == p.n_tiles - 1);
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+
+      float mean = 0.f, rstd = 1.f;
+      if (p.norm) {
+        // pass 1: mean over the real channels; pass 2: unbiased variance (two-pass, fp32)
+        float sum = 0.f;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = c0 + j;
+            if (c < p.cout) sum += __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+          }
+        }
+        mean = sum / static_cast<float>(p.cout);
+        float ssq = 0.f;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = c0 + j;
+            if (c < p.cout) {
+              const float d = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f) - mean;
+              ssq += d * d;
+            }
+          }
+        }
+        rstd = rsqrtf(ssq / static_cast<float>(p.cout - 1) + p.eps);
+      }
+
+      // target rows / cols of the (bordered) NHWC fp16 buffer
+      int rows[3], cols[3];
+      int nr = 0, nc = 0;
+      if (p.out_mode == HFC_OUT_NHWC_F16) {
+        rows[nr++] = oh + p.out_pt;
+        cols[nc++] = ow + p.out_pl;
+        if (p.out_reflect) {
+          if (oh >= 1 && oh <= p.out_pt) rows[nr++] = p.out_pt - oh;
+          if (oh <= p.out_h - 2 && oh >= p.out_h - 1 - p.out_pb)
+            rows[nr++] = p.out_pt + 2 * (p.out_h - 1) - oh;
+          if (ow >= 1 && ow <= p.out_pl) cols[nc++] = p.out_pl - ow;
+          if (ow <= p.out_w - 2 && ow >= p.out_w - 1 - p.out_pr)
+            cols[nc++] = p.out_pl + 2 * (p.out_w - 1) - ow;
+        }
+      }
+      const int Hp = p.out_h + p.out_pt + p.out_pb;
+      const int Wp = p.out_w + p.out_pl + p.out_pr;
+
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = c_base + c0 + j;
+          float x = 0.f;
+          if (c < p.cout) {
+            x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+            if (p.norm) x = __ldg(p.gamma + c) * ((x - mean) * rstd) + __ldg(p.beta + c);
+            x = apply_act(x, p.act);
+          }
+          f[j] = x;
+        }
+        const int cc = c_base + c0;
+        if (!valid) {
+          // nothing to store for rows outside the image / batch (their A rows were zero-filled)
+        } else if (p.out_mode == HFC_OUT_NHWC_F16) {
+          if (cc < p.out_cpad) {
+            uint4 lo, hi;
+            lo.x = pack_half2(f[0], f[1]);   lo.y = pack_half2(f[2], f[3]);
+            lo.z = pack_half2(f[4], f[5]);   lo.w = pack_half2(f[6], f[7]);
+            hi.x = pack_half2(f[8], f[9]);   hi.y = pack_half2(f[10], f[11]);
+            hi.z = pack_half2(f[12], f[13]); hi.w = pack_half2(f[14], f[15]);
+            for (int ri = 0; ri < nr; ++ri) {
+              for (int ci = 0; ci < nc; ++ci) {
+                __half* dst = reinterpret_cast<__half*>(p.out) +
+                              ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) *
+                                  p.out_cpad + cc;
+                reinterpret_cast<uint4*>(dst)[0] = lo;
+                if (cc + 8 < p.out_cpad) reinterpret_cast<uint4*>(dst)[1] = hi;
+              }
+            }
+          }
+        } else if (p.out_mode == HFC_OUT_NHWC_F32) {
+          if (cc < p.out_cpad) {
+            float* dst = reinterpret_cast<float*>(p.out) +
+                         ((static_cast<size_t>(n) * p.out_h + oh) * p.out_w + ow) * p.out_cpad + cc;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              if (cc + 4 * j4 < p.out_cpad)
+                reinterpret_cast<float4*>(dst)[j4] =
+                    make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+            }
+          }
+        } else {  // NCHW fp32
+          float* dst = reinterpret_cast<float*>(p.out);
+          const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = cc + j;
+            if (c < p.cout)
+              dst[(static_cast<size_t>(n) * p.cout + c) * plane + static_cast<size_t>(oh) * p.out_w +
+                  ow] = f[j];
+          }
+        }
+      }
+      // zero the channel padding no N tile covers (e.g. cout 220 -> block_n 224 -> cpad 256)
+      if (valid && last_nt && p.out_mode != HFC_OUT_NCHW_F32) {
+        const int c_end = p.n_tiles * p.block_n;
+        if (p.out_mode == HFC_OUT_NHWC_F16) {
+          for (int c = c_end; c < p.out_cpad; c += 8) {
+            for (int ri = 0; ri < nr; ++ri)
+              for (int ci = 0; ci < nc; ++ci) {
+                __half* dst = reinterpret_cast<__half*>(p.out) +
+                              ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) *
+                                  p.out_cpad + c;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+              }
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.out) +
+                       ((static_cast<size_t>(n) * p.out_h + oh) * p.out_w + ow) * p.out_cpad;
+          for (int c = c_end; c < p.out_cpad; c += 4)
+            *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: torch layout fp32 -> K-major [cout_rows][ktot] 16-bit, K ordered (tap, cin_pad)
+// ------------------------------------------------------------------------------------------------
+struct PackParams {
+  int32_t cout, cin, kh, kw;
+  int32_t cin_pad, ntaps, ktot, rows;
+  int32_t transposed, window;
+  uint32_t fmt;
+  int8_t ky[kMaxTaps];
+  int8_t kx[kMaxTaps];
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
+                                    const __grid_constant__ PackParams pp) {
+  const size_t total = static_cast<size_t>(pp.rows) * pp.ktot;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i / pp.ktot);
+    const int k = static_cast<int>(i % pp.ktot);
+    float val = 0.f;
+    if (co < pp.cout) {
+      int tap, ci, ky, kx;
+      bool ok;
+      if (pp.window) {
+        tap = k / 64;
+        const int r = k % 64;
+        kx = r / pp.cin_pad;          // cin_pad == 8: 8 pixels x 8 channels per filter row
+        ci = r % pp.cin_pad;
+        ky = pp.ky[tap];
+        ok = (kx < pp.kw) && (ci < pp.cin);
+      } else {
+        tap = k / pp.cin_pad;
+        ci = k % pp.cin_pad;
+        ky = pp.ky[tap];
+        kx = pp.kx[tap];
+        ok = ci < pp.cin;
+      }
+      if (ok) {
+        const size_t idx = pp.transposed
+                               ? ((static_cast<size_t>(ci) * pp.cout + co) * pp.kh + ky) * pp.kw + kx
+                               : ((static_cast<size_t>(co) * pp.cin + ci) * pp.kh + ky) * pp.kw + kx;
+        val = w[idx];
+      }
+    }
+    uint16_t bits;
+    if (pp.fmt == 0) {
+      __half h = __float2half_rn(val);
+      bits = *reinterpret_cast<uint16_t*>(&h);
+    } else {
+      __nv_bfloat16 h = __float2bfloat16_rn(val);
+      bits = *reinterpret_cast<uint16_t*>(&h);
+    }
+    out[i] = bits;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-side planning
+// ------------------------------------------------------------------------------------------------
+struct Phase {
+  int ntaps;
+  int8_t dh[kMaxTaps], dw[kMaxTaps], ky[kMaxTaps], kx[kMaxTaps];
+  int grid_h, grid_w;
+  int osh, osw, ooh, oow;
+  int sh, sw;
+  int ktot;
+  size_t w_offset;  // element offset into the packed weight buffer
+};
+
+struct Plan {
+  int nphases;
+  Phase ph[4];
+  int out_h, out_w;
+  int block_n, n_tiles, rows;   // rows = n_tiles * block_n (packed weight rows)
+  int c_chunks;
+  int kblk_per_tap;
+  size_t packed_elems;
+  double flops;
+};
+
+static int next_pow2(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+static int make_plan(const hfc_conv_desc* d, Plan* pl) {
+  if (!d) return set_error(HFC_ERR_INVALID, "conv: null descriptor");
+  const hfc_act_geom& in = d->in;
+  if (in.n <= 0 || in.h <= 0 || in.w <= 0 || in.c <= 0 || d->cout <= 0)
+    return set_error(HFC_ERR_INVALID, "conv: non-positive dimension");
+  if (d->kh <= 0 || d->kw <= 0 || d->kh * d->kw > kMaxTaps)
+    return set_error(HFC_ERR_INVALID, "conv: unsupported filter size %dx%d", d->kh, d->kw);
+  if (d->stride != 1 && d->stride != 2)
+    return set_error(HFC_ERR_INVALID, "conv: stride must be 1 or 2");
+  if (d->precision != HFC_PREC_F16)
+    return set_error(HFC_ERR_UNSUPPORTED, "conv: precision mode %d not built", d->precision);
+  if (d->window) {
+    if (d->transposed || in.cpad != 8 || d->kw > 8 || in.c > 8 || d->stride != 1)
+      return set_error(HFC_ERR_INVALID, "conv: window packing needs cpad==8, kw<=8, stride 1");
+  } else if (in.cpad % 64 != 0) {
+    return set_error(HFC_ERR_INVALID, "conv: input cpad (%d) must be a multiple of 64", in.cpad);
+  }
+  if (in.c > in.cpad) return set_error(HFC_ERR_INVALID, "conv: in.c > in.cpad");
+
+  memset(pl, 0, sizeof(*pl));
+  const int s = d->stride;
+  if (!d->transposed) {
+    pl->out_h = (in.h + d->pad_t + d->pad_b - d->kh) / s + 1;
+    pl->out_w = (in.w + d->pad_l + d->pad_r - d->kw) / s + 1;
+    if (d->pad_mode == HFC_PAD_REFLECT &&
+        (in.pt < d->pad_t || in.pl < d->pad_l || in.pb < d->pad_b || in.pr < d->pad_r))
+      return set_error(HFC_ERR_INVALID, "conv: reflect padding needs a materialised input border");
+    if (d->pad_mode == HFC_PAD_ZERO && (in.pt | in.pl | in.pb | in.pr))
+      return set_error(HFC_ERR_INVALID, "conv: zero padding expects a border-less input buffer");
+    pl->nphases = 1;
+    Phase& p = pl->ph[0];
+    p.grid_h = pl->out_h; p.grid_w = pl->out_w;
+    p.osh = p.osw = 1; p.ooh = p.oow = 0;
+    p.sh = p.sw = s;
+    if (d->window) {
+      for (int ky = 0; ky < d->kh; ++ky) {
+        p.dh[p.ntaps] = static_cast<int8_t>(ky - d->pad_t);
+        p.dw[p.ntaps] = static_cast<int8_t>(-d->pad_l);
+        p.ky[p.ntaps] = static_cast<int8_t>(ky); p.kx[p.ntaps] = 0;
+        ++p.ntaps;
+      }
+    } else {
+      for (int ky = 0; ky < d->kh; ++ky)
+        for (int kx = 0; kx < d->kw; ++kx) {
+          p.dh[p.ntaps] = static_cast<int8_t>(ky - d->pad_t);
+          p.dw[p.ntaps] = static_cast<int8_t>(kx - d->pad_l);
+          p.ky[p.ntaps] = static_cast<int8_t>(ky); p.kx[p.ntaps] = static_cast<int8_t>(kx);
+          ++p.ntaps;
+        }
+    }
+  } else {
+    if (in.pt | in.pl | in.pb | in.pr)
+      return set_error(HFC_ERR_INVALID, "conv_transpose: expects a border-less input buffer");
+    const int op = s - 1;
+    pl->out_h = (in.h - 1) * s - 2 * d->pad_t + d->kh + op;
+    pl->out_w = (in.w - 1) * s - 2 * d->pad_l + d->kw + op;
+    pl->nphases = s * s;
+    for (int a = 0; a < s; ++a)
+      for (int b = 0; b < s; ++b) {
+        Phase& p = pl->ph[a * s + b];
+        p.grid_h = (pl->out_h - a + s - 1) / s;
+        p.grid_w = (pl->out_w - b + s - 1) / s;
+        p.osh = p.osw = s; p.ooh = a; p.oow = b;
+        p.sh = p.sw = 1;
+        // out[o] += in[i] * w[k] with o = i*s - pad + k  =>  i = (o + pad - k)/s, o = g*s + a
+        for (int ky = 0; ky < d->kh; ++ky) {
+          if (((a + d->pad_t - ky) % s) != 0) continue;
+          for (int kx = 0; kx < d->kw; ++kx) {
+            if (((b + d->pad_l - kx) % s) != 0) continue;
+            p.dh[p.ntaps] = static_cast<int8_t>((a + d->pad_t - ky) / s);
+            p.dw[p.ntaps] = static_cast<int8_t>((b + d->pad_l - kx) / s);
+            p.ky[p.ntaps] = static_cast<int8_t>(ky); p.kx[p.ntaps] = static_cast<int8_t>(kx);
+            ++p.ntaps;
+          }
+        }
+      }
+  }
+  if (pl->out_h <= 0 || pl->out_w <= 0)
+    return set_error(HFC_ERR_INVALID, "conv: empty output (%d x %d)", pl->out_h, pl->out_w);
+
+  // N tiling
+  int bn = d->block_n;
+  if (bn == 0) {
+    const int nt = (d->cout + 255) / 256;
+    bn = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
+  }
+  if (bn % 16 != 0 || bn < 16 || bn > 256)
+    return set_error(HFC_ERR_INVALID, "conv: block_n %d must be a multiple of 16 in [16,256]", bn);
+  pl->block_n = bn;
+  pl->n_tiles = (d->cout + bn - 1) / bn;
+  pl->rows = pl->n_tiles * bn;
+  if (d->norm && pl->n_tiles != 1)
+    return set_error(HFC_ERR_INVALID,
+                     "conv: fused ChannelNorm needs cout <= 256 (use NHWC_F32 + hfc_channelnorm)");
+  if (d->norm && d->cout < 2) return set_error(HFC_ERR_INVALID, "conv: ChannelNorm needs cout >= 2");
+
+  pl->c_chunks = d->window ? 1 : in.cpad / kBlockK;
+  size_t off = 0;
+  for (int i = 0; i < pl->nphases; ++i) {
+    Phase& p = pl->ph[i];
+    p.ktot = p.ntaps * pl->c_chunks * kBlockK;
+    p.w_offset = off;
+    off += static_cast<size_t>(pl->rows) * p.ktot;
+  }
+  pl->packed_elems = off;
+  pl->flops = 2.0 * in.n * (d->transposed ? in.h * in.w : pl->out_h * pl->out_w) * (double)d->cout *
+              in.c * d->kh * d->kw;
+
+  // output checks
+  const hfc_act_geom& o = d->out;
+  if (o.n != in.n || o.h != pl->out_h || o.w != pl->out_w)
+    return set_error(HFC_ERR_INVALID, "conv: out geometry (%d,%d,%d) != expected (%d,%d,%d)", o.n,
+                     o.h, o.w, in.n, pl->out_h, pl->out_w);
+  if (d->out_mode == HFC_OUT_NHWC_F16) {
+    if (o.cpad % 8 != 0 || o.cpad < d->cout)
+      return set_error(HFC_ERR_INVALID, "conv: out.cpad must be a multiple of 8 and >= cout");
+    if (d->out_reflect && (o.pt >= o.h || o.pb >= o.h || o.pl >= o.w || o.pr >= o.w))
+      return set_error(HFC_ERR_INVALID, "conv: reflected border wider than the image");
+  } else if (d->out_mode == HFC_OUT_NHWC_F32) {
+    if (o.cpad % 4 != 0 || o.cpad < d->cout)
+      return set_error(HFC_ERR_INVALID, "conv: fp32 row pitch must be a multiple of 4 and >= cout");
+  } else if (d->out_mode != HFC_OUT_NCHW_F32) {
+    return set_error(HFC_ERR_INVALID, "conv: bad out_mode");
+  }
+  return HFC_OK;
+}
+
+static int tile_and_stages(const Plan& pl, const Phase& ph, int batch, ConvKernelParams* kp) {
+  kp->tw = std::min(16, next_pow2(ph.grid_w));
+  kp->th = std::min(kBlockM / kp->tw, next_pow2(ph.grid_h));
+  kp->tn = kBlockM / (kp->tw * kp->th);
+  kp->tiles_w = (ph.grid_w + kp->tw - 1) / kp->tw;
+  kp->tiles_h = (ph.grid_h + kp->th - 1) / kp->th;
+  kp->tiles_n = (batch + kp->tn - 1) / kp->tn;
+  const int stage_bytes = kABytes + pl.block_n * kBlockK * 2;
+  int stages = (225 * 1024 - 2048) / stage_bytes;
+  stages = std::max(2, std::min(stages, kMaxStages));
+  kp->stages = stages;
+  return stage_bytes;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+}  // namespace hfc
+
+using namespace hfc;
+
+extern "C" int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info) {
+  Plan pl;
+  int rc = make_plan(d, &pl);
+  if (rc != HFC_OK) return rc;
+  if (!info) return set_error(HFC_ERR_INVALID, "conv_query: null info");
+  ConvKernelParams kp;
+  tile_and_stages(pl, pl.ph[0], d->in.n, &kp);
+  info->packed_weight_bytes = pl.packed_elems * 2;
+  info->out_h = pl.out_h;
+  info->out_w = pl.out_w;
+  info->phases = pl.nphases;
+  info->block_n = pl.block_n;
+  info->n_tiles = pl.n_tiles;
+  info->m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
+  info->stages = kp.stages;
+  info->k_total = 0;
+  for (int i = 0; i < pl.nphases; ++i) info->k_total += pl.ph[i].ktot;
+  info->flops = pl.flops;
+  return HFC_OK;
+}
+
+extern "C" int hfc_conv_pack_weights(const hfc_conv_desc* d, const float* w, void* packed,
+                                     void* stream) {
+  Plan pl;
+  int rc = make_plan(d, &pl);
+  if (rc != HFC_OK) return rc;
+  if (!w || !packed) return set_error(HFC_ERR_INVALID, "conv_pack_weights: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < pl.nphases; ++i) {
+    const Phase& ph = pl.ph[i];
+    PackParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.cout = d->cout; pp.cin = d->in.c; pp.kh = d->kh; pp.kw = d->kw;
+    pp.cin_pad = d->in.cpad; pp.ntaps = ph.ntaps; pp.ktot = ph.ktot; pp.rows = pl.rows;
+    pp.transposed = d->transposed; pp.window = d->window; pp.fmt = 0;
+    memcpy(pp.ky, ph.ky, sizeof(pp.ky));
+    memcpy(pp.kx, ph.kx, sizeof(pp.kx));
+    const size_t total = static_cast<size_t>(pl.rows) * ph.ktot;
+    const int threads = 256;
+    const int blocks = static_cast<int>(std::min<size_t>((total + threads - 1) / threads, 148 * 16));
+    pack_weights_kernel<<<blocks, threads, 0, st>>>(
+        w, reinterpret_cast<uint16_t*>(packed) + ph.w_offset, pp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return set_error(HFC_ERR_LAUNCH, "pack_weights launch: %s", cudaGetErrorString(e));
+  }
+  return HFC_OK;
+}
+
+extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const void* packed,
+                                const float* bias, const float* gamma, const float* beta, void* out,
+                                void* stream) {
+  Plan pl;
+  int rc = make_plan(d, &pl);
+  if (rc != HFC_OK) return rc;
+  if (!in || !packed || !out) return set_error(HFC_ERR_INVALID, "conv_forward: null pointer");
+  if (d->norm && (!gamma || !beta))
+    return set_error(HFC_ERR_INVALID, "conv_forward: fused norm needs gamma and beta");
+  int sm_count = 0;
+  rc = device_sm_count(&sm_count);
+  if (rc != HFC_OK) return rc;
+  PFN_encodeTiled encode = get_encode_fn();
+  if (!encode) return set_error(HFC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not found");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const hfc_act_geom& ig = d->in;
+  const int Hp = ig.h + ig.pt + ig.pb;
+  const int Wp = ig.w + ig.pl + ig.pr;
+
+  for (int i = 0; i < pl.nphases; ++i) {
+    const Phase& ph = pl.ph[i];
+    ConvKernelParams kp;
+    memset(&kp, 0, sizeof(kp));
+    const int stage_bytes = tile_and_stages(pl, ph, ig.n, &kp);
+    kp.n_tiles = pl.n_tiles;
+    kp.block_n = pl.block_n;
+    kp.c_chunks = pl.c_chunks;
+    kp.ntaps = ph.ntaps;
+    kp.num_kb = ph.ntaps * pl.c_chunks;
+    kp.grid_h = ph.grid_h; kp.grid_w = ph.grid_w; kp.batch = ig.n;
+    kp.sh = ph.sh; kp.sw = ph.sw;
+    kp.ih0 = ig.pt; kp.iw0 = ig.pl;
+    kp.out_mode = d->out_mode;
+    kp.osh = ph.osh; kp.osw = ph.osw; kp.ooh = ph.ooh; kp.oow = ph.oow;
+    kp.out_h = pl.out_h; kp.out_w = pl.out_w;
+    kp.out_cpad = (d->out_mode == HFC_OUT_NCHW_F32) ? d->cout : d->out.cpad;
+    kp.out_pt = d->out.pt; kp.out_pl = d->out.pl; kp.out_pb = d->out.pb; kp.out_pr = d->out.pr;
+    if (d->out_mode != HFC_OUT_NHWC_F16) kp.out_pt = kp.out_pl = kp.out_pb = kp.out_pr = 0;
+    kp.out_reflect = d->out_reflect;
+    kp.cout = d->cout;
+    kp.act = d->act; kp.norm = d->norm; kp.eps = d->eps;
+    kp.fmt = 0;
+    kp.bias = bias; kp.gamma = gamma; kp.beta = beta;
+    kp.out = out;
+    memcpy(kp.tap_dh, ph.dh, sizeof(kp.tap_dh));
+    memcpy(kp.tap_dw, ph.dw, sizeof(kp.tap_dw));
+
+    // A: 4-D map over the NHWC buffer {channels, W, H, N}
+    CUtensorMap tmA, tmB;
+    {
+      cuuint64_t dims[4], strides[3];
+      cuuint32_t box[4], estr[4];
+      if (d->window) {
+        // dim0 = 64 elements = 8 consecutive pixels x 8 channels, dim1 = window start (pixel)
+        if (Wp < 8) return set_error(HFC_ERR_INVALID, "conv: window packing needs Wp >= 8");
+        dims[0] = 64; dims[1] = static_cast<cuuint64_t>(Wp - 7);
+      } else {
+        dims[0] = static_cast<cuuint64_t>(ig.cpad); dims[1] = static_cast<cuuint64_t>(Wp);
+      }
+      dims[2] = static_cast<cuuint64_t>(Hp); dims[3] = static_cast<cuuint64_t>(ig.n);
+      strides[0] = static_cast<cuuint64_t>(ig.cpad) * 2;
+      strides[1] = static_cast<cuuint64_t>(Wp) * ig.cpad * 2;
+      strides[2] = static_cast<cuuint64_t>(Hp) * Wp * ig.cpad * 2;
+      box[0] = kBlockK; box[1] = kp.tw * ph.sw; box[2] = kp.th * ph.sh; box[3] = kp.tn;
+      estr[0] = 1; estr[1] = ph.sw; estr[2] = ph.sh; estr[3] = 1;
+      CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS)
+        return set_error(HFC_ERR_LAUNCH, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+    }
+    {
+      cuuint64_t dims[2] = {static_cast<cuuint64_t>(ph.ktot), static_cast<cuuint64_t>(pl.rows)};
+      cuuint64_t strides[1] = {static_cast<cuuint64_t>(ph.ktot) * 2};
+      cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(pl.block_n)};
+      cuuint32_t estr[2] = {1, 1};
+      void* wptr = const_cast<uint16_t*>(reinterpret_cast<const uint16_t*>(packed) + ph.w_offset);
+      CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wptr, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS)
+        return set_error(HFC_ERR_LAUNCH, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    }
+
+    const int total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_tiles;
+    const int grid = std::min(total_tiles, sm_count);
+    const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 /*align*/ + 256 /*bars*/;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess)
+        return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      smem_set = 227 * 1024;
+    }
+    conv_igemm_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return set_error(HFC_ERR_LAUNCH, "conv_igemm launch: %s", cudaGetErrorString(e));
+    note_launch();
+  }
+  return HFC_OK;
+}

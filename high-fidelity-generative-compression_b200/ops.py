@@ -1,0 +1,217 @@
+"""Host wrappers over the libhfc C ABI: torch tensors own the device memory, raw pointers cross
+the boundary, work is enqueued on torch's current CUDA stream.  Nothing here computes on the CPU
+or falls back to torch operators.
+"""
+import ctypes
+from dataclasses import dataclass, replace
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY02, ACT_NONE, ACT_RELU, OUT_NCHW_F32, OUT_NHWC_F16, OUT_NHWC_F32,
+                   PAD_REFLECT, PAD_ZERO, PREC_F16, check, lib)
+
+CN_EPS = 1e-3  # ChannelNorm2D eps (reference: src/normalisation/channel.py:35)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+@dataclass(frozen=True)
+class Geom:
+    """NHWC 16-bit activation buffer geometry (``hfc_act_geom``)."""
+    n: int
+    h: int
+    w: int
+    c: int
+    cpad: int
+    pt: int = 0
+    pl: int = 0
+    pb: int = 0
+    pr: int = 0
+
+    def c_struct(self):
+        return _lib.ActGeom(self.n, self.h, self.w, self.c, self.cpad, self.pt, self.pl, self.pb, self.pr)
+
+    @property
+    def shape(self):
+        return (self.n, self.h + self.pt + self.pb, self.w + self.pl + self.pr, self.cpad)
+
+    def alloc(self, device):
+        return torch.empty(self.shape, dtype=torch.float16, device=device)
+
+    def interior(self, buf):
+        """(n, c, h, w) fp32 view of the logical content of an act buffer (tests / debugging)."""
+        x = buf[:, self.pt:self.pt + self.h, self.pl:self.pl + self.w, :self.c]
+        return x.permute(0, 3, 1, 2).float()
+
+
+def device_info():
+    sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib.hfc_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)), "device_info")
+    return sm.value, ma.value, mi.value
+
+
+def launch_count():
+    return int(lib.hfc_launch_count())
+
+
+def nchw_to_act(x, geom, reflect=False, norm=False, gamma=None, beta=None, out=None):
+    """fp32 NCHW tensor -> act buffer (optionally ChannelNorm2D first)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    assert tuple(x.shape) == (geom.n, geom.c, geom.h, geom.w), (tuple(x.shape), geom)
+    if out is None:
+        out = geom.alloc(x.device)
+    g = geom.c_struct()
+    gm = gamma.reshape(-1) if gamma is not None else None
+    bt = beta.reshape(-1) if beta is not None else None
+    check(lib.hfc_nchw_to_act(_ptr(x), ctypes.byref(g), int(reflect), int(norm), _ptr(gm), _ptr(bt),
+                              CN_EPS, _ptr(out), _stream()), "nchw_to_act")
+    return out
+
+
+def channelnorm(x_rows, geom, gamma, beta, act=ACT_NONE, reflect=False, res1=None, res2=None,
+                want_f32=False, want_act=True, out_act=None, out_f32=None):
+    """Stand-alone ChannelNorm2D over NHWC fp32 rows ``x_rows`` of shape (n*h*w, ld)."""
+    assert x_rows.dtype == torch.float32 and x_rows.is_contiguous()
+    ld = x_rows.shape[-1]
+    if want_act and out_act is None:
+        out_act = geom.alloc(x_rows.device)
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((geom.n * geom.h * geom.w, geom.c), dtype=torch.float32, device=x_rows.device)
+    g = geom.c_struct()
+    check(lib.hfc_channelnorm(_ptr(x_rows), ld, ctypes.byref(g), int(reflect), _ptr(gamma.reshape(-1)),
+                              _ptr(beta.reshape(-1)), CN_EPS, act, _ptr(res1), _ptr(res2),
+                              _ptr(out_f32 if want_f32 else None), _ptr(out_act if want_act else None),
+                              _stream()), "channelnorm")
+    return out_act, out_f32
+
+
+class Conv:
+    """One convolution / transposed convolution of the hot path bound to fixed geometry.
+
+    Holds the descriptor, the packed (K-major fp16) weights and re-packs them when the source
+    parameter changes (``_version`` / storage pointer), so optimizer steps and ``.to()`` are seen.
+    """
+
+    def __init__(self, in_geom, cout, k, stride=1, transposed=False, pad_mode=PAD_ZERO, pad=(0, 0, 0, 0),
+                 out_mode=OUT_NHWC_F16, out_geom=None, out_reflect=False, act=ACT_NONE, norm=False,
+                 window=False, block_n=0, precision=PREC_F16):
+        kh, kw = (k, k) if isinstance(k, int) else k
+        pt, pl, pb, pr = pad
+        d = _lib.ConvDesc()
+        d.inp = in_geom.c_struct()
+        d.kh, d.kw, d.stride, d.transposed = kh, kw, stride, int(transposed)
+        d.pad_mode = pad_mode
+        d.pad_t, d.pad_l, d.pad_b, d.pad_r = pt, pl, pb, pr
+        d.cout, d.window = cout, int(window)
+        d.out_mode = out_mode
+        d.out_reflect, d.act, d.norm = int(out_reflect), act, int(norm)
+        d.eps = CN_EPS
+        d.block_n, d.precision = block_n, precision
+        # output dims
+        if transposed:
+            oh = (in_geom.h - 1) * stride - 2 * pt + kh + (stride - 1)
+            ow = (in_geom.w - 1) * stride - 2 * pl + kw + (stride - 1)
+        else:
+            oh = (in_geom.h + pt + pb - kh) // stride + 1
+            ow = (in_geom.w + pl + pr - kw) // stride + 1
+        if out_geom is None:
+            out_geom = Geom(in_geom.n, oh, ow, cout, round_up(cout, 8) if out_mode != OUT_NCHW_F32 else cout)
+        assert (out_geom.h, out_geom.w) == (oh, ow), (out_geom, oh, ow)
+        d.out = out_geom.c_struct()
+        self.desc = d
+        self.in_geom, self.out_geom, self.out_mode = in_geom, out_geom, out_mode
+        self.cout = cout
+        info = _lib.ConvInfo()
+        check(lib.hfc_conv_query(ctypes.byref(d), ctypes.byref(info)), "conv_query")
+        self.info = info
+        self.flops = info.flops
+        self._packed = None
+        self._packed_key = None
+
+    def alloc_out(self, device):
+        g = self.out_geom
+        if self.out_mode == OUT_NHWC_F16:
+            return g.alloc(device)
+        if self.out_mode == OUT_NHWC_F32:
+            return torch.empty((g.n * g.h * g.w, g.cpad), dtype=torch.float32, device=device)
+        return torch.empty((g.n, self.cout, g.h, g.w), dtype=torch.float32, device=device)
+
+    def packed_weights(self, weight):
+        key = (weight.data_ptr(), weight._version, weight.device)
+        if self._packed is None or self._packed_key != key:
+            w = weight.detach()
+            assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+            if self._packed is None or self._packed.device != w.device:
+                self._packed = torch.empty(self.info.packed_weight_bytes // 2, dtype=torch.float16, device=w.device)
+            check(lib.hfc_conv_pack_weights(ctypes.byref(self.desc), _ptr(w), _ptr(self._packed), _stream()),
+                  "conv_pack_weights")
+            self._packed_key = key
+        return self._packed
+
+    def __call__(self, x_act, weight, bias=None, gamma=None, beta=None, out=None):
+        assert x_act.is_cuda and x_act.dtype == torch.float16 and tuple(x_act.shape) == self.in_geom.shape, \
+            (tuple(x_act.shape), self.in_geom.shape)
+        packed = self.packed_weights(weight)
+        if out is None:
+            out = self.alloc_out(x_act.device)
+        b = bias.detach().reshape(-1) if bias is not None else None
+        g = gamma.detach().reshape(-1) if gamma is not None else None
+        bt = beta.detach().reshape(-1) if beta is not None else None
+        check(lib.hfc_conv_forward(ctypes.byref(self.desc), _ptr(x_act), _ptr(packed), _ptr(b), _ptr(g),
+                                   _ptr(bt), _ptr(out), _stream()), "conv_forward")
+        return out
+
+
+def latent_likelihood(y, mean, scale_raw, noise=None, scale_lower_bound=0.11, likelihood_type="gaussian"):
+    """Fused conditional likelihood; returns (decoded, sums) with sums = [sum log p_noisy, sum log p_quant]
+    (natural log, fp64, on device)."""
+    for t in (y, mean, scale_raw) + ((noise,) if noise is not None else ()):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == y.shape
+    decoded = torch.empty_like(y)
+    sums = torch.zeros(2, dtype=torch.float64, device=y.device)
+    lt = {"gaussian": 0, "logistic": 1}[likelihood_type]
+    check(lib.hfc_latent_likelihood(_ptr(y), _ptr(mean), _ptr(scale_raw), _ptr(noise), y.numel(),
+                                    float(scale_lower_bound), lt, _ptr(decoded), _ptr(sums), _stream()),
+          "latent_likelihood")
+    return decoded, sums
+
+
+def pack_density_params(Hs, a_s, bs):
+    """(H_k, a_k, b_k), k=0..3, shapes (C,f_{k+1},f_k)/(C,f_{k+1},1) -> (C, 64) fp32 rows in the order
+    the kernel expects: softplus(H_k) row-major, b_k, tanh(a_k) per layer."""
+    C = Hs[0].shape[0]
+    parts = []
+    for H, a, b in zip(Hs, a_s, bs):
+        parts += [torch.nn.functional.softplus(H.detach()).reshape(C, -1), b.detach().reshape(C, -1),
+                  torch.tanh(a.detach()).reshape(C, -1)]
+    p = torch.cat(parts, dim=1)
+    assert p.shape[1] == 44, p.shape
+    out = torch.zeros((C, 64), dtype=torch.float32, device=p.device)
+    out[:, :44] = p
+    return out.contiguous()
+
+
+def hyperlatent_likelihood(z, params64, noise=None):
+    """Factorized-density likelihood of z at z+noise and round(z). Returns (z_noisy|None, z_quant, sums)."""
+    assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 4
+    n, c, h, w = z.shape
+    assert tuple(params64.shape) == (c, 64) and params64.is_contiguous()
+    z_quant = torch.empty_like(z)
+    z_noisy = torch.empty_like(z) if noise is not None else None
+    sums = torch.zeros(2, dtype=torch.float64, device=z.device)
+    check(lib.hfc_hyperlatent_likelihood(_ptr(z), _ptr(noise), _ptr(params64), n, c, h * w, _ptr(z_noisy),
+                                         _ptr(z_quant), _ptr(sums), _stream()), "hyperlatent_likelihood")
+    return z_noisy, z_quant, sums

@@ -1,0 +1,165 @@
+/*
+ * hfc.h -- C ABI of libhfc (B200 / sm_100a kernels for the HiFIC forward/backward hot path).
+ *
+ * The reference (Justin-Tan/high-fidelity-generative-compression @ 7d4e9e7) has no FFI of its own:
+ * every operator on the hot path is an eager torch call issued from its nn.Module classes.  The
+ * entry points below are therefore cut at exactly those call sites -- one entry point per torch
+ * operator group the reference issues -- so a maintainer can bind them from the reference modules
+ * with ctypes.  Each declaration cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types; all pointers are DEVICE pointers unless the
+ *     name ends in _host;
+ *   - every call enqueues work on the caller's `stream` (a cudaStream_t passed as void*) and
+ *     returns without synchronising;
+ *   - returns 0 on success, a negative hfc_status otherwise; never throws; hfc_last_error()
+ *     gives a thread-local message;
+ *   - the library never allocates device memory: the caller owns inputs, outputs and workspaces;
+ *   - there is NO CPU fallback: on a machine without an sm_100 GPU the compute calls return
+ *     HFC_ERR_NO_DEVICE.
+ *
+ * Internal activation format ("act buffer"): NHWC, 16-bit (fp16, or bf16 hi/lo planes in the
+ * split-precision mode), channels padded to `cpad` (multiple of 8; multiples of 64 for conv
+ * inputs), with an optional materialised spatial border (pt, pl, pb, pr) that the PRODUCING
+ * kernel fills by reflection so that the consuming convolution's ReflectionPad2d is free.
+ */
+#ifndef HFC_H_
+#define HFC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFC_ABI_VERSION 1
+
+typedef enum hfc_status {
+  HFC_OK = 0,
+  HFC_ERR_INVALID = -1,     /* bad descriptor / unsupported combination */
+  HFC_ERR_NO_DEVICE = -2,   /* no sm_100 device or driver entry point missing */
+  HFC_ERR_LAUNCH = -3,      /* CUDA launch / runtime error (message has the CUDA string) */
+  HFC_ERR_UNSUPPORTED = -4  /* valid request that this build does not implement */
+} hfc_status;
+
+enum { HFC_PAD_ZERO = 0, HFC_PAD_REFLECT = 1 };
+enum { HFC_ACT_NONE = 0, HFC_ACT_RELU = 1, HFC_ACT_LEAKY02 = 2 };
+enum { HFC_OUT_NHWC_F16 = 0, HFC_OUT_NHWC_F32 = 1, HFC_OUT_NCHW_F32 = 2 };
+enum { HFC_PREC_F16 = 0, HFC_PREC_BF16X3 = 1 };
+
+/* NHWC 16-bit activation buffer geometry (see "Internal activation format"). */
+typedef struct hfc_act_geom {
+  int32_t n, h, w;          /* logical batch / height / width (without border) */
+  int32_t c, cpad;          /* real and padded channel count */
+  int32_t pt, pl, pb, pr;   /* materialised border rows/cols (top, left, bottom, right) */
+} hfc_act_geom;
+
+/*
+ * One convolution / transposed convolution as issued by the reference:
+ *   F.conv2d            : src/network/encoder.py:56-101, generator.py:33-44,98-103,139-142,
+ *                         hyper.py:52-63, discriminator.py:66-86
+ *   F.conv_transpose2d  : src/network/generator.py:115-137, hyper.py:83-97
+ * fused (optionally) with what follows it in the reference module:
+ *   bias, ChannelNorm2D (src/normalisation/channel.py:48-59), ReLU / LeakyReLU(0.2),
+ *   and the ReflectionPad2d of the NEXT layer (materialised into the output border).
+ */
+typedef struct hfc_conv_desc {
+  hfc_act_geom in;          /* input act buffer */
+  int32_t kh, kw;           /* filter size */
+  int32_t stride;           /* 1 or 2 */
+  int32_t transposed;       /* 0: conv2d, 1: conv_transpose2d (output_padding = stride-1) */
+  int32_t pad_mode;         /* HFC_PAD_ZERO | HFC_PAD_REFLECT (reflect needs in.p* >= pad_*) */
+  int32_t pad_t, pad_l, pad_b, pad_r; /* logical padding; for transposed: `padding` arg in pad_t/pad_l */
+  int32_t cout;             /* real output channels */
+  int32_t window;           /* 1: 'window' packing for tiny cin (cin<=8, cpad==8, kw<=8): one
+                               K block covers a whole filter row (kw x cin) */
+  /* output */
+  int32_t out_mode;         /* HFC_OUT_* */
+  hfc_act_geom out;         /* NHWC_F16: full geometry; NHWC_F32: cpad = row pitch in floats,
+                               borders ignored; NCHW_F32: plain (n, cout, h, w) */
+  int32_t out_reflect;      /* fill out border by reflection (NHWC_F16 only) */
+  int32_t act;              /* HFC_ACT_* applied after bias (and after the norm when fused) */
+  int32_t norm;             /* 1: fuse ChannelNorm2D (needs cout <= 256) */
+  float eps;                /* ChannelNorm eps (reference: 1e-3) */
+  int32_t block_n;          /* 0 = auto; else N tile (multiple of 16, <= 256) */
+  int32_t precision;        /* HFC_PREC_* */
+} hfc_conv_desc;
+
+typedef struct hfc_conv_info {
+  size_t packed_weight_bytes;   /* size of the packed weight buffer hfc_conv_pack_weights fills */
+  int32_t out_h, out_w;         /* logical output dims */
+  int32_t phases;               /* kernel launches per forward (4 for stride-2 transposed) */
+  int32_t block_n, n_tiles, m_tiles, stages, k_total;
+  double flops;                 /* algorithmic 2*MACs of the layer (real channels) */
+} hfc_conv_info;
+
+/* library / device */
+int hfc_abi_version(void);
+const char* hfc_last_error(void);
+int hfc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched in the calling process (bench.py: gpu_launches) */
+unsigned long long hfc_launch_count(void);
+
+/* convolution */
+int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info);
+/* w: fp32 (cout, cin, kh, kw) for conv2d, (cin, cout, kh, kw) for conv_transpose2d (torch layout) */
+int hfc_conv_pack_weights(const hfc_conv_desc* d, const float* w, void* packed, void* stream);
+/* in: act buffer (d->in); packed: from hfc_conv_pack_weights; bias/gamma/beta: fp32 [cout] or NULL;
+ * out: buffer of d->out_mode/d->out */
+int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const void* packed, const float* bias,
+                     const float* gamma, const float* beta, void* out, void* stream);
+
+/*
+ * Layout conversion at module boundaries (the reference modules exchange NCHW fp32):
+ * x (n, c, h, w) fp32 -> act buffer `g` (border by reflection or zeros), optionally applying
+ * ChannelNorm2D first (Generator.conv_block_init[0], src/network/generator.py:98-103).
+ */
+int hfc_nchw_to_act(const float* x, const hfc_act_geom* g, int32_t reflect, int32_t norm,
+                    const float* gamma, const float* beta, float eps, void* out, void* stream);
+
+/*
+ * Stand-alone ChannelNorm2D (src/normalisation/channel.py:48-59) for channel counts that do not
+ * fit one accumulator tile (480, 960): x = raw conv output, NHWC fp32 rows of pitch `ld`;
+ * y = act(gamma * (x - mean) * rsqrt(var_unbiased + eps) + beta) [+ res1] [+ res2];
+ * writes y as fp32 rows (out_f32, optional) and as act buffer `g` (out_act, optional).
+ * res1/res2 implement ResidualBlock's `torch.add(res, identity_map)` (generator.py:44) and
+ * Generator's `x += head` (generator.py:161).
+ */
+int hfc_channelnorm(const float* x, int32_t ld, const hfc_act_geom* g, int32_t reflect,
+                    const float* gamma, const float* beta, float eps, int32_t act,
+                    const float* res1, const float* res2, float* out_f32, void* out_act,
+                    void* stream);
+
+/*
+ * Hyperprior likelihoods (src/hyperprior.py:57-139, 277-330; src/helpers/maths.py:87-109;
+ * src/compression/hyperprior_model.py:305-384).  All tensors NCHW fp32.
+ *
+ * hfc_latent_likelihood: one pass over (y, mean, scale_raw[, noise]):
+ *   scale = max(scale_raw, scale_lower_bound)                        (LowerBoundToward)
+ *   noisy  = y + noise ; p_n = Phi((.5-|noisy-mean|)/scale) - Phi(-(.5+|noisy-mean|)/scale)
+ *   quant  = floor(y-mean+.5)+mean ; p_q likewise ;  p = max(p, 1e-9)
+ *   sums[0] += sum log(p_n + 1e-9) ; sums[1] += sum log(p_q + 1e-9)   (natural log, fp64 accum)
+ *   decoded = quant (the straight-through value, hyperprior.py:108-122)
+ * likelihood_type: 0 gaussian (erfc), 1 logistic (sigmoid).  noise may be NULL (=> no noisy term).
+ * `sums` (2 doubles) must be zeroed by the caller.
+ */
+int hfc_latent_likelihood(const float* y, const float* mean, const float* scale_raw,
+                          const float* noise, int64_t count, float scale_lower_bound,
+                          int32_t likelihood_type, float* decoded, double* sums, void* stream);
+/*
+ * hfc_hyperlatent_likelihood: factorized density (4-layer monotone MLP per channel) evaluated at
+ * z+noise and at round(z):  z (n, c, h, w); params packed per channel as 44 floats:
+ *   softplus(H0)[3], b0[3], tanh(a0)[3], softplus(H1)[3x3 row-major], b1[3], tanh(a1)[3],
+ *   softplus(H2)[3x3], b2[3], tanh(a2)[3], softplus(H3)[3], b3[1], tanh(a3)[1]
+ *   (each channel's block padded to 64 floats)
+ * outputs: z_noisy, z_quant (either may be NULL), sums[0] (noisy) and sums[1] (quantised) as above.
+ */
+int hfc_hyperlatent_likelihood(const float* z, const float* noise, const float* params64,
+                               int32_t n, int32_t c, int32_t hw, float* z_noisy, float* z_quant,
+                               double* sums, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFC_H_ */
