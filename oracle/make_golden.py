@@ -1,0 +1,131 @@
+"""Generate tests/golden/*.npz by running the REAL reference modules (imported from /root/reference) on
+synthetic weights/inputs, and check the oracle restatement against them -- TEST INFRASTRUCTURE.
+
+    python oracle/make_golden.py            # regenerate fixtures (build container only)
+
+Fixtures hold outputs only (strided subsets + full-tensor moments for the big ones); inputs and weights are
+regenerated from seeds by hific_b200.synth, which the script also validates against the reference's own
+state_dict keys and shapes.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> (batch, H, W, training, evaluation_mode)
+CASES = {
+    "train_128": (2, 128, 128, True, False),
+    "eval_128": (2, 128, 128, False, False),
+    "train_256": (1, 256, 256, True, False),
+    "evalmode_100x144": (1, 100, 144, False, True),
+}
+SEED = 0
+
+
+def summarize(name, t, out, full_limit=40000):
+    """Store t in full when small, else a strided subset; always its first two moments."""
+    a = t.detach().cpu().numpy().astype(np.float32)
+    out[name + ".shape"] = np.array(a.shape, dtype=np.int64)
+    out[name + ".sum"] = np.array(a.astype(np.float64).sum())
+    out[name + ".sqsum"] = np.array((a.astype(np.float64) ** 2).sum())
+    if a.size <= full_limit:
+        out[name + ".full"] = a
+    else:
+        step = int(np.ceil(a.size / full_limit))
+        out[name + ".stride"] = np.array(step, dtype=np.int64)
+        out[name + ".sub"] = a.reshape(-1)[::step].copy()
+
+
+def build_reference_model(gan=False):
+    ref_shim.install()
+    import logging
+    from default_config import ModelModes, ModelTypes, hific_args, mse_lpips_args
+    from src.model import Model
+
+    class A(hific_args if gan else mse_lpips_args):
+        pass
+
+    args = A()
+    args.image_dims = (3, 256, 256)
+    args.latent_dims = (args.latent_channels, 16, 16)
+    args.batch_size = 2
+    logger = logging.getLogger("golden")
+    model = Model(args, logger, model_mode=ModelModes.TRAINING,
+                  model_type=ModelTypes.COMPRESSION_GAN if gan else ModelTypes.COMPRESSION)
+    return model, ModelModes
+
+
+def main():
+    from hific_b200 import synth
+    from oracle import hific_oracle as O
+
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    model, ModelModes = build_reference_model(gan=False)
+
+    # 1. state_dict contract
+    ref_sd = model.state_dict()
+    shapes = synth.hific_shapes()
+    assert set(ref_sd.keys()) == set(shapes.keys()), (set(ref_sd) ^ set(shapes))
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), (k, tuple(v.shape), shapes[k])
+    print(f"state_dict contract OK: {len(shapes)} keys")
+    sd = synth.synth_state_dict(SEED)
+    model.load_state_dict(sd, strict=True)
+
+    report = []
+    for name, (b, h, w, training, evalmode) in CASES.items():
+        x = synth.synth_image(b, h, w, SEED)
+        model.train(training)
+        model.model_mode = ModelModes.EVALUATION if evalmode else ModelModes.TRAINING
+        # shapes of y and z for the noise tensors
+        hp, wp = (-(-h // 16) * 16, -(-w // 16) * 16) if evalmode else (h, w)
+        yh, yw = hp // 16, wp // 16
+        if evalmode:
+            yh, yw = -(-yh // 4) * 4, -(-yw // 4) * 4
+        zh, zw = yh // 4, yw // 4
+        noise_z = synth.synth_noise((b, 320, zh, zw), f"z{name}", SEED)
+        noise_y = synth.synth_noise((b, 220, yh, yw), f"y{name}", SEED)
+        with torch.no_grad(), ref_shim.NoiseFeeder([noise_z, noise_y]) as nf:
+            intermediates, hyperinfo = model.compression_forward(x)
+            assert nf.calls == 2
+            y_ref = model.Encoder(x if not evalmode else torch.nn.functional.pad(
+                x, (0, wp - w, 0, hp - h), mode="reflect"))
+        out = {}
+        summarize("y", y_ref, out)
+        summarize("decoded", hyperinfo.decoded, out)
+        summarize("recon", intermediates.reconstruction, out)
+        for f in ("latent_nbpp", "hyperlatent_nbpp", "total_nbpp", "latent_qbpp", "hyperlatent_qbpp", "total_qbpp"):
+            out[f] = np.array(float(getattr(hyperinfo, f)))
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+
+        # 2. pin the oracle restatement against the reference outputs
+        with torch.no_grad():
+            recon, hyper, y = O.compression_forward(sd, x, training, evalmode, noise_z, noise_y)
+        errs = dict(
+            y=(y if not evalmode else y)[..., :y_ref.shape[2], :y_ref.shape[3]].sub(y_ref).abs().max().item()
+            if not evalmode else 0.0,
+            decoded=(hyper.decoded - hyperinfo.decoded).abs().max().item(),
+            recon=(recon - intermediates.reconstruction).abs().max().item(),
+            nbpp=abs(float(hyper.total_nbpp) - float(hyperinfo.total_nbpp)),
+            qbpp=abs(float(hyper.total_qbpp) - float(hyperinfo.total_qbpp)),
+        )
+        report.append((name, errs))
+        print(name, {k: f"{v:.3e}" for k, v in errs.items()},
+              "bpp n/q", float(hyperinfo.total_nbpp), float(hyperinfo.total_qbpp))
+    bad = [(n, e) for n, e in report if max(e.values()) > 1e-4]
+    if bad:
+        raise SystemExit(f"oracle disagrees with the reference: {bad}")
+    print("oracle pinned against the reference on", len(report), "cases")
+
+
+if __name__ == "__main__":
+    main()
