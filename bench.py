@@ -1,0 +1,298 @@
+#!/usr/bin/env python3
+"""Benchmark of the HiFIC encode+decode forward hot path (Encoder -> Hyperprior -> Generator).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path over one batch of B synthetic 3x256x256 images per GPU (weak scaling,
+no data-path collective: samples are independent).  Prints ONE JSON line (rank 0):
+  value     images/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the public API with HOST buffers (pinned H2D of x, D2H of x_hat + q_bpp)
+  roofline  the dominant kernel (960->960 3x3 residual conv, tcgen05 implicit GEMM) timed alone, live
+  cpu_baseline  the CPU oracle (port of the reference path) on a bounded sample, rank 0 at N=1 only
+`--impl reference` times the reference's CPU implementation of the path (oracle port) instead.
+"""
+import argparse
+import json
+import logging
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "images/sec (256x256) encode+decode fwd"
+RES_FLOPS_PER_IMAGE = 2.0 * 256 * 960 * 960 * 9       # one 960->960 3x3 conv on a 16x16 map
+E_H_G_FLOPS_PER_IMAGE = 99.89e9                        # forward, per 256x256 image
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(burst=float(d["bf16_tflops"]), sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        load = [s for s, p in zip(sm, power) if p > 250] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def oracle_forward_factory(batch):
+    """CPU port of the reference path (the oracle), eval mode, forward only."""
+    from hific_b200 import synth
+    from oracle import hific_oracle as O
+    sd = synth.synth_state_dict(0)
+    x = synth.synth_image(batch, 256, 256, 0)
+
+    def step():
+        with torch.no_grad():
+            recon, hyper, _ = O.compression_forward(sd, x, training=False)
+        return recon, hyper
+
+    return step
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    sample_b = 4
+    step = oracle_forward_factory(sample_b)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample_b * args.steps / dt
+    sample = f"{args.steps} forward passes of {sample_b}x3x256x256 (bounded sample of the B={args.batch} workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_b),
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, batch):
+    return {"workload": f"c2 shapes: compression (no GAN) regime=low, batch={batch}/GPU 3x256x256, "
+                        "Encoder+Hyperprior(analysis, factorized+conditional likelihood, synthesis)+Generator forward "
+                        "(eval mode, ANS bypassed)",
+            "per_gpu_batch": batch, "image": "3x256x256", "latent_channels": 220, "n_residual_blocks": 9,
+            "l2": "no explicit flush: per-step working set (363 MB packed fp16 weights + activations) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling mode (ncu): device-resident steps only, no e2e / roofline / CPU legs")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hific_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from hific_b200 import ops, synth
+    from hific_b200.config import ModelModes, ModelTypes, mse_lpips_args
+    from hific_b200.model import Model
+
+    cfg = mse_lpips_args()
+    cfg.batch_size = args.batch
+    model = Model(cfg, logging.getLogger("bench"), model_mode=ModelModes.EVALUATION, model_type=ModelTypes.COMPRESSION)
+    model.load_state_dict(synth.synth_state_dict(0), strict=True)     # identical weights on every rank
+    model.to(dev).eval()
+    B = args.batch
+    x_host = synth.synth_image(B, 256, 256, seed=1 + rank).pin_memory()  # rank-offset data seed
+    x_dev = x_host.to(dev)
+    out_host = torch.empty((B, 3, 256, 256), dtype=torch.float32).pin_memory()
+    bpp_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_device():
+        with torch.no_grad():
+            return model(x_dev, writeout=False)
+
+    def step_e2e():
+        with torch.no_grad():
+            xd = x_host.to(dev, non_blocking=True)
+            recon, q_bpp = model(xd, writeout=False)
+            out_host.copy_(recon, non_blocking=True)
+            bpp_host.copy_(q_bpp, non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    if args.profile:
+        ms = timed(step_device, args.steps)
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step_under_profiler": ms / args.steps}))
+        return
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = ops.launch_count() - l0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # --- roofline of the dominant kernel, timed alone on this stream (rank 0) ---
+    roof = None
+    if rank == 0:
+        peaks = measured_peaks()
+        plan = model.Generator._plans.get(torch.empty((B, 220, 16, 16), device=dev))
+        conv = plan.res_convs[0][0]
+        blk = model.Generator.resblock_0
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        reps, tot = 20, 0.0
+        for _ in range(3):
+            conv(plan.act_a, blk.conv1.weight, blk.conv1.bias, out=plan.rows)
+        for _ in range(reps):
+            flush.zero_()                                   # evict weights/activations: cold-L2 launch, as in the step
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            conv(plan.act_a, blk.conv1.weight, blk.conv1.bias, out=plan.rows)
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        k_ms = tot / reps
+        flops = RES_FLOPS_PER_IMAGE * B
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        roof = {"kernel": "conv_igemm_kernel (Generator residual conv 960->960 3x3, M=%d N=960 K=8640)" % (B * 256),
+                "bound": "tensor", "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["burst"], "traffic": None, "ms_per_launch": k_ms,
+                "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", bf16 burst",
+                "l2": "flushed (256 MiB memset) before every timed launch",
+                "step_tensor_frac": (E_H_G_FLOPS_PER_IMAGE * B / (ms / args.steps * 1e-3) / 1e12) / peaks["sustained"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        sb = 4
+        step = oracle_forward_factory(sb)
+        step()
+        n, t0 = 0, time.perf_counter()
+        while n < 3 or (time.perf_counter() - t0 < 10 and n < 50):
+            step()
+            n += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": sb * n / dt, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{n} forward passes of {sb}x3x256x256 through the CPU oracle (torch fp32, {cores} threads)"}
+
+    if rank == 0:
+        per_step = ms / args.steps
+        print(json.dumps({
+            "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 operands, fp32 accumulate (tcgen05 kind::f16); fp32 elementwise",
+            "data": "synthetic", "config": workload_config(args, B),
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4 + 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "tflops_per_step_algorithmic": E_H_G_FLOPS_PER_IMAGE * B / 1e12,
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

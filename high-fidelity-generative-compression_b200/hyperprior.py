@@ -1,0 +1,97 @@
+"""Hyperprior entropy model with the reference's API (src/hyperprior.py:144-330): analysis / synthesis
+networks run as fused sm_100a plans; the factorized and conditional likelihoods, the noise / round
+quantisation, the -log2 bit sums and the straight-through latents are two fused elementwise kernels.
+"""
+import math
+from collections import namedtuple
+
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+from .compression import hyperprior_model
+from .network import hyper
+
+MIN_SCALE = 0.11
+LOG_SCALES_MIN = -3.
+MIN_LIKELIHOOD = 1e-9
+MAX_LIKELIHOOD = 1e3
+SMALL_HYPERLATENT_FILTERS = 192
+LARGE_HYPERLATENT_FILTERS = 320
+
+HyperInfo = namedtuple(
+    "HyperInfo",
+    "decoded "
+    "latent_nbpp hyperlatent_nbpp total_nbpp latent_qbpp hyperlatent_qbpp total_qbpp",
+)
+
+
+class CodingModel(nn.Module):
+    """Base class kept for API parity (src/hyperprior.py:43-139)."""
+
+    def __init__(self, n_channels, min_likelihood=MIN_LIKELIHOOD, max_likelihood=MAX_LIKELIHOOD):
+        super().__init__()
+        self.n_channels = n_channels
+        self.min_likelihood = float(min_likelihood)
+        self.max_likelihood = float(max_likelihood)
+
+    @staticmethod
+    def _bits_and_bpp(log_sum, batch_size, spatial_shape):
+        """hyperprior.py:80-93 with the log-likelihood sum already reduced on device (fp64)."""
+        n_pixels = float(spatial_shape[0] * spatial_shape[1])
+        n_bits = log_sum.to(torch.float32) / (batch_size * -math.log(2.))
+        return n_bits, n_bits / n_pixels
+
+
+class Hyperprior(CodingModel):
+    def __init__(self, bottleneck_capacity=220, hyperlatent_filters=LARGE_HYPERLATENT_FILTERS, mode='large',
+                 likelihood_type='gaussian', scale_lower_bound=MIN_SCALE, entropy_code=False,
+                 vectorize_encoding=True, block_encode=True):
+        super().__init__(n_channels=bottleneck_capacity)
+        self.bottleneck_capacity = bottleneck_capacity
+        self.scale_lower_bound = scale_lower_bound
+        if mode == 'small':
+            hyperlatent_filters = SMALL_HYPERLATENT_FILTERS
+        if likelihood_type not in ('gaussian', 'logistic'):
+            raise ValueError('Unknown likelihood model: {}'.format(likelihood_type))
+        self.likelihood_type = likelihood_type
+        self.analysis_net = hyper.HyperpriorAnalysis(C=bottleneck_capacity, N=hyperlatent_filters)
+        self.synthesis_mu = hyper.HyperpriorSynthesis(C=bottleneck_capacity, N=hyperlatent_filters)
+        self.synthesis_std = hyper.HyperpriorSynthesis(C=bottleneck_capacity, N=hyperlatent_filters)
+        self.amortization_models = [self.analysis_net, self.synthesis_mu, self.synthesis_std]
+        self.hyperlatent_likelihood = hyperprior_model.HyperpriorDensity(n_channels=hyperlatent_filters)
+        if entropy_code is True:
+            raise NotImplementedError(
+                "entropy_code=True builds the host rANS tables (src/hyperprior.py:183-193): the sequential ANS "
+                "coder is out of scope of the B200 hot path (BASELINE.json north_star); use the reference's "
+                "src/compression for actual bitstreams")
+
+    def forward(self, latents, spatial_shape, **kwargs):
+        engine._require_cuda(latents, "Hyperprior")
+        engine.require_inference(self, "Hyperprior")
+        latents = latents.contiguous()
+        batch = latents.shape[0]
+        hyperlatents = self.analysis_net(latents)
+        # Same RNG call as the reference (hyperprior.py:65) so seeds / patched generators line up.
+        noise_z = torch.nn.init.uniform_(torch.zeros_like(hyperlatents), -0.5, 0.5)
+        z_noisy, z_quant, sums_z = ops.hyperlatent_likelihood(
+            hyperlatents, self.hyperlatent_likelihood.packed_params(), noise_z)
+        _, noisy_hyperlatent_bpp = self._bits_and_bpp(sums_z[0], batch, spatial_shape)
+        _, quantized_hyperlatent_bpp = self._bits_and_bpp(sums_z[1], batch, spatial_shape)
+        hyperlatents_decoded = z_noisy if self.training else z_quant            # hyperprior.py:294-297
+        latent_means = self.synthesis_mu(hyperlatents_decoded)
+        latent_scales = self.synthesis_std(hyperlatents_decoded)                 # lower bound applied in-kernel
+        noise_y = torch.nn.init.uniform_(torch.zeros_like(latents), -0.5, 0.5)
+        latents_decoded, sums_y = ops.latent_likelihood(latents, latent_means, latent_scales, noise_y,
+                                                        self.scale_lower_bound, self.likelihood_type)
+        _, noisy_latent_bpp = self._bits_and_bpp(sums_y[0], batch, spatial_shape)
+        _, quantized_latent_bpp = self._bits_and_bpp(sums_y[1], batch, spatial_shape)
+        return HyperInfo(
+            decoded=latents_decoded,
+            latent_nbpp=noisy_latent_bpp,
+            hyperlatent_nbpp=noisy_hyperlatent_bpp,
+            total_nbpp=noisy_latent_bpp + noisy_hyperlatent_bpp,
+            latent_qbpp=quantized_latent_bpp,
+            hyperlatent_qbpp=quantized_hyperlatent_bpp,
+            total_qbpp=quantized_latent_bpp + quantized_hyperlatent_bpp,
+        )

@@ -1,0 +1,62 @@
+"""Generator with the reference's constructor and state_dict (src/network/generator.py:9-169), executed by
+hific_b200.engine.GeneratorPlan.
+"""
+import torch
+import torch.nn as nn
+
+from .. import engine
+from ..normalisation.channel import ChannelNorm2D
+
+
+class ResidualBlock(nn.Module):
+    """Parameter holder for one residual block (conv1, conv2, norm1, norm2 -- generator.py:9-44)."""
+
+    def __init__(self, input_dims, kernel_size=3, stride=1, channel_norm=True, activation='relu'):
+        super().__init__()
+        if kernel_size != 3 or stride != 1 or activation != 'relu' or channel_norm is not True:
+            raise NotImplementedError("hific_b200.ResidualBlock implements the HiFIC default block")
+        c = input_dims[1]
+        self.conv1 = nn.Conv2d(c, c, kernel_size, stride=stride)
+        self.conv2 = nn.Conv2d(c, c, kernel_size, stride=stride)
+        self.norm1 = ChannelNorm2D(c)
+        self.norm2 = ChannelNorm2D(c)
+
+    def forward(self, x):
+        raise NotImplementedError("ResidualBlock runs fused inside hific_b200 Generator.forward")
+
+
+class Generator(nn.Module):
+    def __init__(self, input_dims, batch_size, C=16, activation='relu', n_residual_blocks=8, channel_norm=True,
+                 sample_noise=False, noise_dim=32):
+        super().__init__()
+        if activation != 'relu' or channel_norm is not True:
+            raise NotImplementedError("hific_b200.Generator implements the HiFIC default (ReLU + ChannelNorm)")
+        if sample_noise:
+            raise NotImplementedError("sample_noise=True is a non-default variant (SURVEY.md 8f) not built yet")
+        filters = engine.GeneratorPlan.FILTERS
+        self.C, self.n_residual_blocks = C, n_residual_blocks
+        self.sample_noise, self.noise_dim = sample_noise, noise_dim
+        self.n_upsampling_layers = 4
+        self.conv_block_init = nn.Sequential(ChannelNorm2D(C), nn.ReflectionPad2d(1),
+                                             nn.Conv2d(C, filters[0], kernel_size=(3, 3), stride=1),
+                                             ChannelNorm2D(filters[0]))
+        for m in range(n_residual_blocks):
+            self.add_module(f"resblock_{m}", ResidualBlock((batch_size, filters[0], 0, 0)))
+        for i in range(1, 5):
+            up = nn.ConvTranspose2d(filters[i - 1], filters[i], 3, stride=2, padding=1, output_padding=1)
+            setattr(self, f"upconv_block{i}", nn.Sequential(up, ChannelNorm2D(filters[i]), nn.ReLU()))
+        self.conv_block_out = nn.Sequential(nn.ReflectionPad2d(3), nn.Conv2d(filters[-1], 3, kernel_size=(7, 7), stride=1))
+        self._plans = engine.PlanCache(self._make_plan)
+
+    def _make_plan(self, y):
+        n, _, h, w = y.shape
+        return engine.GeneratorPlan(n, h, w, self.C, self.n_residual_blocks, 3, y.device)
+
+    def _apply(self, fn, *a, **k):
+        self._plans.clear()
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, x):
+        engine._require_cuda(x, "Generator")
+        engine.require_inference(self, "Generator")
+        return self._plans.get(x).run(self, x.contiguous())
