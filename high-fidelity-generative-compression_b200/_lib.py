@@ -33,6 +33,8 @@ class ConvDesc(ctypes.Structure):
         ("act", ctypes.c_int32), ("norm", ctypes.c_int32),
         ("eps", ctypes.c_float),
         ("block_n", ctypes.c_int32), ("precision", ctypes.c_int32),
+        ("cluster_m", ctypes.c_int32), ("cluster_n", ctypes.c_int32),
+        ("wide", ctypes.c_int32),
     ]
 
 
@@ -43,6 +45,7 @@ class ConvInfo(ctypes.Structure):
         ("out_h", ctypes.c_int32), ("out_w", ctypes.c_int32), ("phases", ctypes.c_int32),
         ("block_n", ctypes.c_int32), ("n_tiles", ctypes.c_int32), ("m_tiles", ctypes.c_int32),
         ("stages", ctypes.c_int32), ("k_total", ctypes.c_int32),
+        ("cluster_m", ctypes.c_int32), ("cluster_n", ctypes.c_int32), ("wide", ctypes.c_int32),
         ("flops", ctypes.c_double),
     ]
 

@@ -11,7 +11,7 @@
 // * tcgen05.mma (cta_group::1, kind::f16, M=128, N=block_n, K=16) accumulates into TMEM; two
 //   accumulator stages of 256 columns let the epilogue of tile i overlap the main loop of i+1.
 // * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer,
-//   warps 2..5 = epilogue (one TMEM lane quadrant each; thread == output pixel, so the per-pixel
+//   warps 2..9 = epilogue (two per TMEM lane quadrant; thread == output pixel, so the per-pixel
 //   ChannelNorm over channels is an in-thread reduction with no shuffles).
 // * Epilogue: + bias, optional fused ChannelNorm2D (unbiased variance, eps), ReLU / LeakyReLU,
 //   then one of: NHWC fp16 with reflected border (input of the next conv), NHWC fp32 rows (input
@@ -29,11 +29,14 @@ namespace hfc {
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;                       // 64 x 16-bit = one 128 B swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-static constexpr int kThreads = 192;                     // 6 warps
+static constexpr int kEpiThreads = 256;                  // 8 epilogue warps (2 per TMEM lane quadrant)
+static constexpr int kThreads = 64 + kEpiThreads;        // + TMA producer warp + MMA issuer warp
 static constexpr int kMaxTaps = 64;
 static constexpr int kAccStride = 256;                   // TMEM columns per accumulator stage
 static constexpr int kTmemCols = 512;
 static constexpr int kMaxStages = 8;
+static constexpr int kParamStride = 256;                 // floats per epilogue parameter row (>= block_n)
+static constexpr int kTailBytes = 256 + 2 * 3 * kParamStride * 4 + 512 * 4;  // barriers + parameter rows + stats exchange
 
 struct ConvKernelParams {
   int32_t tw, th, tn;                 // tile extents, tw*th*tn == 128
@@ -42,6 +45,10 @@ struct ConvKernelParams {
   int32_t block_n;
   int32_t num_kb, c_chunks, ntaps;
   int32_t stages;
+  int32_t cm, cn;                     // cluster extent along M tiles / N tiles (1 or 2 each)
+  int32_t a_split_n;                  // A slice split: 1 = along the batch dim of the box, 0 = along rows
+  int32_t wide, kw;                   // 'wide' mode: row-resident A halo (128+kw-1 pixels), resident weights
+  int32_t a_region;                   // bytes per A stage (wide mode: halo row rounded up to 1024)
   int32_t grid_h, grid_w, batch;
   int32_t sh, sw;                     // input coordinate scale
   int32_t ih0, iw0;                   // input coordinate offset (materialised border)
@@ -82,28 +89,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int b_bytes = p.block_n * kBlockK * 2;
-  const int stage_bytes = kABytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  const int stage_bytes = p.wide ? p.a_region : kABytes + b_bytes;
+  // wide mode: every weight sub-tile (num_kb * kw of them) stays resident behind the A ring
+  uint8_t* w_res = smem + p.stages * stage_bytes;
+  const int w_res_bytes = p.wide ? p.num_kb * p.kw * b_bytes : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_res + w_res_bytes);
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + kMaxStages;       // [stages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* wfull_bar = tempty_bar + 2;          // [1] resident weights landed (wide mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+  float* s_par = reinterpret_cast<float*>(bars + 32);  // [2][3][kParamStride] bias / gamma / beta
+  float* s_red = s_par + 2 * 3 * kParamStride;         // [2 (sum, ssq)][2 warps][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+
+  // Cluster geometry: CTA (m_idx, n_idx) of a cm x cn cluster works on M tile mg*cm+m_idx and N tile
+  // ng*cn+n_idx.  The A tile is shared by the cn CTAs of a cluster row, the B tile by the cm CTAs of a
+  // column: each CTA fetches 1/cn of A and 1/cm of B and TMA-multicasts its slice to the sharers, which
+  // divides the L2->SM operand traffic (the measured limiter, ~6.3 KB/clk chip-wide) by up to 2.
+  const int csize = p.cm * p.cn;
+  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
+  const int m_idx = static_cast<int>(crank) % p.cm;
+  const int n_idx = static_cast<int>(crank) / p.cm;
+  uint16_t mask_a = 0, mask_b = 0;  // CTAs sharing my A tile (same m_idx) / my B tile (same n_idx)
+  for (int j = 0; j < p.cn; ++j) mask_a |= static_cast<uint16_t>(1u << (m_idx + p.cm * j));
+  for (int i = 0; i < p.cm; ++i) mask_b |= static_cast<uint16_t>(1u << (i + p.cm * n_idx));
+  const uint16_t mask_e = mask_a | mask_b;  // producers that write into my stages == consumers I must release
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], static_cast<uint32_t>(p.cm + p.cn - 1));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiThreads / 32);
     }
+    mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -112,36 +139,72 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = tiles_m * p.n_tiles;
+  const int m_groups = (tiles_m + p.cm - 1) / p.cm;
+  const int n_groups = (p.n_tiles + p.cn - 1) / p.cn;
+  const int total_ctiles = m_groups * n_groups;      // work items per cluster
+  const int cid = blockIdx.x / csize;
+  const int ncl = gridDim.x / csize;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
+      const int a_slice_bytes = kABytes / p.cn;
+      const int b_slice_rows = p.block_n / p.cm;
+      if (p.wide) {
+        // weights: loaded once, resident for the whole kernel (n_tiles == 1 in this mode)
+        mbar_arrive_expect_tx(wfull_bar, static_cast<uint32_t>(w_res_bytes));
+        for (int j = 0; j < p.num_kb * p.kw; ++j)
+          tma_load_2d(w_res + j * b_bytes, &tmap_b, wfull_bar, j * kBlockK, 0);
+        const uint32_t a_bytes = static_cast<uint32_t>((kBlockM + p.kw - 1) * kBlockK * 2);
+        for (int ct = cid; ct < total_ctiles; ct += ncl) {
+          int mt = ct;
+          const int twi = mt % p.tiles_w;
+          mt /= p.tiles_w;
+          const int thi = mt % p.tiles_h;
+          const int tni = mt / p.tiles_h;
+          for (int kb = 0; kb < p.num_kb; ++kb) {   // one K block = one filter row: halo row of 128+kw-1 pixels
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], a_bytes);
+            tma_load_4d(smem + s * stage_bytes, &tmap_a, &full_bar[s], 0, twi * kBlockM + p.iw0 + p.tap_dw[kb],
+                        thi + p.ih0 + p.tap_dh[kb], tni);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      } else
+      for (int ct = cid; ct < total_ctiles; ct += ncl) {
+        const int nt = (ct % n_groups) * p.cn + n_idx;
+        int mt = (ct / n_groups) * p.cm + m_idx;
         const int twi = mt % p.tiles_w;
         mt /= p.tiles_w;
         const int thi = mt % p.tiles_h;
-        const int tni = mt / p.tiles_h;
+        const int tni = mt / p.tiles_h;   // >= tiles_n for padding tiles: every row is out of bounds (zero fill)
         const int w_base = twi * p.tw * p.sw + p.iw0;
-        const int h_base = thi * p.th * p.sh + p.ih0;
-        const int n_base = tni * p.tn;
+        // my slice of the shared A tile: rows [n_idx*128/cn, (n_idx+1)*128/cn)
+        const int h_base = (thi * p.th + (p.a_split_n ? 0 : n_idx * (p.th / p.cn))) * p.sh + p.ih0;
+        const int n_base = tni * p.tn + (p.a_split_n ? n_idx * (p.tn / p.cn) : 0);
         int tap = 0, chunk = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + kABytes;
           mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
-          tma_load_4d(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
-                      h_base + p.tap_dh[tap], n_base);
-          tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, nt * p.block_n);
+          if (csize > 1) {
+            tma_load_4d_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], chunk * kBlockK,
+                           w_base + p.tap_dw[tap], h_base + p.tap_dh[tap], n_base, mask_a);
+            tma_load_2d_mc(sb + m_idx * b_slice_rows * (kBlockK * 2), &tmap_b, &full_bar[s], kb * kBlockK,
+                           nt * p.block_n + m_idx * b_slice_rows, mask_b);
+          } else {
+            tma_load_4d(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
+                        h_base + p.tap_dh[tap], n_base);
+            tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, nt * p.block_n);
+          }
           if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -154,14 +217,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    if (p.wide) mbar_wait(wfull_bar, 0);
+    for (int ct = cid; ct < total_ctiles; ct += ncl) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (lane == 0 && p.wide) {
+          // A operand for filter column t = the halo row shifted by t pixels: the descriptor start moves by
+          // t*128 B inside the 1024 B swizzle atom, which the base-offset field (bits 49..51) accounts for.
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t w_addr = smem_u32(w_res) + static_cast<uint32_t>(kb * p.kw * b_bytes);
+          for (int t = 0; t < p.kw; ++t) {
+            const uint64_t a_desc = make_sw128_kmajor_desc(a_addr + t * 128) |
+                                    (static_cast<uint64_t>(t & 7) << 49);
+            const uint64_t b_desc = make_sw128_kmajor_desc(w_addr + t * b_bytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);
+        } else if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
           const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
@@ -170,7 +249,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4)
             umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if (csize > 1) umma_commit_mc(&empty_bar[s], mask_e);
+          else umma_commit(&empty_bar[s]);
           if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
@@ -179,17 +259,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quadrant: both own the same 32 pixel rows and take alternate 16-column
+    // chunks, so every scheduler has two epilogue warps to interleave (a lone warp issues one dependent
+    // instruction every ~5 cycles, which made the 128-wide epilogues the bottleneck of the big-map layers).
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int hsel = (warp - 2) >> 2;  // which of the two warps of the quadrant
     const int m = q * 32 + lane;
+    const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
     const int twi_in = m % p.tw;
     const int thi_in = (m / p.tw) % p.th;
     const int tni_in = m / (p.tw * p.th);
+    const float inv_c = 1.f / static_cast<float>(p.cout);
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
+    int cur_nt = -1, pbuf = 1;
+    float mean_b = 0.f;
+    for (int ct = cid; ct < total_ctiles; ct += ncl) {
+      const int nt = (ct % n_groups) * p.cn + n_idx;
+      int mt = (ct / n_groups) * p.cm + m_idx;
       const int twi = mt % p.tiles_w;
       mt /= p.tiles_w;
       const int thi = mt % p.tiles_h;
@@ -200,9 +288,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int oh = gh * p.osh + p.ooh;
       const int ow = gw * p.osw + p.oow;
       const bool valid = (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
-                         (ow < p.out_w);
+                         (ow < p.out_w) && (nt < p.n_tiles);
       const int c_base = nt * p.block_n;
       const bool last_nt = (nt == p.n_tiles - 1);
+
+      // Per-channel epilogue parameters live in shared memory: with ~220 KB of dynamic smem the
+      // L1 is (almost) gone, so per-element __ldg's would each be an L2 round trip.  Reloaded only
+      // when the N tile changes; double-buffered so no thread can still be reading the old copy.
+      if (nt != cur_nt) {
+        cur_nt = nt;
+        pbuf ^= 1;
+        float* sp = s_par + pbuf * (3 * kParamStride);
+        for (int i = et; i < p.block_n; i += kEpiThreads) {
+          const int c = c_base + i;
+          const bool real = c < p.cout;
+          sp[i] = (real && p.bias) ? __ldg(p.bias + c) : 0.f;
+          sp[kParamStride + i] = (real && p.norm) ? __ldg(p.gamma + c) : 0.f;
+          sp[2 * kParamStride + i] = (real && p.norm) ? __ldg(p.beta + c) : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+        if (p.norm) {  // mean of the bias over the real channels (padding entries are 0)
+          float sb = 0.f;
+          for (int i = 0; i < p.block_n; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sp + i);
+            sb += (b4.x + b4.y) + (b4.z + b4.w);
+          }
+          mean_b = sb * inv_c;
+        }
+      }
+      const float* s_bias = s_par + pbuf * (3 * kParamStride);
+      const float* s_gamma = s_bias + kParamStride;
+      const float* s_beta = s_bias + 2 * kParamStride;
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
@@ -210,34 +326,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
       float mean = 0.f, rstd = 1.f;
       if (p.norm) {
-        // pass 1: mean over the real channels; pass 2: unbiased variance (two-pass, fp32)
+        // ChannelNorm statistics over the channel row held in TMEM.  Padding columns hold exact zeros
+        // (zero weights, zero bias).  pass 1: sum of the accumulators (+ mean of the bias);
+        // pass 2: sum of squared deviations (two-pass, fp32); the padding contribution (-mean each) is
+        // removed analytically.  The two warps of a quadrant combine their partial sums through smem.
         float sum = 0.f;
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        for (int c0 = 16 * hsel; c0 < p.block_n; c0 += 32) {
           uint32_t v[16];
           tmem_ld16(t_row + c0, v);
           tmem_ld_wait();
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            if (c < p.cout) sum += __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
-          }
+          for (int j = 0; j < 16; ++j) s4[j & 3] += __uint_as_float(v[j]);
+          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
         }
-        mean = sum / static_cast<float>(p.cout);
+        s_red[hsel * 128 + m] = sum;
+        asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");
+        mean = (s_red[m] + s_red[128 + m]) * inv_c + mean_b;
         float ssq = 0.f;
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        for (int c0 = 16 * hsel; c0 < p.block_n; c0 += 32) {
           uint32_t v[16];
           tmem_ld16(t_row + c0, v);
           tmem_ld_wait();
+          float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            if (c < p.cout) {
-              const float d = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f) - mean;
-              ssq += d * d;
-            }
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j4);
+            const float d0 = (__uint_as_float(v[4 * j4 + 0]) + b4.x) - mean;
+            const float d1 = (__uint_as_float(v[4 * j4 + 1]) + b4.y) - mean;
+            const float d2 = (__uint_as_float(v[4 * j4 + 2]) + b4.z) - mean;
+            const float d3 = (__uint_as_float(v[4 * j4 + 3]) + b4.w) - mean;
+            q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]);
+            q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
           }
+          ssq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
         }
-        rstd = rsqrtf(ssq / static_cast<float>(p.cout - 1) + p.eps);
+        s_red[256 + hsel * 128 + m] = ssq;
+        asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");
+        ssq = s_red[256 + m] + s_red[384 + m];
+        ssq -= static_cast<float>(p.block_n - p.cout) * mean * mean;
+        rstd = rsqrtf(fmaxf(ssq, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
       }
 
       // target rows / cols of the (bordered) NHWC fp16 buffer
@@ -258,21 +386,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int Hp = p.out_h + p.out_pt + p.out_pb;
       const int Wp = p.out_w + p.out_pl + p.out_pr;
 
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      for (int c0 = 16 * hsel; c0 < p.block_n; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = c_base + c0 + j;
-          float x = 0.f;
-          if (c < p.cout) {
-            x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
-            if (p.norm) x = __ldg(p.gamma + c) * ((x - mean) * rstd) + __ldg(p.beta + c);
-            x = apply_act(x, p.act);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          // padding columns: acc = 0, bias = gamma = beta = 0  ->  exactly 0 after norm / activation
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j4);
+          float x0 = __uint_as_float(v[4 * j4 + 0]) + b4.x, x1 = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+          float x2 = __uint_as_float(v[4 * j4 + 2]) + b4.z, x3 = __uint_as_float(v[4 * j4 + 3]) + b4.w;
+          if (p.norm) {
+            const float4 g4 = *reinterpret_cast<const float4*>(s_gamma + c0 + 4 * j4);
+            const float4 e4 = *reinterpret_cast<const float4*>(s_beta + c0 + 4 * j4);
+            x0 = fmaf(g4.x * rstd, x0 - mean, e4.x); x1 = fmaf(g4.y * rstd, x1 - mean, e4.y);
+            x2 = fmaf(g4.z * rstd, x2 - mean, e4.z); x3 = fmaf(g4.w * rstd, x3 - mean, e4.w);
           }
-          f[j] = x;
+          f[4 * j4 + 0] = apply_act(x0, p.act); f[4 * j4 + 1] = apply_act(x1, p.act);
+          f[4 * j4 + 2] = apply_act(x2, p.act); f[4 * j4 + 3] = apply_act(x3, p.act);
         }
         const int cc = c_base + c0;
         if (!valid) {
@@ -318,7 +450,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
       // zero the channel padding no N tile covers (e.g. cout 220 -> block_n 224 -> cpad 256)
-      if (valid && last_nt && p.out_mode != HFC_OUT_NCHW_F32) {
+      if (valid && last_nt && hsel == 0 && p.out_mode != HFC_OUT_NCHW_F32) {
         const int c_end = p.n_tiles * p.block_n;
         if (p.out_mode == HFC_OUT_NHWC_F16) {
           for (int c = c_end; c < p.out_cpad; c += 8) {
@@ -346,6 +478,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // nobody exits while a peer may still arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -562,17 +695,55 @@ static int make_plan(const hfc_conv_desc* d, Plan* pl) {
   return HFC_OK;
 }
 
-static int tile_and_stages(const Plan& pl, const Phase& ph, int batch, ConvKernelParams* kp) {
+static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& ph, int batch,
+                           ConvKernelParams* kp) {
   kp->tw = std::min(16, next_pow2(ph.grid_w));
   kp->th = std::min(kBlockM / kp->tw, next_pow2(ph.grid_h));
   kp->tn = kBlockM / (kp->tw * kp->th);
+  // 'wide' mode (few output channels, big maps, e.g. the 7x7 60->3 head): a tile is 128 consecutive
+  // pixels of one row; per filter ROW one halo row of 128+kw-1 pixels is fetched and the kw filter
+  // columns are served from it by shifting the UMMA descriptor; all weights stay resident in smem.
+  // L2->SM traffic drops from kh*kw*16 KB to kh*(128+kw-1)*128 B per tile.
+  const int w_bytes_total = ph.ntaps * pl.c_chunks * pl.block_n * kBlockK * 2;
+  kp->wide = (d->wide != 2) && !d->transposed && !d->window && d->stride == 1 && d->kw > 1 && pl.c_chunks == 1 &&
+             pl.n_tiles == 1 && ph.grid_w >= 64 && w_bytes_total <= 112 * 1024 && (d->wide == 1 || pl.block_n <= 32);
+  kp->kw = d->kw;
+  kp->a_region = 0;
+  if (kp->wide) {
+    kp->tw = kBlockM; kp->th = 1; kp->tn = 1;
+  }
   kp->tiles_w = (ph.grid_w + kp->tw - 1) / kp->tw;
   kp->tiles_h = (ph.grid_h + kp->th - 1) / kp->th;
   kp->tiles_n = (batch + kp->tn - 1) / kp->tn;
-  const int stage_bytes = kABytes + pl.block_n * kBlockK * 2;
-  int stages = (225 * 1024 - 2048) / stage_bytes;
+  int stage_bytes = kABytes + pl.block_n * kBlockK * 2;
+  int budget = 226 * 1024 - 1024 - kTailBytes;
+  if (kp->wide) {
+    kp->a_region = ((kBlockM + d->kw - 1) * kBlockK * 2 + 1023) / 1024 * 1024;
+    stage_bytes = kp->a_region;
+    budget -= w_bytes_total;
+  }
+  int stages = budget / stage_bytes;
   stages = std::max(2, std::min(stages, kMaxStages));
   kp->stages = stages;
+  // Cluster shape (TMA multicast of the shared operand tiles).  Auto: only for launches with enough tiles
+  // to fill the machine, along N when the N tiles pair up, along M when the M tiles pair up.
+  const int tiles_m = kp->tiles_w * kp->tiles_h * kp->tiles_n;
+  int cm = d->cluster_m, cn = d->cluster_n;
+  if (cm == 0 || cn == 0) {
+    const bool big = static_cast<long long>(tiles_m) * pl.n_tiles >= 128;
+    cn = (cn == 0) ? ((big && pl.n_tiles % 2 == 0) ? 2 : 1) : cn;
+    cm = (cm == 0) ? ((big && tiles_m % 2 == 0) ? 2 : 1) : cm;
+  }
+  if (cm < 1 || cm > 2 || cn < 1 || cn > 2) return -1;
+  if (kp->wide) cm = cn = 1;
+  if ((pl.block_n / cm) % 8 != 0 || pl.block_n % cm != 0) cm = 1;
+  kp->a_split_n = 0;
+  if (cn > 1) {
+    if (kp->tn % cn == 0) kp->a_split_n = 1;
+    else if (kp->th % cn != 0) cn = 1;
+  }
+  kp->cm = cm;
+  kp->cn = cn;
   return stage_bytes;
 }
 
@@ -606,7 +777,8 @@ extern "C" int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info) {
   if (rc != HFC_OK) return rc;
   if (!info) return set_error(HFC_ERR_INVALID, "conv_query: null info");
   ConvKernelParams kp;
-  tile_and_stages(pl, pl.ph[0], d->in.n, &kp);
+  if (tile_and_stages(d, pl, pl.ph[0], d->in.n, &kp) < 0)
+    return set_error(HFC_ERR_INVALID, "conv: cluster_m / cluster_n must be 0 (auto), 1 or 2");
   info->packed_weight_bytes = pl.packed_elems * 2;
   info->out_h = pl.out_h;
   info->out_w = pl.out_w;
@@ -615,6 +787,9 @@ extern "C" int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info) {
   info->n_tiles = pl.n_tiles;
   info->m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
   info->stages = kp.stages;
+  info->wide = kp.wide;
+  info->cluster_m = kp.cm;
+  info->cluster_n = kp.cn;
   info->k_total = 0;
   for (int i = 0; i < pl.nphases; ++i) info->k_total += pl.ph[i].ktot;
   info->flops = pl.flops;
@@ -673,12 +848,14 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     const Phase& ph = pl.ph[i];
     ConvKernelParams kp;
     memset(&kp, 0, sizeof(kp));
-    const int stage_bytes = tile_and_stages(pl, ph, ig.n, &kp);
+    const int stage_bytes = tile_and_stages(d, pl, ph, ig.n, &kp);
+    if (stage_bytes < 0)
+      return set_error(HFC_ERR_INVALID, "conv: cluster_m / cluster_n must be 0 (auto), 1 or 2");
     kp.n_tiles = pl.n_tiles;
     kp.block_n = pl.block_n;
     kp.c_chunks = pl.c_chunks;
     kp.ntaps = ph.ntaps;
-    kp.num_kb = ph.ntaps * pl.c_chunks;
+    kp.num_kb = kp.wide ? d->kh : ph.ntaps * pl.c_chunks;
     kp.grid_h = ph.grid_h; kp.grid_w = ph.grid_w; kp.batch = ig.n;
     kp.sh = ph.sh; kp.sw = ph.sw;
     kp.ih0 = ig.pt; kp.iw0 = ig.pl;
@@ -696,6 +873,12 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     kp.out = out;
     memcpy(kp.tap_dh, ph.dh, sizeof(kp.tap_dh));
     memcpy(kp.tap_dw, ph.dw, sizeof(kp.tap_dw));
+    if (kp.wide) {  // one entry per filter row: (ky - pad_t, -pad_l)
+      for (int ky = 0; ky < d->kh; ++ky) {
+        kp.tap_dh[ky] = static_cast<int8_t>(ky - d->pad_t);
+        kp.tap_dw[ky] = static_cast<int8_t>(-d->pad_l);
+      }
+    }
 
     // A: 4-D map over the NHWC buffer {channels, W, H, N}
     CUtensorMap tmA, tmB;
@@ -713,7 +896,11 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
       strides[0] = static_cast<cuuint64_t>(ig.cpad) * 2;
       strides[1] = static_cast<cuuint64_t>(Wp) * ig.cpad * 2;
       strides[2] = static_cast<cuuint64_t>(Hp) * Wp * ig.cpad * 2;
-      box[0] = kBlockK; box[1] = kp.tw * ph.sw; box[2] = kp.th * ph.sh; box[3] = kp.tn;
+      // per-CTA slice of the A tile when it is shared across a cluster row (multicast)
+      const int th_box = kp.a_split_n ? kp.th : kp.th / kp.cn;
+      const int tn_box = kp.a_split_n ? kp.tn / kp.cn : kp.tn;
+      box[0] = kBlockK; box[1] = kp.tw * ph.sw; box[2] = th_box * ph.sh; box[3] = tn_box;
+      if (kp.wide) { box[1] = kBlockM + d->kw - 1; box[2] = 1; box[3] = 1; }
       estr[0] = 1; estr[1] = ph.sw; estr[2] = ph.sh; estr[3] = 1;
       CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -725,7 +912,7 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     {
       cuuint64_t dims[2] = {static_cast<cuuint64_t>(ph.ktot), static_cast<cuuint64_t>(pl.rows)};
       cuuint64_t strides[1] = {static_cast<cuuint64_t>(ph.ktot) * 2};
-      cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(pl.block_n)};
+      cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(pl.block_n / kp.cm)};
       cuuint32_t estr[2] = {1, 1};
       void* wptr = const_cast<uint16_t*>(reinterpret_cast<const uint16_t*>(packed) + ph.w_offset);
       CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wptr, dims, strides, box, estr,
@@ -735,19 +922,36 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
         return set_error(HFC_ERR_LAUNCH, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
 
-    const int total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_tiles;
-    const int grid = std::min(total_tiles, sm_count);
-    const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 /*align*/ + 256 /*bars*/;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    const int tiles_m = kp.tiles_w * kp.tiles_h * kp.tiles_n;
+    const int csize = kp.cm * kp.cn;
+    const int ctiles = ((tiles_m + kp.cm - 1) / kp.cm) * ((kp.n_tiles + kp.cn - 1) / kp.cn);
+    // clusters of 2 can use all 148 SMs; clusters of 4 only 132 (GPCs of 16/18/20 SMs)
+    const int max_clusters = csize == 4 ? (sm_count * 132 / 148) / 4 : sm_count / csize;
+    const int grid = std::min(ctiles, std::max(1, max_clusters)) * csize;
+    const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 /*align*/ + kTailBytes +
+                        (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
+    static bool attr_set = false;
+    if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess)
         return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      smem_set = 227 * 1024;
+      attr_set = true;
     }
-    conv_igemm_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, kp);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmB, kp);
     if (e != cudaSuccess)
       return set_error(HFC_ERR_LAUNCH, "conv_igemm launch: %s", cudaGetErrorString(e));
     note_launch();

@@ -107,7 +107,7 @@ class Conv:
 
     def __init__(self, in_geom, cout, k, stride=1, transposed=False, pad_mode=PAD_ZERO, pad=(0, 0, 0, 0),
                  out_mode=OUT_NHWC_F16, out_geom=None, out_reflect=False, act=ACT_NONE, norm=False,
-                 window=False, block_n=0, precision=PREC_F16):
+                 window=False, block_n=0, precision=PREC_F16, cluster=(0, 0), wide=0):
         kh, kw = (k, k) if isinstance(k, int) else k
         pt, pl, pb, pr = pad
         d = _lib.ConvDesc()
@@ -120,6 +120,8 @@ class Conv:
         d.out_reflect, d.act, d.norm = int(out_reflect), act, int(norm)
         d.eps = CN_EPS
         d.block_n, d.precision = block_n, precision
+        d.cluster_m, d.cluster_n = cluster
+        d.wide = wide
         # output dims
         if transposed:
             oh = (in_geom.h - 1) * stride - 2 * pt + kh + (stride - 1)

@@ -84,6 +84,10 @@ typedef struct hfc_conv_desc {
   float eps;                /* ChannelNorm eps (reference: 1e-3) */
   int32_t block_n;          /* 0 = auto; else N tile (multiple of 16, <= 256) */
   int32_t precision;        /* HFC_PREC_* */
+  int32_t cluster_m;        /* 0 = auto; else 1 or 2: CTAs per cluster along M tiles (share the weight tile) */
+  int32_t cluster_n;        /* 0 = auto; else 1 or 2: CTAs per cluster along N tiles (share the pixel tile) */
+  int32_t wide;             /* 0 = auto, 1 = force, 2 = forbid the row-resident 'wide' mode (few output channels on
+                               big maps: halo row + resident weights, filter columns by descriptor shift) */
 } hfc_conv_desc;
 
 typedef struct hfc_conv_info {
@@ -91,6 +95,8 @@ typedef struct hfc_conv_info {
   int32_t out_h, out_w;         /* logical output dims */
   int32_t phases;               /* kernel launches per forward (4 for stride-2 transposed) */
   int32_t block_n, n_tiles, m_tiles, stages, k_total;
+  int32_t cluster_m, cluster_n; /* cluster shape the launch will use (TMA multicast) */
+  int32_t wide;                 /* 1 if the row-resident 'wide' mode is used */
   double flops;                 /* algorithmic 2*MACs of the layer (real channels) */
 } hfc_conv_info;
 

@@ -1,0 +1,53 @@
+"""GPU tests of the two traffic-saving modes of the conv kernel: thread-block clusters with TMA multicast of
+the shared operand tiles, and the row-resident 'wide' mode (halo row + resident weights + descriptor shift).
+Kept in their own file so that a protocol bug here (trap) cannot poison the CUDA context of the other tests."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from test_gpu_ops import run_conv_case  # noqa: E402
+from hific_b200.ops import (ACT_RELU, OUT_NCHW_F32, OUT_NHWC_F16, OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO)  # noqa: E402
+
+
+@pytest.mark.parametrize("cluster", [(2, 1), (1, 2), (2, 2)])
+def test_cluster_multicast_resblock_shape(cluster):
+    run_conv_case(4, 960, 16, 16, 960, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F32,
+                  cluster=cluster, expect=dict(cluster_m=cluster[0], cluster_n=cluster[1]))
+
+
+def test_cluster_auto_on_big_layer():
+    # 8 x 64x64 -> 256 M tiles, 1 N tile: auto picks 2x1 (weights shared by two pixel tiles)
+    run_conv_case(8, 64, 64, 64, 120, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F16,
+                  out_border=(1, 0, 0, 1), norm=True, act=ACT_RELU, expect=dict(cluster_m=2, cluster_n=1))
+
+
+def test_cluster_with_padding_tiles():
+    # odd tile counts in both directions: 3 M tiles (batch 3 of 16x8), 3 N tiles of 160 -> dummy tiles
+    run_conv_case(3, 64, 8, 16, 480, 3, pad=(1, 1, 1, 1), pad_mode=PAD_ZERO, out_mode=OUT_NHWC_F32, block_n=160,
+                  cluster=(2, 2))
+
+
+def test_cluster_stride2_and_small_maps():
+    run_conv_case(16, 128, 32, 32, 240, 3, stride=2, pad=(1, 0, 0, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F16,
+                  out_border=(1, 1, 1, 1), norm=True, act=ACT_RELU, cluster=(2, 1))
+    # 4x4 maps: tile = 4x4x8 images, A slice split along the batch dimension of the box
+    run_conv_case(32, 320, 8, 8, 320, 5, stride=2, pad=(2, 2, 2, 2), pad_mode=PAD_REFLECT, out_mode=OUT_NCHW_F32,
+                  cluster=(1, 2), block_n=160)
+
+
+def test_cluster_transposed():
+    run_conv_case(8, 256, 32, 32, 120, 3, stride=2, pad=(1, 1, 1, 1), transposed=True, out_mode=OUT_NHWC_F16,
+                  norm=True, act=ACT_RELU, cluster=(2, 1))
+
+
+@pytest.mark.parametrize("w", [128, 256, 200])
+def test_wide_mode_7x7_head(w):
+    run_conv_case(2, 60, 24, w, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, expect=dict(wide=1))
+
+
+def test_wide_mode_forced_3x3_and_forbidden():
+    run_conv_case(2, 64, 16, 128, 16, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, wide=1, expect=dict(wide=1))
+    run_conv_case(1, 60, 32, 128, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, wide=2, expect=dict(wide=0))

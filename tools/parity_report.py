@@ -72,7 +72,7 @@ def stage_report(model, sd, b, h, w, training, seed=0, rnd=None):
         # hyperprior as a whole, fed the oracle's y
         with Feed([noise_z, noise_y]):
             info = model.Hyperprior(y_o.to(dev), spatial_shape=(h, w))
-        flips = (info.decoded.cpu() != hyp_o.decoded).float().mean().item()
+        flips = ((info.decoded.cpu() - hyp_o.decoded).abs() > 0.5).float().mean().item()
         rep["yhat_mismatch_fraction"] = flips
         for f in ("latent_nbpp", "hyperlatent_nbpp", "latent_qbpp", "hyperlatent_qbpp", "total_nbpp", "total_qbpp"):
             rep[f + "_abs_err"] = abs(float(getattr(info, f)) - float(getattr(hyp_o, f)))
