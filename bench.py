@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true",
                     help="profiling mode (ncu): device-resident steps only, no e2e / roofline / CPU legs")
     args = ap.parse_args()
@@ -212,6 +213,15 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    # kernels launched per step, counted on one eager step (graph replays do not pass through the C ABI)
+    step_device()
+    torch.cuda.synchronize()
+    l0 = ops.launch_count()
+    step_device()
+    launches_per_step = ops.launch_count() - l0
+    use_graph = not (args.no_graph or args.profile)
+    if use_graph:
+        model.enable_cuda_graph(True)
     for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
@@ -224,9 +234,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ops.launch_count()
     ms = timed(step_device, args.steps)
-    launches = ops.launch_count() - l0
+    launches = launches_per_step * args.steps
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -287,7 +296,8 @@ def main():
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4 + 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "cuda_graph": use_graph,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "tflops_per_step_algorithmic": E_H_G_FLOPS_PER_IMAGE * B / 1e12,
         }))
     if dist is not None:

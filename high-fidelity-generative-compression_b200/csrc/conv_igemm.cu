@@ -21,6 +21,8 @@
 #include "hfc_internal.h"
 #include "hfc_ptx.cuh"
 
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
@@ -36,7 +38,7 @@ static constexpr int kAccStride = 256;                   // TMEM columns per acc
 static constexpr int kTmemCols = 512;
 static constexpr int kMaxStages = 8;
 static constexpr int kParamStride = 256;                 // floats per epilogue parameter row (>= block_n)
-static constexpr int kTailBytes = 256 + 2 * 3 * kParamStride * 4 + 512 * 4;  // barriers + parameter rows + stats exchange
+static constexpr int kTailBytes = 256 + 2 * 3 * kParamStride * 4 + 2 * 512 * 4;  // barriers + parameter rows + stats exchange
 
 struct ConvKernelParams {
   int32_t tw, th, tn;                 // tile extents, tw*th*tn == 128
@@ -47,6 +49,7 @@ struct ConvKernelParams {
   int32_t stages;
   int32_t cm, cn;                     // cluster extent along M tiles / N tiles (1 or 2 each)
   int32_t a_split_n;                  // A slice split: 1 = along the batch dim of the box, 0 = along rows
+  int32_t wide_boff;                  // debugging: set the descriptor base-offset field for shifted starts
   int32_t wide, kw;                   // 'wide' mode: row-resident A halo (128+kw-1 pixels), resident weights
   int32_t a_region;                   // bytes per A stage (wide mode: halo row rounded up to 1024)
   int32_t grid_h, grid_w, batch;
@@ -101,7 +104,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* wfull_bar = tempty_bar + 2;          // [1] resident weights landed (wide mode)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   float* s_par = reinterpret_cast<float*>(bars + 32);  // [2][3][kParamStride] bias / gamma / beta
-  float* s_red = s_par + 2 * 3 * kParamStride;         // [2 (sum, ssq)][2 warps][128 rows]
+  float* s_red = s_par + 2 * 3 * kParamStride;         // [2 acc stages][2 (sum, ssq)][2 warps][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -231,8 +234,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t w_addr = smem_u32(w_res) + static_cast<uint32_t>(kb * p.kw * b_bytes);
           for (int t = 0; t < p.kw; ++t) {
+            // The 128B swizzle is a function of the absolute smem address bits (which is also why the +32 B
+            // K advance works), so a start address that is only 128 B aligned needs no base offset.
             const uint64_t a_desc = make_sw128_kmajor_desc(a_addr + t * 128) |
-                                    (static_cast<uint64_t>(t & 7) << 49);
+                                    (p.wide_boff ? (static_cast<uint64_t>(t & 7) << 49) : 0ull);
             const uint64_t b_desc = make_sw128_kmajor_desc(w_addr + t * b_bytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
@@ -274,7 +279,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int as = 0;
     uint32_t aph = 0;
     int cur_nt = -1, pbuf = 1;
-    float mean_b = 0.f;
     for (int ct = cid; ct < total_ctiles; ct += ncl) {
       const int nt = (ct % n_groups) * p.cn + n_idx;
       int mt = (ct / n_groups) * p.cm + m_idx;
@@ -307,14 +311,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           sp[2 * kParamStride + i] = (real && p.norm) ? __ldg(p.beta + c) : 0.f;
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-        if (p.norm) {  // mean of the bias over the real channels (padding entries are 0)
-          float sb = 0.f;
-          for (int i = 0; i < p.block_n; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sp + i);
-            sb += (b4.x + b4.y) + (b4.z + b4.w);
-          }
-          mean_b = sb * inv_c;
-        }
       }
       const float* s_bias = s_par + pbuf * (3 * kParamStride);
       const float* s_gamma = s_bias + kParamStride;
@@ -324,48 +320,60 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       const uint32_t t_row = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
+      // Walks this warp's 16-column chunks (alternate chunks belong to the partner warp of the quadrant);
+      // the TMEM load of the next chunk is in flight while the current one is processed.
+      auto for_chunks = [&](auto&& body) {
+        uint32_t va[16], vb[16];
+        int c0 = 16 * hsel;
+        if (c0 < p.block_n) tmem_ld16(t_row + c0, va);
+        while (c0 < p.block_n) {
+          tmem_ld_wait();
+          if (c0 + 32 < p.block_n) tmem_ld16(t_row + c0 + 32, vb);
+          body(va, c0);
+          c0 += 32;
+          if (c0 >= p.block_n) break;
+          tmem_ld_wait();
+          if (c0 + 32 < p.block_n) tmem_ld16(t_row + c0 + 32, va);
+          body(vb, c0);
+          c0 += 32;
+        }
+      };
+
       float mean = 0.f, rstd = 1.f;
       if (p.norm) {
-        // ChannelNorm statistics over the channel row held in TMEM.  Padding columns hold exact zeros
-        // (zero weights, zero bias).  pass 1: sum of the accumulators (+ mean of the bias);
-        // pass 2: sum of squared deviations (two-pass, fp32); the padding contribution (-mean each) is
-        // removed analytically.  The two warps of a quadrant combine their partial sums through smem.
-        float sum = 0.f;
-        for (int c0 = 16 * hsel; c0 < p.block_n; c0 += 32) {
-          uint32_t v[16];
-          tmem_ld16(t_row + c0, v);
-          tmem_ld_wait();
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s4[j & 3] += __uint_as_float(v[j]);
-          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        }
-        s_red[hsel * 128 + m] = sum;
-        asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");
-        mean = (s_red[m] + s_red[128 + m]) * inv_c + mean_b;
-        float ssq = 0.f;
-        for (int c0 = 16 * hsel; c0 < p.block_n; c0 += 32) {
-          uint32_t v[16];
-          tmem_ld16(t_row + c0, v);
-          tmem_ld_wait();
-          float q4[4] = {0.f, 0.f, 0.f, 0.f};
+        // ChannelNorm statistics in ONE pass over the channel row held in TMEM, using shifted sums
+        // (shift = the row's first channel) so that sum(d^2) - sum(d)^2/C does not cancel:
+        //   d = (acc + bias) - shift ;  mean = shift + sum(d)/C ;  var = (sum(d^2) - sum(d)^2/C)/(C-1).
+        // Padding columns hold exact zeros (d = -shift) and are removed analytically.  The two warps of a
+        // quadrant combine their partial sums through shared memory (double-buffered by accumulator stage).
+        uint32_t first;
+        tmem_ld1(t_row, first);
+        tmem_ld_wait();
+        const float shift = __uint_as_float(first) + s_bias[0];
+        float sd4[4] = {0.f, 0.f, 0.f, 0.f}, sq4[4] = {0.f, 0.f, 0.f, 0.f};
+        for_chunks([&](const uint32_t (&v)[16], int c0) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * j4);
-            const float d0 = (__uint_as_float(v[4 * j4 + 0]) + b4.x) - mean;
-            const float d1 = (__uint_as_float(v[4 * j4 + 1]) + b4.y) - mean;
-            const float d2 = (__uint_as_float(v[4 * j4 + 2]) + b4.z) - mean;
-            const float d3 = (__uint_as_float(v[4 * j4 + 3]) + b4.w) - mean;
-            q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]);
-            q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
+            const float d0 = (__uint_as_float(v[4 * j4 + 0]) + b4.x) - shift;
+            const float d1 = (__uint_as_float(v[4 * j4 + 1]) + b4.y) - shift;
+            const float d2 = (__uint_as_float(v[4 * j4 + 2]) + b4.z) - shift;
+            const float d3 = (__uint_as_float(v[4 * j4 + 3]) + b4.w) - shift;
+            sd4[0] += d0; sd4[1] += d1; sd4[2] += d2; sd4[3] += d3;
+            sq4[0] = fmaf(d0, d0, sq4[0]); sq4[1] = fmaf(d1, d1, sq4[1]);
+            sq4[2] = fmaf(d2, d2, sq4[2]); sq4[3] = fmaf(d3, d3, sq4[3]);
           }
-          ssq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
-        }
-        s_red[256 + hsel * 128 + m] = ssq;
+        });
+        float* red = s_red + as * 512;
+        red[hsel * 128 + m] = (sd4[0] + sd4[1]) + (sd4[2] + sd4[3]);
+        red[256 + hsel * 128 + m] = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
         asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");
-        ssq = s_red[256 + m] + s_red[384 + m];
-        ssq -= static_cast<float>(p.block_n - p.cout) * mean * mean;
-        rstd = rsqrtf(fmaxf(ssq, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
+        const float npad = static_cast<float>(p.block_n - p.cout);
+        const float sd = red[m] + red[128 + m] + npad * shift;
+        const float sq = red[256 + m] + red[384 + m] - npad * shift * shift;
+        const float mean_d = sd * inv_c;
+        mean = shift + mean_d;
+        rstd = rsqrtf(fmaxf(sq - sd * mean_d, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
       }
 
       // target rows / cols of the (bordered) NHWC fp16 buffer
@@ -386,10 +394,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int Hp = p.out_h + p.out_pt + p.out_pb;
       const int Wp = p.out_w + p.out_pl + p.out_pr;
 
-      for (int c0 = 16 * hsel; c0 < p.block_n; c0 += 32) {
-        uint32_t v[16];
-        tmem_ld16(t_row + c0, v);
-        tmem_ld_wait();
+      for_chunks([&](const uint32_t (&v)[16], int c0) {
         float f[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
@@ -448,7 +453,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   ow] = f[j];
           }
         }
-      }
+      });
       // zero the channel padding no N tile covers (e.g. cout 220 -> block_n 224 -> cpad 256)
       if (valid && last_nt && hsel == 0 && p.out_mode != HFC_OUT_NCHW_F32) {
         const int c_end = p.n_tiles * p.block_n;
@@ -705,9 +710,13 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   // columns are served from it by shifting the UMMA descriptor; all weights stay resident in smem.
   // L2->SM traffic drops from kh*kw*16 KB to kh*(128+kw-1)*128 B per tile.
   const int w_bytes_total = ph.ntaps * pl.c_chunks * pl.block_n * kBlockK * 2;
-  kp->wide = (d->wide != 2) && !d->transposed && !d->window && d->stride == 1 && d->kw > 1 && pl.c_chunks == 1 &&
+  static const bool env_no_wide = getenv("HFC_NO_WIDE") != nullptr;       // debugging switches
+  static const bool env_no_cluster = getenv("HFC_NO_CLUSTER") != nullptr;
+  kp->wide = (d->wide != 2) && !(env_no_wide && d->wide == 0) && !d->transposed && !d->window && d->stride == 1 && d->kw > 1 && pl.c_chunks == 1 &&
              pl.n_tiles == 1 && ph.grid_w >= 64 && w_bytes_total <= 112 * 1024 && (d->wide == 1 || pl.block_n <= 32);
   kp->kw = d->kw;
+  static const bool env_wide_boff = getenv("HFC_WIDE_BASEOFF") != nullptr;
+  kp->wide_boff = env_wide_boff ? 1 : 0;
   kp->a_region = 0;
   if (kp->wide) {
     kp->tw = kBlockM; kp->th = 1; kp->tn = 1;
@@ -729,6 +738,8 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   // to fill the machine, along N when the N tiles pair up, along M when the M tiles pair up.
   const int tiles_m = kp->tiles_w * kp->tiles_h * kp->tiles_n;
   int cm = d->cluster_m, cn = d->cluster_n;
+  if (env_no_cluster && cm == 0) cm = 1;
+  if (env_no_cluster && cn == 0) cn = 1;
   if (cm == 0 || cn == 0) {
     const bool big = static_cast<long long>(tiles_m) * pl.n_tiles >= 128;
     cn = (cn == 0) ? ((big && pl.n_tiles % 2 == 0) ? 2 : 1) : cn;

@@ -94,6 +94,36 @@ nchw_to_act_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
+// Few-channel variant (the RGB image: c <= 8, cpad == 8): one thread per pixel, channel planes read
+// coalesced along W, one 16 B store per (mirrored) target pixel.
+__global__ void __launch_bounds__(256)
+nchw_small_to_act_kernel(const float* __restrict__ x, __half* __restrict__ out,
+                         const __grid_constant__ ToActParams p) {
+  const size_t plane = static_cast<size_t>(p.h) * p.w;
+  const size_t total = static_cast<size_t>(p.n) * plane;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ww = static_cast<int>(idx % p.w);
+  const int hh = static_cast<int>((idx / p.w) % p.h);
+  const int nn = static_cast<int>(idx / plane);
+  float f[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    f[c] = (c < p.c) ? x[(static_cast<size_t>(nn) * p.c + c) * plane + static_cast<size_t>(hh) * p.w + ww] : 0.f;
+  uint4 pk;
+  __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+  __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+  pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+  int rows[3], cols[3];
+  const int nr = mirror_targets(hh, p.h, p.pt, p.pb, p.reflect != 0, rows);
+  const int nc = mirror_targets(ww, p.w, p.pl, p.pr, p.reflect != 0, cols);
+  const int Hp = p.h + p.pt + p.pb, Wp = p.w + p.pl + p.pr;
+  for (int ri = 0; ri < nr; ++ri)
+    for (int ci = 0; ci < nc; ++ci)
+      *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(nn) * Hp + rows[ri]) * Wp + cols[ci]) * 8) = pk;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Stand-alone ChannelNorm2D over NHWC fp32 rows (one warp per pixel, row held in registers)
 // ------------------------------------------------------------------------------------------------
@@ -381,6 +411,15 @@ extern "C" int hfc_nchw_to_act(const float* x, const hfc_act_geom* g, int32_t re
   p.n = g->n; p.c = g->c; p.h = g->h; p.w = g->w; p.cpad = g->cpad;
   p.pt = g->pt; p.pl = g->pl; p.pb = g->pb; p.pr = g->pr;
   p.reflect = reflect; p.norm = norm; p.eps = eps;
+  if (g->cpad == 8 && !norm) {
+    const long long npix = static_cast<long long>(g->n) * g->h * g->w;
+    nchw_small_to_act_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0,
+                               static_cast<cudaStream_t>(stream)>>>(x, reinterpret_cast<__half*>(out), p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "nchw_to_act launch: %s", cudaGetErrorString(e));
+    note_launch();
+    return HFC_OK;
+  }
   const size_t smem = static_cast<size_t>(g->c) * 33 * sizeof(float);
   if (smem > 200 * 1024) return set_error(HFC_ERR_INVALID, "nchw_to_act: too many channels (%d)", g->c);
   if (smem > 48 * 1024) {

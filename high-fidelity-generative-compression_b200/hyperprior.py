@@ -72,20 +72,30 @@ class Hyperprior(CodingModel):
         latents = latents.contiguous()
         batch = latents.shape[0]
         hyperlatents = self.analysis_net(latents)
+        # sums = [ln p(noisy z), ln p(round z), ln p(noisy y), ln p(round y)], accumulated in fp64 on device
+        sums = torch.zeros(4, dtype=torch.float64, device=latents.device)
         # Same RNG call as the reference (hyperprior.py:65) so seeds / patched generators line up.
         noise_z = torch.nn.init.uniform_(torch.zeros_like(hyperlatents), -0.5, 0.5)
-        z_noisy, z_quant, sums_z = ops.hyperlatent_likelihood(
-            hyperlatents, self.hyperlatent_likelihood.packed_params(), noise_z)
-        _, noisy_hyperlatent_bpp = self._bits_and_bpp(sums_z[0], batch, spatial_shape)
-        _, quantized_hyperlatent_bpp = self._bits_and_bpp(sums_z[1], batch, spatial_shape)
+        z_noisy, z_quant, _ = ops.hyperlatent_likelihood(
+            hyperlatents, self.hyperlatent_likelihood.packed_params(), noise_z, sums=sums[0:2])
         hyperlatents_decoded = z_noisy if self.training else z_quant            # hyperprior.py:294-297
+        # The two synthesis networks are independent and individually too small to fill the GPU:
+        # run the scale network on a side stream (fork / join is capturable in a CUDA graph).
+        cur = torch.cuda.current_stream()
+        side = self._side_stream(latents.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            latent_scales = self.synthesis_std(hyperlatents_decoded)             # lower bound applied in-kernel
         latent_means = self.synthesis_mu(hyperlatents_decoded)
-        latent_scales = self.synthesis_std(hyperlatents_decoded)                 # lower bound applied in-kernel
+        cur.wait_stream(side)
+        latent_scales.record_stream(cur)
         noise_y = torch.nn.init.uniform_(torch.zeros_like(latents), -0.5, 0.5)
-        latents_decoded, sums_y = ops.latent_likelihood(latents, latent_means, latent_scales, noise_y,
-                                                        self.scale_lower_bound, self.likelihood_type)
-        _, noisy_latent_bpp = self._bits_and_bpp(sums_y[0], batch, spatial_shape)
-        _, quantized_latent_bpp = self._bits_and_bpp(sums_y[1], batch, spatial_shape)
+        latents_decoded, _ = ops.latent_likelihood(latents, latent_means, latent_scales, noise_y,
+                                                   self.scale_lower_bound, self.likelihood_type, sums=sums[2:4])
+        # hyperprior.py:80-93: n_bits = sum(log p) / (-ln2 * B); bpp = n_bits / n_pixels
+        n_pixels = float(spatial_shape[0] * spatial_shape[1])
+        bpp = sums.to(torch.float32) / (batch * -math.log(2.)) / n_pixels
+        noisy_hyperlatent_bpp, quantized_hyperlatent_bpp, noisy_latent_bpp, quantized_latent_bpp = bpp.unbind(0)
         return HyperInfo(
             decoded=latents_decoded,
             latent_nbpp=noisy_latent_bpp,
@@ -95,3 +105,9 @@ class Hyperprior(CodingModel):
             hyperlatent_qbpp=quantized_hyperlatent_bpp,
             total_qbpp=quantized_latent_bpp + quantized_hyperlatent_bpp,
         )
+
+    def _side_stream(self, device):
+        key = (device.type, device.index)
+        if getattr(self, "_side", None) is None or self._side[0] != key:
+            self._side = (key, torch.cuda.Stream(device=device))
+        return self._side[1]

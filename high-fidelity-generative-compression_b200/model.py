@@ -10,6 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import hyperprior
+from .graph import GraphedCall
 from .config import ModelModes, ModelTypes
 from .network import encoder, generator
 
@@ -63,9 +64,37 @@ class Model(nn.Module):
         self.discriminator_steps = 0
         if self.use_discriminator:
             raise NotImplementedError("the Discriminator path is not built yet (SURVEY.md 8a rows D1-D3)")
+        self._use_graph = False
+        self._graphs = {}
+
+    def enable_cuda_graph(self, enabled=True):
+        """Replay `compression_forward` from a captured CUDA graph (one per input shape / train-eval state).
+        Not part of the reference API: an opt-in for serving / benchmarking.  Weights are read through the
+        packed copies made at capture time, so call it again (or disable) after changing parameters."""
+        self._use_graph = bool(enabled)
+        self._graphs.clear()
+        return self
+
+    def _apply(self, fn, *a, **k):
+        self._graphs = {}
+        return super()._apply(fn, *a, **k)
 
     def compression_forward(self, x):
         """src/model.py:119-165."""
+        if self._use_graph and x.is_cuda and not torch.is_grad_enabled():
+            key = (tuple(x.shape), x.device, self.training, self.model_mode)
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._graphs[key] = GraphedCall(self._compression_forward_impl, [x])
+            inter, info = g(x)
+            # fresh tensors, as the eager path returns (the graph's static outputs are overwritten on replay)
+            inter = Intermediates(x, inter.reconstruction.clone(), inter.latents_quantized.clone(),
+                                  inter.n_bpp.clone(), inter.q_bpp.clone())
+            info = type(info)(*[t.clone() for t in info])
+            return inter, info
+        return self._compression_forward_impl(x)
+
+    def _compression_forward_impl(self, x):
         image_dims = tuple(x.size()[1:])
         pad = self.model_mode == ModelModes.EVALUATION and (self.training is False)
         if pad:

@@ -177,13 +177,14 @@ class Conv:
         return out
 
 
-def latent_likelihood(y, mean, scale_raw, noise=None, scale_lower_bound=0.11, likelihood_type="gaussian"):
+def latent_likelihood(y, mean, scale_raw, noise=None, scale_lower_bound=0.11, likelihood_type="gaussian", sums=None):
     """Fused conditional likelihood; returns (decoded, sums) with sums = [sum log p_noisy, sum log p_quant]
     (natural log, fp64, on device)."""
     for t in (y, mean, scale_raw) + ((noise,) if noise is not None else ()):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == y.shape
     decoded = torch.empty_like(y)
-    sums = torch.zeros(2, dtype=torch.float64, device=y.device)
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float64, device=y.device)   # else: caller-provided, already zeroed
     lt = {"gaussian": 0, "logistic": 1}[likelihood_type]
     check(lib.hfc_latent_likelihood(_ptr(y), _ptr(mean), _ptr(scale_raw), _ptr(noise), y.numel(),
                                     float(scale_lower_bound), lt, _ptr(decoded), _ptr(sums), _stream()),
@@ -206,14 +207,15 @@ def pack_density_params(Hs, a_s, bs):
     return out.contiguous()
 
 
-def hyperlatent_likelihood(z, params64, noise=None):
+def hyperlatent_likelihood(z, params64, noise=None, sums=None):
     """Factorized-density likelihood of z at z+noise and round(z). Returns (z_noisy|None, z_quant, sums)."""
     assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 4
     n, c, h, w = z.shape
     assert tuple(params64.shape) == (c, 64) and params64.is_contiguous()
     z_quant = torch.empty_like(z)
     z_noisy = torch.empty_like(z) if noise is not None else None
-    sums = torch.zeros(2, dtype=torch.float64, device=z.device)
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float64, device=z.device)
     check(lib.hfc_hyperlatent_likelihood(_ptr(z), _ptr(noise), _ptr(params64), n, c, h * w, _ptr(z_noisy),
                                          _ptr(z_quant), _ptr(sums), _stream()), "hyperlatent_likelihood")
     return z_noisy, z_quant, sums

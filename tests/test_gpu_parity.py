@@ -161,3 +161,22 @@ def test_refuses_cpu_and_grad(model):
             model.Encoder(torch.zeros(1, 3, 64, 64))
     with pytest.raises(NotImplementedError):
         model.Encoder(torch.zeros(1, 3, 64, 64, device="cuda"))
+
+
+def test_cuda_graph_replay_matches_eager(sd):
+    """Opt-in CUDA-graph path: same kernels, so eval-mode outputs must be bit-identical to the eager path."""
+    m = Model(mse_lpips_args(), logging.getLogger("graph"))
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    x1 = synth.synth_image(2, 128, 128, 5).cuda()
+    x2 = synth.synth_image(2, 128, 128, 6).cuda()
+    with torch.no_grad():
+        e1, i1 = m.compression_forward(x1)
+        e2, i2 = m.compression_forward(x2)
+        m.enable_cuda_graph(True)
+        g1, j1 = m.compression_forward(x1)
+        g2, j2 = m.compression_forward(x2)      # replay with new input
+        g1b, _ = m.compression_forward(x1)
+    assert torch.equal(e1.reconstruction, g1.reconstruction) and torch.equal(e2.reconstruction, g2.reconstruction)
+    assert torch.equal(g1.reconstruction, g1b.reconstruction)
+    assert float(i1.total_qbpp) == float(j1.total_qbpp) and float(i2.total_qbpp) == float(j2.total_qbpp)
