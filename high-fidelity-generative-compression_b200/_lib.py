@@ -34,7 +34,7 @@ class ConvDesc(ctypes.Structure):
         ("eps", ctypes.c_float),
         ("block_n", ctypes.c_int32), ("precision", ctypes.c_int32),
         ("cluster_m", ctypes.c_int32), ("cluster_n", ctypes.c_int32),
-        ("wide", ctypes.c_int32),
+        ("wide", ctypes.c_int32), ("pair", ctypes.c_int32),
     ]
 
 
@@ -46,6 +46,7 @@ class ConvInfo(ctypes.Structure):
         ("block_n", ctypes.c_int32), ("n_tiles", ctypes.c_int32), ("m_tiles", ctypes.c_int32),
         ("stages", ctypes.c_int32), ("k_total", ctypes.c_int32),
         ("cluster_m", ctypes.c_int32), ("cluster_n", ctypes.c_int32), ("wide", ctypes.c_int32),
+        ("pair", ctypes.c_int32),
         ("flops", ctypes.c_double),
     ]
 

@@ -48,7 +48,10 @@ struct ConvKernelParams {
   int32_t num_kb, c_chunks, ntaps;
   int32_t stages;
   int32_t cm, cn;                     // cluster extent along M tiles / N tiles (1 or 2 each)
+  int32_t pair;                       // 1: CTA pairs (cta_group::2 UMMA, M = 256 across two SMs); needs cm == 2
+  int32_t b_rows;                     // rows of the B tile held by one CTA (block_n, or block_n/2 in pair mode)
   int32_t a_split_n;                  // A slice split: 1 = along the batch dim of the box, 0 = along rows
+  int32_t dbg;                        // debugging bits (env HFC_DBG): 1 skip stores, 2 skip norm stats, 4 skip epilogue body
   int32_t wide_boff;                  // debugging: set the descriptor base-offset field for shifted starts
   int32_t wide, kw;                   // 'wide' mode: row-resident A halo (128+kw-1 pixels), resident weights
   int32_t a_region;                   // bytes per A stage (wide mode: halo row rounded up to 1024)
@@ -91,7 +94,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // 1024 B alignment for the 128B-swizzled tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const int b_bytes = p.block_n * kBlockK * 2;
+  const int b_bytes = p.b_rows * kBlockK * 2;
   const int stage_bytes = p.wide ? p.a_region : kABytes + b_bytes;
   // wide mode: every weight sub-tile (num_kb * kw of them) stays resident behind the A ring
   uint8_t* w_res = smem + p.stages * stage_bytes;
@@ -127,18 +130,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], static_cast<uint32_t>(p.cm + p.cn - 1));
+      // arrivals that free a stage: one commit per CTA (pair: per pair leader) that reads what lands here
+      mbar_init(&empty_bar[s], static_cast<uint32_t>(p.pair ? p.cn : p.cm + p.cn - 1));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiThreads / 32);
+      // pair mode: the leader's MMA warp waits for the epilogue warps of BOTH CTAs
+      mbar_init(&tempty_bar[s], (p.pair ? 2 : 1) * (kEpiThreads / 32));
     }
     mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (p.pair) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -197,6 +207,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + kABytes;
+          if (p.pair) {
+            // both CTAs of the pair fill their own stage; all bytes are accounted on the LEADER's barrier
+            if (m_idx == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+            if (p.cn > 1)
+              tma_load_4d_pair_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], chunk * kBlockK,
+                                  w_base + p.tap_dw[tap], h_base + p.tap_dh[tap], n_base, mask_a);
+            else
+              tma_load_4d_pair(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
+                               h_base + p.tap_dh[tap], n_base);
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[s], kb * kBlockK, nt * p.block_n + m_idx * p.b_rows);
+            if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
           if (csize > 1) {
             tma_load_4d_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], chunk * kBlockK,
@@ -211,6 +235,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+      }
+    }
+  } else if (warp == 1 && p.pair) {
+    // ===================== MMA issuer, CTA pair: only the leader (even rank) issues =====================
+    if (m_idx == 0) {
+      const uint32_t idesc = make_idesc_f16(p.fmt, 2 * kBlockM, static_cast<uint32_t>(p.block_n));
+      const uint16_t mask_pair = static_cast<uint16_t>(3u << (2 * n_idx));
+      const uint16_t mask_all = static_cast<uint16_t>((1u << csize) - 1u);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int ct = cid; ct < total_ctiles; ct += ncl) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+            const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+            const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair_mc(&empty_bar[s], mask_all);   // every CTA that writes into this pair's stages
+            if (kb == p.num_kb - 1) umma_commit_pair_mc(&tfull_bar[as], mask_pair);
+          }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -340,7 +397,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       };
 
       float mean = 0.f, rstd = 1.f;
-      if (p.norm) {
+      if (p.norm && !(p.dbg & 6)) {
         // ChannelNorm statistics in ONE pass over the channel row held in TMEM, using shifted sums
         // (shift = the row's first channel) so that sum(d^2) - sum(d)^2/C does not cancel:
         //   d = (acc + bias) - shift ;  mean = shift + sum(d)/C ;  var = (sum(d^2) - sum(d)^2/C)/(C-1).
@@ -394,6 +451,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int Hp = p.out_h + p.out_pt + p.out_pb;
       const int Wp = p.out_w + p.out_pl + p.out_pr;
 
+      if (!(p.dbg & 4))
       for_chunks([&](const uint32_t (&v)[16], int c0) {
         float f[16];
 #pragma unroll
@@ -412,7 +470,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           f[4 * j4 + 2] = apply_act(x2, p.act); f[4 * j4 + 3] = apply_act(x3, p.act);
         }
         const int cc = c_base + c0;
-        if (!valid) {
+        if (!valid || ((p.dbg & 1) && f[0] != 12345.678f)) {
           // nothing to store for rows outside the image / batch (their A rows were zero-filled)
         } else if (p.out_mode == HFC_OUT_NHWC_F16) {
           if (cc < p.out_cpad) {
@@ -476,7 +534,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (p.pair) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
@@ -484,7 +545,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_before();
   __syncthreads();
   if (csize > 1) cluster_sync_all();  // nobody exits while a peer may still arrive on its barriers
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) {
+    if (p.pair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,6 +779,8 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   kp->wide = (d->wide != 2) && !(env_no_wide && d->wide == 0) && !d->transposed && !d->window && d->stride == 1 && d->kw > 1 && pl.c_chunks == 1 &&
              pl.n_tiles == 1 && ph.grid_w >= 64 && w_bytes_total <= 112 * 1024 && (d->wide == 1 || pl.block_n <= 32);
   kp->kw = d->kw;
+  static const char* env_dbg = getenv("HFC_DBG");
+  kp->dbg = env_dbg ? atoi(env_dbg) : 0;
   static const bool env_wide_boff = getenv("HFC_WIDE_BASEOFF") != nullptr;
   kp->wide_boff = env_wide_boff ? 1 : 0;
   kp->a_region = 0;
@@ -755,6 +821,16 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   }
   kp->cm = cm;
   kp->cn = cn;
+  // CTA pairs (cta_group::2): whenever two M tiles share a cluster and the K loop is long enough for the
+  // operand bandwidth to matter.  Each CTA then holds only half of the B tile -> deeper smem ring.
+  static const bool env_no_pair = getenv("HFC_NO_PAIR") != nullptr;
+  kp->pair = (cm == 2 && !kp->wide && !env_no_pair && d->pair != 2 && (pl.block_n / 2) % 8 == 0 &&
+              (d->pair == 1 || ph.ntaps * pl.c_chunks >= 8)) ? 1 : 0;
+  kp->b_rows = kp->pair ? pl.block_n / 2 : pl.block_n;
+  if (kp->pair) {
+    stage_bytes = kABytes + kp->b_rows * kBlockK * 2;
+    kp->stages = std::max(2, std::min(budget / stage_bytes, kMaxStages));
+  }
   return stage_bytes;
 }
 
@@ -799,6 +875,7 @@ extern "C" int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info) {
   info->m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
   info->stages = kp.stages;
   info->wide = kp.wide;
+  info->pair = kp.pair;
   info->cluster_m = kp.cm;
   info->cluster_n = kp.cn;
   info->k_total = 0;

@@ -88,6 +88,8 @@ typedef struct hfc_conv_desc {
   int32_t cluster_n;        /* 0 = auto; else 1 or 2: CTAs per cluster along N tiles (share the pixel tile) */
   int32_t wide;             /* 0 = auto, 1 = force, 2 = forbid the row-resident 'wide' mode (few output channels on
                                big maps: halo row + resident weights, filter columns by descriptor shift) */
+  int32_t pair;             /* 0 = auto, 1 = force, 2 = forbid CTA pairs (cta_group::2 UMMA, M = 256 over two SMs;
+                               needs cluster_m == 2) */
 } hfc_conv_desc;
 
 typedef struct hfc_conv_info {
@@ -97,6 +99,7 @@ typedef struct hfc_conv_info {
   int32_t block_n, n_tiles, m_tiles, stages, k_total;
   int32_t cluster_m, cluster_n; /* cluster shape the launch will use (TMA multicast) */
   int32_t wide;                 /* 1 if the row-resident 'wide' mode is used */
+  int32_t pair;                 /* 1 if CTA pairs (cta_group::2) are used */
   double flops;                 /* algorithmic 2*MACs of the layer (real channels) */
 } hfc_conv_info;
 

@@ -51,3 +51,30 @@ def test_wide_mode_7x7_head(w):
 def test_wide_mode_forced_3x3_and_forbidden():
     run_conv_case(2, 64, 16, 128, 16, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, wide=1, expect=dict(wide=1))
     run_conv_case(1, 60, 32, 128, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, wide=2, expect=dict(wide=0))
+
+
+@pytest.mark.parametrize("cluster", [(2, 1), (2, 2)])
+def test_cta_pair_resblock_shape(cluster):
+    run_conv_case(4, 960, 16, 16, 960, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F32,
+                  cluster=cluster, pair=1, expect=dict(cluster_m=2, cluster_n=cluster[1], pair=1))
+
+
+def test_cta_pair_many_tiles_persistent():
+    # 16 x 32x32 -> 128 M tiles x 2 N tiles (block_n 240): every pair loops over several tiles
+    run_conv_case(16, 256, 32, 32, 480, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F32,
+                  cluster=(2, 2), pair=1, expect=dict(pair=1))
+
+
+def test_cta_pair_stride2_fused_norm_and_padding_tiles():
+    run_conv_case(16, 128, 32, 32, 240, 3, stride=2, pad=(1, 0, 0, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F16,
+                  out_border=(1, 1, 1, 1), norm=True, act=ACT_RELU, cluster=(2, 1), pair=1, expect=dict(pair=1))
+    # odd number of M tiles (3) and of N tiles (3): dummy tiles inside the pair / cluster
+    run_conv_case(3, 64, 8, 16, 480, 3, pad=(1, 1, 1, 1), pad_mode=PAD_ZERO, out_mode=OUT_NHWC_F32, block_n=160,
+                  cluster=(2, 2), pair=1, expect=dict(pair=1))
+
+
+def test_cta_pair_transposed_and_small_maps():
+    run_conv_case(8, 256, 32, 32, 120, 3, stride=2, pad=(1, 1, 1, 1), transposed=True, out_mode=OUT_NHWC_F16,
+                  norm=True, act=ACT_RELU, cluster=(2, 1), pair=1, expect=dict(pair=1))
+    run_conv_case(32, 320, 8, 8, 320, 5, stride=2, pad=(2, 2, 2, 2), pad_mode=PAD_REFLECT, out_mode=OUT_NCHW_F32,
+                  cluster=(2, 2), block_n=160, pair=1, expect=dict(pair=1))

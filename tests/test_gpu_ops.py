@@ -48,7 +48,7 @@ def rel_err(a, b):
 
 def run_conv_case(n, cin, h, w, cout, k, stride=1, pad=(0, 0, 0, 0), pad_mode=PAD_ZERO, transposed=False,
                   out_mode=OUT_NCHW_F32, out_border=(0, 0, 0, 0), act=ACT_NONE, norm=False, window=False,
-                  block_n=0, seed=0, cluster=(0, 0), wide=0, expect=None):
+                  block_n=0, seed=0, cluster=(0, 0), wide=0, pair=0, expect=None):
     g = torch.Generator(device="cpu").manual_seed(seed)
     kh, kw = (k, k) if isinstance(k, int) else k
     x = r16(torch.randn(n, cin, h, w, generator=g)).to(DEV)
@@ -88,7 +88,7 @@ def run_conv_case(n, cin, h, w, cout, k, stride=1, pad=(0, 0, 0, 0), pad_mode=PA
         out_geom = Geom(n, oh, ow, cout, cout)
     conv = Conv(in_geom, cout, k, stride=stride, transposed=transposed, pad_mode=pad_mode, pad=pad,
                 out_mode=out_mode, out_geom=out_geom, out_reflect=any(out_border), act=act, norm=norm,
-                window=window, block_n=block_n, cluster=cluster, wide=wide)
+                window=window, block_n=block_n, cluster=cluster, wide=wide, pair=pair)
     if expect is not None:
         for k, v in expect.items():
             assert getattr(conv.info, k) == v, (k, getattr(conv.info, k), v)
