@@ -86,6 +86,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// kPair = true is the CTA-pair (cta_group::2) instantiation; it must be launched with clusters of 2 or 4
+// (ptxas marks a kernel that contains cta_group::2 instructions as cluster-only), so the single-CTA path
+// is a separate instantiation.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b,
@@ -131,18 +135,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       // arrivals that free a stage: one commit per CTA (pair: per pair leader) that reads what lands here
-      mbar_init(&empty_bar[s], static_cast<uint32_t>(p.pair ? p.cn : p.cm + p.cn - 1));
+      mbar_init(&empty_bar[s], static_cast<uint32_t>(kPair ? p.cn : p.cm + p.cn - 1));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       // pair mode: the leader's MMA warp waits for the epilogue warps of BOTH CTAs
-      mbar_init(&tempty_bar[s], (p.pair ? 2 : 1) * (kEpiThreads / 32));
+      mbar_init(&tempty_bar[s], (kPair ? 2 : 1) * (kEpiThreads / 32));
     }
     mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    if (p.pair) {
+    if constexpr (kPair) {
       tmem_alloc_pair(tmem_slot, kTmemCols);
       tmem_relinquish_pair();
     } else {
@@ -207,7 +211,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + kABytes;
-          if (p.pair) {
+          if constexpr (kPair) {
             // both CTAs of the pair fill their own stage; all bytes are accounted on the LEADER's barrier
             if (m_idx == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
             if (p.cn > 1)
@@ -237,9 +241,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
-  } else if (warp == 1 && p.pair) {
+  } else if (warp == 1 && kPair) {
     // ===================== MMA issuer, CTA pair: only the leader (even rank) issues =====================
-    if (m_idx == 0) {
+    if constexpr (kPair) if (m_idx == 0) {
       const uint32_t idesc = make_idesc_f16(p.fmt, 2 * kBlockM, static_cast<uint32_t>(p.block_n));
       const uint16_t mask_pair = static_cast<uint16_t>(3u << (2 * n_idx));
       const uint16_t mask_all = static_cast<uint16_t>((1u << csize) - 1u);
@@ -535,7 +539,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (p.pair) mbar_arrive_leader(&tempty_bar[as]);
+        if constexpr (kPair) mbar_arrive_leader(&tempty_bar[as]);
         else mbar_arrive(&tempty_bar[as]);
       }
       if (++as == 2) { as = 0; aph ^= 1; }
@@ -546,7 +550,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   if (csize > 1) cluster_sync_all();  // nobody exits while a peer may still arrive on its barriers
   if (warp == 1) {
-    if (p.pair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
@@ -1020,8 +1024,11 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
                         (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel,
+      cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024);
       if (e != cudaSuccess)
         return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       attr_set = true;
@@ -1039,7 +1046,8 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel, tmA, tmB, kp);
+    cudaError_t e = kp.pair ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmA, tmB, kp)
+                            : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmA, tmB, kp);
     if (e != cudaSuccess)
       return set_error(HFC_ERR_LAUNCH, "conv_igemm launch: %s", cudaGetErrorString(e));
     note_launch();

@@ -7,6 +7,7 @@ tcgen05 path (10-bit mantissa, the same as the TF32 cuDNN path the reference run
 REL_TOL below, measured as relative L2 per stage.
 """
 import logging
+import math
 import os
 
 import numpy as np
@@ -91,13 +92,39 @@ def test_stagewise_parity(model, sd, b, h, w, training, tag):
         assert rel_l2(model.Hyperprior.synthesis_mu(z_dec.to(dev)), hyp_o.latent_means) < REL_TOL
         sg = model.Hyperprior.synthesis_std(z_dec.to(dev)).clamp(min=0.11)
         assert rel_l2(sg, hyp_o.latent_scales) < REL_TOL
+        # Likelihood kernels fed the oracle's tensors: identical inputs -> y_hat must agree (up to a vanishing
+        # number of ties) and the four bit-rates tightly.
+        from hific_b200 import ops
+        H = model.Hyperprior
+        zn, zq, sz = ops.hyperlatent_likelihood(hyp_o.hyperlatents.to(dev), H.hyperlatent_likelihood.packed_params(),
+                                                nz.to(dev))
+        assert torch.equal(zq.cpu(), hyp_o.quantized_hyperlatents)
+        dec, sy = ops.latent_likelihood(y_o.to(dev), hyp_o.latent_means.to(dev), hyp_o.latent_scales.to(dev),
+                                        ny.to(dev), 0.11, "gaussian")
+        assert ((dec.cpu() - hyp_o.decoded).abs() > 0.5).float().mean().item() < 1e-5
+        assert (dec.cpu() - hyp_o.decoded).abs().median().item() < 1e-6
+        scale = 1.0 / (b * -math.log(2.0) * h * w)
+        for got, ref in ((sz[0], hyp_o.hyperlatent_nbpp), (sz[1], hyp_o.hyperlatent_qbpp),
+                         (sy[0], hyp_o.latent_nbpp), (sy[1], hyp_o.latent_qbpp)):
+            assert abs(float(got) * scale - float(ref)) <= 2e-5 * max(1.0, abs(float(ref)))
+        # The module as a whole, fed the oracle's y.  In training mode everything upstream of the rounding is
+        # continuous (noisy z feeds the synthesis nets): strict.  In eval mode round(z) feeds them, and a z
+        # element within ~5e-4 of a half-integer may round the other way under fp16 operands (2 of 2560 do in
+        # this fixture, exactly as the oracle's own fp16-rounding emulation predicts); one such flip moves
+        # mu/sigma of a whole neighbourhood, so there only the flip FRACTION of round(z) is asserted.
         with Feed([nz, ny]) as f:
-            info = model.Hyperprior(y_o.to(dev), spatial_shape=(h, w))
+            info = H(y_o.to(dev), spatial_shape=(h, w))
             assert f.calls == 2
-        assert ((info.decoded.cpu() - hyp_o.decoded).abs() > 0.5).float().mean().item() < FLIP_TOL
-        for fld in ("latent_nbpp", "hyperlatent_nbpp", "total_nbpp", "latent_qbpp", "hyperlatent_qbpp", "total_qbpp"):
-            ref = float(getattr(hyp_o, fld))
-            assert abs(float(getattr(info, fld)) - ref) <= BPP_TOL * max(1.0, abs(ref)), fld
+        if training:
+            assert ((info.decoded.cpu() - hyp_o.decoded).abs() > 0.5).float().mean().item() < FLIP_TOL
+            for fld in ("latent_nbpp", "hyperlatent_nbpp", "total_nbpp", "latent_qbpp", "hyperlatent_qbpp", "total_qbpp"):
+                ref = float(getattr(hyp_o, fld))
+                assert abs(float(getattr(info, fld)) - ref) <= BPP_TOL * max(1.0, abs(ref)), fld
+        else:
+            z_ours = H.analysis_net(y_o.to(dev)).cpu()
+            assert (torch.floor(z_ours + 0.5) != hyp_o.quantized_hyperlatents).float().mean().item() < FLIP_TOL
+            assert abs(float(info.hyperlatent_qbpp) - float(hyp_o.hyperlatent_qbpp)) <= 0.02 * float(hyp_o.hyperlatent_qbpp)
+            assert abs(float(info.total_qbpp) - float(hyp_o.total_qbpp)) <= 0.05 * float(hyp_o.total_qbpp)
         assert rel_l2(model.Generator(hyp_o.decoded.to(dev)), recon_o) < REL_TOL
 
 
