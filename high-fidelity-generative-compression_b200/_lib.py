@@ -46,7 +46,7 @@ class ConvInfo(ctypes.Structure):
         ("block_n", ctypes.c_int32), ("n_tiles", ctypes.c_int32), ("m_tiles", ctypes.c_int32),
         ("stages", ctypes.c_int32), ("k_total", ctypes.c_int32),
         ("cluster_m", ctypes.c_int32), ("cluster_n", ctypes.c_int32), ("wide", ctypes.c_int32),
-        ("pair", ctypes.c_int32),
+        ("pair", ctypes.c_int32), ("tapn", ctypes.c_int32),
         ("flops", ctypes.c_double),
     ]
 

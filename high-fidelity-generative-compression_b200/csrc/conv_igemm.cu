@@ -39,6 +39,8 @@ static constexpr int kTmemCols = 512;
 static constexpr int kMaxStages = 8;
 static constexpr int kParamStride = 256;                 // floats per epilogue parameter row (>= block_n)
 static constexpr int kTailBytes = 256 + 2 * 3 * kParamStride * 4 + 2 * 512 * 4;  // barriers + parameter rows + stats exchange
+static constexpr int kTapnLd = 33;                       // padded row pitch (floats) of the tap-in-N staging tile
+static constexpr int kTapnBytes = 2 * kBlockM * kTapnLd * 4;  // double-buffered [128][33] fp32
 
 struct ConvKernelParams {
   int32_t tw, th, tn;                 // tile extents, tw*th*tn == 128
@@ -51,6 +53,8 @@ struct ConvKernelParams {
   int32_t pair;                       // 1: CTA pairs (cta_group::2 UMMA, M = 256 across two SMs); needs cm == 2
   int32_t b_rows;                     // rows of the B tile held by one CTA (block_n, or block_n/2 in pair mode)
   int32_t a_split_n;                  // A slice split: 1 = along the batch dim of the box, 0 = along rows
+  int32_t tapn, w_step;               // 'tap-in-N' mode (tiny cout): N = kw*cout, shifted sum in the epilogue;
+                                      // tiles advance by w_step = 128-kw+1 output pixels
   int32_t dbg;                        // debugging bits (env HFC_DBG): 1 skip stores, 2 skip norm stats, 4 skip epilogue body
   int32_t wide_boff;                  // debugging: set the descriptor base-offset field for shifted starts
   int32_t wide, kw;                   // 'wide' mode: row-resident A halo (128+kw-1 pixels), resident weights
@@ -112,6 +116,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   float* s_par = reinterpret_cast<float*>(bars + 32);  // [2][3][kParamStride] bias / gamma / beta
   float* s_red = s_par + 2 * 3 * kParamStride;         // [2 acc stages][2 (sum, ssq)][2 warps][128 rows]
+  float* s_tapn = s_red + 2 * 512;                     // [2 acc stages][128][kTapnLd] (tap-in-N mode only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,7 +207,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mt /= p.tiles_w;
         const int thi = mt % p.tiles_h;
         const int tni = mt / p.tiles_h;   // >= tiles_n for padding tiles: every row is out of bounds (zero fill)
-        const int w_base = twi * p.tw * p.sw + p.iw0;
+        const int w_base = (p.tapn ? twi * p.w_step : twi * p.tw * p.sw) + p.iw0;
         // my slice of the shared A tile: rows [n_idx*128/cn, (n_idx+1)*128/cn)
         const int h_base = (thi * p.th + (p.a_split_n ? 0 : n_idx * (p.th / p.cn))) * p.sh + p.ih0;
         const int n_base = tni * p.tn + (p.a_split_n ? n_idx * (p.tn / p.cn) : 0);
@@ -337,6 +342,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int thi_in = (m / p.tw) % p.th;
     const int tni_in = m / (p.tw * p.th);
     const float inv_c = 1.f / static_cast<float>(p.cout);
+    const int act_now = p.tapn ? HFC_ACT_NONE : p.act;  // tap-in-N applies the activation after the shifted sum
     int as = 0;
     uint32_t aph = 0;
     int cur_nt = -1, pbuf = 1;
@@ -347,13 +353,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mt /= p.tiles_w;
       const int thi = mt % p.tiles_h;
       const int tni = mt / p.tiles_h;
-      const int gw = twi * p.tw + twi_in;
+      const int gw = (p.tapn ? twi * p.w_step : twi * p.tw) + twi_in;
       const int gh = thi * p.th + thi_in;
       const int n = tni * p.tn + tni_in;
       const int oh = gh * p.osh + p.ooh;
       const int ow = gw * p.osw + p.oow;
       const bool valid = (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
-                         (ow < p.out_w) && (nt < p.n_tiles);
+                         (ow < p.out_w) && (nt < p.n_tiles) && (!p.tapn || m < p.w_step);
       const int c_base = nt * p.block_n;
       const bool last_nt = (nt == p.n_tiles - 1);
 
@@ -367,7 +373,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int i = et; i < p.block_n; i += kEpiThreads) {
           const int c = c_base + i;
           const bool real = c < p.cout;
-          sp[i] = (real && p.bias) ? __ldg(p.bias + c) : 0.f;
+          sp[i] = (real && p.bias && !p.tapn) ? __ldg(p.bias + c) : 0.f;
           sp[kParamStride + i] = (real && p.norm) ? __ldg(p.gamma + c) : 0.f;
           sp[2 * kParamStride + i] = (real && p.norm) ? __ldg(p.beta + c) : 0.f;
         }
@@ -470,11 +476,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             x0 = fmaf(g4.x * rstd, x0 - mean, e4.x); x1 = fmaf(g4.y * rstd, x1 - mean, e4.y);
             x2 = fmaf(g4.z * rstd, x2 - mean, e4.z); x3 = fmaf(g4.w * rstd, x3 - mean, e4.w);
           }
-          f[4 * j4 + 0] = apply_act(x0, p.act); f[4 * j4 + 1] = apply_act(x1, p.act);
-          f[4 * j4 + 2] = apply_act(x2, p.act); f[4 * j4 + 3] = apply_act(x3, p.act);
+          f[4 * j4 + 0] = apply_act(x0, act_now); f[4 * j4 + 1] = apply_act(x1, act_now);
+          f[4 * j4 + 2] = apply_act(x2, act_now); f[4 * j4 + 3] = apply_act(x3, act_now);
         }
         const int cc = c_base + c0;
-        if (!valid || ((p.dbg & 1) && f[0] != 12345.678f)) {
+        if (p.tapn) {
+          // stage the partial products D[pixel][tap*cout + co]; the shifted sum over taps follows below
+          float* st = s_tapn + as * (kBlockM * kTapnLd) + m * kTapnLd + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) st[j] = f[j];
+        } else if (!valid || ((p.dbg & 1) && f[0] != 12345.678f)) {
           // nothing to store for rows outside the image / batch (their A rows were zero-filled)
         } else if (p.out_mode == HFC_OUT_NHWC_F16) {
           if (cc < p.out_cpad) {
@@ -516,8 +527,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       });
+      if (p.tapn) {
+        // out[w, co] = bias[co] + sum_t D[w + t][t*cout + co]   (NCHW fp32 output)
+        asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");
+        if (valid && hsel == 0) {
+          const float* st = s_tapn + as * (kBlockM * kTapnLd);
+          float* dst = reinterpret_cast<float*>(p.out);
+          const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
+          for (int co = 0; co < p.cout; ++co) {
+            float acc = p.bias ? __ldg(p.bias + co) : 0.f;
+            for (int t = 0; t < p.kw; ++t) acc += st[(m + t) * kTapnLd + t * p.cout + co];
+            dst[(static_cast<size_t>(n) * p.cout + co) * plane + static_cast<size_t>(oh) * p.out_w + ow] =
+                apply_act(acc, p.act);
+          }
+        }
+      }
       // zero the channel padding no N tile covers (e.g. cout 220 -> block_n 224 -> cpad 256)
-      if (valid && last_nt && hsel == 0 && p.out_mode != HFC_OUT_NCHW_F32) {
+      if (valid && last_nt && hsel == 0 && !p.tapn && p.out_mode != HFC_OUT_NCHW_F32) {
         const int c_end = p.n_tiles * p.block_n;
         if (p.out_mode == HFC_OUT_NHWC_F16) {
           for (int c = c_end; c < p.out_cpad; c += 8) {
@@ -561,7 +587,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 struct PackParams {
   int32_t cout, cin, kh, kw;
   int32_t cin_pad, ntaps, ktot, rows;
-  int32_t transposed, window;
+  int32_t cout_real;                  // tap-in-N: real cout (pp.cout then counts kw*cout rows)
+  int32_t transposed, window, tapn;
   uint32_t fmt;
   int8_t ky[kMaxTaps];
   int8_t kx[kMaxTaps];
@@ -578,7 +605,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
     if (co < pp.cout) {
       int tap, ci, ky, kx;
       bool ok;
-      if (pp.window) {
+      if (pp.tapn) {
+        // row = filter column t * cout + co ; K = (filter row r, input channel)
+        tap = k / pp.cin_pad;
+        ci = k % pp.cin_pad;
+        ky = pp.ky[tap];
+        kx = co / pp.cout_real;
+        ok = (ci < pp.cin) && (kx < pp.kw);
+      } else if (pp.window) {
         tap = k / 64;
         const int r = k % 64;
         kx = r / pp.cin_pad;          // cin_pad == 8: 8 pixels x 8 channels per filter row
@@ -593,9 +627,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
         ok = ci < pp.cin;
       }
       if (ok) {
+        const int co_w = pp.tapn ? co % pp.cout_real : co;
+        const int cout_w = pp.tapn ? pp.cout_real : pp.cout;
         const size_t idx = pp.transposed
-                               ? ((static_cast<size_t>(ci) * pp.cout + co) * pp.kh + ky) * pp.kw + kx
-                               : ((static_cast<size_t>(co) * pp.cin + ci) * pp.kh + ky) * pp.kw + kx;
+                               ? ((static_cast<size_t>(ci) * cout_w + co_w) * pp.kh + ky) * pp.kw + kx
+                               : ((static_cast<size_t>(co_w) * pp.cin + ci) * pp.kh + ky) * pp.kw + kx;
         val = w[idx];
       }
     }
@@ -630,6 +666,7 @@ struct Plan {
   int out_h, out_w;
   int block_n, n_tiles, rows;   // rows = n_tiles * block_n (packed weight rows)
   int c_chunks;
+  int tapn;                     // tap-in-N mode
   int kblk_per_tap;
   size_t packed_elems;
   double flops;
@@ -675,7 +712,11 @@ static int make_plan(const hfc_conv_desc* d, Plan* pl) {
     p.grid_h = pl->out_h; p.grid_w = pl->out_w;
     p.osh = p.osw = 1; p.ooh = p.oow = 0;
     p.sh = p.sw = s;
-    if (d->window) {
+    static const bool env_no_tapn = getenv("HFC_NO_TAPN") != nullptr;
+    pl->tapn = (!d->window && s == 1 && d->out_mode == HFC_OUT_NCHW_F32 && !d->norm && d->kw > 1 &&
+                d->kw * d->cout <= 32 && pl->out_w >= 64 && d->block_n == 0 &&
+                (d->wide == 3 || (d->wide == 0 && !env_no_tapn))) ? 1 : 0;
+    if (d->window || pl->tapn) {
       for (int ky = 0; ky < d->kh; ++ky) {
         p.dh[p.ntaps] = static_cast<int8_t>(ky - d->pad_t);
         p.dw[p.ntaps] = static_cast<int8_t>(-d->pad_l);
@@ -723,6 +764,8 @@ static int make_plan(const hfc_conv_desc* d, Plan* pl) {
 
   // N tiling
   int bn = d->block_n;
+  const int n_cols = pl->tapn ? d->kw * d->cout : d->cout;   // GEMM columns
+  if (pl->tapn) bn = (n_cols + 15) / 16 * 16;
   if (bn == 0) {
     const int nt = (d->cout + 255) / 256;
     bn = ((d->cout + nt - 1) / nt + 15) / 16 * 16;
@@ -730,7 +773,7 @@ static int make_plan(const hfc_conv_desc* d, Plan* pl) {
   if (bn % 16 != 0 || bn < 16 || bn > 256)
     return set_error(HFC_ERR_INVALID, "conv: block_n %d must be a multiple of 16 in [16,256]", bn);
   pl->block_n = bn;
-  pl->n_tiles = (d->cout + bn - 1) / bn;
+  pl->n_tiles = (n_cols + bn - 1) / bn;
   pl->rows = pl->n_tiles * bn;
   if (d->norm && pl->n_tiles != 1)
     return set_error(HFC_ERR_INVALID,
@@ -788,14 +831,18 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   static const bool env_wide_boff = getenv("HFC_WIDE_BASEOFF") != nullptr;
   kp->wide_boff = env_wide_boff ? 1 : 0;
   kp->a_region = 0;
-  if (kp->wide) {
+  kp->tapn = pl.tapn;
+  kp->w_step = kBlockM - d->kw + 1;
+  if (pl.tapn) kp->wide = 0;
+  if (kp->wide || pl.tapn) {
     kp->tw = kBlockM; kp->th = 1; kp->tn = 1;
   }
-  kp->tiles_w = (ph.grid_w + kp->tw - 1) / kp->tw;
+  kp->tiles_w = pl.tapn ? (ph.grid_w + (kBlockM - d->kw + 1) - 1) / (kBlockM - d->kw + 1)
+                        : (ph.grid_w + kp->tw - 1) / kp->tw;
   kp->tiles_h = (ph.grid_h + kp->th - 1) / kp->th;
   kp->tiles_n = (batch + kp->tn - 1) / kp->tn;
   int stage_bytes = kABytes + pl.block_n * kBlockK * 2;
-  int budget = 226 * 1024 - 1024 - kTailBytes;
+  int budget = 226 * 1024 - 1024 - kTailBytes - (pl.tapn ? kTapnBytes : 0);
   if (kp->wide) {
     kp->a_region = ((kBlockM + d->kw - 1) * kBlockK * 2 + 1023) / 1024 * 1024;
     stage_bytes = kp->a_region;
@@ -816,7 +863,7 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
     cm = (cm == 0) ? ((big && tiles_m % 2 == 0) ? 2 : 1) : cm;
   }
   if (cm < 1 || cm > 2 || cn < 1 || cn > 2) return -1;
-  if (kp->wide) cm = cn = 1;
+  if (kp->wide || pl.tapn) cm = cn = 1;
   if ((pl.block_n / cm) % 8 != 0 || pl.block_n % cm != 0) cm = 1;
   kp->a_split_n = 0;
   if (cn > 1) {
@@ -880,6 +927,7 @@ extern "C" int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info) {
   info->stages = kp.stages;
   info->wide = kp.wide;
   info->pair = kp.pair;
+  info->tapn = kp.tapn;
   info->cluster_m = kp.cm;
   info->cluster_n = kp.cn;
   info->k_total = 0;
@@ -902,6 +950,8 @@ extern "C" int hfc_conv_pack_weights(const hfc_conv_desc* d, const float* w, voi
     pp.cout = d->cout; pp.cin = d->in.c; pp.kh = d->kh; pp.kw = d->kw;
     pp.cin_pad = d->in.cpad; pp.ntaps = ph.ntaps; pp.ktot = ph.ktot; pp.rows = pl.rows;
     pp.transposed = d->transposed; pp.window = d->window; pp.fmt = 0;
+    pp.tapn = pl.tapn; pp.cout_real = d->cout;
+    if (pl.tapn) pp.cout = d->kw * d->cout;   // GEMM rows = (filter column, output channel)
     memcpy(pp.ky, ph.ky, sizeof(pp.ky));
     memcpy(pp.kx, ph.kx, sizeof(pp.kx));
     const size_t total = static_cast<size_t>(pl.rows) * ph.ktot;
@@ -1021,7 +1071,7 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     const int max_clusters = csize == 4 ? (sm_count * 132 / 148) / 4 : sm_count / csize;
     const int grid = std::min(ctiles, std::max(1, max_clusters)) * csize;
     const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 /*align*/ + kTailBytes +
-                        (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
+                        (kp.tapn ? kTapnBytes : 0) + (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false>,

@@ -86,8 +86,10 @@ typedef struct hfc_conv_desc {
   int32_t precision;        /* HFC_PREC_* */
   int32_t cluster_m;        /* 0 = auto; else 1 or 2: CTAs per cluster along M tiles (share the weight tile) */
   int32_t cluster_n;        /* 0 = auto; else 1 or 2: CTAs per cluster along N tiles (share the pixel tile) */
-  int32_t wide;             /* 0 = auto, 1 = force, 2 = forbid the row-resident 'wide' mode (few output channels on
-                               big maps: halo row + resident weights, filter columns by descriptor shift) */
+  int32_t wide;             /* tiny-cout convs on big maps (the 7x7 60->3 head): 0 = auto (tap-in-N), 1 = force the
+                               row-resident 'wide' mode (halo row + resident weights, filter columns by descriptor
+                               shift), 2 = forbid both, 3 = force 'tap-in-N' (GEMM columns = (filter column, cout),
+                               filter columns summed with a pixel shift in the epilogue) */
   int32_t pair;             /* 0 = auto, 1 = force, 2 = forbid CTA pairs (cta_group::2 UMMA, M = 256 over two SMs;
                                needs cluster_m == 2) */
 } hfc_conv_desc;
@@ -100,6 +102,7 @@ typedef struct hfc_conv_info {
   int32_t cluster_m, cluster_n; /* cluster shape the launch will use (TMA multicast) */
   int32_t wide;                 /* 1 if the row-resident 'wide' mode is used */
   int32_t pair;                 /* 1 if CTA pairs (cta_group::2) are used */
+  int32_t tapn;                 /* 1 if the tap-in-N mode is used */
   double flops;                 /* algorithmic 2*MACs of the layer (real channels) */
 } hfc_conv_info;
 

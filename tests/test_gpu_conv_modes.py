@@ -78,3 +78,14 @@ def test_cta_pair_transposed_and_small_maps():
                   norm=True, act=ACT_RELU, cluster=(2, 1), pair=1, expect=dict(pair=1))
     run_conv_case(32, 320, 8, 8, 320, 5, stride=2, pad=(2, 2, 2, 2), pad_mode=PAD_REFLECT, out_mode=OUT_NCHW_F32,
                   cluster=(2, 2), block_n=160, pair=1, expect=dict(pair=1))
+
+
+@pytest.mark.parametrize("w", [128, 256, 200, 122, 123])
+def test_tap_in_n_mode_7x7_head(w):
+    run_conv_case(2, 60, 20, w, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, expect=dict(tapn=1))
+
+
+def test_tap_in_n_other_shapes():
+    run_conv_case(1, 64, 16, 128, 4, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, expect=dict(tapn=1))       # 3x3, cout 4
+    run_conv_case(2, 128, 9, 130, 2, 5, pad=(2, 2, 2, 2), pad_mode=PAD_ZERO, expect=dict(tapn=1))          # 2 K chunks, zero pad
+    run_conv_case(1, 60, 16, 128, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, wide=1, expect=dict(tapn=0, wide=1))
