@@ -65,6 +65,11 @@ SIGNATURES = {
     "hfc_launch_count": (ctypes.c_ulonglong, []),
     "hfc_conv_query": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ConvInfo)]),
     "hfc_conv_pack_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "hfc_conv_pack_weights_scaled": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "hfc_disc_input": (ctypes.c_int, [_vp, _i32, _vp, ctypes.POINTER(ActGeom), _i32, ctypes.POINTER(ActGeom), _vp, _vp]),
+    "hfc_spectral_sigma": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "hfc_gan_sums": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
+    "hfc_sqdiff_sum": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
     "hfc_conv_forward": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hfc_nchw_to_act": (ctypes.c_int, [_vp, ctypes.POINTER(ActGeom), _i32, _i32, _vp, _vp, _f32, _vp, _vp]),
     "hfc_channelnorm": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _vp, _f32, _i32,

@@ -594,8 +594,9 @@ struct PackParams {
   int8_t kx[kMaxTaps];
 };
 
-__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
-                                    const __grid_constant__ PackParams pp) {
+__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                    uint16_t* __restrict__ out, const __grid_constant__ PackParams pp) {
+  const float mul = scale ? *scale : 1.f;
   const size_t total = static_cast<size_t>(pp.rows) * pp.ktot;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -632,7 +633,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
         const size_t idx = pp.transposed
                                ? ((static_cast<size_t>(ci) * cout_w + co_w) * pp.kh + ky) * pp.kw + kx
                                : ((static_cast<size_t>(co_w) * pp.cin + ci) * pp.kh + ky) * pp.kw + kx;
-        val = w[idx];
+        val = w[idx] * mul;
       }
     }
     uint16_t bits;
@@ -936,8 +937,22 @@ extern "C" int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info) {
   return HFC_OK;
 }
 
+static int pack_weights_impl(const hfc_conv_desc* d, const float* w, const float* scale, void* packed,
+                             void* stream);
+
 extern "C" int hfc_conv_pack_weights(const hfc_conv_desc* d, const float* w, void* packed,
                                      void* stream) {
+  return pack_weights_impl(d, w, nullptr, packed, stream);
+}
+
+extern "C" int hfc_conv_pack_weights_scaled(const hfc_conv_desc* d, const float* w, const float* scale,
+                                            void* packed, void* stream) {
+  if (!scale) return set_error(HFC_ERR_INVALID, "conv_pack_weights_scaled: null scale");
+  return pack_weights_impl(d, w, scale, packed, stream);
+}
+
+static int pack_weights_impl(const hfc_conv_desc* d, const float* w, const float* scale, void* packed,
+                             void* stream) {
   Plan pl;
   int rc = make_plan(d, &pl);
   if (rc != HFC_OK) return rc;
@@ -958,7 +973,7 @@ extern "C" int hfc_conv_pack_weights(const hfc_conv_desc* d, const float* w, voi
     const int threads = 256;
     const int blocks = static_cast<int>(std::min<size_t>((total + threads - 1) / threads, 148 * 16));
     pack_weights_kernel<<<blocks, threads, 0, st>>>(
-        w, reinterpret_cast<uint16_t*>(packed) + ph.w_offset, pp);
+        w, scale, reinterpret_cast<uint16_t*>(packed) + ph.w_offset, pp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
       return set_error(HFC_ERR_LAUNCH, "pack_weights launch: %s", cudaGetErrorString(e));

@@ -117,6 +117,10 @@ unsigned long long hfc_launch_count(void);
 int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info);
 /* w: fp32 (cout, cin, kh, kw) for conv2d, (cin, cout, kh, kw) for conv_transpose2d (torch layout) */
 int hfc_conv_pack_weights(const hfc_conv_desc* d, const float* w, void* packed, void* stream);
+/* same, with every weight multiplied by *scale (a DEVICE scalar), e.g. 1/sigma of spectral normalisation
+ * (torch.nn.utils.spectral_norm divides weight_orig by sigma, src/network/discriminator.py:46-62) */
+int hfc_conv_pack_weights_scaled(const hfc_conv_desc* d, const float* w, const float* scale, void* packed,
+                                 void* stream);
 /* in: act buffer (d->in); packed: from hfc_conv_pack_weights; bias/gamma/beta: fp32 [cout] or NULL;
  * out: buffer of d->out_mode/d->out */
 int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const void* packed, const float* bias,
@@ -170,6 +174,33 @@ int hfc_latent_likelihood(const float* y, const float* mean, const float* scale_
 int hfc_hyperlatent_likelihood(const float* z, const float* noise, const float* params64,
                                int32_t n, int32_t c, int32_t hw, float* z_noisy, float* z_quant,
                                double* sums, void* stream);
+
+/*
+ * Discriminator input (src/network/discriminator.py:75-79): torch.cat((x, Upsample(scale, 'nearest')(ctx)), 1)
+ * written straight into the bordered NHWC act buffer conv1 reads.  x: (n, x_channels, h, w) fp32 NCHW;
+ * ctx_act: border-less act buffer `ctx` (n, h/scale, w/scale, c) from the context conv.
+ */
+int hfc_disc_input(const float* x, int32_t x_channels, const void* ctx_act, const hfc_act_geom* ctx,
+                   int32_t scale, const hfc_act_geom* out_geom, void* out, void* stream);
+
+/*
+ * Spectral norm of a (rows x cols) row-major weight matrix as torch.nn.utils.spectral_norm computes it:
+ * power_iteration != 0 (training): v = normalize(W^T u), u = normalize(W v) (u, v updated in place),
+ * sigma = u.(W v); power_iteration == 0 (eval): sigma = u.(W v) from the stored u, v.
+ * workspace: rows + cols floats.  sigma / inv_sigma: device scalars (inv_sigma may be NULL).
+ */
+int hfc_spectral_sigma(const float* w, int32_t rows, int32_t cols, float* u, float* v, int32_t power_iteration,
+                       float* workspace, float* sigma, float* inv_sigma, void* stream);
+
+/*
+ * GAN loss sums (src/loss/losses.py:30-41): logits = [real | generated] halves of half_count elements;
+ * sums5 (caller-zeroed doubles): sum BCE(real,1), sum BCE(gen,0), sum BCE(gen,1), sum sigmoid(real),
+ * sum sigmoid(gen).
+ */
+int hfc_gan_sums(const float* logits, int64_t half_count, double* sums5, void* stream);
+
+/* Distortion loss sum (src/model.py:190-194): *sum += sum((scale*a - scale*b)^2); caller zeroes *sum. */
+int hfc_sqdiff_sum(const float* a, const float* b, int64_t count, float scale, double* sum, void* stream);
 
 #ifdef __cplusplus
 }
