@@ -165,6 +165,44 @@ __global__ void __launch_bounds__(256) sqdiff_sum_kernel(const float* __restrict
   }
 }
 
+
+// ---- LPIPS feature loss of one trunk layer ------------------------------------------------------------
+// networks_basic.py:61-89 + perceptual_loss.py:42-46: per pixel  sum_c w_c (f0_c/|f0| - f1_c/|f1|)^2 with
+// |f| = sqrt(sum_c f_c^2 + 1e-10), then the spatial mean, accumulated into out[image].
+// One thread per pixel; channel planes are read coalesced along (h, w); two passes (norms, then distance).
+__global__ void __launch_bounds__(256) lpips_layer_kernel(const float* __restrict__ f0, const float* __restrict__ f1,
+                                                          const float* __restrict__ lin_w, int c, int hw,
+                                                          float* __restrict__ out) {
+  __shared__ float red[8];
+  const int img = blockIdx.y;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (px < hw) {
+    const float* a = f0 + static_cast<size_t>(img) * c * hw + px;
+    const float* b = f1 + static_cast<size_t>(img) * c * hw + px;
+    float na = 0.f, nb = 0.f;
+    for (int k = 0; k < c; ++k) {
+      const float x = a[static_cast<size_t>(k) * hw], y = b[static_cast<size_t>(k) * hw];
+      na = fmaf(x, x, na);
+      nb = fmaf(y, y, nb);
+    }
+    const float ia = 1.f / sqrtf(na + 1e-10f), ib = 1.f / sqrtf(nb + 1e-10f);
+    for (int k = 0; k < c; ++k) {
+      const float d = a[static_cast<size_t>(k) * hw] * ia - b[static_cast<size_t>(k) * hw] * ib;
+      acc = fmaf(lin_w[k] * d, d, acc);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float v = warp_sum(acc);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) atomicAdd(&out[img], t / static_cast<float>(hw));
+  }
+}
+
 }  // namespace hfc
 
 using namespace hfc;
@@ -243,5 +281,18 @@ extern "C" int hfc_sqdiff_sum(const float* a, const float* b, int64_t count, flo
   const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((count / 4 + 255) / 256, sms * 8LL)));
   sqdiff_sum_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, count, scale, sum);
   HFC_CHECK_LAUNCH("sqdiff_sum launch");
+  return HFC_OK;
+}
+
+extern "C" int hfc_lpips_layer(const float* f0, const float* f1, const float* lin_w, int32_t n, int32_t c,
+                               int32_t hw, float* out_per_image, void* stream) {
+  if (!f0 || !f1 || !lin_w || !out_per_image || n <= 0 || c <= 0 || hw <= 0)
+    return set_error(HFC_ERR_INVALID, "lpips_layer: null pointer or empty input");
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc != HFC_OK) return rc;
+  dim3 grid((hw + 255) / 256, n);
+  lpips_layer_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(f0, f1, lin_w, c, hw, out_per_image);
+  HFC_CHECK_LAUNCH("lpips_layer launch");
   return HFC_OK;
 }

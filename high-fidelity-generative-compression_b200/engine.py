@@ -14,7 +14,7 @@ Layer lists follow the reference networks:
 import torch
 
 from . import ops
-from .ops import (ACT_NONE, ACT_RELU, OUT_NCHW_F32, OUT_NHWC_F16, OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO, Conv,
+from .ops import (ACT_LEAKY02, ACT_NONE, ACT_RELU, OUT_NCHW_F32, OUT_NHWC_F16, OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO, Conv,
                   Geom, round_up)
 
 
@@ -211,6 +211,52 @@ class HyperSynthesisPlan:
         h = self.c1(self.in_act, mod.conv1.weight, mod.conv1.bias, out=self.b1)
         h = self.c2(h, mod.conv2.weight, mod.conv2.bias, out=self.b2)
         return self.c3(h, mod.conv3.weight, mod.conv3.bias)
+
+
+class DiscriminatorPlan:
+    """Discriminator.forward (src/network/discriminator.py:66-86) for n = 2B stacked real / generated images."""
+    FILTERS = (64, 128, 256, 512)
+    CONTEXT_C = 12
+
+    def __init__(self, n, h, w, im_channels, C, ctx_h, ctx_w, device):
+        if h % ctx_h or w % ctx_w or h // ctx_h != w // ctx_w:
+            raise ValueError("Discriminator: image size must be an integer multiple of the context size")
+        self.scale = h // ctx_h
+        b1 = (1, 1, 1, 1)
+        self.g_y = Geom(n, ctx_h, ctx_w, C, round_up(C, 64), *b1)
+        self.y_act = self.g_y.alloc(device)
+        self.g_ctx = Geom(n, ctx_h, ctx_w, self.CONTEXT_C, 16)
+        self.c_ctx = Conv(self.g_y, self.CONTEXT_C, 3, pad_mode=PAD_REFLECT, pad=b1, out_geom=self.g_ctx, act=ACT_LEAKY02)
+        self.ctx_act = self.c_ctx.alloc_out(device)
+        self.g_in = Geom(n, h, w, im_channels + self.CONTEXT_C, 64, *b1)
+        self.in_act = self.g_in.alloc(device)
+        self.convs, self.bufs = [], []
+        g = self.g_in
+        for i, f in enumerate(self.FILTERS):
+            last = i == len(self.FILTERS) - 1
+            g_next = Geom(n, g.h // 2, g.w // 2, f, round_up(f, 64), *((0, 0, 0, 0) if last else b1))
+            conv = Conv(g, f, 4, stride=2, pad_mode=PAD_REFLECT, pad=b1, out_geom=g_next, out_reflect=not last,
+                        act=ACT_LEAKY02)
+            self.convs.append(conv)
+            self.bufs.append(conv.alloc_out(device))
+            g = g_next
+        self.c_out = Conv(g, 1, 1, out_mode=OUT_NCHW_F32)
+        self.ws = [torch.empty(f + c.in_geom.c * 16, dtype=torch.float32, device=device)
+                   for f, c in zip(self.FILTERS, self.convs)]
+        self.flops = self.c_ctx.flops + sum(c.flops for c in self.convs) + self.c_out.flops
+
+    def run(self, mod, x, y):
+        ops.nchw_to_act(y, self.g_y, reflect=True, out=self.y_act)
+        self.c_ctx(self.y_act, mod.context_conv.weight, mod.context_conv.bias, out=self.ctx_act)
+        ops.disc_input(x, self.ctx_act, self.g_ctx, self.g_in, self.scale, out=self.in_act)
+        h = self.in_act
+        for i, conv in enumerate(self.convs):
+            layer = getattr(mod, f"conv{i + 1}")
+            # spectral norm (discriminator.py:46-62): one power iteration per training forward, W = W_orig / sigma
+            _, inv_sigma = ops.spectral_sigma(layer.weight_orig, layer.weight_u, layer.weight_v, mod.training, self.ws[i])
+            key = (layer.weight_u._version, layer.weight_v._version) if not mod.training else object()
+            h = conv(h, layer.weight_orig, layer.bias, out=self.bufs[i], scale=inv_sigma, scale_key=key)
+        return self.c_out(h, mod.conv_out.weight, mod.conv_out.bias)
 
 
 def require_inference(module, who):

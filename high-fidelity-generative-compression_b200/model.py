@@ -1,7 +1,7 @@
 """`Model` with the reference's constructor, attributes and return types (src/model.py:35-387) on top of the
-B200 kernels.  Built so far: `compression_forward` (train / eval / EVALUATION-mode padding) and the
-EVALUATION `forward` (reconstruction, q_bpp) -- i.e. the encode+decode forward path of the headline metric.
-The loss / discriminator / backward half of the training step is not built yet and raises loudly.
+B200 kernels: `compression_forward`, `discriminator_forward`, `compression_loss`, `GAN_loss` and `forward` in all
+three model modes.  Everything runs forward-only for now (call under torch.no_grad(); the backward kernels are
+the next step), which already covers validation / evaluation and the encode+decode headline metric.
 """
 from collections import defaultdict, namedtuple
 
@@ -9,10 +9,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import hyperprior
+from functools import partial
+
+from . import hyperprior, ops
+from .loss import losses
+from .loss.perceptual import PerceptualLoss
 from .graph import GraphedCall
 from .config import ModelModes, ModelTypes
-from .network import encoder, generator
+from .network import discriminator, encoder, generator
 
 Intermediates = namedtuple("Intermediates",
                            ["input_image", "reconstruction", "latents_quantized", "n_bpp", "q_bpp"])
@@ -60,10 +64,20 @@ class Model(nn.Module):
         self.amortization_models.extend(self.Hyperprior.amortization_models)
         self.use_discriminator = (self.model_type == ModelTypes.COMPRESSION_GAN
                                   and self.model_mode != ModelModes.EVALUATION)
-        self.Discriminator = None
-        self.discriminator_steps = 0
-        if self.use_discriminator:
-            raise NotImplementedError("the Discriminator path is not built yet (SURVEY.md 8a rows D1-D3)")
+        if self.use_discriminator is True:
+            assert self.args.discriminator_steps > 0, 'Must specify nonzero training steps for D!'
+            self.discriminator_steps = self.args.discriminator_steps
+            self.logger.info('GAN mode enabled. Training discriminator for {} steps.'.format(self.discriminator_steps))
+            self.Discriminator = discriminator.Discriminator(image_dims=self.image_dims,
+                                                             context_dims=self.args.latent_dims,
+                                                             C=self.args.latent_channels)
+            self.gan_loss = partial(losses.gan_loss, args.gan_loss_type)
+        else:
+            self.discriminator_steps = 0
+            self.Discriminator = None
+        # As in the reference (model.py:104-105) the LPIPS network is held in a plain attribute-less container so that
+        # its weights stay out of Model.parameters() / state_dict(); it follows the model across devices via _apply.
+        self._lpips = [None]
         self._use_graph = False
         self._graphs = {}
 
@@ -77,7 +91,22 @@ class Model(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._graphs = {}
+        if self._lpips[0] is not None:
+            self._lpips[0]._apply(fn)
         return super()._apply(fn, *a, **k)
+
+    @property
+    def perceptual_loss(self):
+        if self._lpips[0] is None:
+            dev = next(self.parameters()).device
+            self._lpips[0] = PerceptualLoss(model='net-lin', net='alex', use_gpu=dev.type == 'cuda').to(dev)
+        return self._lpips[0]
+
+    def store_loss(self, key, loss):
+        assert type(loss) == float, 'Call .item() on loss before storage'
+        storage = self.storage_train if self.training is True else self.storage_test
+        if self.writeout is True:
+            storage[key].append(loss)
 
     def compression_forward(self, x):
         """src/model.py:119-165."""
@@ -116,6 +145,7 @@ class Model(nn.Module):
     def forward(self, x, train_generator=False, return_intermediates=False, writeout=True):
         """src/model.py:346-387 (EVALUATION branch)."""
         self.writeout = writeout
+        losses_out = dict()
         if train_generator is True:
             self.step_counter += 1
         intermediates, hyperinfo = self.compression_forward(x)
@@ -125,6 +155,95 @@ class Model(nn.Module):
                 reconstruction = (reconstruction + 1.) / 2.
             reconstruction = torch.clamp(reconstruction, min=0., max=1.)
             return reconstruction, intermediates.q_bpp
-        raise NotImplementedError(
-            "Model.forward in TRAINING/VALIDATION mode needs the loss kernels (MSE, LPIPS feature loss, GAN) "
-            "and the backward kernels, which are not built yet; compression_forward() is available in all modes")
+        compression_model_loss = self.compression_loss(intermediates, hyperinfo)
+        if self.use_discriminator is True:
+            D_loss, G_loss = self.GAN_loss(intermediates, train_generator)
+            weighted_G_loss = self.args.beta * G_loss
+            compression_model_loss = compression_model_loss + weighted_G_loss
+            losses_out['disc'] = D_loss
+        losses_out['compression'] = compression_model_loss
+        if (self.step_counter % self.log_interval == 1):
+            self.store_loss('weighted_compression_loss', compression_model_loss.item())
+        if return_intermediates is True:
+            return losses_out, intermediates
+        return losses_out
+
+    # ------------------------------------------------------------------ discriminator / losses
+    def discriminator_forward(self, intermediates, train_generator):
+        """src/model.py:167-188 (including its pairing quirk: images are stacked [real..., gen...] while the
+        context latents are repeat_interleave'd)."""
+        x_gen = intermediates.reconstruction
+        x_real = intermediates.input_image
+        if train_generator is False:
+            x_gen = x_gen.detach()
+        D_in = torch.cat([x_real, x_gen], dim=0)
+        latents = intermediates.latents_quantized.detach()
+        latents = torch.repeat_interleave(latents, 2, dim=0)
+        D_out, D_out_logits = self.Discriminator(D_in, latents)
+        D_out = torch.squeeze(D_out)
+        D_out_logits = torch.squeeze(D_out_logits)
+        D_real, D_gen = torch.chunk(D_out, 2, dim=0)
+        D_real_logits, D_gen_logits = torch.chunk(D_out_logits, 2, dim=0)
+        return Disc_out(D_real, D_gen, D_real_logits, D_gen_logits)
+
+    def distortion_loss(self, x_gen, x_real):
+        """mean((255 x_gen - 255 x_real)^2) -- src/model.py:190-194, one fused reduction."""
+        x_gen, x_real = x_gen.contiguous(), x_real.contiguous()
+        return (ops.sqdiff_sum(x_gen, x_real, 255.) / x_gen.numel()).to(torch.float32)
+
+    def perceptual_loss_wrapper(self, x_gen, x_real, normalize=True):
+        LPIPS_loss = self.perceptual_loss.forward(x_gen, x_real, normalize=normalize)
+        return torch.mean(LPIPS_loss)
+
+    def compression_loss(self, intermediates, hyperinfo):
+        """src/model.py:201-241."""
+        x_real = intermediates.input_image
+        x_gen = intermediates.reconstruction
+        if self.args.normalize_input_image is True:
+            x_real = (x_real + 1.) / 2.
+            x_gen = (x_gen + 1.) / 2.
+        distortion_loss = self.distortion_loss(x_gen, x_real)
+        perceptual_loss = self.perceptual_loss_wrapper(x_gen, x_real, normalize=True)
+        weighted_distortion = self.args.k_M * distortion_loss
+        weighted_perceptual = self.args.k_P * perceptual_loss
+        weighted_rate, rate_penalty = losses.weighted_rate_loss(
+            self.args, total_nbpp=intermediates.n_bpp, total_qbpp=intermediates.q_bpp,
+            step_counter=self.step_counter, ignore_schedule=self.args.ignore_schedule)
+        weighted_R_D_loss = weighted_rate + weighted_distortion
+        weighted_compression_loss = weighted_R_D_loss + weighted_perceptual
+        if (self.step_counter % self.log_interval == 1):
+            self.store_loss('rate_penalty', rate_penalty)
+            self.store_loss('distortion', distortion_loss.item())
+            self.store_loss('perceptual', perceptual_loss.item())
+            self.store_loss('n_rate', intermediates.n_bpp.item())
+            self.store_loss('q_rate', intermediates.q_bpp.item())
+            self.store_loss('n_rate_latent', hyperinfo.latent_nbpp.item())
+            self.store_loss('q_rate_latent', hyperinfo.latent_qbpp.item())
+            self.store_loss('n_rate_hyperlatent', hyperinfo.hyperlatent_nbpp.item())
+            self.store_loss('q_rate_hyperlatent', hyperinfo.hyperlatent_qbpp.item())
+            self.store_loss('weighted_rate', weighted_rate.item())
+            self.store_loss('weighted_distortion', weighted_distortion.item())
+            self.store_loss('weighted_perceptual', weighted_perceptual.item())
+            self.store_loss('weighted_R_D', weighted_R_D_loss.item())
+            self.store_loss('weighted_compression_loss_sans_G', weighted_compression_loss.item())
+        return weighted_compression_loss
+
+    def GAN_loss(self, intermediates, train_generator=False):
+        """src/model.py:244-260."""
+        disc_out = self.discriminator_forward(intermediates, train_generator)
+        D_loss = self.gan_loss(disc_out, mode='discriminator_loss')
+        G_loss = self.gan_loss(disc_out, mode='generator_loss')
+        if (self.step_counter % self.log_interval == 1):
+            self.store_loss('D_gen', torch.mean(disc_out.D_gen).item())
+            self.store_loss('D_real', torch.mean(disc_out.D_real).item())
+            self.store_loss('disc_loss', D_loss.item())
+            self.store_loss('gen_loss', G_loss.item())
+            self.store_loss('weighted_gen_loss', (self.args.beta * G_loss).item())
+        return D_loss, G_loss
+
+    def compress(self, x, silent=False):
+        raise NotImplementedError("Model.compress drives the host rANS coder (src/model.py:262-310), which is out of "
+                                  "scope of the B200 hot path; use the reference's src/compression with this model's weights")
+
+    def decompress(self, compression_output):
+        raise NotImplementedError("Model.decompress drives the host rANS coder (src/model.py:312-344): out of scope")

@@ -152,22 +152,28 @@ class Conv:
             return torch.empty((g.n * g.h * g.w, g.cpad), dtype=torch.float32, device=device)
         return torch.empty((g.n, self.cout, g.h, g.w), dtype=torch.float32, device=device)
 
-    def packed_weights(self, weight):
-        key = (weight.data_ptr(), weight._version, weight.device)
+    def packed_weights(self, weight, scale=None, scale_key=None):
+        """scale: optional device scalar multiplied into every weight while packing (spectral norm's 1/sigma);
+        scale_key: anything hashable that changes whenever the scale value may have changed."""
+        key = (weight.data_ptr(), weight._version, weight.device, scale_key)
         if self._packed is None or self._packed_key != key:
             w = weight.detach()
             assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
             if self._packed is None or self._packed.device != w.device:
                 self._packed = torch.empty(self.info.packed_weight_bytes // 2, dtype=torch.float16, device=w.device)
-            check(lib.hfc_conv_pack_weights(ctypes.byref(self.desc), _ptr(w), _ptr(self._packed), _stream()),
-                  "conv_pack_weights")
+            if scale is None:
+                check(lib.hfc_conv_pack_weights(ctypes.byref(self.desc), _ptr(w), _ptr(self._packed), _stream()),
+                      "conv_pack_weights")
+            else:
+                check(lib.hfc_conv_pack_weights_scaled(ctypes.byref(self.desc), _ptr(w), _ptr(scale),
+                                                       _ptr(self._packed), _stream()), "conv_pack_weights_scaled")
             self._packed_key = key
         return self._packed
 
-    def __call__(self, x_act, weight, bias=None, gamma=None, beta=None, out=None):
+    def __call__(self, x_act, weight, bias=None, gamma=None, beta=None, out=None, scale=None, scale_key=None):
         assert x_act.is_cuda and x_act.dtype == torch.float16 and tuple(x_act.shape) == self.in_geom.shape, \
             (tuple(x_act.shape), self.in_geom.shape)
-        packed = self.packed_weights(weight)
+        packed = self.packed_weights(weight, scale, scale_key)
         if out is None:
             out = self.alloc_out(x_act.device)
         b = bias.detach().reshape(-1) if bias is not None else None
@@ -220,3 +226,55 @@ def hyperlatent_likelihood(z, params64, noise=None, sums=None):
     check(lib.hfc_hyperlatent_likelihood(_ptr(z), _ptr(noise), _ptr(params64), n, c, h * w, _ptr(z_noisy),
                                          _ptr(z_quant), _ptr(sums), _stream()), "hyperlatent_likelihood")
     return z_noisy, z_quant, sums
+
+
+def disc_input(x, ctx_act, ctx_geom, out_geom, scale, out=None):
+    """cat(x, nearest-upsample(ctx)) -> bordered act buffer (Discriminator.forward, discriminator.py:75-79)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = out_geom.alloc(x.device)
+    cg, og = ctx_geom.c_struct(), out_geom.c_struct()
+    check(lib.hfc_disc_input(_ptr(x), x.shape[1], _ptr(ctx_act), ctypes.byref(cg), scale, ctypes.byref(og), _ptr(out),
+                             _stream()), "disc_input")
+    return out
+
+
+def spectral_sigma(weight_orig, u, v, power_iteration, workspace=None):
+    """torch.nn.utils.spectral_norm's sigma for `weight_orig` (cout, ...) with buffers u, v (updated in place when
+    power_iteration).  Returns (sigma, inv_sigma) device scalars."""
+    w = weight_orig.detach()
+    rows, cols = w.shape[0], w.numel() // w.shape[0]
+    assert w.is_contiguous() and u.numel() == rows and v.numel() == cols
+    if workspace is None:
+        workspace = torch.empty(rows + cols, dtype=torch.float32, device=w.device)
+    out = torch.empty(2, dtype=torch.float32, device=w.device)
+    check(lib.hfc_spectral_sigma(_ptr(w), rows, cols, _ptr(u), _ptr(v), int(power_iteration), _ptr(workspace),
+                                 _ptr(out[0:1]), _ptr(out[1:2]), _stream()), "spectral_sigma")
+    return out[0], out[1:2]
+
+
+def gan_sums(logits):
+    """[sum BCE(real,1), sum BCE(gen,0), sum BCE(gen,1), sum sigmoid(real), sum sigmoid(gen)] (fp64, device)."""
+    lg = logits.reshape(-1)
+    assert lg.is_cuda and lg.dtype == torch.float32 and lg.is_contiguous() and lg.numel() % 2 == 0
+    sums = torch.zeros(5, dtype=torch.float64, device=lg.device)
+    check(lib.hfc_gan_sums(_ptr(lg), lg.numel() // 2, _ptr(sums), _stream()), "gan_sums")
+    return sums
+
+
+def sqdiff_sum(a, b, scale=255.0):
+    assert a.shape == b.shape and a.is_cuda and a.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+    out = torch.zeros(1, dtype=torch.float64, device=a.device)
+    check(lib.hfc_sqdiff_sum(_ptr(a), _ptr(b), a.numel(), float(scale), _ptr(out), _stream()), "sqdiff_sum")
+    return out[0]
+
+
+def lpips_layer(f0, f1, lin_w, out):
+    """out[i] += spatial mean of the LIN-weighted squared distance between channel-normalised features."""
+    assert f0.shape == f1.shape and f0.is_cuda and f0.dtype == torch.float32
+    f0, f1 = f0.contiguous(), f1.contiguous()
+    n, c, h, w = f0.shape
+    lw = lin_w.reshape(-1).contiguous()
+    assert lw.numel() == c and out.numel() == n and out.dtype == torch.float32
+    check(lib.hfc_lpips_layer(_ptr(f0), _ptr(f1), _ptr(lw), n, c, h * w, _ptr(out), _stream()), "lpips_layer")
+    return out

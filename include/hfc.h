@@ -202,6 +202,14 @@ int hfc_gan_sums(const float* logits, int64_t half_count, double* sums5, void* s
 /* Distortion loss sum (src/model.py:190-194): *sum += sum((scale*a - scale*b)^2); caller zeroes *sum. */
 int hfc_sqdiff_sum(const float* a, const float* b, int64_t count, float scale, double* sum, void* stream);
 
+/*
+ * LPIPS feature loss of one trunk layer (src/loss/perceptual_similarity/networks_basic.py:61-89,
+ * perceptual_loss.py:42-46): f0, f1 (n, c, h*w) fp32 trunk features of the two images, lin_w (c) the
+ * non-negative 1x1 'lin' weights; out_per_image[i] += mean_hw sum_c w_c (f0/|f0| - f1/|f1|)^2.
+ */
+int hfc_lpips_layer(const float* f0, const float* f1, const float* lin_w, int32_t n, int32_t c, int32_t hw,
+                    float* out_per_image, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -312,6 +312,39 @@ def discriminator_forward(sd, x, y, prefix="Discriminator.", training=True, rnd=
 
 
 # ------------------------------------------------------------------------------------------------
+# LPIPS -- src/loss/perceptual_similarity/networks_basic.py:61-98, perceptual_loss.py:26-46
+# ------------------------------------------------------------------------------------------------
+LPIPS_SLICES = ((0, 2), (2, 5), (5, 8), (8, 10), (10, 12))   # pretrained_networks.py:67-76
+
+
+def lpips_forward(trunk_features, lin_weights, pred, target, normalize=True):
+    """trunk_features: torchvision alexnet().features (frozen); lin_weights: 5 tensors (C_k,).
+    Returns (N,1,1,1) like PerceptualLoss.forward(pred, target, normalize)."""
+    if normalize:
+        target, pred = 2 * target - 1, 2 * pred - 1
+    shift = torch.tensor([-.030, -.088, -.188]).view(1, 3, 1, 1)
+    scale = torch.tensor([.458, .448, .450]).view(1, 3, 1, 1)
+
+    def feats(x):
+        h = (x - shift) / scale
+        outs = []
+        for lo, hi in LPIPS_SLICES:
+            for i in range(lo, hi):
+                h = trunk_features[i](h)
+            outs.append(h)
+        return outs
+
+    f0, f1 = feats(target), feats(pred)          # DistModel.forward(in0=target, in1=pred)
+    val = 0
+    for k in range(5):
+        n0 = f0[k] / torch.sqrt(torch.sum(f0[k] ** 2, dim=1, keepdim=True) + 1e-10)
+        n1 = f1[k] / torch.sqrt(torch.sum(f1[k] ** 2, dim=1, keepdim=True) + 1e-10)
+        d = (n0 - n1) ** 2
+        val = val + (d * lin_weights[k].view(1, -1, 1, 1)).sum(dim=1, keepdim=True).mean(dim=(2, 3), keepdim=True)
+    return val
+
+
+# ------------------------------------------------------------------------------------------------
 # helpers for precision studies (not part of the reference): emulate 16-bit operand rounding
 # ------------------------------------------------------------------------------------------------
 def round_fp16(t):

@@ -62,6 +62,63 @@ def build_reference_model(gan=False):
     return model, ModelModes
 
 
+def gan_case(synth, O):
+    """COMPRESSION_GAN training forward of the real reference (discriminator, LPIPS, all loss terms) on a 2x128x128
+    batch; also exports the vendored LPIPS lin weights (data, not code) for the product's PerceptualLoss."""
+    import torchvision
+    model, ModelModes = build_reference_model(gan=True)
+    sd = synth.synth_state_dict(SEED, gan=True)
+    model.load_state_dict(sd, strict=True)
+    model.train(True)
+    model.args.latent_dims = (220, 8, 8)
+    b, h, w = 2, 128, 128
+    x = synth.synth_image(b, h, w, SEED)
+    noise_z = synth.synth_noise((b, 320, 2, 2), "zgan", SEED)
+    noise_y = synth.synth_noise((b, 220, 8, 8), "ygan", SEED)
+    u_before = {i: sd[f"Discriminator.conv{i}.weight_u"].clone() for i in range(1, 5)}
+    with torch.no_grad(), ref_shim.NoiseFeeder([noise_z, noise_y]):
+        losses, inter = model(x, train_generator=True, return_intermediates=True)
+        disc = model.discriminator_forward(inter, train_generator=True)   # second power iteration (from updated u)
+    pnet = model.perceptual_loss.model.net
+    pnet = pnet.module if hasattr(pnet, "module") else pnet
+    lins = [getattr(pnet, f"lin{k}").model[1].weight.detach().reshape(-1).clone() for k in range(5)]
+    os.makedirs(os.path.join(ROOT, "high-fidelity-generative-compression_b200", "weights"), exist_ok=True)
+    np.savez(os.path.join(ROOT, "high-fidelity-generative-compression_b200", "weights", "lpips_alex_lin_v0.1.npz"),
+             **{f"lin{k}": l.numpy() for k, l in enumerate(lins)})
+    out = {"compression_loss": np.array(float(losses["compression"])), "disc_loss": np.array(float(losses["disc"]))}
+    with torch.no_grad():
+        out["distortion"] = np.array(float(model.distortion_loss(inter.reconstruction, inter.input_image)))
+        out["perceptual"] = np.array(float(model.perceptual_loss_wrapper(inter.reconstruction, inter.input_image)))
+    summarize("recon", inter.reconstruction, out)
+    out["n_bpp"], out["q_bpp"] = np.array(float(inter.n_bpp)), np.array(float(inter.q_bpp))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "gan_train_128.npz"), **out)
+
+    # pin the oracle: same pipeline restated
+    with torch.no_grad():
+        recon, hyper, y = O.compression_forward(sd, x, True, False, noise_z, noise_y)
+        trunk = pnet.net
+        feats = torch.nn.Sequential(*[m for sl in (trunk.slice1, trunk.slice2, trunk.slice3, trunk.slice4, trunk.slice5)
+                                      for m in sl])
+        lp = O.lpips_forward(feats, lins, recon, x).mean()
+        dist = O.distortion_loss(recon, x)
+        sd1 = dict(sd)
+        d_in = torch.cat([x, recon], 0)
+        lat = torch.repeat_interleave(hyper.decoded, 2, dim=0)
+        _, logits, new_uv = O.discriminator_forward(sd1, d_in, lat, training=True)
+        d_real, d_gen = torch.chunk(logits.squeeze(), 2, dim=0)
+        d_loss, g_loss = O.gan_losses_non_saturating(d_real, d_gen)
+        cfg = dict(lambda_A=2 ** 1, lambda_B=2 ** (-4), target_rate=0.14, lambda_schedule=dict(vals=[2., 1.], steps=[50000]),
+                   target_schedule=dict(vals=[0.20 / 0.14, 1.], steps=[50000]))
+        rate, _ = O.weighted_rate_loss(cfg, hyper.total_nbpp, hyper.total_qbpp, step=1)
+        total = rate + 0.075 * 2 ** (-5) * dist + 1.0 * lp + 0.15 * g_loss
+    errs = dict(recon=(recon - inter.reconstruction).abs().max().item(),
+                perceptual=abs(float(lp) - float(out["perceptual"])), distortion=abs(float(dist) - float(out["distortion"])) / float(out["distortion"]),
+                disc_loss=abs(float(d_loss) - float(out["disc_loss"])), total=abs(float(total) - float(out["compression_loss"])) / abs(float(out["compression_loss"])))
+    print("gan_train_128", {k: f"{v:.3e}" for k, v in errs.items()}, "losses", float(out["compression_loss"]), float(out["disc_loss"]),
+          float(out["perceptual"]), float(out["distortion"]))
+    return [("gan_train_128", errs)]
+
+
 def main():
     from hific_b200 import synth
     from oracle import hific_oracle as O
@@ -121,6 +178,7 @@ def main():
         report.append((name, errs))
         print(name, {k: f"{v:.3e}" for k, v in errs.items()},
               "bpp n/q", float(hyperinfo.total_nbpp), float(hyperinfo.total_qbpp))
+    report += gan_case(synth, O)
     bad = [(n, e) for n, e in report if max(e.values()) > 1e-4]
     if bad:
         raise SystemExit(f"oracle disagrees with the reference: {bad}")
