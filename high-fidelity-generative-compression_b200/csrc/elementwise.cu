@@ -157,22 +157,6 @@ channelnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
-  // residual inputs do not depend on the statistics: fetch them now so their latency overlaps the two
-  // warp reductions (res1 + res2 are pre-added; the kernel is latency-, not bandwidth-limited)
-  float4 r[kCnMaxVec];
-  const bool has_res = res1 != nullptr;
-#pragma unroll
-  for (int i = 0; i < kCnMaxVec; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_res && c < p.c) {
-      r[i] = *reinterpret_cast<const float4*>(res1 + pix * p.c + c);
-      if (res2) {
-        const float4 t = *reinterpret_cast<const float4*>(res2 + pix * p.c + c);
-        r[i].x += t.x; r[i].y += t.y; r[i].z += t.z; r[i].w += t.w;
-      }
-    }
-  }
   s = warp_sum(s);
   const float mean = s / static_cast<float>(p.c);
   float q = 0.f;
@@ -207,7 +191,14 @@ channelnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
       y.y = act_apply(g.y * ((v[i].y - mean) * rstd) + b.y, p.act);
       y.z = act_apply(g.z * ((v[i].z - mean) * rstd) + b.z, p.act);
       y.w = act_apply(g.w * ((v[i].w - mean) * rstd) + b.w, p.act);
-      y.x += r[i].x; y.y += r[i].y; y.z += r[i].z; y.w += r[i].w;
+      if (res1) {
+        const float4 r = *reinterpret_cast<const float4*>(res1 + pix * p.c + c);
+        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+      }
+      if (res2) {
+        const float4 r = *reinterpret_cast<const float4*>(res2 + pix * p.c + c);
+        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+      }
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + pix * p.c + c) = y;
     }
     if (out_act && c < p.cpad) {

@@ -35,9 +35,10 @@ class PerceptualLoss(nn.Module):
             raise NotImplementedError("only LPIPS net-lin / alex / v0.1 (what HiFIC uses) is built")
         if trunk is None:
             import torchvision
-            try:   # pretrained weights if torchvision has them cached; there is no network here
+            cached = os.path.join(torch.hub.get_dir(), "checkpoints", "alexnet-owt-7be5be79.pth")
+            if os.path.exists(cached):   # ImageNet weights only if already cached: never touch the network
                 trunk = torchvision.models.alexnet(weights="IMAGENET1K_V1").features
-            except Exception:
+            else:                        # offline stand-in (same seed as oracle/ref_shim.py)
                 state = torch.random.get_rng_state()
                 torch.manual_seed(1234)
                 trunk = torchvision.models.alexnet(weights=None).features

@@ -117,7 +117,18 @@ def synth_tensor(key, shape, seed=0):
 
 
 def synth_state_dict(seed=0, **kw):
-    return {k: synth_tensor(k, shp, seed) for k, shp in hific_shapes(**kw).items()}
+    sd = {k: synth_tensor(k, shp, seed) for k, shp in hific_shapes(**kw).items()}
+    # spectral-norm buffers of a trained discriminator are (nearly) converged singular vectors; random unit vectors
+    # would make sigma = u.W v tiny and W / sigma explode.  Converge them with a few power iterations.
+    for k in [k for k in sd if k.endswith(".weight_u")]:
+        w = sd[k.replace("weight_u", "weight_orig")]
+        wm = w.reshape(w.shape[0], -1)
+        u, v = sd[k], sd[k.replace("weight_u", "weight_v")]
+        for _ in range(12):
+            v = torch.nn.functional.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12)
+            u = torch.nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+        sd[k], sd[k.replace("weight_u", "weight_v")] = u, v
+    return sd
 
 
 def synth_image(n, h, w, seed=0, channels=3):

@@ -44,6 +44,8 @@ class Feed:
         self._orig = torch.nn.init.uniform_
 
         def fake(t, a=0.0, b=1.0):
+            if (a, b) != (-0.5, 0.5) or self.calls >= len(self.noises):
+                return self._orig(t, a, b)       # e.g. parameter initialisers running inside the context
             n = self.noises[self.calls]
             self.calls += 1
             with torch.no_grad():
