@@ -34,7 +34,8 @@ class ConvDesc(ctypes.Structure):
         ("eps", ctypes.c_float),
         ("block_n", ctypes.c_int32), ("precision", ctypes.c_int32),
         ("cluster_m", ctypes.c_int32), ("cluster_n", ctypes.c_int32),
-        ("wide", ctypes.c_int32), ("pair", ctypes.c_int32),
+        ("wide", ctypes.c_int32), ("a_bf16", ctypes.c_int32), ("b_bf16", ctypes.c_int32),
+        ("dgrad", ctypes.c_int32), ("pair", ctypes.c_int32),
     ]
 
 
@@ -71,6 +72,14 @@ SIGNATURES = {
     "hfc_gan_sums": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "hfc_sqdiff_sum": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
     "hfc_lpips_layer": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "hfc_gemm_nt": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "hfc_rows_to_act": (ctypes.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "hfc_im2col_t": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                    ctypes.c_char_p, ctypes.c_char_p, _i32, _i64, _vp, _vp]),
+    "hfc_permute_wgrad": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.c_char_p, ctypes.c_char_p,
+                                         _f32, _i32, _vp, _vp]),
+    "hfc_col_sums": (ctypes.c_int, [_vp, _i32, _i64, _i32, _f32, _vp, _vp]),
+    "hfc_pad_fold": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _i32, _vp]),
     "hfc_conv_forward": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hfc_nchw_to_act": (ctypes.c_int, [_vp, ctypes.POINTER(ActGeom), _i32, _i32, _vp, _vp, _f32, _vp, _vp]),
     "hfc_channelnorm": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _vp, _f32, _i32,

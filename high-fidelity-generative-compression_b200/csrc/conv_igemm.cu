@@ -70,7 +70,10 @@ struct ConvKernelParams {
   int32_t cout;
   int32_t act, norm;
   float eps;
-  uint32_t fmt;                       // 0 fp16, 1 bf16
+  uint32_t fmt_a, fmt_b;              // operand formats: 0 fp16, 1 bf16
+  int32_t gemm;                       // plain GEMM mode: A rows = 128 consecutive rows of a [M][K] matrix
+  int32_t k_splits, kb_per_split;     // split-K (gemm mode): tile index carries the K range; fp32 atomics out
+  int32_t out_atomic;                 // NHWC_F32 output accumulated with atomicAdd
   const float* bias;
   const float* gamma;
   const float* beta;
@@ -168,7 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int m_groups = (tiles_m + p.cm - 1) / p.cm;
   const int n_groups = (p.n_tiles + p.cn - 1) / p.cn;
-  const int total_ctiles = m_groups * n_groups;      // work items per cluster
+  const int total_ctiles = m_groups * n_groups * p.k_splits;   // work items per cluster (x K splits in gemm mode)
   const int cid = blockIdx.x / csize;
   const int ncl = gridDim.x / csize;
 
@@ -201,8 +204,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       } else
       for (int ct = cid; ct < total_ctiles; ct += ncl) {
-        const int nt = (ct % n_groups) * p.cn + n_idx;
-        int mt = (ct / n_groups) * p.cm + m_idx;
+        const int ks = ct % p.k_splits;          // K split (gemm mode), else 0
+        const int ctile = ct / p.k_splits;
+        const int nt = (ctile % n_groups) * p.cn + n_idx;
+        int mt = (ctile / n_groups) * p.cm + m_idx;
         const int twi = mt % p.tiles_w;
         mt /= p.tiles_w;
         const int thi = mt % p.tiles_h;
@@ -211,7 +216,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // my slice of the shared A tile: rows [n_idx*128/cn, (n_idx+1)*128/cn)
         const int h_base = (thi * p.th + (p.a_split_n ? 0 : n_idx * (p.th / p.cn))) * p.sh + p.ih0;
         const int n_base = tni * p.tn + (p.a_split_n ? n_idx * (p.tn / p.cn) : 0);
-        int tap = 0, chunk = 0;
+        int tap = 0, chunk = ks * p.kb_per_split;   // split-K only exists with a single tap (gemm mode)
+        const int kb0 = ks * p.kb_per_split;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
@@ -225,8 +231,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else
               tma_load_4d_pair(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
                                h_base + p.tap_dh[tap], n_base);
-            tma_load_2d_pair(sb, &tmap_b, &full_bar[s], kb * kBlockK, nt * p.block_n + m_idx * p.b_rows);
-            if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, nt * p.block_n + m_idx * p.b_rows);
+            if (p.gemm) ++chunk; else if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
             if (++s == p.stages) { s = 0; ph ^= 1; }
             continue;
           }
@@ -234,14 +240,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (csize > 1) {
             tma_load_4d_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], chunk * kBlockK,
                            w_base + p.tap_dw[tap], h_base + p.tap_dh[tap], n_base, mask_a);
-            tma_load_2d_mc(sb + m_idx * b_slice_rows * (kBlockK * 2), &tmap_b, &full_bar[s], kb * kBlockK,
+            tma_load_2d_mc(sb + m_idx * b_slice_rows * (kBlockK * 2), &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK,
                            nt * p.block_n + m_idx * b_slice_rows, mask_b);
           } else {
             tma_load_4d(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
                         h_base + p.tap_dh[tap], n_base);
-            tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBlockK, nt * p.block_n);
+            tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, nt * p.block_n);
           }
-          if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
+          if (p.gemm) ++chunk; else if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -249,7 +255,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1 && kPair) {
     // ===================== MMA issuer, CTA pair: only the leader (even rank) issues =====================
     if constexpr (kPair) if (m_idx == 0) {
-      const uint32_t idesc = make_idesc_f16(p.fmt, 2 * kBlockM, static_cast<uint32_t>(p.block_n));
+      const uint32_t idesc = make_idesc_f16(p.fmt_a, p.fmt_b, 2 * kBlockM, static_cast<uint32_t>(p.block_n));
       const uint16_t mask_pair = static_cast<uint16_t>(3u << (2 * n_idx));
       const uint16_t mask_all = static_cast<uint16_t>((1u << csize) - 1u);
       int s = 0;
@@ -281,7 +287,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_f16(p.fmt, kBlockM, static_cast<uint32_t>(p.block_n));
+    const uint32_t idesc = make_idesc_f16(p.fmt_a, p.fmt_b, kBlockM, static_cast<uint32_t>(p.block_n));
     int s = 0;
     uint32_t ph = 0;
     int as = 0;
@@ -347,8 +353,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t aph = 0;
     int cur_nt = -1, pbuf = 1;
     for (int ct = cid; ct < total_ctiles; ct += ncl) {
-      const int nt = (ct % n_groups) * p.cn + n_idx;
-      int mt = (ct / n_groups) * p.cm + m_idx;
+      const int ctile = ct / p.k_splits;
+      const int nt = (ctile % n_groups) * p.cn + n_idx;
+      int mt = (ctile / n_groups) * p.cm + m_idx;
       const int twi = mt % p.tiles_w;
       mt /= p.tiles_w;
       const int thi = mt % p.tiles_h;
@@ -508,11 +515,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (cc < p.out_cpad) {
             float* dst = reinterpret_cast<float*>(p.out) +
                          ((static_cast<size_t>(n) * p.out_h + oh) * p.out_w + ow) * p.out_cpad + cc;
+            if (p.out_atomic) {   // split-K partial sums
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              if (cc + 4 * j4 < p.out_cpad)
-                reinterpret_cast<float4*>(dst)[j4] =
-                    make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+              for (int j = 0; j < 16; ++j)
+                if (cc + j < p.out_cpad) atomicAdd(dst + j, f[j]);
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                if (cc + 4 * j4 < p.out_cpad)
+                  reinterpret_cast<float4*>(dst)[j4] =
+                      make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+              }
             }
           }
         } else {  // NCHW fp32
@@ -543,7 +556,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
       // zero the channel padding no N tile covers (e.g. cout 220 -> block_n 224 -> cpad 256)
-      if (valid && last_nt && hsel == 0 && !p.tapn && p.out_mode != HFC_OUT_NCHW_F32) {
+      if (valid && last_nt && hsel == 0 && !p.tapn && !p.out_atomic && p.out_mode != HFC_OUT_NCHW_F32) {
         const int c_end = p.n_tiles * p.block_n;
         if (p.out_mode == HFC_OUT_NHWC_F16) {
           for (int c = c_end; c < p.out_cpad; c += 8) {
@@ -588,7 +601,7 @@ struct PackParams {
   int32_t cout, cin, kh, kw;
   int32_t cin_pad, ntaps, ktot, rows;
   int32_t cout_real;                  // tap-in-N: real cout (pp.cout then counts kw*cout rows)
-  int32_t transposed, window, tapn;
+  int32_t transposed, window, tapn, dgrad;
   uint32_t fmt;
   int8_t ky[kMaxTaps];
   int8_t kx[kMaxTaps];
@@ -630,7 +643,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
       if (ok) {
         const int co_w = pp.tapn ? co % pp.cout_real : co;
         const int cout_w = pp.tapn ? pp.cout_real : pp.cout;
-        const size_t idx = pp.transposed
+        // dgrad of a stride-1 conv: this conv's (out=co_w, in=ci) weight is the forward weight W[ci][co_w] with the
+        // filter flipped in both directions
+        const size_t idx = pp.dgrad
+                               ? ((static_cast<size_t>(ci) * cout_w + co_w) * pp.kh + (pp.kh - 1 - ky)) * pp.kw +
+                                     (pp.kw - 1 - kx)
+                           : pp.transposed
                                ? ((static_cast<size_t>(ci) * cout_w + co_w) * pp.kh + ky) * pp.kw + kx
                                : ((static_cast<size_t>(co_w) * pp.cin + ci) * pp.kh + ky) * pp.kw + kx;
         val = w[idx] * mul;
@@ -964,7 +982,8 @@ static int pack_weights_impl(const hfc_conv_desc* d, const float* w, const float
     memset(&pp, 0, sizeof(pp));
     pp.cout = d->cout; pp.cin = d->in.c; pp.kh = d->kh; pp.kw = d->kw;
     pp.cin_pad = d->in.cpad; pp.ntaps = ph.ntaps; pp.ktot = ph.ktot; pp.rows = pl.rows;
-    pp.transposed = d->transposed; pp.window = d->window; pp.fmt = 0;
+    pp.transposed = d->transposed; pp.window = d->window; pp.fmt = d->b_bf16 ? 1u : 0u;
+    pp.dgrad = d->dgrad;
     pp.tapn = pl.tapn; pp.cout_real = d->cout;
     if (pl.tapn) pp.cout = d->kw * d->cout;   // GEMM rows = (filter column, output channel)
     memcpy(pp.ky, ph.ky, sizeof(pp.ky));
@@ -1025,7 +1044,9 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     kp.out_reflect = d->out_reflect;
     kp.cout = d->cout;
     kp.act = d->act; kp.norm = d->norm; kp.eps = d->eps;
-    kp.fmt = 0;
+    kp.k_splits = 1; kp.kb_per_split = kp.num_kb; kp.gemm = 0; kp.out_atomic = 0;
+    kp.fmt_a = d->a_bf16 ? 1u : 0u;
+    kp.fmt_b = d->b_bf16 ? 1u : 0u;
     kp.bias = bias; kp.gamma = gamma; kp.beta = beta;
     kp.out = out;
     memcpy(kp.tap_dh, ph.dh, sizeof(kp.tap_dh));
@@ -1117,5 +1138,95 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
       return set_error(HFC_ERR_LAUNCH, "conv_igemm launch: %s", cudaGetErrorString(e));
     note_launch();
   }
+  return HFC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Plain GEMM  C[M][N] (fp32) = A[M][K] * B[N][K]^T  on the same kernel (one filter tap, K-major 16-bit
+// operands, optional split-K with fp32 atomics).  Used by the weight-gradient path: A = gradient (or
+// activation) matrix transposed to [channels][pixels], B = the transposed im2col matrix.
+// ------------------------------------------------------------------------------------------------
+extern "C" int hfc_gemm_nt(const void* a, int32_t a_bf16, const void* b, int32_t b_bf16, int32_t m, int32_t n,
+                           int32_t k, float* c, int32_t ldc, int32_t k_splits, void* stream) {
+  if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0) return set_error(HFC_ERR_INVALID, "gemm_nt: null pointer or empty matrix");
+  if (k % kBlockK != 0) return set_error(HFC_ERR_INVALID, "gemm_nt: K (%d) must be a multiple of 64", k);
+  if (ldc % 4 != 0 || ldc < n) return set_error(HFC_ERR_INVALID, "gemm_nt: ldc must be a multiple of 4 and >= N");
+  int sm_count = 0;
+  int rc = device_sm_count(&sm_count);
+  if (rc != HFC_OK) return rc;
+  PFN_encodeTiled encode = get_encode_fn();
+  if (!encode) return set_error(HFC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not found");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  ConvKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int nt = (n + 255) / 256;
+  kp.block_n = ((n + nt - 1) / nt + 15) / 16 * 16;
+  kp.n_tiles = (n + kp.block_n - 1) / kp.block_n;
+  kp.tw = kBlockM; kp.th = 1; kp.tn = 1;
+  kp.tiles_w = (m + kBlockM - 1) / kBlockM; kp.tiles_h = 1; kp.tiles_n = 1;
+  kp.c_chunks = k / kBlockK; kp.ntaps = 1;
+  const int tiles = kp.tiles_w * kp.n_tiles;
+  int ks = k_splits;
+  if (ks <= 0) ks = std::max(1, std::min(sm_count / std::max(1, tiles), kp.c_chunks / 8));
+  ks = std::max(1, std::min(ks, kp.c_chunks));
+  kp.kb_per_split = (kp.c_chunks + ks - 1) / ks;
+  kp.k_splits = (kp.c_chunks + kp.kb_per_split - 1) / kp.kb_per_split;
+  kp.num_kb = kp.kb_per_split;
+  kp.out_atomic = kp.k_splits > 1;
+  kp.gemm = 1;
+  kp.cm = kp.cn = 1; kp.b_rows = kp.block_n;
+  kp.grid_h = 1; kp.grid_w = m; kp.batch = 1; kp.sh = kp.sw = 1;
+  kp.out_mode = HFC_OUT_NHWC_F32; kp.osh = kp.osw = 1;
+  kp.out_h = 1; kp.out_w = m; kp.out_cpad = ldc; kp.cout = n;
+  kp.fmt_a = a_bf16 ? 1u : 0u; kp.fmt_b = b_bf16 ? 1u : 0u;
+  kp.out = c;
+  kp.kw = 1; kp.w_step = kBlockM;
+  const int stage_bytes = kABytes + kp.block_n * kBlockK * 2;
+  kp.stages = std::max(2, std::min((226 * 1024 - 1024 - kTailBytes) / stage_bytes, kMaxStages));
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(m), 1, 1};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(k) * 2, static_cast<cuuint64_t>(m) * k * 2,
+                             static_cast<cuuint64_t>(m) * k * 2};
+    cuuint32_t box[4] = {kBlockK, kBlockM, 1, 1}, estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(HFC_ERR_LAUNCH, "gemm_nt: cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+    cuuint64_t bdims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(n)};
+    cuuint64_t bstr[1] = {static_cast<cuuint64_t>(k) * 2};
+    cuuint32_t bbox[2] = {kBlockK, static_cast<cuuint32_t>(kp.block_n)}, bes[2] = {1, 1};
+    r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(b), bdims, bstr, bbox, bes,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(HFC_ERR_LAUNCH, "gemm_nt: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  if (kp.out_atomic) {
+    cudaError_t e = cudaMemsetAsync(c, 0, static_cast<size_t>(m) * ldc * sizeof(float), st);
+    if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "gemm_nt: memset: %s", cudaGetErrorString(e));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int work = tiles * kp.k_splits;
+  const int grid = std::min(work, sm_count);
+  const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 + kTailBytes;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmA, tmB, kp);
+  if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "gemm_nt launch: %s", cudaGetErrorString(e));
+  note_launch();
   return HFC_OK;
 }

@@ -168,9 +168,9 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
-// fmt: 0 = fp16, 1 = bf16.
-__device__ __forceinline__ uint32_t make_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// fmt_a / fmt_b: 0 = fp16, 1 = bf16 (the two operands may differ: gradients are bf16, activations fp16).
+__device__ __forceinline__ uint32_t make_idesc_f16(uint32_t fmt_a, uint32_t fmt_b, uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -1,0 +1,205 @@
+"""Backward of one convolution / transposed convolution on the B200 kernels (autograd of F.conv2d /
+F.conv_transpose2d as issued by the reference's training step, train.py:49-59).
+
+  data gradient    the same tcgen05 implicit-GEMM kernel run on the gradient tensor:
+                     conv stride 1          -> stride-1 conv with transposed + flipped weights over the PADDED input
+                                               domain, then the adjoint of the (reflect / zero) padding (hfc_pad_fold)
+                     conv stride 2          -> transposed conv (4 sub-pixel phases) with the forward weights
+                     transposed conv        -> (strided) conv with the forward weights
+  weight gradient  one tcgen05 GEMM over K = pixels: dW[c1][(tap, c2)] = A1T . COLT^T with both operands built by
+                   the tiled transposes in csrc/backward.cu (explicit transposed im2col: simple and correct; an
+                   implicit wgrad kernel is the obvious next optimisation)
+  bias gradient    column sums of the gradient rows
+
+Gradients travel as fp32 rows [pixels][channels]; GEMM operands derived from them are bf16 (fp32 exponent range, so
+no loss scaling), multiplied against the fp16 activations / weights saved by the forward pass.
+"""
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+from .ops import OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO, Conv, Geom, _ptr, _stream, round_up
+
+
+class Workspace:
+    """Grow-only scratch buffers shared by all layers of a device (the backward pass is sequential)."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, name, numel, dtype, device):
+        key = (name, dtype, device.type, device.index)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < numel:
+            buf = cls._bufs[key] = torch.empty(int(numel), dtype=dtype, device=device)
+        return buf[:numel]
+
+
+def _i8(vals):
+    return bytes((v + 256) % 256 for v in vals)
+
+
+def gemm_nt(a, a_bf16, b, b_bf16, m, n, k, out=None, k_splits=0):
+    """C[m][n] fp32 = A[m][k] . B[n][k]^T for K-major 16-bit operands (raw buffers)."""
+    ldc = round_up(n, 4)
+    if out is None:
+        out = torch.empty((m, ldc), dtype=torch.float32, device=a.device)
+    check(lib.hfc_gemm_nt(_ptr(a), int(a_bf16), _ptr(b), int(b_bf16), m, n, k, _ptr(out), ldc, k_splits, _stream()),
+          "gemm_nt")
+    return out
+
+
+def im2col_t(src, src_f32, n, hp, wp, cpad, c_src, gh, gw, stride, oh0, ow0, taps, c_rows, out):
+    p_pad = out.shape[-1]
+    dh, dw = _i8([t[0] for t in taps]), _i8([t[1] for t in taps])
+    check(lib.hfc_im2col_t(_ptr(src), int(src_f32), n, hp, wp, cpad, c_src, gh, gw, stride, oh0, ow0, len(taps), dh, dw,
+                           c_rows, p_pad, _ptr(out), _stream()), "im2col_t")
+    return out
+
+
+class ConvGrad:
+    """Backward of the conv described by the same arguments as `ops.Conv` (forward geometry)."""
+
+    def __init__(self, in_geom, cout, k, stride=1, transposed=False, pad_mode=PAD_ZERO, pad=(0, 0, 0, 0)):
+        kh, kw = (k, k) if isinstance(k, int) else k
+        assert kh == kw
+        self.k, self.stride, self.transposed, self.pad_mode, self.pad = kh, stride, transposed, pad_mode, pad
+        self.in_geom, self.cin, self.cout = in_geom, in_geom.c, cout
+        n, h, w = in_geom.n, in_geom.h, in_geom.w
+        pt, pl, pb, pr = pad
+        if transposed:
+            self.oh = (h - 1) * stride - 2 * pt + kh + (stride - 1)
+            self.ow = (w - 1) * stride - 2 * pl + kw + (stride - 1)
+        else:
+            self.oh = (h + pt + pb - kh) // stride + 1
+            self.ow = (w + pl + pr - kw) // stride + 1
+        self.p_out, self.p_in = n * self.oh * self.ow, n * h * w
+        self.dy_geom = Geom(n, self.oh, self.ow, cout, round_up(cout, 64))
+        cin4 = round_up(self.cin, 4)
+        self.fold = None
+        if not transposed and stride == 1:
+            hq, wq = h + pt + pb, w + pl + pr
+            self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=1, pad_mode=PAD_ZERO, pad=(kh - 1,) * 4,
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, dgrad=True)
+            self.fold = (hq, wq)
+        elif not transposed:
+            hq = 2 * self.oh + kh - 1
+            wq = 2 * self.ow + kw - 1
+            self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=2, transposed=True, pad=(0, 0, 0, 0),
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True)
+            self.fold = (hq, wq)
+        elif stride == 2:
+            hi = kh - 2 - pt
+            self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=2, pad_mode=PAD_ZERO, pad=(pt, pl, hi, hi),
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=True)
+        else:
+            self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=1, pad_mode=PAD_ZERO, pad=(pt, pl, pt, pl),
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=True)
+        self.cin4 = cin4
+        self.taps = [(ky, kx) for ky in range(kh) for kx in range(kw)]
+        # weight-gradient GEMM operands: which side is transposed plainly (A1) and which is im2col'ed (A2).
+        # The im2col side should be the one with FEWER channels (its matrix has ntaps times more rows).
+        self.swap = (not transposed) and stride == 1 and cout <= 8
+
+    # ------------------------------------------------------------------ data gradient
+    def data_grad(self, dy_rows, weight, out=None):
+        """dy_rows: fp32 [n*oh*ow][ld >= cout] -> dx fp32 rows [n*h*w][cin4]."""
+        dev = dy_rows.device
+        g = self.dy_geom
+        dy_act = Workspace.get("dy_act", g.n * g.h * g.w * g.cpad, torch.int16, dev).view(g.shape)
+        check(lib.hfc_rows_to_act(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, g.cpad, 1, _ptr(dy_act),
+                                  _stream()), "rows_to_act")
+        if self.fold is None:
+            if out is None:
+                out = torch.empty((self.p_in, self.cin4), dtype=torch.float32, device=dev)
+            self.dgrad(dy_act.view(torch.float16), weight, out=out)
+            return out
+        hq, wq = self.fold
+        dxp = Workspace.get("dxp", self.in_geom.n * hq * wq * self.cin4, torch.float32, dev).view(-1, self.cin4)
+        self.dgrad(dy_act.view(torch.float16), weight, out=dxp)
+        if out is None:
+            out = torch.empty((self.p_in, self.cin4), dtype=torch.float32, device=dev)
+        n, h, w = self.in_geom.n, self.in_geom.h, self.in_geom.w
+        pt, pl, pb, pr = self.pad
+        fg = Geom(n, h, w, self.cin4, self.cin4, pt, pl, pb, pr).c_struct()
+        check(lib.hfc_pad_fold(_ptr(dxp), self.cin4, hq, wq, ctypes.byref(fg), int(self.pad_mode == PAD_REFLECT),
+                               _ptr(out), self.cin4, _stream()), "pad_fold")
+        return out
+
+    # ------------------------------------------------------------------ weight / bias gradient
+    def weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, scale=1.0):
+        """x_act: the forward input act buffer (fp16, with its border); dy_rows fp32 [n*oh*ow][ld].
+        Returns dW in the torch layout of the forward weight."""
+        dev = dy_rows.device
+        ig = self.in_geom
+        n, h, w = ig.n, ig.h, ig.w
+        hp, wp = h + ig.pt + ig.pb, w + ig.pl + ig.pr
+        ld_dy = dy_rows.shape[-1]
+        pt, pl = self.pad[0], self.pad[1]
+        k, s = self.k, self.stride
+        if not self.transposed and not self.swap:
+            # pixels = output pixels; A1 = dy^T (bf16), COLT = im2col(x)^T (fp16)
+            p_pad = round_up(self.p_out, 64)
+            c1_rows, c2_rows = round_up(self.cout, 64), (8 if ig.cpad == 8 else round_up(self.cin, 64))
+            a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
+            im2col_t(dy_rows, True, n, self.oh, self.ow, ld_dy, self.cout, self.oh, self.ow, 1, 0, 0, [(0, 0)], c1_rows, a1)
+            col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
+            im2col_t(x_act, False, n, hp, wp, ig.cpad, self.cin, self.oh, self.ow, s, ig.pt - pt, ig.pl - pl, self.taps,
+                     c2_rows, col)
+            m, c2, a_bf, b_bf = self.cout, self.cin, True, False
+            shape = (self.cout, self.cin, k, k)
+        elif not self.transposed:
+            # tiny cout: pixels = padded input pixels q; A1 = x^T (fp16), COLT[(tap, co)][q] = dy[q - tap] (bf16)
+            if self.pad_mode == PAD_REFLECT:
+                assert (ig.pt, ig.pl, ig.pb, ig.pr) == tuple(self.pad), "swap wgrad expects the border to equal the padding"
+                gh, gw, o0h, o0w = hp, wp, 0, 0
+            else:
+                gh, gw, o0h, o0w = h + self.pad[0] + self.pad[2], w + self.pad[1] + self.pad[3], -pt, -pl
+            p_pad = round_up(n * gh * gw, 64)
+            c1_rows, c2_rows = round_up(self.cin, 64), 8
+            a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
+            im2col_t(x_act, False, n, hp, wp, ig.cpad, self.cin, gh, gw, 1, o0h, o0w, [(0, 0)], c1_rows, a1)
+            col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
+            im2col_t(dy_rows, True, n, self.oh, self.ow, ld_dy, self.cout, gh, gw, 1, 0, 0,
+                     [(-ky, -kx) for ky, kx in self.taps], c2_rows, col)
+            m, c2, a_bf, b_bf = self.cin, self.cout, False, True
+            shape = (self.cout, self.cin, k, k)
+        else:
+            # transposed conv: pixels = input pixels i; A1 = x^T (fp16), COLT[(tap, co)][i] = dy[i*s - p + tap] (bf16)
+            p_pad = round_up(self.p_in, 64)
+            c1_rows, c2_rows = round_up(self.cin, 64), round_up(self.cout, 64)
+            a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
+            im2col_t(x_act, False, n, hp, wp, ig.cpad, self.cin, h, w, 1, ig.pt, ig.pl, [(0, 0)], c1_rows, a1)
+            col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
+            im2col_t(dy_rows, True, n, self.oh, self.ow, ld_dy, self.cout, h, w, s, -pt, -pl, self.taps, c2_rows, col)
+            m, c2, a_bf, b_bf = self.cin, self.cout, False, True
+            shape = (self.cin, self.cout, k, k)
+        ncols = len(self.taps) * c2_rows
+        cbuf = Workspace.get("wgrad_c", m * round_up(ncols, 4), torch.float32, dev).view(m, round_up(ncols, 4))
+        gemm_nt(a1, a_bf, col, b_bf, m, ncols, p_pad, out=cbuf)
+        if dw_out is None:
+            dw_out = torch.empty(shape, dtype=torch.float32, device=dev)
+        ky, kx = _i8([t[0] for t in self.taps]), _i8([t[1] for t in self.taps])
+        if self.swap:
+            # C is [ci][(tap, co)] but dW is [co][ci][ky][kx]: permute into a temporary and transpose the two leading dims
+            tmp = torch.empty((self.cin, self.cout, k, k), dtype=torch.float32, device=dev)
+            check(lib.hfc_permute_wgrad(_ptr(cbuf), cbuf.shape[1], m, c2, c2_rows, k, k, len(self.taps), ky, kx, float(scale),
+                                        0, _ptr(tmp), _stream()), "permute_wgrad")
+            if accumulate:
+                dw_out += tmp.transpose(0, 1)
+            else:
+                dw_out.copy_(tmp.transpose(0, 1))
+            return dw_out
+        check(lib.hfc_permute_wgrad(_ptr(cbuf), cbuf.shape[1], m, c2, c2_rows, k, k, len(self.taps), ky, kx, float(scale),
+                                    int(accumulate), _ptr(dw_out), _stream()), "permute_wgrad")
+        return dw_out
+
+    def bias_grad(self, dy_rows, db_out=None, accumulate=False, scale=1.0):
+        if db_out is None:
+            db_out = torch.zeros(self.cout, dtype=torch.float32, device=dy_rows.device)
+        elif not accumulate:
+            db_out.zero_()
+        check(lib.hfc_col_sums(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, float(scale), _ptr(db_out),
+                               _stream()), "col_sums")
+        return db_out

@@ -107,7 +107,7 @@ class Conv:
 
     def __init__(self, in_geom, cout, k, stride=1, transposed=False, pad_mode=PAD_ZERO, pad=(0, 0, 0, 0),
                  out_mode=OUT_NHWC_F16, out_geom=None, out_reflect=False, act=ACT_NONE, norm=False,
-                 window=False, block_n=0, precision=PREC_F16, cluster=(0, 0), wide=0, pair=0):
+                 window=False, block_n=0, precision=PREC_F16, cluster=(0, 0), wide=0, pair=0, a_bf16=False, b_bf16=False, dgrad=False):
         kh, kw = (k, k) if isinstance(k, int) else k
         pt, pl, pb, pr = pad
         d = _lib.ConvDesc()
@@ -123,6 +123,7 @@ class Conv:
         d.cluster_m, d.cluster_n = cluster
         d.wide = wide
         d.pair = pair
+        d.a_bf16, d.b_bf16, d.dgrad = int(a_bf16), int(b_bf16), int(dgrad)
         # output dims
         if transposed:
             oh = (in_geom.h - 1) * stride - 2 * pt + kh + (stride - 1)

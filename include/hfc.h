@@ -90,6 +90,10 @@ typedef struct hfc_conv_desc {
                                row-resident 'wide' mode (halo row + resident weights, filter columns by descriptor
                                shift), 2 = forbid both, 3 = force 'tap-in-N' (GEMM columns = (filter column, cout),
                                filter columns summed with a pixel shift in the epilogue) */
+  int32_t a_bf16, b_bf16;   /* operand formats: 0 = fp16, 1 = bf16 (activation operand / weight operand); the backward
+                               pass feeds bf16 gradients against fp16 activations / weights */
+  int32_t dgrad;            /* 1: pack the weights for the data gradient of a stride-1 conv2d: W'[ci][co][r][s] =
+                               W[co][ci][kh-1-r][kw-1-s] (cout of this descriptor = cin of the forward conv) */
   int32_t pair;             /* 0 = auto, 1 = force, 2 = forbid CTA pairs (cta_group::2 UMMA, M = 256 over two SMs;
                                needs cluster_m == 2) */
 } hfc_conv_desc;
@@ -209,6 +213,38 @@ int hfc_sqdiff_sum(const float* a, const float* b, int64_t count, float scale, d
  */
 int hfc_lpips_layer(const float* f0, const float* f1, const float* lin_w, int32_t n, int32_t c, int32_t hw,
                     float* out_per_image, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Backward pass building blocks (autograd of F.conv2d / F.conv_transpose2d, train.py:49-59).
+ *   data gradient   : hfc_conv_forward on the gradient tensor with the transposed role of the weights
+ *                     (stride-1 conv: desc.dgrad = 1; stride-2 conv: a transposed conv; transposed conv: a conv)
+ *   weight gradient : one GEMM  dW[c1][(tap, c2)] = A1T[c1][pixels] * COLT[(tap, c2)][pixels]^T
+ * Gradients travel between layers as fp32 rows [pixels][channels]; GEMM operands made of them are bf16.
+ * --------------------------------------------------------------------------------------------------------- */
+/* C[m][n] (fp32, row pitch ldc, overwritten) = A[m][k] * B[n][k]^T; A, B: K-major 16-bit (fp16 or bf16), k % 64 == 0.
+ * k_splits: 0 = auto, else number of K partitions accumulated with fp32 atomics (C is zeroed first). */
+int hfc_gemm_nt(const void* a, int32_t a_bf16, const void* b, int32_t b_bf16, int32_t m, int32_t n, int32_t k,
+                float* c, int32_t ldc, int32_t k_splits, void* stream);
+/* fp32 rows [npix][ld] -> border-less 16-bit act buffer [npix][cpad] (bf16 if to_bf16 else fp16), padding = 0 */
+int hfc_rows_to_act(const float* rows, int32_t ld, int64_t npix, int32_t c, int32_t cpad, int32_t to_bf16, void* out,
+                    void* stream);
+/* transposed im2col (see csrc/backward.cu): out[(tap*c_rows + ch)][p], p over the (n, gh, gw) pixel grid, source
+ * coordinate (g*stride + d[tap] + o0) in a physical buffer of n x hp x wp pixels with cpad channels (pitch, for fp32
+ * rows), zero outside; src_f32: source is fp32 rows (converted to bf16) instead of a 16-bit act buffer.
+ * dh_host / dw_host are HOST arrays of ntaps offsets. */
+int hfc_im2col_t(const void* src, int32_t src_f32, int32_t n, int32_t hp, int32_t wp, int32_t cpad, int32_t c_src,
+                 int32_t gh, int32_t gw, int32_t stride, int32_t oh0, int32_t ow0, int32_t ntaps,
+                 const int8_t* dh_host, const int8_t* dw_host, int32_t c_rows, int64_t p_pad, void* out, void* stream);
+/* GEMM result C[m][(tap, c2)] -> dW[m][c2][ky][kx] (torch layout) * scale (+= if accumulate) */
+int hfc_permute_wgrad(const float* c, int32_t ldc, int32_t m, int32_t c2, int32_t c2_rows, int32_t kh, int32_t kw,
+                      int32_t ntaps, const int8_t* ky_host, const int8_t* kx_host, float scale, int32_t accumulate,
+                      float* dw, void* stream);
+/* out[c] += scale * sum over rows of rows[.][c]   (bias gradient) */
+int hfc_col_sums(const float* rows, int32_t ld, int64_t npix, int32_t c, float scale, float* out, void* stream);
+/* adjoint of the materialised padding: gradient over the padded domain (fp32 rows of an n x hq x wq grid, pitch
+ * ld_in) -> gradient of the un-padded (n, h, w, c) tensor (fp32 rows, pitch ld_out); reflect: mirrored positions add */
+int hfc_pad_fold(const float* dxp, int32_t ld_in, int32_t hq, int32_t wq, const hfc_act_geom* g, int32_t reflect,
+                 float* dx, int32_t ld_out, void* stream);
 
 #ifdef __cplusplus
 }

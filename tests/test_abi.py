@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from hific_b200 import _lib
     assert ctypes.sizeof(_lib.ActGeom) == 9 * 4
-    # hfc_conv_desc: 2 geoms + 22 int32/float fields
-    assert ctypes.sizeof(_lib.ConvDesc) == 2 * 36 + 22 * 4
+    # hfc_conv_desc: 2 geoms + 25 int32/float fields
+    assert ctypes.sizeof(_lib.ConvDesc) == 2 * 36 + 25 * 4
 
 
 def test_conv_query_runs_without_gpu_and_validates():
