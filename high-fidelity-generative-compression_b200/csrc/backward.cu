@@ -52,7 +52,7 @@ struct ColTParams {
   int32_t gh, gw;                   // pixel grid
   int32_t stride, oh0, ow0;         // source coordinate = g*stride + d + o0
   int32_t ntaps, c_rows, c_src;     // channels emitted per tap (multiple of 64), real source channels
-  int32_t src_f32;
+  int32_t src_f32;                  // 0: 16-bit copied verbatim, 1: fp32 -> bf16, 2: fp16 -> bf16
   long long p_total, p_pad;
   int8_t dh[64], dw[64];
 };
@@ -83,7 +83,8 @@ im2col_t_kernel(const void* __restrict__ src, uint16_t* __restrict__ out, const 
       const int ch = c0 + cg + j;
       uint16_t v = 0;
       if (ok && ch < p.c_src) {
-        if (p.src_f32) v = f32_to_bf16_bits(reinterpret_cast<const float*>(src)[base + ch]);
+        if (p.src_f32 == 1) v = f32_to_bf16_bits(reinterpret_cast<const float*>(src)[base + ch]);
+        else if (p.src_f32 == 2) v = f32_to_bf16_bits(__half2float(reinterpret_cast<const __half*>(src)[base + ch]));
         else v = reinterpret_cast<const uint16_t*>(src)[base + ch];
       }
       tile[cg + j][px] = v;
@@ -120,8 +121,9 @@ im2col_t_c8_kernel(const void* __restrict__ src, uint16_t* __restrict__ out, con
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (j < p.c_src)
-          v[j] = p.src_f32 ? f32_to_bf16_bits(reinterpret_cast<const float*>(src)[base + j])
-                           : reinterpret_cast<const uint16_t*>(src)[base + j];
+          v[j] = p.src_f32 == 1 ? f32_to_bf16_bits(reinterpret_cast<const float*>(src)[base + j])
+                 : p.src_f32 == 2 ? f32_to_bf16_bits(__half2float(reinterpret_cast<const __half*>(src)[base + j]))
+                                  : reinterpret_cast<const uint16_t*>(src)[base + j];
     }
   }
 #pragma unroll

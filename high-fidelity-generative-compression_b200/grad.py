@@ -12,7 +12,8 @@ F.conv_transpose2d as issued by the reference's training step, train.py:49-59).
   bias gradient    column sums of the gradient rows
 
 Gradients travel as fp32 rows [pixels][channels]; GEMM operands derived from them are bf16 (fp32 exponent range, so
-no loss scaling), multiplied against the fp16 activations / weights saved by the forward pass.
+no loss scaling); the fp16 activations saved by the forward pass and the weights are converted to bf16 on the fly
+so that every backward GEMM is bf16 x bf16 with fp32 accumulation.
 """
 import ctypes
 
@@ -50,10 +51,10 @@ def gemm_nt(a, a_bf16, b, b_bf16, m, n, k, out=None, k_splits=0):
     return out
 
 
-def im2col_t(src, src_f32, n, hp, wp, cpad, c_src, gh, gw, stride, oh0, ow0, taps, c_rows, out):
+def im2col_t(src, src_kind, n, hp, wp, cpad, c_src, gh, gw, stride, oh0, ow0, taps, c_rows, out):
     p_pad = out.shape[-1]
     dh, dw = _i8([t[0] for t in taps]), _i8([t[1] for t in taps])
-    check(lib.hfc_im2col_t(_ptr(src), int(src_f32), n, hp, wp, cpad, c_src, gh, gw, stride, oh0, ow0, len(taps), dh, dw,
+    check(lib.hfc_im2col_t(_ptr(src), int(src_kind), n, hp, wp, cpad, c_src, gh, gw, stride, oh0, ow0, len(taps), dh, dw,
                            c_rows, p_pad, _ptr(out), _stream()), "im2col_t")
     return out
 
@@ -81,21 +82,21 @@ class ConvGrad:
         if not transposed and stride == 1:
             hq, wq = h + pt + pb, w + pl + pr
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=1, pad_mode=PAD_ZERO, pad=(kh - 1,) * 4,
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, dgrad=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, b_bf16=True, dgrad=True)
             self.fold = (hq, wq)
         elif not transposed:
             hq = 2 * self.oh + kh - 1
             wq = 2 * self.ow + kw - 1
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=2, transposed=True, pad=(0, 0, 0, 0),
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, b_bf16=True)
             self.fold = (hq, wq)
         elif stride == 2:
             hi = kh - 2 - pt
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=2, pad_mode=PAD_ZERO, pad=(pt, pl, hi, hi),
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=True, b_bf16=True)
         else:
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=1, pad_mode=PAD_ZERO, pad=(pt, pl, pt, pl),
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=True, b_bf16=True)
         self.cin4 = cin4
         self.taps = [(ky, kx) for ky in range(kh) for kx in range(kw)]
         # weight-gradient GEMM operands: which side is transposed plainly (A1) and which is im2col'ed (A2).
@@ -143,11 +144,11 @@ class ConvGrad:
             p_pad = round_up(self.p_out, 64)
             c1_rows, c2_rows = round_up(self.cout, 64), (8 if ig.cpad == 8 else round_up(self.cin, 64))
             a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
-            im2col_t(dy_rows, True, n, self.oh, self.ow, ld_dy, self.cout, self.oh, self.ow, 1, 0, 0, [(0, 0)], c1_rows, a1)
+            im2col_t(dy_rows, 1, n, self.oh, self.ow, ld_dy, self.cout, self.oh, self.ow, 1, 0, 0, [(0, 0)], c1_rows, a1)
             col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
-            im2col_t(x_act, False, n, hp, wp, ig.cpad, self.cin, self.oh, self.ow, s, ig.pt - pt, ig.pl - pl, self.taps,
+            im2col_t(x_act, 2, n, hp, wp, ig.cpad, self.cin, self.oh, self.ow, s, ig.pt - pt, ig.pl - pl, self.taps,
                      c2_rows, col)
-            m, c2, a_bf, b_bf = self.cout, self.cin, True, False
+            m, c2, a_bf, b_bf = self.cout, self.cin, True, True
             shape = (self.cout, self.cin, k, k)
         elif not self.transposed:
             # tiny cout: pixels = padded input pixels q; A1 = x^T (fp16), COLT[(tap, co)][q] = dy[q - tap] (bf16)
@@ -159,21 +160,21 @@ class ConvGrad:
             p_pad = round_up(n * gh * gw, 64)
             c1_rows, c2_rows = round_up(self.cin, 64), 8
             a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
-            im2col_t(x_act, False, n, hp, wp, ig.cpad, self.cin, gh, gw, 1, o0h, o0w, [(0, 0)], c1_rows, a1)
+            im2col_t(x_act, 2, n, hp, wp, ig.cpad, self.cin, gh, gw, 1, o0h, o0w, [(0, 0)], c1_rows, a1)
             col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
-            im2col_t(dy_rows, True, n, self.oh, self.ow, ld_dy, self.cout, gh, gw, 1, 0, 0,
+            im2col_t(dy_rows, 1, n, self.oh, self.ow, ld_dy, self.cout, gh, gw, 1, 0, 0,
                      [(-ky, -kx) for ky, kx in self.taps], c2_rows, col)
-            m, c2, a_bf, b_bf = self.cin, self.cout, False, True
+            m, c2, a_bf, b_bf = self.cin, self.cout, True, True
             shape = (self.cout, self.cin, k, k)
         else:
             # transposed conv: pixels = input pixels i; A1 = x^T (fp16), COLT[(tap, co)][i] = dy[i*s - p + tap] (bf16)
             p_pad = round_up(self.p_in, 64)
             c1_rows, c2_rows = round_up(self.cin, 64), round_up(self.cout, 64)
             a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
-            im2col_t(x_act, False, n, hp, wp, ig.cpad, self.cin, h, w, 1, ig.pt, ig.pl, [(0, 0)], c1_rows, a1)
+            im2col_t(x_act, 2, n, hp, wp, ig.cpad, self.cin, h, w, 1, ig.pt, ig.pl, [(0, 0)], c1_rows, a1)
             col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
-            im2col_t(dy_rows, True, n, self.oh, self.ow, ld_dy, self.cout, h, w, s, -pt, -pl, self.taps, c2_rows, col)
-            m, c2, a_bf, b_bf = self.cin, self.cout, False, True
+            im2col_t(dy_rows, 1, n, self.oh, self.ow, ld_dy, self.cout, h, w, s, -pt, -pl, self.taps, c2_rows, col)
+            m, c2, a_bf, b_bf = self.cin, self.cout, True, True
             shape = (self.cin, self.cout, k, k)
         ncols = len(self.taps) * c2_rows
         cbuf = Workspace.get("wgrad_c", m * round_up(ncols, 4), torch.float32, dev).view(m, round_up(ncols, 4))

@@ -230,7 +230,8 @@ int hfc_rows_to_act(const float* rows, int32_t ld, int64_t npix, int32_t c, int3
                     void* stream);
 /* transposed im2col (see csrc/backward.cu): out[(tap*c_rows + ch)][p], p over the (n, gh, gw) pixel grid, source
  * coordinate (g*stride + d[tap] + o0) in a physical buffer of n x hp x wp pixels with cpad channels (pitch, for fp32
- * rows), zero outside; src_f32: source is fp32 rows (converted to bf16) instead of a 16-bit act buffer.
+ * rows), zero outside; src_f32: 0 = 16-bit source copied verbatim, 1 = fp32 rows converted to bf16, 2 = fp16 act
+ * buffer converted to bf16 (the backward GEMMs run bf16 x bf16).
  * dh_host / dw_host are HOST arrays of ntaps offsets. */
 int hfc_im2col_t(const void* src, int32_t src_f32, int32_t n, int32_t hp, int32_t wp, int32_t cpad, int32_t c_src,
                  int32_t gh, int32_t gw, int32_t stride, int32_t oh0, int32_t ow0, int32_t ntaps,

@@ -45,7 +45,7 @@ def test_cluster_transposed():
 
 @pytest.mark.parametrize("w", [128, 256, 200])
 def test_wide_mode_7x7_head(w):
-    run_conv_case(2, 60, 24, w, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, expect=dict(wide=1))
+    run_conv_case(2, 60, 24, w, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, wide=1, expect=dict(wide=1))
 
 
 def test_wide_mode_forced_3x3_and_forbidden():

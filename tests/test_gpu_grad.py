@@ -24,15 +24,18 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
+@pytest.mark.parametrize("fmt", ["f16", "bf16", "mixed"])
 @pytest.mark.parametrize("m,n,k,splits", [(128, 64, 256, 0), (960, 8640 // 8, 2048, 0), (60, 392, 64 * 700, 0),
                                           (200, 100, 64 * 37, 5)])
-def test_gemm_nt(m, n, k, splits):
+def test_gemm_nt(m, n, k, splits, fmt):
     g = torch.Generator().manual_seed(1)
     a = torch.randn(m, k, generator=g).to(DEV)
     b = torch.randn(n, k, generator=g).to(DEV)
-    a16, b16 = a.bfloat16(), b.half()
+    a_bf, b_bf = fmt in ("bf16", "mixed"), fmt == "bf16"
+    a16 = a.bfloat16() if a_bf else a.half()
+    b16 = b.bfloat16() if b_bf else b.half()
     ref = a16.float() @ b16.float().t()
-    out = gemm_nt(a16.view(torch.int16), True, b16.view(torch.int16), False, m, n, k, k_splits=splits)
+    out = gemm_nt(a16.view(torch.int16), a_bf, b16.view(torch.int16), b_bf, m, n, k, k_splits=splits)
     torch.cuda.synchronize()
     assert rel(out[:, :n], ref) < 2e-5
 
@@ -40,11 +43,12 @@ def test_gemm_nt(m, n, k, splits):
 def run_grad_case(n, cin, h, w, cout, k, stride=1, pad=(0, 0, 0, 0), pad_mode=PAD_ZERO, transposed=False, window=False,
                   seed=0):
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(n, cin, h, w, generator=g).half().float().to(DEV).requires_grad_(True)
+    # values representable in both fp16 and bf16 so that the operand conversions are exact
+    x = torch.randn(n, cin, h, w, generator=g).bfloat16().float().to(DEV).requires_grad_(True)
     if transposed:
-        wt = (torch.randn(cin, cout, k, k, generator=g) / math.sqrt(cin * k * k)).half().float().to(DEV)
+        wt = (torch.randn(cin, cout, k, k, generator=g) / math.sqrt(cin * k * k)).bfloat16().float().to(DEV)
     else:
-        wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).half().float().to(DEV)
+        wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).bfloat16().float().to(DEV)
     wt.requires_grad_(True)
     bias = torch.zeros(cout, device=DEV, requires_grad=True)
     pt, pl, pb, pr = pad
