@@ -259,10 +259,9 @@ class DiscriminatorPlan:
         return self.c_out(h, mod.conv_out.weight, mod.conv_out.bias)
 
 
-def require_inference(module, who):
-    """The backward kernels (dgrad / wgrad / norm backward) are not built yet: refuse loudly instead of
-    returning tensors that silently carry no autograd graph."""
-    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise NotImplementedError(
-            f"{who}: hific_b200 currently implements the forward path only; call it under torch.no_grad() "
-            "(training through these kernels needs the dgrad/wgrad kernels, which are not built yet)")
+def wants_grad(module, *inputs):
+    """True when the call must be recorded for autograd (training): then the module runs its training plan
+    (hific_b200.train_plan) instead of the fused inference plan."""
+    if not torch.is_grad_enabled():
+        return False
+    return any(t.requires_grad for t in inputs) or any(p.requires_grad for p in module.parameters())

@@ -68,7 +68,8 @@ class Hyperprior(CodingModel):
 
     def forward(self, latents, spatial_shape, **kwargs):
         engine._require_cuda(latents, "Hyperprior")
-        engine.require_inference(self, "Hyperprior")
+        if engine.wants_grad(self, latents):
+            return self._forward_autograd(latents, spatial_shape)
         latents = latents.contiguous()
         batch = latents.shape[0]
         hyperlatents = self.analysis_net(latents)
@@ -92,6 +93,9 @@ class Hyperprior(CodingModel):
         noise_y = torch.nn.init.uniform_(torch.zeros_like(latents), -0.5, 0.5)
         latents_decoded, _ = ops.latent_likelihood(latents, latent_means, latent_scales, noise_y,
                                                    self.scale_lower_bound, self.likelihood_type, sums=sums[2:4])
+        return self._hyperinfo(latents_decoded, sums, batch, spatial_shape)
+
+    def _hyperinfo(self, latents_decoded, sums, batch, spatial_shape):
         # hyperprior.py:80-93: n_bits = sum(log p) / (-ln2 * B); bpp = n_bits / n_pixels
         n_pixels = float(spatial_shape[0] * spatial_shape[1])
         bpp = sums.to(torch.float32) / (batch * -math.log(2.)) / n_pixels
@@ -105,6 +109,25 @@ class Hyperprior(CodingModel):
             hyperlatent_qbpp=quantized_hyperlatent_bpp,
             total_qbpp=quantized_latent_bpp + quantized_hyperlatent_bpp,
         )
+
+    def _forward_autograd(self, latents, spatial_shape):
+        """Same computation recorded for autograd: the networks through their training plans, the two likelihood
+        kernels through autograd Functions with hand-written backward kernels."""
+        latents = latents.contiguous()
+        batch = latents.shape[0]
+        hyperlatents = self.analysis_net(latents)
+        noise_z = torch.nn.init.uniform_(torch.zeros_like(hyperlatents), -0.5, 0.5)
+        d = self.hyperlatent_likelihood
+        packed = ops.pack_density_params_autograd(*d._tensors())
+        z_noisy, z_quant, sums_z = ops.HyperlatentLikelihoodFn.apply(hyperlatents.contiguous(), packed, noise_z)
+        hyperlatents_decoded = z_noisy if self.training else z_quant
+        latent_means = self.synthesis_mu(hyperlatents_decoded)
+        latent_scales = self.synthesis_std(hyperlatents_decoded)
+        noise_y = torch.nn.init.uniform_(torch.zeros_like(latents), -0.5, 0.5)
+        latents_decoded, sums_y = ops.LatentLikelihoodFn.apply(latents, latent_means.contiguous(),
+                                                               latent_scales.contiguous(), noise_y,
+                                                               self.scale_lower_bound, self.likelihood_type)
+        return self._hyperinfo(latents_decoded, torch.cat([sums_z, sums_y]), batch, spatial_shape)
 
     def _side_stream(self, device):
         key = (device.type, device.index)

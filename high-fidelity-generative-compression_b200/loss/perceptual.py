@@ -87,11 +87,19 @@ class PerceptualLoss(nn.Module):
         """Returns (N, 1, 1, 1) like the reference."""
         if not pred.is_cuda:
             raise RuntimeError("PerceptualLoss: hific_b200 has no CPU path")
-        if torch.is_grad_enabled() and pred.requires_grad:
-            raise NotImplementedError("PerceptualLoss backward is not built yet; call under torch.no_grad()")
         if normalize:
             target = 2 * target - 1
             pred = 2 * pred - 1
+        if torch.is_grad_enabled() and pred.requires_grad:
+            # training: torch autograd carries the gradient through the frozen cuDNN trunk; the per-layer feature
+            # loss and its gradient w.r.t. the reconstruction's features are the fused kernels
+            with torch.no_grad():
+                f0 = self.features(target)
+            f1 = self.features(pred)
+            out = 0
+            for k in range(5):
+                out = out + ops.LpipsLayerFn.apply(f0[k], f1[k], self.lins[k])
+            return out.view(-1, 1, 1, 1)
         with torch.no_grad():
             f0, f1 = self.features(target), self.features(pred)    # model.forward(target, pred), perceptual_loss.py:40
             out = torch.zeros(pred.shape[0], dtype=torch.float32, device=pred.device)

@@ -1,7 +1,8 @@
 """`Model` with the reference's constructor, attributes and return types (src/model.py:35-387) on top of the
 B200 kernels: `compression_forward`, `discriminator_forward`, `compression_loss`, `GAN_loss` and `forward` in all
-three model modes.  Everything runs forward-only for now (call under torch.no_grad(); the backward kernels are
-the next step), which already covers validation / evaluation and the encode+decode headline metric.
+three model modes.  The compression model (Encoder / Hyperprior / Generator + distortion, LPIPS and rate losses) is
+differentiable end to end through hand-written backward kernels (hific_b200.train_plan / grad), so the reference's
+`optimize_compression_loss` (train.py:54-59) works on it; the Discriminator is forward-only so far.
 """
 from collections import defaultdict, namedtuple
 
@@ -188,6 +189,8 @@ class Model(nn.Module):
 
     def distortion_loss(self, x_gen, x_real):
         """mean((255 x_gen - 255 x_real)^2) -- src/model.py:190-194, one fused reduction."""
+        if torch.is_grad_enabled() and x_gen.requires_grad:
+            return ops.SqDiffMeanFn.apply(x_gen, x_real, 255.)
         x_gen, x_real = x_gen.contiguous(), x_real.contiguous()
         return (ops.sqdiff_sum(x_gen, x_real, 255.) / x_gen.numel()).to(torch.float32)
 

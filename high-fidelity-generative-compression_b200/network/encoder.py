@@ -4,7 +4,7 @@ fused sm_100a plan in hific_b200.engine (tcgen05 implicit-GEMM convs, ChannelNor
 import torch
 import torch.nn as nn
 
-from .. import engine
+from .. import engine, train_plan
 from ..normalisation.channel import ChannelNorm2D
 
 
@@ -26,6 +26,8 @@ class Encoder(nn.Module):
             cin = cout
         self.conv_block_out = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(cin, C, 3, stride=1))
         self._plans = engine.PlanCache(self._make_plan)
+        self._train_plans = engine.PlanCache(lambda x: train_plan.EncoderTrainPlan(
+            x.shape[0], x.shape[2], x.shape[3], self.im_channels, self.C, x.device))
 
     def _make_plan(self, x):
         n, _, h, w = x.shape
@@ -33,9 +35,11 @@ class Encoder(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._plans.clear()          # buffers and packed weights live on the old device
+        self._train_plans.clear()
         return super()._apply(fn, *a, **k)
 
     def forward(self, x):
         engine._require_cuda(x, "Encoder")
-        engine.require_inference(self, "Encoder")
+        if engine.wants_grad(self, x):
+            return train_plan.run_training(self._train_plans.get(x), x, list(self.parameters()))
         return self._plans.get(x).run(self, x.contiguous())

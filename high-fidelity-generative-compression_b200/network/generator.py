@@ -4,7 +4,7 @@ hific_b200.engine.GeneratorPlan.
 import torch
 import torch.nn as nn
 
-from .. import engine
+from .. import engine, train_plan
 from ..normalisation.channel import ChannelNorm2D
 
 
@@ -47,6 +47,8 @@ class Generator(nn.Module):
             setattr(self, f"upconv_block{i}", nn.Sequential(up, ChannelNorm2D(filters[i]), nn.ReLU()))
         self.conv_block_out = nn.Sequential(nn.ReflectionPad2d(3), nn.Conv2d(filters[-1], 3, kernel_size=(7, 7), stride=1))
         self._plans = engine.PlanCache(self._make_plan)
+        self._train_plans = engine.PlanCache(lambda y: train_plan.GeneratorTrainPlan(
+            y.shape[0], y.shape[2], y.shape[3], self.C, self.n_residual_blocks, 3, y.device))
 
     def _make_plan(self, y):
         n, _, h, w = y.shape
@@ -54,9 +56,11 @@ class Generator(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._plans.clear()
+        self._train_plans.clear()
         return super()._apply(fn, *a, **k)
 
     def forward(self, x):
         engine._require_cuda(x, "Generator")
-        engine.require_inference(self, "Generator")
+        if engine.wants_grad(self, x):
+            return train_plan.run_training(self._train_plans.get(x), x, list(self.parameters()))
         return self._plans.get(x).run(self, x.contiguous())

@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from .. import engine
+from .. import engine, train_plan
 
 
 class HyperpriorAnalysis(nn.Module):
@@ -17,14 +17,18 @@ class HyperpriorAnalysis(nn.Module):
         self.conv3 = nn.Conv2d(N, N, kernel_size=5, stride=2, padding=2, padding_mode='reflect')
         self._plans = engine.PlanCache(lambda y: engine.HyperAnalysisPlan(y.shape[0], y.shape[2], y.shape[3],
                                                                             self.C, self.N, y.device))
+        self._train_plans = engine.PlanCache(lambda y: train_plan.HyperAnalysisTrainPlan(
+            y.shape[0], y.shape[2], y.shape[3], self.C, self.N, y.device))
 
     def _apply(self, fn, *a, **k):
         self._plans.clear()
+        self._train_plans.clear()
         return super()._apply(fn, *a, **k)
 
     def forward(self, x):
         engine._require_cuda(x, "HyperpriorAnalysis")
-        engine.require_inference(self, "HyperpriorAnalysis")
+        if engine.wants_grad(self, x):
+            return train_plan.run_training(self._train_plans.get(x), x, list(self.parameters()))
         return self._plans.get(x).run(self, x.contiguous())
 
 
@@ -40,12 +44,16 @@ class HyperpriorSynthesis(nn.Module):
         self.conv3 = nn.ConvTranspose2d(N, C, kernel_size=3, stride=1, padding=1)
         self._plans = engine.PlanCache(lambda z: engine.HyperSynthesisPlan(z.shape[0], z.shape[2], z.shape[3],
                                                                              self.C, self.N, z.device))
+        self._train_plans = engine.PlanCache(lambda z: train_plan.HyperSynthesisTrainPlan(
+            z.shape[0], z.shape[2], z.shape[3], self.C, self.N, z.device))
 
     def _apply(self, fn, *a, **k):
         self._plans.clear()
+        self._train_plans.clear()
         return super()._apply(fn, *a, **k)
 
     def forward(self, x):
         engine._require_cuda(x, "HyperpriorSynthesis")
-        engine.require_inference(self, "HyperpriorSynthesis")
+        if engine.wants_grad(self, x):
+            return train_plan.run_training(self._train_plans.get(x), x, list(self.parameters()))
         return self._plans.get(x).run(self, x.contiguous())

@@ -279,3 +279,101 @@ def lpips_layer(f0, f1, lin_w, out):
     assert lw.numel() == c and out.numel() == n and out.dtype == torch.float32
     check(lib.hfc_lpips_layer(_ptr(f0), _ptr(f1), _ptr(lw), n, c, h * w, _ptr(out), _stream()), "lpips_layer")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# autograd wrappers of the fused elementwise kernels (training path)
+# ------------------------------------------------------------------------------------------------------------
+class LatentLikelihoodFn(torch.autograd.Function):
+    """(y, mean, scale_raw, noise) -> (decoded, sums[2]); gradient flows through decoded (straight-through to y)
+    and sums[0] (the noisy log-likelihood sum); sums[1] is consumed via .item() in the reference (losses.py:21)."""
+
+    @staticmethod
+    def forward(ctx, y, mean, scale_raw, noise, lb, kind):
+        decoded, sums = latent_likelihood(y, mean, scale_raw, noise, lb, kind)
+        ctx.save_for_backward(y, mean, scale_raw, noise)
+        ctx.lb, ctx.kind = lb, kind
+        return decoded, sums
+
+    @staticmethod
+    def backward(ctx, d_decoded, d_sums):
+        y, mean, scale_raw, noise = ctx.saved_tensors
+        dy, dm, ds = torch.empty_like(y), torch.empty_like(y), torch.empty_like(y)
+        g = d_sums[0:1].to(torch.float32).contiguous() if d_sums is not None else torch.zeros(1, device=y.device)
+        dd = d_decoded.contiguous() if d_decoded is not None else None
+        lt = {"gaussian": 0, "logistic": 1}[ctx.kind]
+        check(lib.hfc_latent_likelihood_bwd(_ptr(y), _ptr(mean), _ptr(scale_raw), _ptr(noise), _ptr(dd), _ptr(g), 1.0,
+                                            y.numel(), float(ctx.lb), lt, _ptr(dy), _ptr(dm), _ptr(ds), _stream()),
+              "latent_likelihood_bwd")
+        return dy, dm, ds, None, None, None
+
+
+class HyperlatentLikelihoodFn(torch.autograd.Function):
+    """(z, packed_params, noise) -> (z_noisy, z_quant, sums[2]); gradient through z_noisy and sums[0]."""
+
+    @staticmethod
+    def forward(ctx, z, params64, noise):
+        z_noisy, z_quant, sums = hyperlatent_likelihood(z, params64, noise)
+        ctx.save_for_backward(z_noisy, params64)
+        ctx.mark_non_differentiable(z_quant)
+        return z_noisy, z_quant, sums
+
+    @staticmethod
+    def backward(ctx, d_noisy, d_quant, d_sums):
+        z_noisy, params64 = ctx.saved_tensors
+        n, c, h, w = z_noisy.shape
+        dz = torch.empty_like(z_noisy)
+        dp = torch.empty_like(params64)
+        g = d_sums[0:1].to(torch.float32).contiguous() if d_sums is not None else torch.zeros(1, device=dz.device)
+        dn = d_noisy.contiguous() if d_noisy is not None else None
+        check(lib.hfc_hyperlatent_likelihood_bwd(_ptr(z_noisy), _ptr(dn), _ptr(params64), _ptr(g), 1.0, n, c, h * w,
+                                                 _ptr(dz), _ptr(dp), _stream()), "hyperlatent_likelihood_bwd")
+        return dz, dp, None
+
+
+def pack_density_params_autograd(Hs, a_s, bs):
+    """Differentiable version of pack_density_params (14 080 scalars: plain torch ops carry the chain rule back to
+    H_k, a_k, b_k)."""
+    C = Hs[0].shape[0]
+    parts = []
+    for H, a, b in zip(Hs, a_s, bs):
+        parts += [torch.nn.functional.softplus(H).reshape(C, -1), b.reshape(C, -1), torch.tanh(a).reshape(C, -1)]
+    p = torch.cat(parts, dim=1)
+    return torch.nn.functional.pad(p, (0, 64 - p.shape[1])).contiguous()
+
+
+class LpipsLayerFn(torch.autograd.Function):
+    """per-image LPIPS distance of one trunk layer; gradient w.r.t. f1 (the reconstruction's features) only."""
+
+    @staticmethod
+    def forward(ctx, f0, f1, lin_w):
+        f0, f1 = f0.contiguous(), f1.contiguous()
+        out = torch.zeros(f0.shape[0], dtype=torch.float32, device=f0.device)
+        lpips_layer(f0, f1, lin_w, out)
+        ctx.save_for_backward(f0, f1, lin_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        f0, f1, lin_w = ctx.saved_tensors
+        n, c, h, w = f1.shape
+        df1 = torch.empty_like(f1)
+        check(lib.hfc_lpips_layer_bwd(_ptr(f0), _ptr(f1), _ptr(lin_w.reshape(-1).contiguous()), _ptr(d_out.contiguous()),
+                                      n, c, h * w, _ptr(df1), _stream()), "lpips_layer_bwd")
+        return None, df1, None
+
+
+class SqDiffMeanFn(torch.autograd.Function):
+    """mean((s*a - s*b)^2) with gradient w.r.t. a (src/model.py:190-194)."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        a, b = a.contiguous(), b.contiguous()
+        ctx.save_for_backward(a, b)
+        ctx.scale = scale
+        return (sqdiff_sum(a, b, scale) / a.numel()).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return (a - b) * (g * (2.0 * ctx.scale * ctx.scale / a.numel())), None, None

@@ -1,0 +1,322 @@
+"""Training-mode (autograd) execution of the HiFIC networks on the B200 kernels.
+
+The inference plans in `engine.py` fuse ChannelNorm into conv epilogues and recycle buffers.  Training needs the
+pre-norm conv outputs and every layer input for the backward pass, so the training plans run each layer un-fused
+(conv -> fp32 rows -> ChannelNorm kernel -> fp16 act buffer), keep all of it, and walk the same list backwards:
+ChannelNorm backward -> weight / bias gradient (tcgen05 GEMM over the pixels) -> data gradient (tcgen05 conv on the
+gradient).  Each network is exposed to torch as ONE autograd.Function (inputs: boundary tensor + parameters), so
+`loss.backward()` and the reference's optimizers (train.py:49-59, 287-300) work unchanged.
+
+Reference autograd paths replaced: Encoder (src/network/encoder.py:104-111), Generator (generator.py:145-169),
+HyperpriorAnalysis / HyperpriorSynthesis (hyper.py:56-63, 90-97).
+"""
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+from .grad import ConvGrad
+from .ops import (ACT_NONE, ACT_RELU, OUT_NCHW_F32, OUT_NHWC_F16, OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO, CN_EPS, Conv,
+                  Geom, _ptr, _stream, round_up)
+
+
+def nchw_to_rows(t):
+    """(n, c, h, w) fp32 -> fp32 rows [n*h*w][round_up(c, 4)] (pure data movement)."""
+    n, c, h, w = t.shape
+    r = t.permute(0, 2, 3, 1).reshape(-1, c)
+    if c % 4:
+        r = torch.nn.functional.pad(r, (0, 4 - c % 4))
+    return r.contiguous()
+
+
+def rows_to_nchw(r, n, c, h, w):
+    return r.view(n, h, w, -1)[..., :c].permute(0, 3, 1, 2).contiguous()
+
+
+def norm_bwd(z, g, gamma, beta, act):
+    """ChannelNorm(+ReLU) backward on fp32 rows.  Returns (dz, dgamma, dbeta)."""
+    c = gamma.numel()
+    npix = z.shape[0]
+    dz = torch.empty((npix, round_up(c, 4)), dtype=torch.float32, device=z.device)
+    dgb = torch.zeros((2, c), dtype=torch.float32, device=z.device)
+    check(lib.hfc_channelnorm_bwd(_ptr(z), z.shape[1], _ptr(g), g.shape[1], _ptr(gamma.detach().reshape(-1)),
+                                  _ptr(beta.detach().reshape(-1)), c, npix, CN_EPS, act, _ptr(dz), dz.shape[1],
+                                  _ptr(dgb[0]), _ptr(dgb[1]), _stream()), "channelnorm_bwd")
+    return dz, dgb[0].view_as(gamma), dgb[1].view_as(beta)
+
+
+def relu_mask(g, y_act, geom):
+    out = torch.empty((g.shape[0], round_up(geom.c, 4)), dtype=torch.float32, device=g.device)
+    if out.shape[1] != geom.c:
+        out.zero_()
+    gs = geom.c_struct()
+    check(lib.hfc_relu_mask(_ptr(g), g.shape[1], _ptr(y_act), ctypes.byref(gs), _ptr(out), out.shape[1], _stream()),
+          "relu_mask")
+    return out
+
+
+class Layer:
+    """One conv / transposed conv of a training plan with its forward kernel, its backward and its saved tensors."""
+
+    def __init__(self, in_geom, cout, k, stride=1, transposed=False, pad_mode=PAD_ZERO, pad=(0, 0, 0, 0), window=False,
+                 fused_relu_geom=None, nchw_out=False):
+        self.in_geom, self.cout = in_geom, cout
+        kw = dict(stride=stride, transposed=transposed, pad_mode=pad_mode, pad=pad, window=window)
+        if nchw_out:
+            self.conv = Conv(in_geom, cout, k, out_mode=OUT_NCHW_F32, **kw)
+        elif fused_relu_geom is not None:    # bias + ReLU in the epilogue, bordered fp16 output (hyper networks)
+            self.conv = Conv(in_geom, cout, k, out_geom=fused_relu_geom, out_reflect=any(
+                (fused_relu_geom.pt, fused_relu_geom.pl, fused_relu_geom.pb, fused_relu_geom.pr)), act=ACT_RELU, **kw)
+        else:
+            og = self.conv_out_geom(in_geom, cout, k, stride, transposed, pad)
+            self.conv = Conv(in_geom, cout, k, out_mode=OUT_NHWC_F32, out_geom=og, **kw)
+        self.grad = ConvGrad(in_geom, cout, k, stride=stride, transposed=transposed, pad_mode=pad_mode, pad=pad)
+        self.oh, self.ow = self.grad.oh, self.grad.ow
+        self.x_act = None
+
+    @staticmethod
+    def conv_out_geom(in_geom, cout, k, stride, transposed, pad):
+        n, h, w = in_geom.n, in_geom.h, in_geom.w
+        if transposed:
+            oh, ow = (h - 1) * stride - 2 * pad[0] + k + stride - 1, (w - 1) * stride - 2 * pad[1] + k + stride - 1
+        else:
+            oh, ow = (h + pad[0] + pad[2] - k) // stride + 1, (w + pad[1] + pad[3] - k) // stride + 1
+        return Geom(n, oh, ow, cout, round_up(cout, 4))
+
+    def forward(self, x_act, weight, bias):
+        self.x_act = x_act
+        return self.conv(x_act, weight, bias)
+
+    def backward(self, dz_rows, weight, need_dx=True):
+        dw = self.grad.weight_grad(self.x_act, dz_rows)
+        db = self.grad.bias_grad(dz_rows)
+        dx = self.grad.data_grad(dz_rows, weight.detach()) if need_dx else None
+        return dx, dw, db
+
+
+def norm_fwd(z, geom, gamma, beta, act, reflect, res1=None, res2=None, want_f32=False):
+    return ops.channelnorm(z, geom, gamma, beta, act=act, reflect=reflect, res1=res1, res2=res2, want_f32=want_f32)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Encoder
+# ------------------------------------------------------------------------------------------------------------
+class EncoderTrainPlan:
+    FILTERS = (60, 120, 240, 480, 960)
+
+    def __init__(self, n, h, w, im_channels, C, device):
+        f = self.FILTERS
+        self.n = n
+        self.g_in = Geom(n, h, w, im_channels, 8, 3, 3, 3, 4)
+        asym = (1, 0, 0, 1)
+        self.layers, self.geoms = [], []
+        self.layers.append(Layer(self.g_in, f[0], 7, pad_mode=PAD_REFLECT, pad=(3, 3, 3, 3), window=True))
+        g = Geom(n, h, w, f[0], 64, *asym)
+        self.geoms.append(g)
+        for i in range(1, 5):
+            self.layers.append(Layer(g, f[i], 3, stride=2, pad_mode=PAD_REFLECT, pad=(1, 0, 0, 1)))
+            lay = self.layers[-1]
+            g = Geom(n, lay.oh, lay.ow, f[i], round_up(f[i], 64), *(asym if i < 4 else (1, 1, 1, 1)))
+            self.geoms.append(g)
+        self.out = Layer(g, C, 3, pad_mode=PAD_REFLECT, pad=(1, 1, 1, 1), nchw_out=True)
+        self.C = C
+
+    def forward(self, x, p):
+        """p: flat parameter list in module.parameters() order: (w, b, gamma, beta) x 5, (w_out, b_out)."""
+        self.z = []
+        h = ops.nchw_to_act(x, self.g_in, reflect=True)
+        for i, lay in enumerate(self.layers):
+            w, b, gm, bt = p[4 * i:4 * i + 4]
+            z = lay.forward(h, w, b)
+            self.z.append(z)
+            h, _ = norm_fwd(z, self.geoms[i], gm, bt, ACT_RELU, True)
+        return self.out.forward(h, p[20], p[21])
+
+    def backward(self, dy, p):
+        grads = [None] * 22
+        g, grads[20], grads[21] = self.out.backward(nchw_to_rows(dy), p[20])
+        for i in range(4, -1, -1):
+            w, b, gm, bt = p[4 * i:4 * i + 4]
+            dz, grads[4 * i + 2], grads[4 * i + 3] = norm_bwd(self.z[i], g, gm, bt, ACT_RELU)
+            g, grads[4 * i], grads[4 * i + 1] = self.layers[i].backward(dz, w, need_dx=i > 0)
+        self.z = None
+        return grads
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Generator
+# ------------------------------------------------------------------------------------------------------------
+class GeneratorTrainPlan:
+    FILTERS = (960, 480, 240, 120, 60)
+
+    def __init__(self, n, h, w, C, n_res, im_channels, device):
+        f = self.FILTERS
+        self.n, self.h, self.w, self.C, self.n_res = n, h, w, C, n_res
+        b1 = (1, 1, 1, 1)
+        self.g_in = Geom(n, h, w, C, round_up(C, 64), *b1)
+        self.g_b1 = Geom(n, h, w, 960, 960, *b1)
+        self.g_flat = Geom(n, h, w, 960, 960)
+        self.init = Layer(self.g_in, 960, 3, pad_mode=PAD_REFLECT, pad=b1)
+        self.res = [(Layer(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1), Layer(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1))
+                    for _ in range(n_res)]
+        self.ups, self.up_geoms = [], []
+        g = self.g_flat
+        for i in range(1, 5):
+            lay = Layer(g, f[i], 3, stride=2, transposed=True, pad=(1, 1, 1, 1))
+            g = Geom(n, lay.oh, lay.ow, f[i], round_up(f[i], 64), *((0, 0, 0, 0) if i < 4 else (3, 3, 3, 3)))
+            self.ups.append(lay)
+            self.up_geoms.append(g)
+        self.out = Layer(g, im_channels, 7, pad_mode=PAD_REFLECT, pad=(3, 3, 3, 3), nchw_out=True)
+
+    # parameter order of hific_b200.network.generator.Generator.parameters():
+    #   init: norm0 (gamma, beta), conv (w, b), norm3 (gamma, beta)                      -> 0..5
+    #   resblock m: conv1 (w, b), conv2 (w, b), norm1 (gamma, beta), norm2 (gamma, beta) -> 6 + 8m ..
+    #   upconv i: convT (w, b), norm (gamma, beta)                                       -> 6 + 8R + 4i ..
+    #   out: conv (w, b)
+    def forward(self, y_hat, p):
+        R = self.n_res
+        self.y_rows = nchw_to_rows(y_hat)
+        a0, _ = norm_fwd(self.y_rows, self.g_in, p[0], p[1], ACT_NONE, True)
+        self.z_init = self.init.forward(a0, p[2], p[3])
+        x_act, head = norm_fwd(self.z_init, self.g_b1 if R else self.g_flat, p[4], p[5], ACT_NONE, bool(R), want_f32=True)
+        self.zr = []
+        x_f32 = head
+        for m in range(R):
+            w1, bb1, w2, bb2, g1, be1, g2, be2 = p[6 + 8 * m:14 + 8 * m]
+            c1, c2 = self.res[m]
+            z1 = c1.forward(x_act, w1, bb1)
+            a1, _ = norm_fwd(z1, self.g_b1, g1, be1, ACT_RELU, True)
+            z2 = c2.forward(a1, w2, bb2)
+            last = m == R - 1
+            x_act, x_new = norm_fwd(z2, self.g_flat if last else self.g_b1, g2, be2, ACT_NONE, not last, res1=x_f32,
+                                    res2=head if last else None, want_f32=not last)
+            self.zr.append((z1, z2))
+            x_f32 = x_new
+        self.zu = []
+        h = x_act
+        o = 6 + 8 * R
+        for i, lay in enumerate(self.ups):
+            w, b, gm, bt = p[o + 4 * i:o + 4 * i + 4]
+            z = lay.forward(h, w, b)
+            self.zu.append(z)
+            gg = self.up_geoms[i]
+            h, _ = norm_fwd(z, gg, gm, bt, ACT_RELU, any((gg.pt, gg.pl, gg.pb, gg.pr)))
+        return self.out.forward(h, p[o + 16], p[o + 17])
+
+    def backward(self, dxhat, p):
+        R = self.n_res
+        o = 6 + 8 * R
+        grads = [None] * len(p)
+        g, grads[o + 16], grads[o + 17] = self.out.backward(nchw_to_rows(dxhat), p[o + 16])
+        for i in range(3, -1, -1):
+            w, b, gm, bt = p[o + 4 * i:o + 4 * i + 4]
+            dz, grads[o + 4 * i + 2], grads[o + 4 * i + 3] = norm_bwd(self.zu[i], g, gm, bt, ACT_RELU)
+            g, grads[o + 4 * i], grads[o + 4 * i + 1] = self.ups[i].backward(dz, w)
+        # g = gradient w.r.t. the trunk output x_R (+ head): identity paths carry it to every block input and to head
+        g_head = g.clone() if R else g
+        for m in range(R - 1, -1, -1):
+            w1, bb1, w2, bb2, g1, be1, g2, be2 = p[6 + 8 * m:14 + 8 * m]
+            c1, c2 = self.res[m]
+            z1, z2 = self.zr[m]
+            dz2, grads[6 + 8 * m + 6], grads[6 + 8 * m + 7] = norm_bwd(z2, g, g2, be2, ACT_NONE)
+            ga1, grads[6 + 8 * m + 2], grads[6 + 8 * m + 3] = c2.backward(dz2, w2)
+            dz1, grads[6 + 8 * m + 4], grads[6 + 8 * m + 5] = norm_bwd(z1, ga1, g1, be1, ACT_RELU)
+            gx, grads[6 + 8 * m], grads[6 + 8 * m + 1] = c1.backward(dz1, w1)
+            g = g + gx                                  # identity_map + residual branch (generator.py:44)
+        if R:
+            g_head = g_head + g                         # block 0 consumed head; the final `x += head` added it again
+        dz0, grads[4], grads[5] = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE)
+        ga0, grads[2], grads[3] = self.init.backward(dz0, p[2])
+        dy_rows, grads[0], grads[1] = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE)
+        self.zr = self.zu = self.z_init = self.y_rows = None
+        return rows_to_nchw(dy_rows, self.n, self.C, self.h, self.w), grads
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Hyper networks (bias + ReLU fused in the conv epilogue; the saved fp16 outputs give the ReLU masks)
+# ------------------------------------------------------------------------------------------------------------
+class HyperAnalysisTrainPlan:
+    def __init__(self, n, h, w, C, N, device):
+        self.n, self.h, self.w, self.C, self.N = n, h, w, C, N
+        b2 = (2, 2, 2, 2)
+        self.g_in = Geom(n, h, w, C, round_up(C, 64))
+        self.g1 = Geom(n, h, w, N, round_up(N, 64), *b2)
+        self.l1 = Layer(self.g_in, N, 3, pad_mode=PAD_ZERO, pad=(1, 1, 1, 1), fused_relu_geom=self.g1)
+        h2, w2 = (h + 4 - 5) // 2 + 1, (w + 4 - 5) // 2 + 1
+        self.g2 = Geom(n, h2, w2, N, round_up(N, 64), *b2)
+        self.l2 = Layer(self.g1, N, 5, stride=2, pad_mode=PAD_REFLECT, pad=b2, fused_relu_geom=self.g2)
+        self.l3 = Layer(self.g2, N, 5, stride=2, pad_mode=PAD_REFLECT, pad=b2, nchw_out=True)
+
+    def forward(self, y, p):
+        a0 = ops.nchw_to_act(y, self.g_in)
+        self.a1 = self.l1.forward(a0, p[0], p[1])
+        self.a2 = self.l2.forward(self.a1, p[2], p[3])
+        return self.l3.forward(self.a2, p[4], p[5])
+
+    def backward(self, dz, p):
+        grads = [None] * 6
+        g, grads[4], grads[5] = self.l3.backward(nchw_to_rows(dz), p[4])
+        g = relu_mask(g, self.a2, self.g2)
+        g, grads[2], grads[3] = self.l2.backward(g, p[2])
+        g = relu_mask(g, self.a1, self.g1)
+        g, grads[0], grads[1] = self.l1.backward(g, p[0])
+        self.a1 = self.a2 = None
+        return rows_to_nchw(g, self.n, self.C, self.h, self.w), grads
+
+
+class HyperSynthesisTrainPlan:
+    def __init__(self, n, h, w, C, N, device):
+        self.n, self.h, self.w, self.C, self.N = n, h, w, C, N
+        self.g_in = Geom(n, h, w, N, round_up(N, 64))
+        self.g1 = Geom(n, 2 * h, 2 * w, N, round_up(N, 64))
+        self.g2 = Geom(n, 4 * h, 4 * w, N, round_up(N, 64))
+        self.l1 = Layer(self.g_in, N, 5, stride=2, transposed=True, pad=(2, 2, 2, 2), fused_relu_geom=self.g1)
+        self.l2 = Layer(self.g1, N, 5, stride=2, transposed=True, pad=(2, 2, 2, 2), fused_relu_geom=self.g2)
+        self.l3 = Layer(self.g2, C, 3, stride=1, transposed=True, pad=(1, 1, 1, 1), nchw_out=True)
+
+    def forward(self, z, p):
+        a0 = ops.nchw_to_act(z, self.g_in)
+        self.a1 = self.l1.forward(a0, p[0], p[1])
+        self.a2 = self.l2.forward(self.a1, p[2], p[3])
+        return self.l3.forward(self.a2, p[4], p[5])
+
+    def backward(self, dout, p):
+        grads = [None] * 6
+        g, grads[4], grads[5] = self.l3.backward(nchw_to_rows(dout), p[4])
+        g = relu_mask(g, self.a2, self.g2)
+        g, grads[2], grads[3] = self.l2.backward(g, p[2])
+        g = relu_mask(g, self.a1, self.g1)
+        g, grads[0], grads[1] = self.l1.backward(g, p[0])
+        self.a1 = self.a2 = None
+        return rows_to_nchw(g, self.n, self.N, self.h, self.w), grads
+
+
+# ------------------------------------------------------------------------------------------------------------
+# autograd glue: one Function per network
+# ------------------------------------------------------------------------------------------------------------
+class PlanFunction(torch.autograd.Function):
+    """forward(plan, x, *params) -> plan.forward(x, params); backward walks the plan in reverse."""
+
+    @staticmethod
+    def forward(ctx, plan, x, *params):
+        ctx.plan = plan
+        ctx.params = params
+        ctx.needs_dx = x.requires_grad
+        with torch.no_grad():
+            return plan.forward(x.contiguous(), [q.detach() for q in params])
+
+    @staticmethod
+    def backward(ctx, dout):
+        with torch.no_grad():
+            res = ctx.plan.backward(dout.contiguous(), [q.detach() for q in ctx.params])
+        if isinstance(res, tuple):
+            dx, grads = res
+        else:
+            dx, grads = None, res
+        grads = [g.reshape(q.shape) if g is not None else None for g, q in zip(grads, ctx.params)]
+        return (None, dx if ctx.needs_dx else None, *grads)
+
+
+def run_training(plan, x, params):
+    return PlanFunction.apply(plan, x, *params)

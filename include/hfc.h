@@ -247,6 +247,29 @@ int hfc_col_sums(const float* rows, int32_t ld, int64_t npix, int32_t c, float s
 int hfc_pad_fold(const float* dxp, int32_t ld_in, int32_t hq, int32_t wq, const hfc_act_geom* g, int32_t reflect,
                  float* dx, int32_t ld_out, void* stream);
 
+/* ChannelNorm2D (+ReLU) backward: z = saved pre-norm rows, g = gradient w.r.t. the block output (both fp32 rows);
+ * writes dz (fp32 rows) and ACCUMULATES dgamma / dbeta (caller zeroes them).  act: HFC_ACT_NONE | HFC_ACT_RELU. */
+int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld_g, const float* gamma,
+                        const float* beta, int32_t c, int64_t npix, float eps, int32_t act, float* dz, int32_t ld_dz,
+                        float* dgamma, float* dbeta, void* stream);
+/* out = g * (y > 0): backward of the fused bias+ReLU epilogue; y_act is that layer's (bordered) NHWC fp16 output */
+int hfc_relu_mask(const float* g, int32_t ld_g, const void* y_act, const hfc_act_geom* geom, float* out,
+                  int32_t ld_out, void* stream);
+/* backward of hfc_latent_likelihood's noisy term: L = (*g_nbpp) * coef * sum ln(p_noisy + 1e-9); dyhat = upstream
+ * gradient of the straight-through latents (may be NULL).  All NCHW fp32. */
+int hfc_latent_likelihood_bwd(const float* y, const float* mean, const float* scale_raw, const float* noise,
+                              const float* dyhat, const float* g_nbpp, float coef, int64_t count,
+                              float scale_lower_bound, int32_t likelihood_type, float* dy, float* dmean, float* dscale,
+                              void* stream);
+/* backward of hfc_hyperlatent_likelihood's noisy term w.r.t. the noisy hyper-latents (dz = dz_in + ...) and the
+ * PACKED density parameters (dparams64, overwritten, same (c, 64) layout) */
+int hfc_hyperlatent_likelihood_bwd(const float* z_noisy, const float* dz_in, const float* params64,
+                                   const float* g_nbpp, float coef, int32_t n, int32_t c, int32_t hw, float* dz,
+                                   float* dparams64, void* stream);
+/* gradient of hfc_lpips_layer w.r.t. f1 (the reconstruction's features): df1 = upstream[image] * d(mean dist)/d f1 */
+int hfc_lpips_layer_bwd(const float* f0, const float* f1, const float* lin_w, const float* upstream, int32_t n,
+                        int32_t c, int32_t hw, float* df1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
