@@ -161,6 +161,52 @@ def workload_config(args, batch):
             "l2": "no explicit flush: per-step working set (363 MB packed fp16 weights + activations) exceeds the 126 MB L2"}
 
 
+def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
+    """One training step of the compression model as train.py runs it (train.py:137-141, 54-59): forward, losses
+    (rate + distortion + LPIPS), backward through the hand-written kernels, gradient all-reduce over NCCL when
+    world > 1 (coalesced, after backward), Adam on the amortization and the hyper-latent parameter groups."""
+    from hific_b200.config import ModelModes
+    B = args.train_batch or args.batch
+    model.enable_cuda_graph(False)
+    model.model_mode = ModelModes.TRAINING
+    model.train()
+    amort = [p for m in model.amortization_models for p in m.parameters()]
+    hyper = list(model.Hyperprior.hyperlatent_likelihood.parameters())
+    opt_a = torch.optim.Adam(amort, lr=1e-4)
+    opt_h = torch.optim.Adam(hyper, lr=1e-4)
+    x = x_host[:B].to(dev)
+    params = amort + hyper
+
+    def step():
+        losses = model(x, train_generator=True)
+        losses['compression'].backward()
+        if dist is not None:
+            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
+                p.grad.copy_(g)
+        opt_a.step()
+        opt_a.zero_grad()
+        opt_h.step()
+        opt_h.zero_grad()
+
+    try:
+        for _ in range(3):
+            step()
+        steps = max(3, args.steps // 4)
+        ms = timed(step, steps)
+    except NotImplementedError as e:      # a piece of the backward is missing: report it, do not fake a number
+        return {"unavailable": str(e)[:200]}
+    finally:
+        model.model_mode = ModelModes.EVALUATION
+        model.eval()
+    return {"ms_per_step": ms / steps, "images_per_s": world * B * steps / (ms * 1e-3), "steps": steps,
+            "per_gpu_batch": B, "n_gpus": world,
+            "what": "compression model (no GAN): fwd + rate/distortion/LPIPS losses + bwd + 2x Adam; bf16 backward GEMMs; "
+                    "LPIPS AlexNet trunk on cuDNN; gradient all-reduce (NCCL, coalesced after backward) when n_gpus > 1"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,6 +215,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--train-batch", type=int, default=0, help="per-GPU batch of the training step (default: --batch)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true",
                     help="profiling mode (ncu): device-resident steps only, no e2e / roofline / CPU legs")
@@ -289,6 +337,11 @@ def main():
                 "l2": "flushed (256 MiB memset) before every timed launch",
                 "step_tensor_frac": (E_H_G_FLOPS_PER_IMAGE * B / (ms / args.steps * 1e-3) / 1e12) / peaks["sustained"]}
 
+    # --- training step (config c2: compression model, fwd + bwd + Adam), second half of BASELINE.json's metric ---
+    train = None
+    if not args.no_train:
+        train = run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores, sb = pick_cpu_threads(4)
@@ -316,6 +369,7 @@ def main():
             "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "cuda_graph": use_graph,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "tflops_per_step_algorithmic": E_H_G_FLOPS_PER_IMAGE * B / 1e12,
+            "train_step": train,
         }))
     if dist is not None:
         dist.destroy_process_group()

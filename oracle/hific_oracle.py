@@ -145,9 +145,23 @@ def density_cdf_logits(sd, x, prefix="Hyperprior.hyperlatent_likelihood."):
     return logits
 
 
+class _LowerBoundToward(torch.autograd.Function):
+    """LowerBoundToward -- src/helpers/maths.py:87-100: forward clamp(min=bound); backward passes the gradient where
+    the input was >= bound OR the gradient is negative (i.e. would move the input up, towards the bound)."""
+
+    @staticmethod
+    def forward(ctx, tensor, bound):
+        ctx.mask = tensor.ge(bound)
+        return torch.clamp(tensor, bound)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        gate = torch.logical_or(ctx.mask, grad_output.lt(0.)).type(grad_output.dtype)
+        return grad_output * gate, None
+
+
 def lower_bound(x, bound):
-    """LowerBoundToward.forward -- src/helpers/maths.py:91-95."""
-    return torch.clamp(x, min=bound)
+    return _LowerBoundToward.apply(x, bound)
 
 
 def density_likelihood(sd, z, prefix="Hyperprior.hyperlatent_likelihood."):
@@ -190,7 +204,7 @@ def estimate_entropy(likelihood, spatial_shape):
 def quantize_st(x, mean):
     """CodingModel.quantize_latents_st -- hyperprior.py:108-122 (forward value)."""
     v = x - mean
-    delta = torch.floor(v + 0.5) - v
+    delta = (torch.floor(v + 0.5) - v).detach()      # "ignore rounding in backward pass" (hyperprior.py:116)
     return (v + delta) + mean
 
 
