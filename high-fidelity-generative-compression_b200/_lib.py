@@ -80,8 +80,11 @@ SIGNATURES = {
                                          _f32, _i32, _vp, _vp]),
     "hfc_col_sums": (ctypes.c_int, [_vp, _i32, _i64, _i32, _f32, _vp, _vp]),
     "hfc_pad_fold": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _i32, _vp]),
-    "hfc_channelnorm_bwd": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _f32, _i32, _vp, _i32, _vp, _vp, _vp]),
-    "hfc_relu_mask": (ctypes.c_int, [_vp, _i32, _vp, ctypes.POINTER(ActGeom), _vp, _i32, _vp]),
+    "hfc_channelnorm_bwd": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _f32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "hfc_relu_mask": (ctypes.c_int, [_vp, _i32, _vp, ctypes.POINTER(ActGeom), _f32, _vp, _i32, _vp]),
+    "hfc_disc_input_bwd": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "hfc_spectral_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "hfc_gan_grad": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "hfc_latent_likelihood_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _f32, _i32, _vp, _vp, _vp, _vp]),
     "hfc_hyperlatent_likelihood_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hfc_lpips_layer_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),

@@ -19,108 +19,156 @@ namespace hfc {
 // ------------------------------------------------------------------------------------------------
 static constexpr int kCnbVec = 8;  // float4 per lane -> up to 1024 channels
 
-__global__ void __launch_bounds__(256, 1)
+template <int GROUP>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// GROUP lanes per pixel and VEC float4 per lane (capacity GROUP * VEC * 4 channels), persistent blocks.  Narrow layers
+// put several pixels in one warp and run many blocks per SM: the kernel is a pure HBM stream (read z, g; write dz)
+// and needs tens of KB in flight per SM.  dbias (optional) receives sum_pixels dz = the gradient of the bias of the
+// convolution in front of the norm, which saves a separate pass over dz.
+template <int VEC, int GROUP, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 channelnorm_bwd_kernel(const float* __restrict__ z, int ld_z, const float* __restrict__ g, int ld_g,
                        const float* __restrict__ gamma, const float* __restrict__ beta, int c, long long npix,
                        float eps, int act, float* __restrict__ dz, int ld_dz, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta) {
-  __shared__ float s_acc[2][kCnbVec * 128];
+                       float* __restrict__ dbeta, float* __restrict__ dbias) {
+  constexpr int kPix = 32 / GROUP;
+  constexpr int kCap = GROUP * VEC * 4;
+  __shared__ float s_acc[3][kCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 2 * kCnbVec * 128; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
+  const int gl = lane % GROUP;
+  for (int i = threadIdx.x; i < 3 * kCap; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
   __syncthreads();
-  float4 ag[kCnbVec], ab[kCnbVec];
+  // gamma / beta live in registers for the narrow variants; the wide ones re-read them (L1 hits) to stay spill-free
+  constexpr bool kCacheGB = VEC <= 1;
+  constexpr int kGB = kCacheGB ? VEC : 1;
+  float4 ag[VEC], ab[VEC], ad[VEC], gmc[kGB], btc[kGB];
 #pragma unroll
-  for (int i = 0; i < kCnbVec; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < VEC; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < kGB; ++i) {
+    const int ch = (i * GROUP + gl) * 4;
+    gmc[i] = btc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kCacheGB && ch < c) {
+      gmc[i] = *reinterpret_cast<const float4*>(gamma + ch);
+      btc[i] = *reinterpret_cast<const float4*>(beta + ch);
+    }
+  }
   const float inv_c = 1.f / static_cast<float>(c), inv_c1 = 1.f / static_cast<float>(c - 1);
-  for (long long pix = static_cast<long long>(blockIdx.x) * 8 + warp; pix < npix;
-       pix += static_cast<long long>(gridDim.x) * 8) {
+  const long long stride = static_cast<long long>(gridDim.x) * 8 * kPix;
+  // the loop bound is warp-uniform (first pixel of the warp): all lanes take part in the shuffles
+  for (long long pix0 = (static_cast<long long>(blockIdx.x) * 8 + warp) * kPix; pix0 < npix; pix0 += stride) {
+    const long long pix = pix0 + lane / GROUP;
+    const bool live = pix < npix;
     const float* zr = z + pix * ld_z;
     const float* gr = g + pix * ld_g;
-    float4 v[kCnbVec], gg[kCnbVec];
+    float4 v[VEC], gg[VEC];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kCnbVec; ++i) {
-      const int ch = (i * 32 + lane) * 4;
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ch < c) {
+    for (int i = 0; i < VEC; ++i) {
+      const int ch = (i * GROUP + gl) * 4;
+      v[i] = gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && ch < c) {
         v[i] = *reinterpret_cast<const float4*>(zr + ch);
+        gg[i] = *reinterpret_cast<const float4*>(gr + ch);     // issued early: both streams in flight together
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
     }
-    s = warp_sum(s);
+    s = group_sum<GROUP>(s);
     const float mean = s * inv_c;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kCnbVec; ++i) {
-      const int ch = (i * 32 + lane) * 4;
+    for (int i = 0; i < VEC; ++i) {
+      const int ch = (i * GROUP + gl) * 4;
       if (ch < c) {
         const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
         q += (a * a + b * b) + (cc * cc + d * d);
       }
     }
-    q = warp_sum(q);
+    q = group_sum<GROUP>(q);
     const float r = rsqrtf(q * inv_c1 + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kCnbVec; ++i) {
-      const int ch = (i * 32 + lane) * 4;
-      gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ch < c) {
-        const float4 gm = *reinterpret_cast<const float4*>(gamma + ch);
-        const float4 bt = *reinterpret_cast<const float4*>(beta + ch);
-        float4 go = *reinterpret_cast<const float4*>(gr + ch);
+    for (int i = 0; i < VEC; ++i) {
+      const int ch = (i * GROUP + gl) * 4;
+      if (live && ch < c) {
+        float4 go = gg[i];
+        const float4 gmi = kCacheGB ? gmc[kCacheGB ? i : 0] : __ldg(reinterpret_cast<const float4*>(gamma + ch));
+        const float4 bti = kCacheGB ? btc[kCacheGB ? i : 0] : __ldg(reinterpret_cast<const float4*>(beta + ch));
         // xhat overwrites v
         v[i].x = (v[i].x - mean) * r; v[i].y = (v[i].y - mean) * r;
         v[i].z = (v[i].z - mean) * r; v[i].w = (v[i].w - mean) * r;
         if (act == 1) {  // ReLU: the gradient passes where the forward output was positive
-          if (!(fmaf(gm.x, v[i].x, bt.x) > 0.f)) go.x = 0.f;
-          if (!(fmaf(gm.y, v[i].y, bt.y) > 0.f)) go.y = 0.f;
-          if (!(fmaf(gm.z, v[i].z, bt.z) > 0.f)) go.z = 0.f;
-          if (!(fmaf(gm.w, v[i].w, bt.w) > 0.f)) go.w = 0.f;
+          if (!(fmaf(gmi.x, v[i].x, bti.x) > 0.f)) go.x = 0.f;
+          if (!(fmaf(gmi.y, v[i].y, bti.y) > 0.f)) go.y = 0.f;
+          if (!(fmaf(gmi.z, v[i].z, bti.z) > 0.f)) go.z = 0.f;
+          if (!(fmaf(gmi.w, v[i].w, bti.w) > 0.f)) go.w = 0.f;
         }
         ab[i].x += go.x; ab[i].y += go.y; ab[i].z += go.z; ab[i].w += go.w;
         ag[i].x = fmaf(go.x, v[i].x, ag[i].x); ag[i].y = fmaf(go.y, v[i].y, ag[i].y);
         ag[i].z = fmaf(go.z, v[i].z, ag[i].z); ag[i].w = fmaf(go.w, v[i].w, ag[i].w);
-        gg[i] = make_float4(go.x * gm.x, go.y * gm.y, go.z * gm.z, go.w * gm.w);
+        gg[i] = make_float4(go.x * gmi.x, go.y * gmi.y, go.z * gmi.z, go.w * gmi.w);
         s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
         s2 += (gg[i].x * v[i].x + gg[i].y * v[i].y) + (gg[i].z * v[i].z + gg[i].w * v[i].w);
+      } else {
+        gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    s1 = warp_sum(s1) * inv_c;
-    s2 = warp_sum(s2) * inv_c1;
+    s1 = group_sum<GROUP>(s1) * inv_c;
+    s2 = group_sum<GROUP>(s2) * inv_c1;
     float* dr = dz + pix * ld_dz;
 #pragma unroll
-    for (int i = 0; i < kCnbVec; ++i) {
-      const int ch = (i * 32 + lane) * 4;
-      if (ch < c) {
+    for (int i = 0; i < VEC; ++i) {
+      const int ch = (i * GROUP + gl) * 4;
+      if (live && ch < c) {
         float4 o;
         o.x = r * (gg[i].x - s1 - v[i].x * s2); o.y = r * (gg[i].y - s1 - v[i].y * s2);
         o.z = r * (gg[i].z - s1 - v[i].z * s2); o.w = r * (gg[i].w - s1 - v[i].w * s2);
         *reinterpret_cast<float4*>(dr + ch) = o;
+        ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
       }
     }
   }
   // block reduction of the per-lane parameter gradients, then one global atomic per channel per block
 #pragma unroll
-  for (int i = 0; i < kCnbVec; ++i) {
-    const int ch = (i * 32 + lane) * 4;
+  for (int i = 0; i < VEC; ++i) {
+    const int ch = (i * GROUP + gl) * 4;
     if (ch < c) {
       atomicAdd(&s_acc[0][ch + 0], ag[i].x); atomicAdd(&s_acc[0][ch + 1], ag[i].y);
       atomicAdd(&s_acc[0][ch + 2], ag[i].z); atomicAdd(&s_acc[0][ch + 3], ag[i].w);
       atomicAdd(&s_acc[1][ch + 0], ab[i].x); atomicAdd(&s_acc[1][ch + 1], ab[i].y);
       atomicAdd(&s_acc[1][ch + 2], ab[i].z); atomicAdd(&s_acc[1][ch + 3], ab[i].w);
+      atomicAdd(&s_acc[2][ch + 0], ad[i].x); atomicAdd(&s_acc[2][ch + 1], ad[i].y);
+      atomicAdd(&s_acc[2][ch + 2], ad[i].z); atomicAdd(&s_acc[2][ch + 3], ad[i].w);
     }
   }
   __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     atomicAdd(dgamma + ch, s_acc[0][ch]);
     atomicAdd(dbeta + ch, s_acc[1][ch]);
+    if (dbias) atomicAdd(dbias + ch, s_acc[2][ch]);
   }
+}
+
+template <int VEC, int GROUP, int MINB>
+static void launch_channelnorm_bwd(const float* z, int ld_z, const float* g, int ld_g, const float* gamma,
+                                   const float* beta, int c, long long npix, float eps, int act, float* dz, int ld_dz,
+                                   float* dgamma, float* dbeta, float* dbias, int sms, cudaStream_t st) {
+  const long long per_block = 8LL * (32 / GROUP);
+  const long long blocks = std::max<long long>(1, std::min<long long>((npix + per_block - 1) / per_block,
+                                                                       static_cast<long long>(sms) * MINB));
+  channelnorm_bwd_kernel<VEC, GROUP, MINB><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+      z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, dbeta, dbias);
 }
 
 // g_out[p][c] = g[p][c] * (y_act[p][c] > 0)   (y_act: bordered NHWC fp16 output of a bias+ReLU conv)
 struct ReluMaskParams {
   int32_t n, h, w, c, cpad, pt, pl, pb, pr, ld_g, ld_out;
+  float slope;   // 0: ReLU ; 0.2: LeakyReLU(0.2) of the discriminator (sign(y) == sign(pre-activation) for slope > 0)
 };
 __global__ void __launch_bounds__(256)
 relu_mask_kernel(const float* __restrict__ g, const __half* __restrict__ y, float* __restrict__ out,
@@ -135,7 +183,8 @@ relu_mask_kernel(const float* __restrict__ g, const __half* __restrict__ y, floa
     const int hh = static_cast<int>((pix / p.w) % p.h);
     const int nn = static_cast<int>(pix / (static_cast<long long>(p.w) * p.h));
     const __half yv = y[((static_cast<size_t>(nn) * Hp + hh + p.pt) * Wp + ww + p.pl) * p.cpad + ch];
-    out[pix * p.ld_out + ch] = __half2float(yv) > 0.f ? g[pix * p.ld_g + ch] : 0.f;
+    const float gv = g[pix * p.ld_g + ch];
+    out[pix * p.ld_out + ch] = __half2float(yv) > 0.f ? gv : gv * p.slope;
   }
 }
 
@@ -363,7 +412,7 @@ using namespace hfc;
 
 extern "C" int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld_g, const float* gamma,
                                    const float* beta, int32_t c, int64_t npix, float eps, int32_t act, float* dz,
-                                   int32_t ld_dz, float* dgamma, float* dbeta, void* stream) {
+                                   int32_t ld_dz, float* dgamma, float* dbeta, float* dbias, void* stream) {
   if (!z || !g || !gamma || !beta || !dz || !dgamma || !dbeta || npix <= 0)
     return set_error(HFC_ERR_INVALID, "channelnorm_bwd: null pointer or empty input");
   if (c % 4 != 0 || c < 4 || c > kCnbVec * 128 || ld_z % 4 != 0 || ld_g % 4 != 0 || ld_dz % 4 != 0)
@@ -372,22 +421,29 @@ extern "C" int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g,
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc != HFC_OK) return rc;
-  const long long blocks = std::max<long long>(1, std::min<long long>((npix + 7) / 8, sms));
-  channelnorm_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, dbeta);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define HFC_CNB(V, G, B) launch_channelnorm_bwd<V, G, B>(z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, \
+                                                        dbeta, dbias, sms, st)
+  if (c <= 32) HFC_CNB(1, 8, 4);
+  else if (c <= 64) HFC_CNB(1, 16, 4);
+  else if (c <= 128) HFC_CNB(1, 32, 4);
+  else if (c <= 256) HFC_CNB(2, 32, 3);
+  else if (c <= 512) HFC_CNB(4, 32, 2);
+  else HFC_CNB(8, 32, 1);
+#undef HFC_CNB
   HFC_CHECK_LAUNCH("channelnorm_bwd launch");
   return HFC_OK;
 }
 
-extern "C" int hfc_relu_mask(const float* g, int32_t ld_g, const void* y_act, const hfc_act_geom* geom, float* out,
-                             int32_t ld_out, void* stream) {
+extern "C" int hfc_relu_mask(const float* g, int32_t ld_g, const void* y_act, const hfc_act_geom* geom, float slope,
+                             float* out, int32_t ld_out, void* stream) {
   if (!g || !y_act || !geom || !out) return set_error(HFC_ERR_INVALID, "relu_mask: null pointer");
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc != HFC_OK) return rc;
   ReluMaskParams p;
   p.n = geom->n; p.h = geom->h; p.w = geom->w; p.c = geom->c; p.cpad = geom->cpad;
-  p.pt = geom->pt; p.pl = geom->pl; p.pb = geom->pb; p.pr = geom->pr; p.ld_g = ld_g; p.ld_out = ld_out;
+  p.pt = geom->pt; p.pl = geom->pl; p.pb = geom->pb; p.pr = geom->pr; p.ld_g = ld_g; p.ld_out = ld_out; p.slope = slope;
   const long long total = static_cast<long long>(p.n) * p.h * p.w * p.c;
   const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, sms * 8LL)));
   relu_mask_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, reinterpret_cast<const __half*>(y_act), out, p);

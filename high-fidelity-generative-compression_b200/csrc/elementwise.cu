@@ -136,39 +136,53 @@ struct CnParams {
 
 static constexpr int kCnMaxVec = 8;  // 8 float4 per lane -> up to 1024 channels
 
+// sum over the GROUP lanes (a power of two <= 32) that share a pixel; every lane of the warp takes part
+template <int GROUP>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// GROUP lanes per pixel, VEC float4 per lane (capacity GROUP * VEC * 4 channels): narrow layers put several pixels
+// in a warp so that every lane carries data and enough bytes are in flight per SM to cover the HBM latency.
+template <int VEC, int GROUP>
 __global__ void __launch_bounds__(256)
 channelnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ res1,
                    const float* __restrict__ res2, float* __restrict__ out_f32,
                    __half* __restrict__ out_act, const __grid_constant__ CnParams p) {
+  constexpr int kPix = 32 / GROUP;                 // pixels per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t pix = static_cast<size_t>(blockIdx.x) * 8 + warp;
+  const int gl = lane % GROUP;
   const size_t npix = static_cast<size_t>(p.n) * p.h * p.w;
-  if (pix >= npix) return;
+  const size_t pix = (static_cast<size_t>(blockIdx.x) * 8 + warp) * kPix + lane / GROUP;
+  const bool live = pix < npix;
   const float* row = x + pix * p.ld;
-  float4 v[kCnMaxVec];
+  float4 v[VEC];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kCnMaxVec; ++i) {
-    const int c = (i * 32 + lane) * 4;
+  for (int i = 0; i < VEC; ++i) {
+    const int c = (i * GROUP + gl) * 4;
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < p.c) {
+    if (live && c < p.c) {
       v[i] = *reinterpret_cast<const float4*>(row + c);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
-  s = warp_sum(s);
+  s = group_sum<GROUP>(s);
   const float mean = s / static_cast<float>(p.c);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kCnMaxVec; ++i) {
-    const int c = (i * 32 + lane) * 4;
+  for (int i = 0; i < VEC; ++i) {
+    const int c = (i * GROUP + gl) * 4;
     if (c < p.c) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
       q += (a * a + b * b) + (cc * cc + d * d);
     }
   }
-  q = warp_sum(q);
+  q = group_sum<GROUP>(q);
+  if (!live) return;
   const float rstd = rsqrtf(q / static_cast<float>(p.c - 1) + p.eps);
 
   const int ww = static_cast<int>(pix % p.w);
@@ -180,8 +194,8 @@ channelnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   const int Hp = p.h + p.pt + p.pb, Wp = p.w + p.pl + p.pr;
 
 #pragma unroll
-  for (int i = 0; i < kCnMaxVec; ++i) {
-    const int c = (i * 32 + lane) * 4;
+  for (int i = 0; i < VEC; ++i) {
+    const int c = (i * GROUP + gl) * 4;
     if (c >= p.cpad && c >= p.c) continue;
     float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < p.c) {
@@ -213,6 +227,16 @@ channelnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         }
     }
   }
+}
+
+template <int VEC, int GROUP>
+static void launch_channelnorm(const float* x, const float* gamma, const float* beta, const float* res1,
+                               const float* res2, float* out_f32, __half* out_act, const CnParams& p,
+                               cudaStream_t st) {
+  const long long npix = static_cast<long long>(p.n) * p.h * p.w;
+  const long long per_block = 8LL * (32 / GROUP);
+  channelnorm_kernel<VEC, GROUP><<<static_cast<unsigned>((npix + per_block - 1) / per_block), 256, 0, st>>>(
+      x, gamma, beta, res1, res2, out_f32, out_act, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -474,10 +498,16 @@ extern "C" int hfc_channelnorm(const float* x, int32_t ld, const hfc_act_geom* g
   p.n = g->n; p.c = g->c; p.h = g->h; p.w = g->w; p.cpad = g->cpad; p.ld = ld;
   p.pt = g->pt; p.pl = g->pl; p.pb = g->pb; p.pr = g->pr;
   p.reflect = reflect; p.act = act; p.eps = eps;
-  const long long npix = static_cast<long long>(g->n) * g->h * g->w;
-  const long long blocks = (npix + 7) / 8;
-  channelnorm_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, gamma, beta, res1, res2, out_f32, reinterpret_cast<__half*>(out_act), p);
+  // the padded channels (cpad > c) are zero-filled by the lanes past c: capacity must cover cpad
+  const int width = std::max(g->c, out_act ? g->cpad : g->c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __half* oa = reinterpret_cast<__half*>(out_act);
+  if (width <= 32) launch_channelnorm<1, 8>(x, gamma, beta, res1, res2, out_f32, oa, p, st);
+  else if (width <= 64) launch_channelnorm<1, 16>(x, gamma, beta, res1, res2, out_f32, oa, p, st);
+  else if (width <= 128) launch_channelnorm<1, 32>(x, gamma, beta, res1, res2, out_f32, oa, p, st);
+  else if (width <= 256) launch_channelnorm<2, 32>(x, gamma, beta, res1, res2, out_f32, oa, p, st);
+  else if (width <= 512) launch_channelnorm<4, 32>(x, gamma, beta, res1, res2, out_f32, oa, p, st);
+  else launch_channelnorm<8, 32>(x, gamma, beta, res1, res2, out_f32, oa, p, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "channelnorm launch: %s", cudaGetErrorString(e));
   note_launch();

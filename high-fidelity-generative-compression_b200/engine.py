@@ -222,6 +222,8 @@ class DiscriminatorPlan:
         if h % ctx_h or w % ctx_w or h // ctx_h != w // ctx_w:
             raise ValueError("Discriminator: image size must be an integer multiple of the context size")
         self.scale = h // ctx_h
+        self.c_x = im_channels
+        self.inv_sigmas = [None] * len(self.FILTERS)
         b1 = (1, 1, 1, 1)
         self.g_y = Geom(n, ctx_h, ctx_w, C, round_up(C, 64), *b1)
         self.y_act = self.g_y.alloc(device)
@@ -255,6 +257,7 @@ class DiscriminatorPlan:
             # spectral norm (discriminator.py:46-62): one power iteration per training forward, W = W_orig / sigma
             _, inv_sigma = ops.spectral_sigma(layer.weight_orig, layer.weight_u, layer.weight_v, mod.training, self.ws[i])
             key = (layer.weight_u._version, layer.weight_v._version) if not mod.training else object()
+            self.inv_sigmas[i] = inv_sigma
             h = conv(h, layer.weight_orig, layer.bias, out=self.bufs[i], scale=inv_sigma, scale_key=key)
         return self.c_out(h, mod.conv_out.weight, mod.conv_out.bias)
 

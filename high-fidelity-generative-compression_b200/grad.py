@@ -104,8 +104,10 @@ class ConvGrad:
         self.swap = (not transposed) and stride == 1 and cout <= 8
 
     # ------------------------------------------------------------------ data gradient
-    def data_grad(self, dy_rows, weight, out=None):
-        """dy_rows: fp32 [n*oh*ow][ld >= cout] -> dx fp32 rows [n*h*w][cin4]."""
+    def data_grad(self, dy_rows, weight, out=None, scale=None):
+        """dy_rows: fp32 [n*oh*ow][ld >= cout] -> dx fp32 rows [n*h*w][cin4].  `scale`: optional device scalar
+        multiplied into the weights while packing (1/sigma of a spectrally normalised layer)."""
+        sk = dict(scale=scale, scale_key=object()) if scale is not None else {}
         dev = dy_rows.device
         g = self.dy_geom
         dy_act = Workspace.get("dy_act", g.n * g.h * g.w * g.cpad, torch.int16, dev).view(g.shape)
@@ -114,11 +116,11 @@ class ConvGrad:
         if self.fold is None:
             if out is None:
                 out = torch.empty((self.p_in, self.cin4), dtype=torch.float32, device=dev)
-            self.dgrad(dy_act.view(torch.float16), weight, out=out)
+            self.dgrad(dy_act.view(torch.float16), weight, out=out, **sk)
             return out
         hq, wq = self.fold
         dxp = Workspace.get("dxp", self.in_geom.n * hq * wq * self.cin4, torch.float32, dev).view(-1, self.cin4)
-        self.dgrad(dy_act.view(torch.float16), weight, out=dxp)
+        self.dgrad(dy_act.view(torch.float16), weight, out=dxp, **sk)
         if out is None:
             out = torch.empty((self.p_in, self.cin4), dtype=torch.float32, device=dev)
         n, h, w = self.in_geom.n, self.in_geom.h, self.in_geom.w

@@ -31,6 +31,8 @@ def gan_loss(gan_loss_type, disc_out, mode='generator_loss'):
     (`hfc_gan_sums`); the least-squares variant is a non-default option and is not built."""
     if gan_loss_type != 'non_saturating':
         raise NotImplementedError("only gan_loss_type='non_saturating' (the HiFIC default) is built")
+    if torch.is_grad_enabled() and (disc_out.D_real_logits.requires_grad or disc_out.D_gen_logits.requires_grad):
+        return ops.GanLossFn.apply(disc_out.D_real_logits, disc_out.D_gen_logits, 0 if mode == 'generator_loss' else 1)
     logits = torch.cat([disc_out.D_real_logits.reshape(-1), disc_out.D_gen_logits.reshape(-1)])
     n = disc_out.D_real_logits.numel()
     sums = ops.gan_sums(logits).to(torch.float32) / n          # means, as F.binary_cross_entropy_with_logits

@@ -43,15 +43,26 @@ class Discriminator(nn.Module):
     def forward(self, x, y):
         engine._require_cuda(x, "Discriminator")
         engine._require_cuda(y, "Discriminator")
-        if engine.wants_grad(self, x, y):
-            raise NotImplementedError("Discriminator backward is not built yet (the compression-model training step is); "
-                                      "call it under torch.no_grad()")
         if x.shape[0] != y.shape[0]:
             raise ValueError("Discriminator: image and context batch sizes differ")
         # the plan cache is keyed on a tensor's shape: fold both shapes into a dummy key
         self._plan_key = (x.shape[0], x.shape[1], x.shape[2], x.shape[3], y.shape[2], y.shape[3])
         key = torch.empty((0,) + tuple(self._plan_key), device=x.device)
         plan = self._plans.get(key)
-        logits = plan.run(self, x.contiguous(), y.contiguous())
+        if engine.wants_grad(self, x, y):
+            if y.requires_grad:
+                raise NotImplementedError("Discriminator: no gradient path into the context latents (the reference "
+                                          "detaches them, src/model.py:178)")
+            from .. import train_plan
+            if getattr(plan, "train", None) is None:
+                plan.train = train_plan.DiscriminatorTrainPlan(plan)
+            params = [self.context_conv.weight, self.context_conv.bias]
+            for i in range(1, 5):
+                layer = getattr(self, f"conv{i}")
+                params += [layer.weight_orig, layer.bias]
+            params += [self.conv_out.weight, self.conv_out.bias]
+            logits = train_plan.DiscriminatorFunction.apply(plan.train, self, x, y, *params)
+        else:
+            logits = plan.run(self, x.contiguous(), y.contiguous())
         out_logits = logits.view(-1, 1)
         return torch.sigmoid(out_logits), out_logits

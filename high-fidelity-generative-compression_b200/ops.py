@@ -377,3 +377,25 @@ class SqDiffMeanFn(torch.autograd.Function):
     def backward(ctx, g):
         a, b = ctx.saved_tensors
         return (a - b) * (g * (2.0 * ctx.scale * ctx.scale / a.numel())), None, None
+
+
+class GanLossFn(torch.autograd.Function):
+    """Non-saturating GAN losses (src/loss/losses.py:30-41) on [real, gen] logits: mode 0 = generator loss
+    mean BCE(gen, 1), mode 1 = discriminator loss mean BCE(real, 1) + mean BCE(gen, 0)."""
+
+    @staticmethod
+    def forward(ctx, logits_real, logits_gen, mode):
+        lg = torch.cat([logits_real.reshape(-1), logits_gen.reshape(-1)]).contiguous()
+        ctx.save_for_backward(lg)
+        ctx.mode, ctx.shapes = mode, (logits_real.shape, logits_gen.shape)
+        sums = gan_sums(lg).to(torch.float32) / logits_real.numel()
+        return sums[0] + sums[1] if mode == 1 else sums[2]
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, = ctx.saved_tensors
+        half = lg.numel() // 2
+        out = torch.empty_like(lg)
+        g = g.to(torch.float32).contiguous()
+        check(lib.hfc_gan_grad(_ptr(lg), half, ctx.mode, _ptr(g), _ptr(out), _stream()), "gan_grad")
+        return out[:half].view(ctx.shapes[0]), out[half:].view(ctx.shapes[1]), None

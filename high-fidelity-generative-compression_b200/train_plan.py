@@ -35,23 +35,26 @@ def rows_to_nchw(r, n, c, h, w):
 
 
 def norm_bwd(z, g, gamma, beta, act):
-    """ChannelNorm(+ReLU) backward on fp32 rows.  Returns (dz, dgamma, dbeta)."""
+    """ChannelNorm(+ReLU) backward on fp32 rows.  Returns (dz, dgamma, dbeta, dbias) with dbias = column sums of dz
+    (the gradient of the bias of the convolution that produced z)."""
     c = gamma.numel()
     npix = z.shape[0]
     dz = torch.empty((npix, round_up(c, 4)), dtype=torch.float32, device=z.device)
-    dgb = torch.zeros((2, c), dtype=torch.float32, device=z.device)
+    dgb = torch.zeros((3, c), dtype=torch.float32, device=z.device)
     check(lib.hfc_channelnorm_bwd(_ptr(z), z.shape[1], _ptr(g), g.shape[1], _ptr(gamma.detach().reshape(-1)),
                                   _ptr(beta.detach().reshape(-1)), c, npix, CN_EPS, act, _ptr(dz), dz.shape[1],
-                                  _ptr(dgb[0]), _ptr(dgb[1]), _stream()), "channelnorm_bwd")
-    return dz, dgb[0].view_as(gamma), dgb[1].view_as(beta)
+                                  _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _stream()), "channelnorm_bwd")
+    return dz, dgb[0].view_as(gamma), dgb[1].view_as(beta), dgb[2]
 
 
-def relu_mask(g, y_act, geom):
+def relu_mask(g, y_act, geom, slope=0.0):
+    """g * act'(.) from the layer's saved fp16 output: ReLU (slope 0) or LeakyReLU(slope)."""
     out = torch.empty((g.shape[0], round_up(geom.c, 4)), dtype=torch.float32, device=g.device)
     if out.shape[1] != geom.c:
         out.zero_()
     gs = geom.c_struct()
-    check(lib.hfc_relu_mask(_ptr(g), g.shape[1], _ptr(y_act), ctypes.byref(gs), _ptr(out), out.shape[1], _stream()),
+    check(lib.hfc_relu_mask(_ptr(g), g.shape[1], _ptr(y_act), ctypes.byref(gs), float(slope), _ptr(out), out.shape[1],
+                             _stream()),
           "relu_mask")
     return out
 
@@ -88,9 +91,10 @@ class Layer:
         self.x_act = x_act
         return self.conv(x_act, weight, bias)
 
-    def backward(self, dz_rows, weight, need_dx=True):
+    def backward(self, dz_rows, weight, need_dx=True, db=None):
         dw = self.grad.weight_grad(self.x_act, dz_rows)
-        db = self.grad.bias_grad(dz_rows)
+        if db is None:
+            db = self.grad.bias_grad(dz_rows)
         dx = self.grad.data_grad(dz_rows, weight.detach()) if need_dx else None
         return dx, dw, db
 
@@ -138,8 +142,8 @@ class EncoderTrainPlan:
         g, grads[20], grads[21] = self.out.backward(nchw_to_rows(dy), p[20])
         for i in range(4, -1, -1):
             w, b, gm, bt = p[4 * i:4 * i + 4]
-            dz, grads[4 * i + 2], grads[4 * i + 3] = norm_bwd(self.z[i], g, gm, bt, ACT_RELU)
-            g, grads[4 * i], grads[4 * i + 1] = self.layers[i].backward(dz, w, need_dx=i > 0)
+            dz, grads[4 * i + 2], grads[4 * i + 3], db = norm_bwd(self.z[i], g, gm, bt, ACT_RELU)
+            g, grads[4 * i], grads[4 * i + 1] = self.layers[i].backward(dz, w, need_dx=i > 0, db=db)
         self.z = None
         return grads
 
@@ -211,24 +215,24 @@ class GeneratorTrainPlan:
         g, grads[o + 16], grads[o + 17] = self.out.backward(nchw_to_rows(dxhat), p[o + 16])
         for i in range(3, -1, -1):
             w, b, gm, bt = p[o + 4 * i:o + 4 * i + 4]
-            dz, grads[o + 4 * i + 2], grads[o + 4 * i + 3] = norm_bwd(self.zu[i], g, gm, bt, ACT_RELU)
-            g, grads[o + 4 * i], grads[o + 4 * i + 1] = self.ups[i].backward(dz, w)
+            dz, grads[o + 4 * i + 2], grads[o + 4 * i + 3], db = norm_bwd(self.zu[i], g, gm, bt, ACT_RELU)
+            g, grads[o + 4 * i], grads[o + 4 * i + 1] = self.ups[i].backward(dz, w, db=db)
         # g = gradient w.r.t. the trunk output x_R (+ head): identity paths carry it to every block input and to head
         g_head = g.clone() if R else g
         for m in range(R - 1, -1, -1):
             w1, bb1, w2, bb2, g1, be1, g2, be2 = p[6 + 8 * m:14 + 8 * m]
             c1, c2 = self.res[m]
             z1, z2 = self.zr[m]
-            dz2, grads[6 + 8 * m + 6], grads[6 + 8 * m + 7] = norm_bwd(z2, g, g2, be2, ACT_NONE)
-            ga1, grads[6 + 8 * m + 2], grads[6 + 8 * m + 3] = c2.backward(dz2, w2)
-            dz1, grads[6 + 8 * m + 4], grads[6 + 8 * m + 5] = norm_bwd(z1, ga1, g1, be1, ACT_RELU)
-            gx, grads[6 + 8 * m], grads[6 + 8 * m + 1] = c1.backward(dz1, w1)
+            dz2, grads[6 + 8 * m + 6], grads[6 + 8 * m + 7], db2 = norm_bwd(z2, g, g2, be2, ACT_NONE)
+            ga1, grads[6 + 8 * m + 2], grads[6 + 8 * m + 3] = c2.backward(dz2, w2, db=db2)
+            dz1, grads[6 + 8 * m + 4], grads[6 + 8 * m + 5], db1 = norm_bwd(z1, ga1, g1, be1, ACT_RELU)
+            gx, grads[6 + 8 * m], grads[6 + 8 * m + 1] = c1.backward(dz1, w1, db=db1)
             g = g + gx                                  # identity_map + residual branch (generator.py:44)
         if R:
             g_head = g_head + g                         # block 0 consumed head; the final `x += head` added it again
-        dz0, grads[4], grads[5] = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE)
-        ga0, grads[2], grads[3] = self.init.backward(dz0, p[2])
-        dy_rows, grads[0], grads[1] = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE)
+        dz0, grads[4], grads[5], db0 = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE)
+        ga0, grads[2], grads[3] = self.init.backward(dz0, p[2], db=db0)
+        dy_rows, grads[0], grads[1], _ = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE)
         self.zr = self.zu = self.z_init = self.y_rows = None
         return rows_to_nchw(dy_rows, self.n, self.C, self.h, self.w), grads
 
@@ -290,6 +294,91 @@ class HyperSynthesisTrainPlan:
         g, grads[0], grads[1] = self.l1.backward(g, p[0])
         self.a1 = self.a2 = None
         return rows_to_nchw(g, self.n, self.N, self.h, self.w), grads
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Discriminator: the forward IS the inference plan (engine.DiscriminatorPlan keeps every layer output in its own
+# buffers: bias + LeakyReLU fused, 1/sigma folded into the weight packing); the backward walks it in reverse.
+# ------------------------------------------------------------------------------------------------------------
+class DiscriminatorTrainPlan:
+    """Autograd of Discriminator.forward (src/network/discriminator.py:66-86) incl. the spectral-norm
+    reparametrisation W = W_orig / sigma (u, v constants, as torch.nn.utils.spectral_norm).
+    Parameter order: context_conv (w, b), conv1..4 (weight_orig, bias), conv_out (w, b).
+    The context latents are detached by the caller (src/model.py:178), so no gradient flows into `y`."""
+    SLOPE = 0.2
+
+    def __init__(self, fwd_plan):
+        from .engine import DiscriminatorPlan
+        assert isinstance(fwd_plan, DiscriminatorPlan)
+        self.f = fwd_plan
+        b1 = (1, 1, 1, 1)
+        self.g_ctx = ConvGrad(fwd_plan.g_y, fwd_plan.CONTEXT_C, 3, pad_mode=PAD_REFLECT, pad=b1)
+        self.grads = [ConvGrad(c.in_geom, f, 4, stride=2, pad_mode=PAD_REFLECT, pad=b1)
+                      for c, f in zip(fwd_plan.convs, fwd_plan.FILTERS)]
+        self.g_out = ConvGrad(fwd_plan.c_out.in_geom, 1, 1)
+        self.out_geoms = [c.out_geom for c in fwd_plan.convs]
+
+    def forward(self, mod, x, y):
+        f = self.f
+        logits = f.run(mod, x, y)
+        # constants of the spectral-norm backward as they were in THIS forward (u, v are updated in place by the next)
+        self.sn = [(getattr(mod, f"conv{i + 1}").weight_u.clone(), getattr(mod, f"conv{i + 1}").weight_v.clone(),
+                    f.inv_sigmas[i]) for i in range(4)]
+        return logits
+
+    def backward(self, dlogits, p, need_dx):
+        f = self.f
+        dev = dlogits.device
+        grads = [None] * 12
+        g, grads[10], grads[11] = self._layer_bwd(self.g_out, f.bufs[3], nchw_to_rows(dlogits), p[10], None)
+        for i in range(3, -1, -1):
+            g = relu_mask(g, f.bufs[i], self.out_geoms[i], self.SLOPE)
+            x_in = f.bufs[i - 1] if i else f.in_act
+            u, v, inv_sigma = self.sn[i]
+            w_orig = p[2 + 2 * i]
+            g_next, dw, grads[3 + 2 * i] = self._layer_bwd(self.grads[i], x_in, g, w_orig, inv_sigma, need_dx=True)
+            dwo = torch.empty_like(w_orig)
+            ws = torch.empty(1, dtype=torch.float32, device=dev)
+            rows, cols = w_orig.shape[0], w_orig.numel() // w_orig.shape[0]
+            check(lib.hfc_spectral_bwd(_ptr(dw), _ptr(w_orig), _ptr(u), _ptr(v), _ptr(inv_sigma), rows, cols, _ptr(ws), 0,
+                                       _ptr(dwo), _stream()), "spectral_bwd")
+            grads[2 + 2 * i] = dwo
+            g = g_next
+        gi = f.g_in
+        dx = torch.empty((gi.n, f.c_x, gi.h, gi.w), dtype=torch.float32, device=dev) if need_dx else None
+        gc = f.g_ctx
+        dctx = torch.empty((gc.n * gc.h * gc.w, round_up(gc.c, 4)), dtype=torch.float32, device=dev)
+        check(lib.hfc_disc_input_bwd(_ptr(g), g.shape[1], gi.n, gi.h, gi.w, f.c_x, gc.c, f.scale, _ptr(dx), _ptr(dctx),
+                                     dctx.shape[1], _stream()), "disc_input_bwd")
+        dctx = relu_mask(dctx, f.ctx_act, gc, self.SLOPE)
+        grads[0] = self.g_ctx.weight_grad(f.y_act, dctx)
+        grads[1] = self.g_ctx.bias_grad(dctx)
+        self.sn = None
+        return dx, grads
+
+    @staticmethod
+    def _layer_bwd(cg, x_act, dz_rows, weight, inv_sigma, need_dx=True):
+        dw = cg.weight_grad(x_act, dz_rows)
+        db = cg.bias_grad(dz_rows)
+        dx = cg.data_grad(dz_rows, weight.detach(), scale=inv_sigma) if need_dx else None
+        return dx, dw, db
+
+
+class DiscriminatorFunction(torch.autograd.Function):
+    """forward(plan, module, x, y, *params) -> logits; y gets no gradient (the reference detaches the latents)."""
+
+    @staticmethod
+    def forward(ctx, plan, mod, x, y, *params):
+        ctx.plan, ctx.params, ctx.needs_dx = plan, params, x.requires_grad
+        with torch.no_grad():
+            return plan.forward(mod, x.contiguous(), y.contiguous())
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        with torch.no_grad():
+            dx, grads = ctx.plan.backward(dlogits.contiguous(), [q.detach() for q in ctx.params], ctx.needs_dx)
+        grads = [g.reshape(q.shape) if g is not None else None for g, q in zip(grads, ctx.params)]
+        return (None, None, dx, None, *grads)
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -248,13 +248,28 @@ int hfc_pad_fold(const float* dxp, int32_t ld_in, int32_t hq, int32_t wq, const 
                  float* dx, int32_t ld_out, void* stream);
 
 /* ChannelNorm2D (+ReLU) backward: z = saved pre-norm rows, g = gradient w.r.t. the block output (both fp32 rows);
- * writes dz (fp32 rows) and ACCUMULATES dgamma / dbeta (caller zeroes them).  act: HFC_ACT_NONE | HFC_ACT_RELU. */
+ * writes dz (fp32 rows) and ACCUMULATES dgamma / dbeta (caller zeroes them) and, when dbias != NULL, the column sums
+ * of dz (= gradient of the bias of the convolution in front of the norm).  act: HFC_ACT_NONE | HFC_ACT_RELU. */
 int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld_g, const float* gamma,
                         const float* beta, int32_t c, int64_t npix, float eps, int32_t act, float* dz, int32_t ld_dz,
-                        float* dgamma, float* dbeta, void* stream);
-/* out = g * (y > 0): backward of the fused bias+ReLU epilogue; y_act is that layer's (bordered) NHWC fp16 output */
-int hfc_relu_mask(const float* g, int32_t ld_g, const void* y_act, const hfc_act_geom* geom, float* out,
+                        float* dgamma, float* dbeta, float* dbias, void* stream);
+/* out = g * (y > 0 ? 1 : slope): backward of the fused bias + ReLU (slope 0) / LeakyReLU (slope 0.2) epilogue; y_act
+ * is that layer's (bordered) NHWC fp16 output */
+int hfc_relu_mask(const float* g, int32_t ld_g, const void* y_act, const hfc_act_geom* geom, float slope, float* out,
                   int32_t ld_out, void* stream);
+/* adjoint of hfc_disc_input (autograd of torch.cat + nn.Upsample(nearest), src/network/discriminator.py:75-79):
+ * g = gradient rows [n*h*w][ld_g] of the (x_channels + ctx_channels)-channel discriminator input; dx (NCHW fp32,
+ * may be NULL) receives the image part, dctx rows [n*(h/scale)*(w/scale)][ld_ctx] the scale x scale block sums. */
+int hfc_disc_input_bwd(const float* g, int32_t ld_g, int32_t n, int32_t h, int32_t w, int32_t x_channels,
+                       int32_t ctx_channels, int32_t scale, float* dx, float* dctx, int32_t ld_ctx, void* stream);
+/* backward of torch.nn.utils.spectral_norm's W = W_orig / sigma (discriminator.py:46-62; u, v are constants):
+ * dw_orig (+)= (dw - <dw, W> u v^T) * inv_sigma.  workspace1: one float of scratch. */
+int hfc_spectral_bwd(const float* dw, const float* w_orig, const float* u, const float* v, const float* inv_sigma,
+                     int32_t rows, int32_t cols, float* workspace1, int32_t accumulate, float* dw_orig, void* stream);
+/* d loss / d logits of the non-saturating GAN losses (src/loss/losses.py:30-41) for logits = [real (half_count),
+ * gen (half_count)]; mode 0 = generator loss, 1 = discriminator loss; upstream = device scalar d L / d loss or NULL */
+int hfc_gan_grad(const float* logits, int64_t half_count, int32_t mode, const float* upstream, float* dlogits,
+                 void* stream);
 /* backward of hfc_latent_likelihood's noisy term: L = (*g_nbpp) * coef * sum ln(p_noisy + 1e-9); dyhat = upstream
  * gradient of the straight-through latents (may be NULL).  All NCHW fp32. */
 int hfc_latent_likelihood_bwd(const float* y, const float* mean, const float* scale_raw, const float* noise,

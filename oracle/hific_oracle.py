@@ -281,7 +281,7 @@ def weighted_rate_loss(cfg, total_nbpp, total_qbpp, step, ignore_schedule=False)
     lam_a = scheduled(cfg["lambda_A"], cfg["lambda_schedule"], step, ignore_schedule)
     lam_b = scheduled(cfg["lambda_B"], cfg["lambda_schedule"], step, ignore_schedule)
     target = scheduled(cfg["target_rate"], cfg["target_schedule"], step, ignore_schedule)
-    penalty = lam_a if float(total_qbpp) > target else lam_b
+    penalty = lam_a if float(total_qbpp.detach()) > target else lam_b
     return penalty * total_nbpp, float(penalty)
 
 
@@ -301,9 +301,10 @@ def spectral_normalize(w_orig, u, v=None, n_power_iterations=1, eps=1e-12, train
     iteration from the stored u (updating u, v), then W = W_orig / sigma.  Returns (W, u_new, v_new)."""
     w_mat = w_orig.reshape(w_orig.shape[0], -1)
     if training:
-        for _ in range(n_power_iterations):
-            v = F.normalize(torch.mv(w_mat.t(), u), dim=0, eps=eps)
-            u = F.normalize(torch.mv(w_mat, v), dim=0, eps=eps)
+        with torch.no_grad():     # torch's hook iterates under no_grad: u, v are constants of the backward pass
+            for _ in range(n_power_iterations):
+                v = F.normalize(torch.mv(w_mat.t(), u), dim=0, eps=eps)
+                u = F.normalize(torch.mv(w_mat, v), dim=0, eps=eps)
     sigma = torch.dot(u, torch.mv(w_mat, v))
     return w_orig / sigma, u, v
 
@@ -356,6 +357,27 @@ def lpips_forward(trunk_features, lin_weights, pred, target, normalize=True):
         d = (n0 - n1) ** 2
         val = val + (d * lin_weights[k].view(1, -1, 1, 1)).sum(dim=1, keepdim=True).mean(dim=(2, 3), keepdim=True)
     return val
+
+
+# ------------------------------------------------------------------------------------------------
+# One COMPRESSION_GAN training forward -- Model.forward src/model.py:346-387 with compression_loss :201-241,
+# GAN_loss :244-260, discriminator_forward :167-188.  Returns (compression_loss, disc_loss, new_uv); call
+# .backward() on the one train.py would (train.py:137-141: compression on generator steps, disc otherwise).
+# ------------------------------------------------------------------------------------------------
+def gan_training_losses(sd, x, noise_z, noise_y, cfg, lpips_trunk, lpips_lins, train_generator, step=1,
+                        n_residual_blocks=9):
+    recon, hyper, _ = compression_forward(sd, x, True, False, noise_z, noise_y, n_residual_blocks=n_residual_blocks)
+    dist = distortion_loss(recon, x)
+    lp = lpips_forward(lpips_trunk, lpips_lins, recon, x).mean()
+    rate, _ = weighted_rate_loss(cfg, hyper.total_nbpp, hyper.total_qbpp, step)
+    x_gen = recon if train_generator else recon.detach()
+    d_in = torch.cat([x, x_gen], 0)
+    lat = torch.repeat_interleave(hyper.decoded.detach(), 2, dim=0)
+    _, logits, new_uv = discriminator_forward(sd, d_in, lat, training=True)
+    d_real, d_gen = torch.chunk(logits.squeeze(), 2, dim=0)
+    d_loss, g_loss = gan_losses_non_saturating(d_real, d_gen)
+    comp = rate + cfg["k_M"] * dist + cfg["k_P"] * lp + cfg["beta"] * g_loss
+    return comp, d_loss, new_uv
 
 
 # ------------------------------------------------------------------------------------------------

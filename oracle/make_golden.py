@@ -116,7 +116,49 @@ def gan_case(synth, O):
                 disc_loss=abs(float(d_loss) - float(out["disc_loss"])), total=abs(float(total) - float(out["compression_loss"])) / abs(float(out["compression_loss"])))
     print("gan_train_128", {k: f"{v:.3e}" for k, v in errs.items()}, "losses", float(out["compression_loss"]), float(out["disc_loss"]),
           float(out["perceptual"]), float(out["distortion"]))
-    return [("gan_train_128", errs)]
+    cfg.update(k_M=0.075 * 2 ** (-5), k_P=1.0, beta=0.15)
+    return [("gan_train_128", errs)] + grad_case(model, sd, x, noise_z, noise_y, cfg, feats, lins, O)
+
+
+def grad_case(model, sd, x, noise_z, noise_y, cfg, feats, lins, O):
+    """BACKWARD pin: every parameter gradient of the real reference's two alternating steps (train.py:137-141 --
+    compression loss on generator steps, discriminator loss otherwise) vs torch autograd of the oracle restatement.
+    The fixture keeps the gradient norms + strided samples of the reference."""
+    out, report = {}, []
+    for tag, train_generator in (("gstep", True), ("dstep", False)):
+        model.load_state_dict(sd, strict=True)          # resets the spectral-norm u / v buffers
+        model.zero_grad(set_to_none=True)
+        model.step_counter = 0
+        with ref_shim.NoiseFeeder([noise_z, noise_y]):
+            losses = model(x, train_generator=train_generator)
+        losses["compression" if train_generator else "disc"].backward()
+        ref = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+        sdg = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("weight_u", "weight_v")))
+               for k, v in sd.items()}
+        comp, d_loss, _ = O.gan_training_losses(sdg, x, noise_z, noise_y, cfg, feats, lins, train_generator, step=1)
+        (comp if train_generator else d_loss).backward()
+        worst, worst_key, n = 0.0, None, 0
+        for k, g in ref.items():
+            if k.startswith("perceptual_loss"):
+                continue
+            og = sdg[k].grad
+            assert og is not None, f"oracle has no gradient for {k} ({tag})"
+            e = ((og - g).norm() / g.norm().clamp_min(1e-30)).item()
+            if e > worst:
+                worst, worst_key = e, k
+            n += 1
+            out[f"{tag}.{k}.norm"] = np.array(float(g.norm()))
+            flat = g.reshape(-1)
+            out[f"{tag}.{k}.sub"] = flat[:: max(1, flat.numel() // 64)][:64].numpy().copy()
+        missing = [k for k, v in sdg.items() if v.requires_grad and v.grad is not None and k not in ref]
+        assert not missing, f"oracle has gradients the reference lacks: {missing[:4]}"
+        print(f"grad pin {tag}: {n} parameter gradients, worst rel L2 {worst:.3e} ({worst_key}); "
+              f"loss ref {float(losses['compression' if train_generator else 'disc']):.6f} "
+              f"oracle {float(comp if train_generator else d_loss):.6f}")
+        report.append((f"grad_{tag}", {"worst_rel_l2": worst}))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "gan_grads_128.npz"), **out)
+    return report
 
 
 def main():

@@ -134,3 +134,94 @@ def test_losses_given_oracle_reconstruction(model, sd):
     assert abs(float(d_loss) - float(d_loss_o)) <= 2e-3 * abs(float(d_loss_o))
     assert abs(float(g_loss) - float(g_loss_o)) <= 2e-3 * abs(float(g_loss_o))
     assert abs(float(dist) - float(dist_o)) <= 1e-5 * float(dist_o)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# backward of the discriminator / GAN losses
+# ------------------------------------------------------------------------------------------------------------
+GRAD_TOL = 5e-2     # bf16-operand backward GEMMs on top of the fp16-operand forward (see tests/test_gpu_train.py)
+D_PARAMS = (["context_conv.weight", "context_conv.bias"] + [f"conv{i}.{s}" for i in range(1, 5) for s in ("weight_orig", "bias")] +
+            ["conv_out.weight", "conv_out.bias"])
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def test_gan_grad_kernel_against_torch():
+    g = torch.Generator().manual_seed(21)
+    for mode in (0, 1):
+        real = (2 * torch.randn(300, generator=g)).cuda().requires_grad_(True)
+        gen = (2 * torch.randn(300, generator=g)).cuda().requires_grad_(True)
+        loss = ops.GanLossFn.apply(real, gen, mode)
+        (3.0 * loss).backward()
+        r2, g2 = real.detach().clone().requires_grad_(True), gen.detach().clone().requires_grad_(True)
+        bce = torch.nn.functional.binary_cross_entropy_with_logits
+        ref = bce(g2, torch.ones_like(g2)) if mode == 0 else bce(r2, torch.ones_like(r2)) + bce(g2, torch.zeros_like(g2))
+        (3.0 * ref).backward()
+        assert torch.allclose(loss, ref, rtol=1e-5)
+        assert torch.allclose(gen.grad, g2.grad, rtol=1e-4, atol=1e-8)
+        if mode == 1:
+            assert torch.allclose(real.grad, r2.grad, rtol=1e-4, atol=1e-8)
+        else:
+            assert real.grad is None or float(real.grad.abs().max()) == 0.0
+
+
+def test_discriminator_backward_vs_oracle(model, sd):
+    """All 12 parameter gradients (incl. the spectral-norm reparametrisation) and d/dx of the discriminator loss
+    against CPU autograd of the oracle (whose backward is pinned to the real reference by oracle/make_golden.py)."""
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand(4, 3, 128, 128, generator=g)
+    y = torch.round(2 * torch.randn(4, 220, 8, 8, generator=g))
+    sd_local = {k: v.clone() for k, v in sd.items()}
+    model.load_state_dict(sd_local, strict=True)
+    model.train(True)
+    xc = x.cuda().requires_grad_(True)
+    _, logits = model.Discriminator(xc, y.cuda())
+    d_real, d_gen = torch.chunk(logits.squeeze(), 2, dim=0)
+    loss = ops.GanLossFn.apply(d_real, d_gen, 1) + 0.5 * ops.GanLossFn.apply(d_real, d_gen, 0)
+    loss.backward()
+
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("weight_u", "weight_v")))
+           for k, v in sd.items() if k.startswith("Discriminator.")}
+    xo = x.clone().requires_grad_(True)
+    _, lo, _ = O.discriminator_forward(sdg, xo, y, training=True)
+    r_o, g_o = torch.chunk(lo.squeeze(), 2, dim=0)
+    dl, gl = O.gan_losses_non_saturating(r_o, g_o)
+    (dl + 0.5 * gl).backward()
+    assert abs(float(loss) - float(dl + 0.5 * gl)) < 2e-3 * abs(float(dl + 0.5 * gl))
+    errs = {n: _rel(dict(model.Discriminator.named_parameters())[n].grad, sdg["Discriminator." + n].grad) for n in D_PARAMS}
+    errs["x"] = _rel(xc.grad, xo.grad)
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < GRAD_TOL, errs
+
+
+def test_discriminator_step_matches_reference_gradients(model, sd):
+    """The D-step and the D-parameter part of the G-step vs the REAL reference's gradients (tests/golden/
+    gan_grads_128.npz), fed the oracle's intermediates so that no y_hat rounding flip is involved."""
+    from hific_b200.model import Intermediates
+    gold = np.load(os.path.join(GOLDEN, "gan_grads_128.npz"))
+    x = synth.synth_image(2, 128, 128, 0)
+    nz = synth.synth_noise((2, 320, 2, 2), "zgan", 0)
+    ny = synth.synth_noise((2, 220, 8, 8), "ygan", 0)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        recon, hyper, _ = O.compression_forward(sd, x, True, False, nz, ny)
+    for tag, train_generator, scale in (("dstep", False, 1.0), ("gstep", True, 0.15)):
+        model.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+        model.train(True)
+        model.zero_grad(set_to_none=True)
+        inter = Intermediates(x.cuda(), recon.cuda().requires_grad_(train_generator), hyper.decoded.cuda(),
+                              hyper.total_nbpp.cuda(), hyper.total_qbpp.cuda())
+        d_loss, g_loss = model.GAN_loss(inter, train_generator=train_generator)
+        (d_loss if not train_generator else scale * g_loss).backward()
+        for n in D_PARAMS:
+            p = dict(model.Discriminator.named_parameters())[n]
+            key = f"{tag}.Discriminator.{n}"
+            norm = float(gold[key + ".norm"])
+            flat = p.grad.reshape(-1).cpu()
+            sub = flat[:: max(1, flat.numel() // 64)][:64].numpy()
+            assert abs(float(p.grad.norm()) - norm) < GRAD_TOL * norm, (key, float(p.grad.norm()), norm)
+            assert np.linalg.norm(sub - gold[key + ".sub"]) < 2 * GRAD_TOL * np.linalg.norm(gold[key + ".sub"]) + 1e-3 * norm / 8, key

@@ -72,13 +72,17 @@ def check_param_grads(module, prefix, sdg, tol=GRAD_TOL, skip=()):
     return worst[0]
 
 
-def test_channelnorm_backward_kernel():
+@pytest.mark.parametrize("c,n,h,w", [(960, 2, 8, 8), (480, 2, 9, 7), (240, 1, 12, 10), (220, 2, 8, 8), (120, 2, 13, 11),
+                                     (60, 2, 17, 19), (12, 1, 9, 21)])
+def test_channelnorm_backward_kernel(c, n, h, w):
+    """Every (VEC, GROUP) instantiation of the backward kernel, odd pixel counts (partially filled warps), the fused
+    bias gradient (column sums of dz), and the forward kernel's fp32 output at the same widths."""
     g = torch.Generator().manual_seed(1)
-    n, c, h, w = 2, 960, 8, 8
     z = (torch.randn(n, c, h, w, generator=g) * 2 + 0.3).cuda().requires_grad_(True)
     gamma = (1 + 0.1 * torch.randn(1, c, 1, 1, generator=g)).cuda().requires_grad_(True)
     beta = (0.1 * torch.randn(1, c, 1, 1, generator=g)).cuda().requires_grad_(True)
     up = torch.randn(n, c, h, w, generator=g).cuda()
+    from hific_b200.train_plan import nchw_to_rows, norm_bwd, norm_fwd
     for act in (ops.ACT_NONE, ops.ACT_RELU):
         for t in (z, gamma, beta):
             t.grad = None
@@ -86,10 +90,17 @@ def test_channelnorm_backward_kernel():
         if act == ops.ACT_RELU:
             y = torch.relu(y)
         y.backward(up)
-        from hific_b200.train_plan import nchw_to_rows, norm_bwd
-        dz, dg, db = norm_bwd(nchw_to_rows(z.detach()), nchw_to_rows(up), gamma.detach(), beta.detach(), act)
+        dz, dg, db, dbias = norm_bwd(nchw_to_rows(z.detach()), nchw_to_rows(up), gamma.detach(), beta.detach(), act)
         assert rel(dz.view(n, h, w, c).permute(0, 3, 1, 2), z.grad) < 1e-4
         assert rel(dg, gamma.grad) < 1e-4 and rel(db, beta.grad) < 1e-4
+        assert rel(dbias, z.grad.sum(dim=(0, 2, 3))) < 1e-3 or float(z.grad.sum(dim=(0, 2, 3)).norm()) < 1e-3
+        geom = ops.Geom(n, h, w, c, ops.round_up(c, 64), 1, 1, 1, 1)
+        act_buf, f32 = norm_fwd(nchw_to_rows(z.detach()), geom, gamma.detach(), beta.detach(), act, True, want_f32=True)
+        assert rel(f32.view(n, h, w, c).permute(0, 3, 1, 2), y) < 1e-5
+        inner = act_buf[:, 1:-1, 1:-1, :c].float().permute(0, 3, 1, 2)
+        assert rel(inner, y) < 1e-3
+        assert float(act_buf[..., c:].abs().max() if geom.cpad > c else 0.0) == 0.0
+        assert torch.equal(act_buf[:, 0, 1:-1], act_buf[:, 2, 1:-1])            # reflected top row
 
 
 def test_likelihood_backward_kernels(sd):

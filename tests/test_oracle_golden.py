@@ -84,3 +84,41 @@ def test_lower_bound_and_quantise_edge_cases():
     lik = O.latent_likelihood(torch.tensor([100.0]), torch.tensor([0.0]), torch.tensor([0.11]))
     assert lik.item() == pytest.approx(1e-9)
     assert O.lower_bound(torch.tensor([0.05, 0.2]), 0.11).tolist() == pytest.approx([0.11, 0.2])
+
+
+def test_oracle_backward_matches_reference_gradients():
+    """The oracle's autograd (LowerBoundToward gates, straight-through quantisation, spectral-norm constants, the
+    alternating G / D steps of train.py:137-141) against the parameter gradients of the REAL reference stored in
+    tests/golden/gan_grads_128.npz (written by oracle/make_golden.py, where the full tensors agreed bit-exactly)."""
+    import torchvision
+    gold = np.load(os.path.join(GOLDEN, "gan_grads_128.npz"))
+    sd = synth.synth_state_dict(0, gan=True)
+    x = synth.synth_image(2, 128, 128, 0)
+    nz = synth.synth_noise((2, 320, 2, 2), "zgan", 0)
+    ny = synth.synth_noise((2, 220, 8, 8), "ygan", 0)
+    state = torch.random.get_rng_state()
+    torch.manual_seed(1234)                               # the offline AlexNet stand-in of oracle/ref_shim.py
+    feats = torchvision.models.alexnet(weights=None).features.eval()
+    torch.random.set_rng_state(state)
+    for p in feats.parameters():
+        p.requires_grad_(False)
+    lin = np.load(os.path.join(os.path.dirname(synth.__file__), "weights", "lpips_alex_lin_v0.1.npz"))
+    lins = [torch.from_numpy(lin[f"lin{k}"]) for k in range(5)]
+    cfg = dict(lambda_A=2 ** 1, lambda_B=2 ** (-4), target_rate=0.14, lambda_schedule=dict(vals=[2., 1.], steps=[50000]),
+               target_schedule=dict(vals=[0.20 / 0.14, 1.], steps=[50000]), k_M=0.075 * 2 ** (-5), k_P=1.0, beta=0.15)
+    torch.set_num_threads(os.cpu_count())
+    for tag, train_generator in (("dstep", False), ("gstep", True)):
+        sdg = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("weight_u", "weight_v")))
+               for k, v in sd.items()}
+        comp, d_loss, _ = O.gan_training_losses(sdg, x, nz, ny, cfg, feats, lins, train_generator, step=1)
+        (comp if train_generator else d_loss).backward()
+        keys = [k[len(tag) + 1:-len(".norm")] for k in gold.files if k.startswith(tag + ".") and k.endswith(".norm")]
+        assert len(keys) == (160 if train_generator else 12)
+        for k in keys:
+            g = sdg[k].grad
+            assert g is not None, k
+            norm = float(gold[f"{tag}.{k}.norm"])
+            flat = g.reshape(-1)
+            sub = flat[:: max(1, flat.numel() // 64)][:64].numpy()
+            assert abs(float(g.norm()) - norm) <= 1e-4 * norm + 1e-12, (tag, k)
+            assert np.allclose(sub, gold[f"{tag}.{k}.sub"], rtol=1e-3, atol=1e-5 * norm + 1e-12), (tag, k)
