@@ -207,6 +207,66 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
                     "LPIPS AlexNet trunk on cuDNN; gradient all-reduce (NCCL, coalesced after backward) when n_gpus > 1"}
 
 
+def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
+    """The alternating generator / discriminator iterations of COMPRESSION_GAN training (configs c3 / c4;
+    train.py:137-141): every iteration runs the full forward (E, H, G, D, all losses); generator iterations
+    back-propagate the compression loss (+ beta * G loss, through D into G) and step the two Adam optimizers,
+    discriminator iterations back-propagate the D loss and step the discriminator's Adam."""
+    from hific_b200 import synth
+    from hific_b200.config import ModelModes, ModelTypes, hific_args
+    from hific_b200.model import Model
+    B = args.gan_batch or args.train_batch or args.batch
+    cfg = hific_args()
+    cfg.batch_size = B
+    model = Model(cfg, logging.getLogger("bench-gan"), model_mode=ModelModes.TRAINING, model_type=ModelTypes.COMPRESSION_GAN)
+    model.load_state_dict(synth.synth_state_dict(0, gan=True), strict=True)
+    model.to(dev).train()
+    amort = [p for m in model.amortization_models for p in m.parameters()]
+    hyper = list(model.Hyperprior.hyperlatent_likelihood.parameters())
+    disc = list(model.Discriminator.parameters())
+    opt_a, opt_h, opt_d = (torch.optim.Adam(g, lr=1e-4) for g in (amort, hyper, disc))
+    x = x_host[:B].to(dev)
+
+    def allreduce(params):
+        if dist is None:
+            return
+        gs = [p.grad for p in params if p.grad is not None]
+        flat = torch._utils._flatten_dense_tensors(gs)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        for g, f in zip(gs, torch._utils._unflatten_dense_tensors(flat, gs)):
+            g.copy_(f)
+
+    def g_step():
+        losses = model(x, train_generator=True)
+        losses['compression'].backward()
+        allreduce(amort + hyper)
+        opt_a.step(); opt_a.zero_grad()
+        opt_h.step(); opt_h.zero_grad()
+
+    def d_step():
+        losses = model(x, train_generator=False)
+        losses['disc'].backward()
+        allreduce(disc)
+        opt_d.step(); opt_d.zero_grad()
+
+    try:
+        for _ in range(2):
+            g_step(); d_step()
+        steps = max(3, args.steps // 4)
+        ms_g = timed(g_step, steps)
+        ms_d = timed(d_step, steps)
+    except NotImplementedError as e:
+        return {"unavailable": str(e)[:200]}
+    pair = (ms_g + ms_d) / steps
+    return {"ms_per_generator_iteration": ms_g / steps, "ms_per_discriminator_iteration": ms_d / steps,
+            "ms_per_iteration": pair / 2, "images_per_s": world * B * 2 / (pair * 1e-3), "steps": steps, "per_gpu_batch": B,
+            "n_gpus": world,
+            "what": "COMPRESSION_GAN alternating iterations (train.py:137-141): full forward incl. discriminator and "
+                    "LPIPS every iteration; G iterations: backward of the compression loss + 2x Adam; D iterations: "
+                    "backward of the D loss + Adam; gradient all-reduce (NCCL) when n_gpus > 1"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +277,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     ap.add_argument("--train-batch", type=int, default=0, help="per-GPU batch of the training step (default: --batch)")
+    ap.add_argument("--gan-batch", type=int, default=0, help="per-GPU batch of the GAN iterations (default: the training batch)")
+    ap.add_argument("--no-gan", action="store_true", help="skip the COMPRESSION_GAN alternating-iteration measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true",
                     help="profiling mode (ncu): device-resident steps only, no e2e / roofline / CPU legs")
@@ -342,6 +404,10 @@ def main():
     if not args.no_train:
         train = run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed)
 
+    gan = None
+    if not args.no_train and not args.no_gan:
+        gan = run_gan_steps(args, dev, dist, rank, world, x_host, timed)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores, sb = pick_cpu_threads(4)
@@ -369,7 +435,7 @@ def main():
             "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "cuda_graph": use_graph,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "tflops_per_step_algorithmic": E_H_G_FLOPS_PER_IMAGE * B / 1e12,
-            "train_step": train,
+            "train_step": train, "gan_train_iteration": gan,
         }))
     if dist is not None:
         dist.destroy_process_group()

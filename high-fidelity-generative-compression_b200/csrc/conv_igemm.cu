@@ -706,6 +706,8 @@ static int make_plan(const hfc_conv_desc* d, Plan* pl) {
     return set_error(HFC_ERR_INVALID, "conv: unsupported filter size %dx%d", d->kh, d->kw);
   if (d->stride != 1 && d->stride != 2)
     return set_error(HFC_ERR_INVALID, "conv: stride must be 1 or 2");
+  if ((d->a_bf16 != 0) != (d->b_bf16 != 0))
+    return set_error(HFC_ERR_UNSUPPORTED, "conv: tcgen05 kind::f16 faults on mixed fp16 x bf16 operands (a_bf16 != b_bf16)");
   if (d->precision != HFC_PREC_F16)
     return set_error(HFC_ERR_UNSUPPORTED, "conv: precision mode %d not built", d->precision);
   if (d->window) {
@@ -1152,6 +1154,8 @@ extern "C" int hfc_gemm_nt(const void* a, int32_t a_bf16, const void* b, int32_t
   if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0) return set_error(HFC_ERR_INVALID, "gemm_nt: null pointer or empty matrix");
   if (k % kBlockK != 0) return set_error(HFC_ERR_INVALID, "gemm_nt: K (%d) must be a multiple of 64", k);
   if (ldc % 4 != 0 || ldc < n) return set_error(HFC_ERR_INVALID, "gemm_nt: ldc must be a multiple of 4 and >= N");
+  if ((a_bf16 != 0) != (b_bf16 != 0))
+    return set_error(HFC_ERR_UNSUPPORTED, "gemm_nt: tcgen05 kind::f16 faults on mixed fp16 x bf16 operands; convert one side");
   int sm_count = 0;
   int rc = device_sm_count(&sm_count);
   if (rc != HFC_OK) return rc;

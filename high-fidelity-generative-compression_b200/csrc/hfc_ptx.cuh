@@ -168,9 +168,28 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
-// fmt_a / fmt_b: 0 = fp16, 1 = bf16 (the two operands may differ: gradients are bf16, activations fp16).
+// fmt_a / fmt_b: 0 = fp16, 1 = bf16.  Measured on B200: the two operands must use the SAME format (a mixed pair
+// raises an illegal-instruction fault), so the backward GEMMs convert the saved fp16 activations to bf16.
 __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t fmt_a, uint32_t fmt_b, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// MN-major, 128-byte-swizzled operand (the layout a TMA box {64 channels, pixels...} produces when the GEMM's K
+// dimension is the PIXEL index: K rows of 128 B = 64 MN elements, 8-row swizzle atoms 1024 B apart).  In 16-byte
+// units the canonical form is ((8,n),(8,k)):((1,LBO),(8,SBO)): LBO = distance between consecutive 64-element chunks
+// along M/N, SBO = distance between consecutive groups of 8 K rows.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;             // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor with both operands MN-major (transpose bits 15 / 16)
+__device__ __forceinline__ uint32_t make_idesc_f16_mn(uint32_t fmt, uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -16,10 +16,11 @@ no loss scaling); the fp16 activations saved by the forward pass and the weights
 so that every backward GEMM is bf16 x bf16 with fp32 accumulation.
 """
 import ctypes
+import os
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import check, lib
 from .ops import OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO, Conv, Geom, _ptr, _stream, round_up
 
@@ -102,17 +103,34 @@ class ConvGrad:
         # weight-gradient GEMM operands: which side is transposed plainly (A1) and which is im2col'ed (A2).
         # The im2col side should be the one with FEWER channels (its matrix has ntaps times more rows).
         self.swap = (not transposed) and stride == 1 and cout <= 8
+        # implicit weight gradient (csrc/wgrad_igemm.cu) for every layer whose operands are 64-channel-pitch NHWC
+        # buffers; the 3-channel image layers (8-channel pitch input / tiny cout) keep the explicit transposed-im2col GEMM
+        self.implicit = (not self.swap) and in_geom.cpad % 64 == 0 and not os.environ.get("HFC_EXPLICIT_WGRAD")
+        if self.implicit:
+            d = _lib.WgradDesc()
+            pt, pl = pad[0], pad[1]
+            if transposed:       # P = x over the input pixels, S = dy sampled at i*s - p + k
+                d.plain, d.shifted = in_geom.c_struct(), self.dy_geom.c_struct()
+                offs = [(ky - pt, kx - pl) for ky, kx in self.taps]
+                self.wg_m, self.wg_c2 = self.cin, cout
+            else:                # P = dy over the output pixels, S = x sampled at o*s + k - p (border-relative)
+                d.plain, d.shifted = self.dy_geom.c_struct(), in_geom.c_struct()
+                offs = [(ky - pt, kx - pl) for ky, kx in self.taps]
+                self.wg_m, self.wg_c2 = cout, self.cin
+            d.ntaps, d.stride, d.bf16, d.k_splits = len(self.taps), stride, 1, 0
+            for i, (a, b) in enumerate(offs):
+                d.tap_dh[i], d.tap_dw[i] = a, b
+            self.wg_desc = d
+            self.wg_c2_rows = round_up(self.wg_c2, 64)
 
     # ------------------------------------------------------------------ data gradient
-    def data_grad(self, dy_rows, weight, out=None, scale=None):
+    def data_grad(self, dy_rows, weight, out=None, scale=None, dy_act=None):
         """dy_rows: fp32 [n*oh*ow][ld >= cout] -> dx fp32 rows [n*h*w][cin4].  `scale`: optional device scalar
         multiplied into the weights while packing (1/sigma of a spectrally normalised layer)."""
         sk = dict(scale=scale, scale_key=object()) if scale is not None else {}
         dev = dy_rows.device
-        g = self.dy_geom
-        dy_act = Workspace.get("dy_act", g.n * g.h * g.w * g.cpad, torch.int16, dev).view(g.shape)
-        check(lib.hfc_rows_to_act(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, g.cpad, 1, _ptr(dy_act),
-                                  _stream()), "rows_to_act")
+        if dy_act is None:
+            dy_act = self.dy_to_act(dy_rows)
         if self.fold is None:
             if out is None:
                 out = torch.empty((self.p_in, self.cin4), dtype=torch.float32, device=dev)
@@ -131,10 +149,39 @@ class ConvGrad:
         return out
 
     # ------------------------------------------------------------------ weight / bias gradient
-    def weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, scale=1.0):
+    def dy_to_act(self, dy_rows):
+        """fp32 gradient rows -> border-less NHWC bf16 buffer (the operand format of the backward GEMMs)."""
+        g = self.dy_geom
+        dy_act = Workspace.get("dy_act", g.n * g.h * g.w * g.cpad, torch.int16, dy_rows.device).view(g.shape)
+        check(lib.hfc_rows_to_act(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, g.cpad, 1, _ptr(dy_act),
+                                  _stream()), "rows_to_act")
+        return dy_act
+
+    def _weight_grad_implicit(self, x_act, dy_rows, dw_out, accumulate, scale, dy_act=None):
+        dev = dy_rows.device
+        if dy_act is None:
+            dy_act = self.dy_to_act(dy_rows)
+        x_bf = Workspace.get("x_bf16", x_act.numel(), torch.int16, dev)
+        check(lib.hfc_act_to_bf16(_ptr(x_act), _ptr(x_bf), x_act.numel(), _stream()), "act_to_bf16")
+        ncols = len(self.taps) * self.wg_c2_rows
+        cbuf = Workspace.get("wgrad_c", self.wg_m * ncols, torch.float32, dev).view(self.wg_m, ncols)
+        plain, shifted = (x_bf, dy_act) if self.transposed else (dy_act, x_bf)
+        check(lib.hfc_wgrad(ctypes.byref(self.wg_desc), _ptr(plain), _ptr(shifted), _ptr(cbuf), ncols, _stream()), "wgrad")
+        k = self.k
+        shape = (self.cin, self.cout, k, k) if self.transposed else (self.cout, self.cin, k, k)
+        if dw_out is None:
+            dw_out = torch.empty(shape, dtype=torch.float32, device=dev)
+        ky, kx = _i8([t[0] for t in self.taps]), _i8([t[1] for t in self.taps])
+        check(lib.hfc_permute_wgrad(_ptr(cbuf), ncols, self.wg_m, self.wg_c2, self.wg_c2_rows, k, k, len(self.taps), ky, kx,
+                                    float(scale), int(accumulate), _ptr(dw_out), _stream()), "permute_wgrad")
+        return dw_out
+
+    def weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, scale=1.0, dy_act=None):
         """x_act: the forward input act buffer (fp16, with its border); dy_rows fp32 [n*oh*ow][ld].
         Returns dW in the torch layout of the forward weight."""
         dev = dy_rows.device
+        if self.implicit:
+            return self._weight_grad_implicit(x_act, dy_rows, dw_out, accumulate, scale, dy_act)
         ig = self.in_geom
         n, h, w = ig.n, ig.h, ig.w
         hp, wp = h + ig.pt + ig.pb, w + ig.pl + ig.pr

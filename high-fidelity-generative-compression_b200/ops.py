@@ -144,6 +144,7 @@ class Conv:
         self.flops = info.flops
         self._packed = None
         self._packed_key = None
+        self._packed_src = None
 
     def alloc_out(self, device):
         g = self.out_geom
@@ -169,6 +170,9 @@ class Conv:
                 check(lib.hfc_conv_pack_weights_scaled(ctypes.byref(self.desc), _ptr(w), _ptr(scale),
                                                        _ptr(self._packed), _stream()), "conv_pack_weights_scaled")
             self._packed_key = key
+            # keep the source storage alive: a NEW tensor can then never reuse this address (caching allocator) with
+            # the same version counter and be mistaken for the packed one
+            self._packed_src = weight.detach()
         return self._packed
 
     def __call__(self, x_act, weight, bias=None, gamma=None, beta=None, out=None, scale=None, scale_key=None):

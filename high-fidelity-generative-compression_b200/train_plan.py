@@ -92,10 +92,11 @@ class Layer:
         return self.conv(x_act, weight, bias)
 
     def backward(self, dz_rows, weight, need_dx=True, db=None):
-        dw = self.grad.weight_grad(self.x_act, dz_rows)
+        dy_act = self.grad.dy_to_act(dz_rows)       # one bf16 copy of the gradient serves both GEMMs
+        dw = self.grad.weight_grad(self.x_act, dz_rows, dy_act=dy_act)
         if db is None:
             db = self.grad.bias_grad(dz_rows)
-        dx = self.grad.data_grad(dz_rows, weight.detach()) if need_dx else None
+        dx = self.grad.data_grad(dz_rows, weight.detach(), dy_act=dy_act) if need_dx else None
         return dx, dw, db
 
 
@@ -358,9 +359,10 @@ class DiscriminatorTrainPlan:
 
     @staticmethod
     def _layer_bwd(cg, x_act, dz_rows, weight, inv_sigma, need_dx=True):
-        dw = cg.weight_grad(x_act, dz_rows)
+        dy_act = cg.dy_to_act(dz_rows)
+        dw = cg.weight_grad(x_act, dz_rows, dy_act=dy_act)
         db = cg.bias_grad(dz_rows)
-        dx = cg.data_grad(dz_rows, weight.detach(), scale=inv_sigma) if need_dx else None
+        dx = cg.data_grad(dz_rows, weight.detach(), scale=inv_sigma, dy_act=dy_act) if need_dx else None
         return dx, dw, db
 
 

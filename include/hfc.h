@@ -240,6 +240,26 @@ int hfc_im2col_t(const void* src, int32_t src_f32, int32_t n, int32_t hp, int32_
 int hfc_permute_wgrad(const float* c, int32_t ldc, int32_t m, int32_t c2, int32_t c2_rows, int32_t kh, int32_t kw,
                       int32_t ntaps, const int8_t* ky_host, const int8_t* kx_host, float scale, int32_t accumulate,
                       float* dw, void* stream);
+/* Implicit weight gradient (autograd of F.conv2d / F.conv_transpose2d w.r.t. the weight, train.py:49-59):
+ *   c[m][tap * c2_rows + j] = sum over the pixels p of `plain`  plain[p][m] * shifted[p * stride + tap][j]
+ * with c2_rows = round_up(shifted.c, 64).  Both operands are NHWC 16-bit activation buffers (same format: fp16 or
+ * bf16) with channel pitches that are multiples of 64; tap offsets are relative to the interior origin of `shifted`
+ * (negative / overhanging positions read its materialised border or zeros outside the buffer).
+ * conv2d: plain = dL/dy (m = cout), shifted = layer input, tap = (ky - pad_t, kx - pad_l);
+ * conv_transpose2d: plain = layer input (m = cin), shifted = dL/dy, tap = (ky - pad, kx - pad). */
+typedef struct hfc_wgrad_desc {
+  hfc_act_geom plain;
+  hfc_act_geom shifted;
+  int32_t ntaps;
+  int32_t stride;      /* sampling stride in `shifted` (1 or 2) */
+  int32_t bf16;        /* operand format: 0 fp16, 1 bf16 */
+  int32_t k_splits;    /* 0 = auto; > 1 splits the pixels across CTAs (fp32 atomics into c, which is zeroed first) */
+  int8_t tap_dh[64];
+  int8_t tap_dw[64];
+} hfc_wgrad_desc;
+int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void* shifted, float* c, int32_t ldc, void* stream);
+/* fp16 -> bf16 copy of an activation buffer (count 16-bit elements, multiple of 8) */
+int hfc_act_to_bf16(const void* src_f16, void* dst_bf16, int64_t count, void* stream);
 /* out[c] += scale * sum over rows of rows[.][c]   (bias gradient) */
 int hfc_col_sums(const float* rows, int32_t ld, int64_t npix, int32_t c, float scale, float* out, void* stream);
 /* adjoint of the materialised padding: gradient over the padded domain (fp32 rows of an n x hq x wq grid, pitch

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--gan", action="store_true")
     ap.add_argument("--out", default="gpurun_out/train_profile.txt")
+    ap.add_argument("--detail", default="", help="comma-separated kernel-name substrings: list every launch (in order) with its duration")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     cfg = hific_args() if args.gan else mse_lpips_args()
@@ -66,11 +67,20 @@ def main():
             t, n = agg.get(k, (0.0, 0))
             agg[k] = (t + ev.device_time_total if hasattr(ev, "device_time_total") else t + ev.cuda_time_total, n + 1)
     tot = sum(t for t, _ in agg.values())
+    detail = []
+    if args.detail:
+        pats = args.detail.split(",")
+        evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and any(q in ev.name for q in pats)]
+        evs.sort(key=lambda ev: ev.time_range.start)
+        for ev in evs:
+            detail.append(f"    {ev.device_time_total:9.1f} us  {ev.name[:60]}")
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         f.write(f"# step {step_ms:.2f} ms wall (CUDA events, 3 steps); sum of kernel times {tot/1e3:.2f} ms; batch {args.batch}\n")
         for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             f.write(f"{t/1e3:9.3f} ms {n:5d}x {100*t/tot:5.1f}%  {k}\n")
+        if detail:
+            f.write("# per-launch detail (launch order)\n" + "\n".join(detail) + "\n")
     print(open(args.out).read()[:6000])
 
 
