@@ -166,14 +166,15 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
     (rate + distortion + LPIPS), backward through the hand-written kernels, gradient all-reduce over NCCL when
     world > 1 (coalesced, after backward), Adam on the amortization and the hyper-latent parameter groups."""
     from hific_b200.config import ModelModes
+    from hific_b200.optim import Adam
     B = args.train_batch or args.batch
     model.enable_cuda_graph(False)
     model.model_mode = ModelModes.TRAINING
     model.train()
     amort = [p for m in model.amortization_models for p in m.parameters()]
     hyper = list(model.Hyperprior.hyperlatent_likelihood.parameters())
-    opt_a = torch.optim.Adam(amort, lr=1e-4)
-    opt_h = torch.optim.Adam(hyper, lr=1e-4)
+    opt_a = Adam(amort, lr=1e-4)
+    opt_h = Adam(hyper, lr=1e-4)
     x = x_host[:B].to(dev)
     params = amort + hyper
 
@@ -203,7 +204,7 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         model.eval()
     return {"ms_per_step": ms / steps, "images_per_s": world * B * steps / (ms * 1e-3), "steps": steps,
             "per_gpu_batch": B, "n_gpus": world,
-            "what": "compression model (no GAN): fwd + rate/distortion/LPIPS losses + bwd + 2x Adam; bf16 backward GEMMs; "
+            "what": "compression model (no GAN): fwd + rate/distortion/LPIPS losses + bwd + 2x Adam (hific_b200.optim.Adam, one launch each); bf16 backward GEMMs; "
                     "LPIPS AlexNet trunk on cuDNN; gradient all-reduce (NCCL, coalesced after backward) when n_gpus > 1"}
 
 
@@ -215,6 +216,7 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
     from hific_b200 import synth
     from hific_b200.config import ModelModes, ModelTypes, hific_args
     from hific_b200.model import Model
+    from hific_b200.optim import Adam
     B = args.gan_batch or args.train_batch or args.batch
     cfg = hific_args()
     cfg.batch_size = B
@@ -224,7 +226,7 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
     amort = [p for m in model.amortization_models for p in m.parameters()]
     hyper = list(model.Hyperprior.hyperlatent_likelihood.parameters())
     disc = list(model.Discriminator.parameters())
-    opt_a, opt_h, opt_d = (torch.optim.Adam(g, lr=1e-4) for g in (amort, hyper, disc))
+    opt_a, opt_h, opt_d = (Adam(g, lr=1e-4) for g in (amort, hyper, disc))
     x = x_host[:B].to(dev)
 
     def allreduce(params):

@@ -41,6 +41,32 @@ rows_to_act_kernel(const float* __restrict__ rows, int ld, int c, int cpad, long
   }
 }
 
+// same, into the interior of a bordered buffer (the border is left alone: the caller zeroes it once)
+struct RowsGeomParams { int32_t n, h, w, c, cpad, pt, pl, pb, pr, ld, to_bf16; };
+__global__ void __launch_bounds__(256)
+rows_to_act_geom_kernel(const float* __restrict__ rows, uint16_t* __restrict__ out, const __grid_constant__ RowsGeomParams p) {
+  const long long groups = static_cast<long long>(p.n) * p.h * p.w * (p.cpad / 8);
+  const int Hp = p.h + p.pt + p.pb, Wp = p.w + p.pl + p.pr;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < groups;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / (p.cpad / 8);
+    const int g = static_cast<int>(i % (p.cpad / 8));
+    const int ww = static_cast<int>(pix % p.w);
+    const int hh = static_cast<int>((pix / p.w) % p.h);
+    const int nn = static_cast<int>(pix / (static_cast<long long>(p.w) * p.h));
+    uint16_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      const float f = ch < p.c ? rows[pix * p.ld + ch] : 0.f;
+      if (p.to_bf16) v[j] = f32_to_bf16_bits(f);
+      else { __half h = __float2half_rn(f); v[j] = *reinterpret_cast<uint16_t*>(&h); }
+    }
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(nn) * Hp + hh + p.pt) * Wp + ww + p.pl) * p.cpad + g * 8) =
+        *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Transposed im2col:  out[(tap * c_rows + ch)][p] = src[n, gh*S + dh[tap] + oh0, gw*S + dw[tap] + ow0, ch]
 // for p = (n, gh, gw) over the pixel grid, 0 outside the physical source buffer / beyond P.
@@ -226,6 +252,22 @@ extern "C" int hfc_rows_to_act(const float* rows, int32_t ld, int64_t npix, int3
   rows_to_act_kernel<<<grid_for(npix * (cpad / 8), sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       rows, ld, c, cpad, npix, to_bf16, reinterpret_cast<uint16_t*>(out));
   HFC_CHECK_LAUNCH("rows_to_act launch");
+  return HFC_OK;
+}
+
+extern "C" int hfc_rows_to_act_geom(const float* rows, int32_t ld, const hfc_act_geom* g, int32_t to_bf16, void* out,
+                                    void* stream) {
+  if (!rows || !g || !out || g->n <= 0 || g->h <= 0 || g->w <= 0 || g->c <= 0 || g->cpad % 8 != 0 || g->cpad < g->c || ld < g->c)
+    return set_error(HFC_ERR_INVALID, "rows_to_act_geom: bad arguments");
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc != HFC_OK) return rc;
+  RowsGeomParams p;
+  p.n = g->n; p.h = g->h; p.w = g->w; p.c = g->c; p.cpad = g->cpad; p.pt = g->pt; p.pl = g->pl; p.pb = g->pb; p.pr = g->pr;
+  p.ld = ld; p.to_bf16 = to_bf16;
+  rows_to_act_geom_kernel<<<grid_for(static_cast<long long>(g->n) * g->h * g->w * (g->cpad / 8), sms), 256, 0,
+                            static_cast<cudaStream_t>(stream)>>>(rows, reinterpret_cast<uint16_t*>(out), p);
+  HFC_CHECK_LAUNCH("rows_to_act_geom launch");
   return HFC_OK;
 }
 

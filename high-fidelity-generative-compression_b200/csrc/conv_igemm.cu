@@ -43,7 +43,8 @@ static constexpr int kTapnLd = 33;                       // padded row pitch (fl
 static constexpr int kTapnBytes = 2 * kBlockM * kTapnLd * 4;  // double-buffered [128][33] fp32
 
 struct ConvKernelParams {
-  int32_t tw, th, tn;                 // tile extents, tw*th*tn == 128
+  int32_t tw, th, tn;                 // tile extents, tw*th*tn <= 128 (rows past the product are idle)
+  int32_t tx_short;                   // bytes of the 16 KB A tile that the (smaller) TMA box does not deliver
   int32_t tiles_w, tiles_h, tiles_n;  // M tiles per dimension
   int32_t n_tiles;                    // N tiles
   int32_t block_n;
@@ -224,7 +225,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint8_t* sb = sa + kABytes;
           if constexpr (kPair) {
             // both CTAs of the pair fill their own stage; all bytes are accounted on the LEADER's barrier
-            if (m_idx == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+            if (m_idx == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * (stage_bytes - p.tx_short)));
             if (p.cn > 1)
               tma_load_4d_pair_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], chunk * kBlockK,
                                   w_base + p.tap_dw[tap], h_base + p.tap_dh[tap], n_base, mask_a);
@@ -236,7 +237,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (++s == p.stages) { s = 0; ph ^= 1; }
             continue;
           }
-          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
+          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes - p.tx_short));
           if (csize > 1) {
             tma_load_4d_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], chunk * kBlockK,
                            w_base + p.tap_dw[tap], h_base + p.tap_dh[tap], n_base, mask_a);
@@ -365,7 +366,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n = tni * p.tn + tni_in;
       const int oh = gh * p.osh + p.ooh;
       const int ow = gw * p.osw + p.oow;
-      const bool valid = (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
+      const bool valid = (tni_in < p.tn) && (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
                          (ow < p.out_w) && (nt < p.n_tiles) && (!p.tapn || m < p.w_step);
       const int c_base = nt * p.block_n;
       const bool last_nt = (nt == p.n_tiles - 1);
@@ -666,6 +667,55 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
   }
 }
 
+// Fast path for the plain layouts (no window / tap-in-N): one block per packed row.  The row's source values are read
+// with consecutive threads on consecutive addresses (the whole [cin][kh*kw] slab of a conv2d filter, or kh*kw-float
+// runs of a conv_transpose2d / dgrad filter), converted, transposed through shared memory and written as one
+// contiguous K-major row.  The generic kernel above issues one 32 B sector request per ELEMENT (the gather stride is
+// kh*kw floats), which made weight packing 1.8 ms of the training step.
+struct PackRowParams {
+  int32_t rows_real, cin, kh, kw, cin_pad, ntaps, ktot;
+  int32_t strided, flip;     // strided: source is W[c][row][ky][kx] (conv_transpose2d / dgrad), else W[row][c][ky][kx]
+  uint32_t fmt;
+  int8_t ky[kMaxTaps];
+  int8_t kx[kMaxTaps];
+};
+
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ w, const float* __restrict__ scale, uint16_t* __restrict__ out,
+                 const __grid_constant__ PackRowParams pp) {
+  extern __shared__ uint16_t s_pack[];               // [cin][T], T odd: conflict-free transposed reads
+  const float mul = scale ? *scale : 1.f;
+  const int r = blockIdx.x;
+  const int khkw = pp.kh * pp.kw;
+  const int T = khkw | 1;
+  const bool real = r < pp.rows_real;
+  if (real) {
+    const int total = pp.cin * khkw;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int c = e / khkw, t = e - c * khkw;
+      const size_t src = pp.strided ? (static_cast<size_t>(c) * pp.rows_real + r) * khkw + t
+                                    : static_cast<size_t>(r) * total + e;
+      const float val = w[src] * mul;
+      uint16_t bits;
+      if (pp.fmt == 0) { __half h = __float2half_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
+      else { __nv_bfloat16 h = __float2bfloat16_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
+      s_pack[c * T + t] = bits;
+    }
+  }
+  __syncthreads();
+  uint16_t* orow = out + static_cast<size_t>(r) * pp.ktot;
+  for (int e = threadIdx.x; e < pp.ktot; e += blockDim.x) {
+    const int tap = e / pp.cin_pad, c = e - tap * pp.cin_pad;
+    uint16_t bits = 0;
+    if (real && c < pp.cin) {
+      int ky = pp.ky[tap], kx = pp.kx[tap];
+      if (pp.flip) { ky = pp.kh - 1 - ky; kx = pp.kw - 1 - kx; }
+      bits = s_pack[c * T + ky * pp.kw + kx];
+    }
+    orow[e] = bits;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host-side planning
 // ------------------------------------------------------------------------------------------------
@@ -837,6 +887,35 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   kp->tw = std::min(16, next_pow2(ph.grid_w));
   kp->th = std::min(kBlockM / kp->tw, next_pow2(ph.grid_h));
   kp->tn = kBlockM / (kp->tw * kp->th);
+  // Grids that the power-of-two tile covers badly (e.g. the 18x18 padded domain of a 3x3 data gradient: 6 tiles of
+  // 16x8 per image, most of them nearly empty) get the free-form tile with the fewest tiles: tw*th*tn <= 128, the
+  // TMA box simply delivers fewer rows and the idle accumulator rows are masked in the epilogue.
+  kp->tx_short = 0;
+  bool free_tile = false;
+  {
+    auto count = [&](int tw, int th, int tn) {
+      return static_cast<long long>((ph.grid_w + tw - 1) / tw) * ((ph.grid_h + th - 1) / th) * ((batch + tn - 1) / tn);
+    };
+    const long long legacy = count(kp->tw, kp->th, kp->tn);
+    long long best = legacy;
+    int bw_ = kp->tw, bh_ = kp->th, bn_ = kp->tn;
+    static const bool env_no_free = getenv("HFC_NO_FREE_TILE") != nullptr;
+    for (int tw = std::min(ph.grid_w, kBlockM); tw >= 8 && !env_no_free; --tw) {
+      if (tw * ph.sw > 256) continue;
+      for (int th = std::min(ph.grid_h, kBlockM / tw); th >= 1; --th) {
+        if (th * ph.sh > 256) continue;
+        const int tn = std::max(1, std::min(batch, kBlockM / (tw * th)));
+        const long long c = count(tw, th, tn);
+        // accept only a clear win (>= 20 % fewer tiles): the power-of-two tiles have the better store pattern
+        if (c * 5 <= legacy * 4 && c < best) { best = c; bw_ = tw; bh_ = th; bn_ = tn; }
+      }
+    }
+    if (best < legacy) {
+      kp->tw = bw_; kp->th = bh_; kp->tn = bn_;
+      kp->tx_short = (kBlockM - bw_ * bh_ * bn_) * kBlockK * 2;
+      free_tile = true;
+    }
+  }
   // 'wide' mode (few output channels, big maps, e.g. the 7x7 60->3 head): a tile is 128 consecutive
   // pixels of one row; per filter ROW one halo row of 128+kw-1 pixels is fetched and the kw filter
   // columns are served from it by shifting the UMMA descriptor; all weights stay resident in smem.
@@ -857,6 +936,8 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   if (pl.tapn) kp->wide = 0;
   if (kp->wide || pl.tapn) {
     kp->tw = kBlockM; kp->th = 1; kp->tn = 1;
+    kp->tx_short = 0;
+    free_tile = false;
   }
   kp->tiles_w = pl.tapn ? (ph.grid_w + (kBlockM - d->kw + 1) - 1) / (kBlockM - d->kw + 1)
                         : (ph.grid_w + kp->tw - 1) / kp->tw;
@@ -885,6 +966,7 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   }
   if (cm < 1 || cm > 2 || cn < 1 || cn > 2) return -1;
   if (kp->wide || pl.tapn) cm = cn = 1;
+  if (free_tile) cn = 1;                 // the multicast A slices assume a full 128-row tile
   if ((pl.block_n / cm) % 8 != 0 || pl.block_n % cm != 0) cm = 1;
   kp->a_split_n = 0;
   if (cn > 1) {
@@ -990,6 +1072,22 @@ static int pack_weights_impl(const hfc_conv_desc* d, const float* w, const float
     if (pl.tapn) pp.cout = d->kw * d->cout;   // GEMM rows = (filter column, output channel)
     memcpy(pp.ky, ph.ky, sizeof(pp.ky));
     memcpy(pp.kx, ph.kx, sizeof(pp.kx));
+    const size_t row_smem = static_cast<size_t>(d->in.c) * ((d->kh * d->kw) | 1) * 2;
+    if (!d->window && !pl.tapn && row_smem <= 48 * 1024) {
+      PackRowParams pr;
+      memset(&pr, 0, sizeof(pr));
+      pr.rows_real = d->cout; pr.cin = d->in.c; pr.kh = d->kh; pr.kw = d->kw; pr.cin_pad = d->in.cpad;
+      pr.ntaps = ph.ntaps; pr.ktot = ph.ktot;
+      pr.strided = (d->dgrad || d->transposed) ? 1 : 0;
+      pr.flip = d->dgrad ? 1 : 0;
+      pr.fmt = d->b_bf16 ? 1u : 0u;
+      memcpy(pr.ky, ph.ky, sizeof(pr.ky));
+      memcpy(pr.kx, ph.kx, sizeof(pr.kx));
+      pack_rows_kernel<<<pl.rows, 256, row_smem, st>>>(w, scale, reinterpret_cast<uint16_t*>(packed) + ph.w_offset, pr);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "pack_rows launch: %s", cudaGetErrorString(e));
+      continue;
+    }
     const size_t total = static_cast<size_t>(pl.rows) * ph.ktot;
     const int threads = 256;
     const int blocks = static_cast<int>(std::min<size_t>((total + threads - 1) / threads, 148 * 16));

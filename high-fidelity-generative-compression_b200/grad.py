@@ -37,6 +37,15 @@ class Workspace:
             buf = cls._bufs[key] = torch.empty(int(numel), dtype=dtype, device=device)
         return buf[:numel]
 
+    @classmethod
+    def named(cls, key, shape, dtype, device, zero=False):
+        """A persistent buffer of its own (not shared between layers), optionally zero-initialised once."""
+        k = (key, dtype, device.type, device.index)
+        buf = cls._bufs.get(k)
+        if buf is None:
+            buf = cls._bufs[k] = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+        return buf
+
 
 def _i8(vals):
     return bytes((v + 256) % 256 for v in vals)
@@ -80,7 +89,19 @@ class ConvGrad:
         self.dy_geom = Geom(n, self.oh, self.ow, cout, round_up(cout, 64))
         cin4 = round_up(self.cin, 4)
         self.fold = None
-        if not transposed and stride == 1:
+        self.dy_window_geom = None
+        if not transposed and stride == 1 and cout <= 8 and kh <= 8 and kh > 1:
+            # tiny cout (the 7x7 60 -> 3 head): padding the 3 gradient channels to a 64-channel K block would waste
+            # 95 % of the MMA work, so dL/dy goes into an 8-channel-pitch buffer with a materialised ZERO border of
+            # k-1 pixels and the conv runs in "window" packing (K = 8 pixels x 8 channels per filter row), exactly
+            # like the forward 7x7 3 -> 60 encoder head.
+            hq, wq = h + pt + pb, w + pl + pr
+            b = kh - 1
+            self.dy_window_geom = Geom(n, self.oh, self.ow, cout, 8, b, b, b, b + 1)
+            self.dgrad = Conv(self.dy_window_geom, self.cin, kh, stride=1, pad_mode=PAD_REFLECT, pad=(b,) * 4, window=True,
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, b_bf16=True, dgrad=True)
+            self.fold = (hq, wq)
+        elif not transposed and stride == 1:
             hq, wq = h + pt + pb, w + pl + pr
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=1, pad_mode=PAD_ZERO, pad=(kh - 1,) * 4,
                               out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, b_bf16=True, dgrad=True)
@@ -129,7 +150,15 @@ class ConvGrad:
         multiplied into the weights while packing (1/sigma of a spectrally normalised layer)."""
         sk = dict(scale=scale, scale_key=object()) if scale is not None else {}
         dev = dy_rows.device
-        if dy_act is None:
+        if self.dy_window_geom is not None:
+            g = self.dy_window_geom
+            key = ("dy_window",) + g.shape
+            buf = Workspace.named(key, g.shape, torch.int16, dev, zero=True)     # border zeroed once, interior rewritten
+            gs = g.c_struct()
+            check(lib.hfc_rows_to_act_geom(_ptr(dy_rows), dy_rows.shape[-1], ctypes.byref(gs), 1, _ptr(buf), _stream()),
+                  "rows_to_act_geom")
+            dy_act = buf
+        elif dy_act is None:
             dy_act = self.dy_to_act(dy_rows)
         if self.fold is None:
             if out is None:

@@ -228,6 +228,8 @@ int hfc_gemm_nt(const void* a, int32_t a_bf16, const void* b, int32_t b_bf16, in
 /* fp32 rows [npix][ld] -> border-less 16-bit act buffer [npix][cpad] (bf16 if to_bf16 else fp16), padding = 0 */
 int hfc_rows_to_act(const float* rows, int32_t ld, int64_t npix, int32_t c, int32_t cpad, int32_t to_bf16, void* out,
                     void* stream);
+/* same, into the INTERIOR of the bordered buffer described by g (the border is not written: zero it once) */
+int hfc_rows_to_act_geom(const float* rows, int32_t ld, const hfc_act_geom* g, int32_t to_bf16, void* out, void* stream);
 /* transposed im2col (see csrc/backward.cu): out[(tap*c_rows + ch)][p], p over the (n, gh, gw) pixel grid, source
  * coordinate (g*stride + d[tap] + o0) in a physical buffer of n x hp x wp pixels with cpad channels (pitch, for fp32
  * rows), zero outside; src_f32: 0 = 16-bit source copied verbatim, 1 = fp32 rows converted to bf16, 2 = fp16 act
@@ -240,6 +242,13 @@ int hfc_im2col_t(const void* src, int32_t src_f32, int32_t n, int32_t hp, int32_
 int hfc_permute_wgrad(const float* c, int32_t ldc, int32_t m, int32_t c2, int32_t c2_rows, int32_t kh, int32_t kw,
                       int32_t ntaps, const int8_t* ky_host, const int8_t* kx_host, float scale, int32_t accumulate,
                       float* dw, void* stream);
+/* torch.optim.Adam step (amsgrad = False) over a list of fp32 tensors in one launch (train.py:287-300, 54-59).
+ * table_dev: 5 x int64 per tensor {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel};
+ * blockmap_dev: 2 x int32 per block {tensor index, chunk index}, one block per hfc_adam_chunk() elements;
+ * step: the 1-based step count used for the bias corrections. */
+int32_t hfc_adam_chunk(void);
+int hfc_adam_multi(const int64_t* table_dev, const int32_t* blockmap_dev, int32_t n_blocks, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int64_t step, void* stream);
 /* Implicit weight gradient (autograd of F.conv2d / F.conv_transpose2d w.r.t. the weight, train.py:49-59):
  *   c[m][tap * c2_rows + j] = sum over the pixels p of `plain`  plain[p][m] * shifted[p * stride + tap][j]
  * with c2_rows = round_up(shifted.c, 64).  Both operands are NHWC 16-bit activation buffers (same format: fp16 or

@@ -328,3 +328,27 @@ def test_hyperlatent_likelihood():
     rn, rq = loglik_sum(z + noise), loglik_sum(torch.floor(z + 0.5))
     assert abs(sums[0].item() - rn.item()) / abs(rn.item()) < 2e-5
     assert abs(sums[1].item() - rq.item()) / abs(rq.item()) < 2e-5
+
+
+def test_adam_matches_torch():
+    """hific_b200.optim.Adam (one launch per step) against torch.optim.Adam over several steps, odd sizes included."""
+    from hific_b200.optim import Adam
+    g = torch.Generator().manual_seed(5)
+    shapes = [(960, 960, 3, 3), (7,), (1, 60, 1, 1), (33, 5), (8192 * 3 + 1,)]
+    ours = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    for wd in (0.0, 0.01):
+        oa, ob = Adam(ours, lr=1e-3, weight_decay=wd), torch.optim.Adam(ref, lr=1e-3, weight_decay=wd)
+        for step in range(4):
+            for p, q in zip(ours, ref):
+                grad = torch.randn(p.shape, generator=g).to(DEV) * (10.0 ** (step - 2))
+                p.grad, q.grad = grad.clone(), grad.clone()
+            if step == 2:
+                ours[1].grad = ref[1].grad = None          # parameters without a gradient are skipped
+            l0 = ops.launch_count()
+            oa.step(); ob.step()
+            assert ops.launch_count() - l0 == (2 if step == 3 else 1)   # one launch per distinct step count
+        for p, q in zip(ours, ref):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+        sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
+        assert torch.allclose(sa[0]["exp_avg_sq"], sb[0]["exp_avg_sq"], rtol=1e-5, atol=1e-12)

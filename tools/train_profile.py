@@ -15,6 +15,7 @@ import hific_b200  # noqa: E402,F401
 from hific_b200 import synth  # noqa: E402
 from hific_b200.config import ModelModes, ModelTypes, mse_lpips_args, hific_args  # noqa: E402
 from hific_b200.model import Model  # noqa: E402
+from hific_b200.optim import Adam  # noqa: E402
 
 
 def main():
@@ -35,8 +36,8 @@ def main():
     model.to(dev).train()
     amort = [p for m in model.amortization_models for p in m.parameters()]
     hyper = list(model.Hyperprior.hyperlatent_likelihood.parameters())
-    opt_a = torch.optim.Adam(amort, lr=1e-4)
-    opt_h = torch.optim.Adam(hyper, lr=1e-4)
+    opt_a = Adam(amort, lr=1e-4)
+    opt_h = Adam(hyper, lr=1e-4)
     x = synth.synth_image(args.batch, 256, 256, 1).to(dev)
 
     def step():
