@@ -44,6 +44,7 @@ class WgradDesc(ctypes.Structure):
     _fields_ = [
         ("plain", ActGeom), ("shifted", ActGeom),
         ("ntaps", ctypes.c_int32), ("stride", ctypes.c_int32), ("bf16", ctypes.c_int32), ("k_splits", ctypes.c_int32),
+        ("window", ctypes.c_int32),
         ("tap_dh", ctypes.c_int8 * 64), ("tap_dw", ctypes.c_int8 * 64),
     ]
 
@@ -89,11 +90,13 @@ SIGNATURES = {
                                          _f32, _i32, _vp, _vp]),
     "hfc_col_sums": (ctypes.c_int, [_vp, _i32, _i64, _i32, _f32, _vp, _vp]),
     "hfc_pad_fold": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _i32, _vp]),
-    "hfc_channelnorm_bwd": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _f32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "hfc_channelnorm_bwd": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _f32, _i32, _vp, _i32, _vp, _vp, _vp, _vp,
+                                          _i32, _vp]),
     "hfc_relu_mask": (ctypes.c_int, [_vp, _i32, _vp, ctypes.POINTER(ActGeom), _f32, _vp, _i32, _vp]),
     "hfc_rows_to_act_geom": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _vp]),
     "hfc_adam_chunk": (ctypes.c_int32, []),
-    "hfc_adam_multi": (ctypes.c_int, [_vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _i64, _vp]),
+    "hfc_adam_multi": (ctypes.c_int, [_vp, _vp, _i32, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_double, _i64, _vp]),
     "hfc_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradDesc), _vp, _vp, _vp, _i32, _vp]),
     "hfc_act_to_bf16": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "hfc_disc_input_bwd": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),

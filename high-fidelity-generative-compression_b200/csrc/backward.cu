@@ -167,17 +167,28 @@ struct PermuteParams {
   int8_t ky[64], kx[64];
 };
 
+// One block per GEMM row m: the row C[m][ntaps * c2_rows] is read with consecutive threads on consecutive addresses,
+// transposed through shared memory and written as the contiguous torch slab dW[m][:][:][:] (c2 * kh * kw floats).
+// (A thread-per-output-element gather reads with a stride of c2_rows floats: one 32 B sector per element.)
 __global__ void __launch_bounds__(256)
 permute_wgrad_kernel(const float* __restrict__ c, float* __restrict__ dw, const __grid_constant__ PermuteParams p) {
-  const long long total = static_cast<long long>(p.m) * p.c2 * p.ntaps;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int tap = static_cast<int>(i % p.ntaps);
-    const int c2 = static_cast<int>((i / p.ntaps) % p.c2);
-    const int m = static_cast<int>(i / (static_cast<long long>(p.ntaps) * p.c2));
-    const float v = c[static_cast<size_t>(m) * p.ldc + tap * p.c2_rows + c2] * p.scale;
-    float* dst = dw + ((static_cast<size_t>(m) * p.c2 + c2) * p.kh + p.ky[tap]) * p.kw + p.kx[tap];
-    *dst = p.accumulate ? *dst + v : v;
+  extern __shared__ float s_row[];                 // [c2][T], T = kh*kw | 1
+  const int m = blockIdx.x;
+  const int khkw = p.kh * p.kw;
+  const int T = khkw | 1;
+  const float* crow = c + static_cast<size_t>(m) * p.ldc;
+  for (int tap = 0; tap < p.ntaps; ++tap) {
+    if (p.ky[tap] < 0) continue;                   // unused column slot (window packing: 8 slots per filter row)
+    const int t = p.ky[tap] * p.kw + p.kx[tap];
+    for (int c2 = threadIdx.x; c2 < p.c2; c2 += blockDim.x) s_row[c2 * T + t] = crow[tap * p.c2_rows + c2];
+  }
+  __syncthreads();
+  float* drow = dw + static_cast<size_t>(m) * p.c2 * khkw;
+  const int total = p.c2 * khkw;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c2 = e / khkw, t = e - c2 * khkw;
+    const float v = s_row[c2 * T + t] * p.scale;
+    drow[e] = p.accumulate ? drow[e] + v : v;
   }
 }
 
@@ -311,7 +322,14 @@ extern "C" int hfc_permute_wgrad(const float* c, int32_t ldc, int32_t m, int32_t
   p.scale = scale;
   memset(p.ky, 0, sizeof(p.ky)); memset(p.kx, 0, sizeof(p.kx));
   memcpy(p.ky, ky_host, ntaps); memcpy(p.kx, kx_host, ntaps);
-  permute_wgrad_kernel<<<grid_for(static_cast<long long>(m) * c2 * ntaps, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(c, dw, p);
+  const size_t smem = static_cast<size_t>(c2) * ((kh * kw) | 1) * sizeof(float);
+  if (smem > 96 * 1024) return set_error(HFC_ERR_UNSUPPORTED, "permute_wgrad: c2 * kh * kw too large for the row buffer");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(permute_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  permute_wgrad_kernel<<<m, 256, smem, static_cast<cudaStream_t>(stream)>>>(c, dw, p);
   HFC_CHECK_LAUNCH("permute_wgrad launch");
   return HFC_OK;
 }

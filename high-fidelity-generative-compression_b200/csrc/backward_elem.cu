@@ -9,6 +9,7 @@
 #include "hfc_device_utils.cuh"
 
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 
 namespace hfc {
 
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(256, MINB)
 channelnorm_bwd_kernel(const float* __restrict__ z, int ld_z, const float* __restrict__ g, int ld_g,
                        const float* __restrict__ gamma, const float* __restrict__ beta, int c, long long npix,
                        float eps, int act, float* __restrict__ dz, int ld_dz, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, float* __restrict__ dbias) {
+                       float* __restrict__ dbeta, float* __restrict__ dbias, uint16_t* __restrict__ dz_act, int act_cpad) {
   constexpr int kPix = 32 / GROUP;
   constexpr int kCap = GROUP * VEC * 4;
   __shared__ float s_acc[3][kCap];
@@ -128,8 +129,17 @@ channelnorm_bwd_kernel(const float* __restrict__ z, int ld_z, const float* __res
         float4 o;
         o.x = r * (gg[i].x - s1 - v[i].x * s2); o.y = r * (gg[i].y - s1 - v[i].y * s2);
         o.z = r * (gg[i].z - s1 - v[i].z * s2); o.w = r * (gg[i].w - s1 - v[i].w * s2);
-        *reinterpret_cast<float4*>(dr + ch) = o;
+        if (dz) *reinterpret_cast<float4*>(dr + ch) = o;
+        if (dz_act) {     // bf16 copy in the operand layout of the backward GEMMs (border-less NHWC, pitch act_cpad)
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(dz_act + pix * act_cpad + ch) = pk;
+        }
         ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
+      } else if (live && dz_act && ch < act_cpad) {
+        *reinterpret_cast<uint2*>(dz_act + pix * act_cpad + ch) = make_uint2(0u, 0u);   // channel padding
       }
     }
   }
@@ -157,12 +167,13 @@ channelnorm_bwd_kernel(const float* __restrict__ z, int ld_z, const float* __res
 template <int VEC, int GROUP, int MINB>
 static void launch_channelnorm_bwd(const float* z, int ld_z, const float* g, int ld_g, const float* gamma,
                                    const float* beta, int c, long long npix, float eps, int act, float* dz, int ld_dz,
-                                   float* dgamma, float* dbeta, float* dbias, int sms, cudaStream_t st) {
+                                   float* dgamma, float* dbeta, float* dbias, uint16_t* dz_act, int act_cpad, int sms,
+                                   cudaStream_t st) {
   const long long per_block = 8LL * (32 / GROUP);
   const long long blocks = std::max<long long>(1, std::min<long long>((npix + per_block - 1) / per_block,
                                                                        static_cast<long long>(sms) * MINB));
   channelnorm_bwd_kernel<VEC, GROUP, MINB><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, dbeta, dbias);
+      z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, dbeta, dbias, dz_act, act_cpad);
 }
 
 // g_out[p][c] = g[p][c] * (y_act[p][c] > 0)   (y_act: bordered NHWC fp16 output of a bias+ReLU conv)
@@ -412,9 +423,13 @@ using namespace hfc;
 
 extern "C" int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld_g, const float* gamma,
                                    const float* beta, int32_t c, int64_t npix, float eps, int32_t act, float* dz,
-                                   int32_t ld_dz, float* dgamma, float* dbeta, float* dbias, void* stream) {
-  if (!z || !g || !gamma || !beta || !dz || !dgamma || !dbeta || npix <= 0)
+                                   int32_t ld_dz, float* dgamma, float* dbeta, float* dbias, void* dz_act,
+                                   int32_t act_cpad, void* stream) {
+  if (!z || !g || !gamma || !beta || (!dz && !dz_act) || !dgamma || !dbeta || npix <= 0)
     return set_error(HFC_ERR_INVALID, "channelnorm_bwd: null pointer or empty input");
+  if (dz_act && (act_cpad % 4 != 0 || act_cpad < c || act_cpad > kCnbVec * 128))
+    return set_error(HFC_ERR_INVALID, "channelnorm_bwd: act_cpad (%d) must be a multiple of 4 in [c, %d]", act_cpad, kCnbVec * 128);
+  const int width = dz_act ? std::max(c, act_cpad) : c;     // the lanes past c zero the operand's channel padding
   if (c % 4 != 0 || c < 4 || c > kCnbVec * 128 || ld_z % 4 != 0 || ld_g % 4 != 0 || ld_dz % 4 != 0)
     return set_error(HFC_ERR_INVALID, "channelnorm_bwd: needs c %% 4 == 0, c <= %d and pitches %% 4 == 0", kCnbVec * 128);
   if (act != HFC_ACT_NONE && act != HFC_ACT_RELU) return set_error(HFC_ERR_INVALID, "channelnorm_bwd: act must be none or relu");
@@ -423,12 +438,12 @@ extern "C" int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g,
   if (rc != HFC_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define HFC_CNB(V, G, B) launch_channelnorm_bwd<V, G, B>(z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, \
-                                                        dbeta, dbias, sms, st)
-  if (c <= 32) HFC_CNB(1, 8, 4);
-  else if (c <= 64) HFC_CNB(1, 16, 4);
-  else if (c <= 128) HFC_CNB(1, 32, 4);
-  else if (c <= 256) HFC_CNB(2, 32, 3);
-  else if (c <= 512) HFC_CNB(4, 32, 2);
+                                                        dbeta, dbias, reinterpret_cast<uint16_t*>(dz_act), act_cpad, sms, st)
+  if (width <= 32) HFC_CNB(1, 8, 4);
+  else if (width <= 64) HFC_CNB(1, 16, 4);
+  else if (width <= 128) HFC_CNB(1, 32, 4);
+  else if (width <= 256) HFC_CNB(2, 32, 3);
+  else if (width <= 512) HFC_CNB(4, 32, 2);
   else HFC_CNB(8, 32, 1);
 #undef HFC_CNB
   HFC_CHECK_LAUNCH("channelnorm_bwd launch");

@@ -680,22 +680,24 @@ struct PackRowParams {
   int8_t kx[kMaxTaps];
 };
 
+// KHKW: kh*kw as a compile-time constant (the index split is then a multiply-shift), 0 = runtime value
+template <int KHKW>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ w, const float* __restrict__ scale, uint16_t* __restrict__ out,
                  const __grid_constant__ PackRowParams pp) {
   extern __shared__ uint16_t s_pack[];               // [cin][T], T odd: conflict-free transposed reads
   const float mul = scale ? *scale : 1.f;
   const int r = blockIdx.x;
-  const int khkw = pp.kh * pp.kw;
+  const int khkw = KHKW ? KHKW : pp.kh * pp.kw;
   const int T = khkw | 1;
   const bool real = r < pp.rows_real;
   if (real) {
     const int total = pp.cin * khkw;
+    const float* src_row = w + static_cast<size_t>(r) * (pp.strided ? khkw : total);
+    const size_t c_stride = pp.strided ? static_cast<size_t>(pp.rows_real) * khkw : static_cast<size_t>(khkw);
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
       const int c = e / khkw, t = e - c * khkw;
-      const size_t src = pp.strided ? (static_cast<size_t>(c) * pp.rows_real + r) * khkw + t
-                                    : static_cast<size_t>(r) * total + e;
-      const float val = w[src] * mul;
+      const float val = src_row[c * c_stride + t] * mul;
       uint16_t bits;
       if (pp.fmt == 0) { __half h = __float2half_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
       else { __nv_bfloat16 h = __float2bfloat16_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
@@ -703,16 +705,18 @@ pack_rows_kernel(const float* __restrict__ w, const float* __restrict__ scale, u
     }
   }
   __syncthreads();
-  uint16_t* orow = out + static_cast<size_t>(r) * pp.ktot;
-  for (int e = threadIdx.x; e < pp.ktot; e += blockDim.x) {
-    const int tap = e / pp.cin_pad, c = e - tap * pp.cin_pad;
-    uint16_t bits = 0;
-    if (real && c < pp.cin) {
-      int ky = pp.ky[tap], kx = pp.kx[tap];
-      if (pp.flip) { ky = pp.kh - 1 - ky; kx = pp.kw - 1 - kx; }
-      bits = s_pack[c * T + ky * pp.kw + kx];
+  uint32_t* orow = reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r) * pp.ktot);   // cin_pad is even: 2 channels / thread
+  const int half = pp.cin_pad >> 1;
+  for (int tap = 0; tap < pp.ntaps; ++tap) {
+    int ky = pp.ky[tap], kx = pp.kx[tap];
+    if (pp.flip) { ky = pp.kh - 1 - ky; kx = pp.kw - 1 - kx; }
+    const int t = ky * pp.kw + kx;
+    for (int c2 = threadIdx.x; c2 < half; c2 += blockDim.x) {
+      const int c = 2 * c2;
+      const uint32_t lo = (real && c < pp.cin) ? s_pack[c * T + t] : 0u;
+      const uint32_t hi = (real && c + 1 < pp.cin) ? s_pack[(c + 1) * T + t] : 0u;
+      orow[tap * half + c2] = lo | (hi << 16);
     }
-    orow[e] = bits;
   }
 }
 
@@ -1083,7 +1087,15 @@ static int pack_weights_impl(const hfc_conv_desc* d, const float* w, const float
       pr.fmt = d->b_bf16 ? 1u : 0u;
       memcpy(pr.ky, ph.ky, sizeof(pr.ky));
       memcpy(pr.kx, ph.kx, sizeof(pr.kx));
-      pack_rows_kernel<<<pl.rows, 256, row_smem, st>>>(w, scale, reinterpret_cast<uint16_t*>(packed) + ph.w_offset, pr);
+      uint16_t* dst = reinterpret_cast<uint16_t*>(packed) + ph.w_offset;
+      switch (d->kh * d->kw) {
+        case 1: pack_rows_kernel<1><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+        case 9: pack_rows_kernel<9><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+        case 16: pack_rows_kernel<16><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+        case 25: pack_rows_kernel<25><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+        case 49: pack_rows_kernel<49><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+        default: pack_rows_kernel<0><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+      }
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "pack_rows launch: %s", cudaGetErrorString(e));
       continue;

@@ -10,7 +10,7 @@ namespace hfc {
 static constexpr int kAdamChunk = 256 * 4 * 8;   // elements per block
 
 struct AdamHyper {
-  float lr_over_bc1, b1, b2, eps, inv_sqrt_bc2, weight_decay;
+  float lr_over_bc1, b1, b2, omb1, omb2, eps, inv_sqrt_bc2, weight_decay;   // omb = 1 - beta, rounded from double like torch
 };
 
 // table: 5 x int64 per tensor {p, g, m, v, numel}; blockmap: 2 x int32 per block {tensor, chunk}
@@ -28,8 +28,8 @@ adam_multi_kernel(const long long* __restrict__ table, const int* __restrict__ b
                      reinterpret_cast<uintptr_t>(v)) & 15) == 0;
   auto upd = [&](float& pw, float gw, float& mw, float& vw) {
     if (h.weight_decay != 0.f) gw = fmaf(h.weight_decay, pw, gw);
-    mw = fmaf(h.b1, mw, (1.f - h.b1) * gw);
-    vw = fmaf(h.b2, vw, (1.f - h.b2) * gw * gw);
+    mw = h.b1 * mw + h.omb1 * gw;              // torch: lerp / mul_ + addcmul_, each rounded separately
+    vw = h.b2 * vw + h.omb2 * gw * gw;
     pw -= h.lr_over_bc1 * mw / (sqrtf(vw) * h.inv_sqrt_bc2 + h.eps);
   };
   if (vec) {
@@ -52,17 +52,19 @@ using namespace hfc;
 
 extern "C" int32_t hfc_adam_chunk(void) { return kAdamChunk; }
 
-extern "C" int hfc_adam_multi(const int64_t* table_dev, const int32_t* blockmap_dev, int32_t n_blocks, float lr, float beta1,
-                              float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+extern "C" int hfc_adam_multi(const int64_t* table_dev, const int32_t* blockmap_dev, int32_t n_blocks, double lr, double beta1,
+                              double beta2, double eps, double weight_decay, int64_t step, void* stream) {
   if (!table_dev || !blockmap_dev || n_blocks <= 0 || step <= 0)
     return set_error(HFC_ERR_INVALID, "adam_multi: null pointer, no blocks or step < 1");
   AdamHyper h;
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   h.lr_over_bc1 = static_cast<float>(lr / bc1);
-  h.b1 = beta1; h.b2 = beta2; h.eps = eps;
+  h.b1 = static_cast<float>(beta1); h.b2 = static_cast<float>(beta2); h.eps = static_cast<float>(eps);
+  h.omb1 = static_cast<float>(1.0 - beta1);
+  h.omb2 = static_cast<float>(1.0 - beta2);
   h.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
-  h.weight_decay = weight_decay;
+  h.weight_decay = static_cast<float>(weight_decay);
   adam_multi_kernel<<<n_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(table_dev), blockmap_dev, h);
   cudaError_t e = cudaGetLastError();

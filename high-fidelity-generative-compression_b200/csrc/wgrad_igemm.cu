@@ -41,6 +41,7 @@ struct WgradParams {
   int32_t tiles_w, tiles_h, tiles_n;   // pixel tiles of the P grid
   int32_t num_kb;                      // tiles_w * tiles_h * tiles_n
   int32_t m_tiles, n_tiles, nch;       // nch = 64-channel chunks per N tile (1..4)
+  int32_t p_chunks;                    // P chunks fetched per stage (1 when P has <= 64 channels: the other half stays zero)
   int32_t ntaps, k_splits, kb_per_split;
   int32_t stages;
   int32_t stride;                      // S sampling stride
@@ -84,6 +85,15 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
     tmem_alloc(tmem_slot, kWgTmemCols);
     tmem_relinquish();
   }
+  if (p.p_chunks == 1) {
+    // P has <= 64 channels: rows 64..127 of the M = 128 tile are never fetched -- zero them once (generic-proxy
+    // stores, made visible to the tensor core's async proxy by the fence) instead of TMA zero-filling them per stage
+    for (int s = 0; s < p.stages; ++s) {
+      uint4* z = reinterpret_cast<uint4*>(smem + s * stage_bytes + kWgChunkBytes);
+      for (int i = threadIdx.x; i < kWgChunkBytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -112,8 +122,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
           const int gw = twi * p.bw, gh = thi * p.bh, gn = tni * p.bn;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));
-          for (int j = 0; j < 2; ++j)
+          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>((p.p_chunks + p.nch) * kWgChunkBytes));
+          for (int j = 0; j < p.p_chunks; ++j)
             tma_load_4d(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 2 + j) * 64, gw + p.p_w0, gh + p.p_h0, gn);
           uint8_t* sb = sa + 2 * kWgChunkBytes;
           const int sw0 = gw * p.stride + p.s_w0 + p.tap_dw[tap];
@@ -228,10 +238,12 @@ static int next_pow2_w(int v) {
 }
 
 static int encode_act_map(PFN_encodeTiledW encode, CUtensorMap* tm, const void* base, const hfc_act_geom& g, int bw, int bh,
-                          int bn, int stride) {
+                          int bn, int stride, bool window = false) {
   const int Hp = g.h + g.pt + g.pb, Wp = g.w + g.pl + g.pr;
-  cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.cpad), static_cast<cuuint64_t>(Wp), static_cast<cuuint64_t>(Hp),
-                        static_cast<cuuint64_t>(g.n)};
+  // window packing (8-channel pitch): "channel" dim = 64 elements = 8 consecutive pixels x 8 channels, pixel dim =
+  // window start; the overlapping 16 B stride makes every K row (pixel p) the 8-pixel window that starts at p
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(window ? 64 : g.cpad), static_cast<cuuint64_t>(window ? Wp - 7 : Wp),
+                        static_cast<cuuint64_t>(Hp), static_cast<cuuint64_t>(g.n)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(g.cpad) * 2, static_cast<cuuint64_t>(Wp) * g.cpad * 2,
                            static_cast<cuuint64_t>(Hp) * Wp * g.cpad * 2};
   cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw * stride), static_cast<cuuint32_t>(bh * stride), static_cast<cuuint32_t>(bn)};
@@ -253,8 +265,11 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
   const hfc_act_geom& sg = d->shifted;
   if (pg.n <= 0 || pg.h <= 0 || pg.w <= 0 || pg.c <= 0 || sg.c <= 0 || pg.n != sg.n)
     return set_error(HFC_ERR_INVALID, "wgrad: bad geometry");
-  if (pg.cpad % 64 != 0 || sg.cpad % 64 != 0 || pg.c > pg.cpad || sg.c > sg.cpad)
+  const bool window = d->window != 0;
+  if (pg.cpad % 64 != 0 || pg.c > pg.cpad || sg.c > sg.cpad || (!window && sg.cpad % 64 != 0))
     return set_error(HFC_ERR_INVALID, "wgrad: both operands need channel pitches that are multiples of 64");
+  if (window && (sg.cpad != 8 || d->stride != 1 || sg.w + sg.pl + sg.pr < 8))
+    return set_error(HFC_ERR_INVALID, "wgrad: window packing needs an 8-channel-pitch shifted operand, stride 1, width >= 8");
   if (d->ntaps <= 0 || d->ntaps > kWgMaxTaps) return set_error(HFC_ERR_INVALID, "wgrad: 1..64 taps");
   if (d->stride != 1 && d->stride != 2) return set_error(HFC_ERR_INVALID, "wgrad: stride must be 1 or 2");
   if (d->bf16 != 0 && d->bf16 != 1) return set_error(HFC_ERR_INVALID, "wgrad: bf16 must be 0 or 1");
@@ -278,7 +293,7 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
     return set_error(HFC_ERR_UNSUPPORTED, "wgrad: a bordered plain operand needs a grid that tiles exactly (%d x %d by %d x %d)",
                      pg.w, pg.h, kp.bw, kp.bh);
   kp.num_kb = kp.tiles_w * kp.tiles_h * kp.tiles_n;
-  const int m_chunks = (pg.c + 63) / 64, n_chunks = (sg.c + 63) / 64;
+  const int m_chunks = (pg.c + 63) / 64, n_chunks = window ? 1 : (sg.c + 63) / 64;
   kp.m_tiles = (m_chunks + 1) / 2;
   int best = 1;
   long long best_cost = -1;
@@ -293,11 +308,13 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
   if (ldc < d->ntaps * kp.c2_rows || ldc % 4 != 0)
     return set_error(HFC_ERR_INVALID, "wgrad: ldc (%d) must be a multiple of 4 and >= ntaps * round_up(c2, 64) = %d", ldc,
                      d->ntaps * kp.c2_rows);
+  kp.p_chunks = m_chunks == 1 ? 1 : 2;
   const int items = kp.m_tiles * kp.ntaps * kp.n_tiles;
   int ks = d->k_splits;
   if (ks <= 0) {
-    // enough items for ~2 waves, but keep >= 8 pixel blocks per item so the pipeline fill / epilogue amortise
-    ks = std::max(1, std::min((2 * sms + items - 1) / items, kp.num_kb / 8));
+    // fill (at most) two full waves of CTAs -- never a partial third one -- but keep >= 8 pixel blocks per item so
+    // that the pipeline fill and the epilogue amortise
+    ks = std::max(1, std::min((2 * sms) / items, kp.num_kb / 8));
   }
   ks = std::max(1, std::min(ks, kp.num_kb));
   kp.kb_per_split = (kp.num_kb + ks - 1) / ks;
@@ -316,7 +333,7 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
   CUtensorMap tmP, tmS;
   int er = encode_act_map(encode, &tmP, plain, pg, kp.bw, kp.bh, kp.bn, 1);
   if (er) return set_error(HFC_ERR_LAUNCH, "cuTensorMapEncodeTiled(P) failed: %d", er);
-  er = encode_act_map(encode, &tmS, shifted, sg, kp.bw, kp.bh, kp.bn, d->stride);
+  er = encode_act_map(encode, &tmS, shifted, sg, kp.bw, kp.bh, kp.bn, d->stride, window);
   if (er) return set_error(HFC_ERR_LAUNCH, "cuTensorMapEncodeTiled(S) failed: %d", er);
 
   if (kp.atomic) {

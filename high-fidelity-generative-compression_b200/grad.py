@@ -126,39 +126,61 @@ class ConvGrad:
         self.swap = (not transposed) and stride == 1 and cout <= 8
         # implicit weight gradient (csrc/wgrad_igemm.cu) for every layer whose operands are 64-channel-pitch NHWC
         # buffers; the 3-channel image layers (8-channel pitch input / tiny cout) keep the explicit transposed-im2col GEMM
-        self.implicit = (not self.swap) and in_geom.cpad % 64 == 0 and not os.environ.get("HFC_EXPLICIT_WGRAD")
-        if self.implicit:
-            d = _lib.WgradDesc()
-            pt, pl = pad[0], pad[1]
+        explicit = bool(os.environ.get("HFC_EXPLICIT_WGRAD"))
+        pt, pl = pad[0], pad[1]
+        k = kh
+        d = _lib.WgradDesc()
+        self.implicit = None
+        if explicit:
+            pass
+        elif (not self.swap) and in_geom.cpad % 64 == 0:
+            self.implicit = "plain"
             if transposed:       # P = x over the input pixels, S = dy sampled at i*s - p + k
                 d.plain, d.shifted = in_geom.c_struct(), self.dy_geom.c_struct()
-                offs = [(ky - pt, kx - pl) for ky, kx in self.taps]
                 self.wg_m, self.wg_c2 = self.cin, cout
             else:                # P = dy over the output pixels, S = x sampled at o*s + k - p (border-relative)
                 d.plain, d.shifted = self.dy_geom.c_struct(), in_geom.c_struct()
-                offs = [(ky - pt, kx - pl) for ky, kx in self.taps]
                 self.wg_m, self.wg_c2 = cout, self.cin
-            d.ntaps, d.stride, d.bf16, d.k_splits = len(self.taps), stride, 1, 0
+            offs = [(ky - pt, kx - pl) for ky, kx in self.taps]
+            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = len(self.taps), stride, 1, 0, 0
+            self.wg_c2_rows = round_up(self.wg_c2, 64)
+            self.wg_taps = self.taps
+        elif (not self.swap) and (not transposed) and stride == 1 and in_geom.cpad == 8 and k <= 8:
+            # 3-channel image layer (window-packed input): S rows are 8-pixel windows of x, the 8 column slots of a
+            # filter row are kx = 0..7
+            self.implicit = "window_x"
+            d.plain, d.shifted = self.dy_geom.c_struct(), in_geom.c_struct()
+            self.wg_m, self.wg_c2 = cout, self.cin
+            offs = [(ky - pt, -pl) for ky in range(k)]
+            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = k, 1, 1, 0, 1
+            self.wg_c2_rows = 8
+            self.wg_taps = [(t // 8, t % 8) if t % 8 < k else (-1, -1) for t in range(8 * k)]
+        elif self.swap and self.dy_window_geom is not None and pad_mode == PAD_REFLECT and \
+                (in_geom.pt, in_geom.pl, in_geom.pb, in_geom.pr) == tuple(pad) and in_geom.cpad % 64 == 0:
+            # tiny cout: P = x over its whole bordered buffer (taken as a border-less grid), S = 8-pixel windows of the
+            # zero-bordered dy buffer; slot j of filter row ky holds kx = k-1-j
+            self.implicit = "window_dy"
+            hp, wp = h + in_geom.pt + in_geom.pb, w + in_geom.pl + in_geom.pr
+            d.plain, d.shifted = Geom(n, hp, wp, self.cin, in_geom.cpad).c_struct(), self.dy_window_geom.c_struct()
+            self.wg_m, self.wg_c2 = self.cin, cout
+            offs = [(-ky, -(k - 1)) for ky in range(k)]
+            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = k, 1, 1, 0, 1
+            self.wg_c2_rows = 8
+            self.wg_taps = [(t // 8, k - 1 - t % 8) if t % 8 < k else (-1, -1) for t in range(8 * k)]
+        if self.implicit:
             for i, (a, b) in enumerate(offs):
                 d.tap_dh[i], d.tap_dw[i] = a, b
             self.wg_desc = d
-            self.wg_c2_rows = round_up(self.wg_c2, 64)
+            self.wg_cols = d.ntaps * (64 if d.window else self.wg_c2_rows)
 
     # ------------------------------------------------------------------ data gradient
     def data_grad(self, dy_rows, weight, out=None, scale=None, dy_act=None):
         """dy_rows: fp32 [n*oh*ow][ld >= cout] -> dx fp32 rows [n*h*w][cin4].  `scale`: optional device scalar
-        multiplied into the weights while packing (1/sigma of a spectrally normalised layer)."""
+        multiplied into the weights while packing (1/sigma of a spectrally normalised layer).  dy_act: the same
+        gradient already in operand format (then dy_rows may be None)."""
         sk = dict(scale=scale, scale_key=object()) if scale is not None else {}
-        dev = dy_rows.device
-        if self.dy_window_geom is not None:
-            g = self.dy_window_geom
-            key = ("dy_window",) + g.shape
-            buf = Workspace.named(key, g.shape, torch.int16, dev, zero=True)     # border zeroed once, interior rewritten
-            gs = g.c_struct()
-            check(lib.hfc_rows_to_act_geom(_ptr(dy_rows), dy_rows.shape[-1], ctypes.byref(gs), 1, _ptr(buf), _stream()),
-                  "rows_to_act_geom")
-            dy_act = buf
-        elif dy_act is None:
+        dev = (dy_rows if dy_rows is not None else dy_act).device
+        if dy_act is None:
             dy_act = self.dy_to_act(dy_rows)
         if self.fold is None:
             if out is None:
@@ -179,7 +201,15 @@ class ConvGrad:
 
     # ------------------------------------------------------------------ weight / bias gradient
     def dy_to_act(self, dy_rows):
-        """fp32 gradient rows -> border-less NHWC bf16 buffer (the operand format of the backward GEMMs)."""
+        """fp32 gradient rows -> NHWC bf16 buffer (the operand format of the backward GEMMs): border-less with a
+        64-channel pitch, or -- tiny cout -- 8-channel pitch with a zero border of k-1 pixels (window packing)."""
+        if self.dy_window_geom is not None:
+            g = self.dy_window_geom
+            buf = Workspace.named(("dy_window",) + g.shape, g.shape, torch.int16, dy_rows.device, zero=True)
+            gs = g.c_struct()      # the border is zeroed once; only the interior is rewritten
+            check(lib.hfc_rows_to_act_geom(_ptr(dy_rows), dy_rows.shape[-1], ctypes.byref(gs), 1, _ptr(buf), _stream()),
+                  "rows_to_act_geom")
+            return buf
         g = self.dy_geom
         dy_act = Workspace.get("dy_act", g.n * g.h * g.w * g.cpad, torch.int16, dy_rows.device).view(g.shape)
         check(lib.hfc_rows_to_act(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, g.cpad, 1, _ptr(dy_act),
@@ -187,30 +217,42 @@ class ConvGrad:
         return dy_act
 
     def _weight_grad_implicit(self, x_act, dy_rows, dw_out, accumulate, scale, dy_act=None):
-        dev = dy_rows.device
+        dev = x_act.device
         if dy_act is None:
             dy_act = self.dy_to_act(dy_rows)
         x_bf = Workspace.get("x_bf16", x_act.numel(), torch.int16, dev)
         check(lib.hfc_act_to_bf16(_ptr(x_act), _ptr(x_bf), x_act.numel(), _stream()), "act_to_bf16")
-        ncols = len(self.taps) * self.wg_c2_rows
+        ncols = self.wg_cols
         cbuf = Workspace.get("wgrad_c", self.wg_m * ncols, torch.float32, dev).view(self.wg_m, ncols)
-        plain, shifted = (x_bf, dy_act) if self.transposed else (dy_act, x_bf)
+        x_is_plain = self.transposed or self.implicit == "window_dy"
+        plain, shifted = (x_bf, dy_act) if x_is_plain else (dy_act, x_bf)
         check(lib.hfc_wgrad(ctypes.byref(self.wg_desc), _ptr(plain), _ptr(shifted), _ptr(cbuf), ncols, _stream()), "wgrad")
         k = self.k
+        ky, kx = _i8([t[0] for t in self.wg_taps]), _i8([t[1] for t in self.wg_taps])
         shape = (self.cin, self.cout, k, k) if self.transposed else (self.cout, self.cin, k, k)
         if dw_out is None:
             dw_out = torch.empty(shape, dtype=torch.float32, device=dev)
-        ky, kx = _i8([t[0] for t in self.taps]), _i8([t[1] for t in self.taps])
-        check(lib.hfc_permute_wgrad(_ptr(cbuf), ncols, self.wg_m, self.wg_c2, self.wg_c2_rows, k, k, len(self.taps), ky, kx,
+        if self.implicit == "window_dy":
+            # C is [ci][(slot, co)] but dW is [co][ci][ky][kx]: permute into a temporary and transpose the leading dims
+            tmp = torch.empty((self.cin, self.cout, k, k), dtype=torch.float32, device=dev)
+            check(lib.hfc_permute_wgrad(_ptr(cbuf), ncols, self.wg_m, self.wg_c2, self.wg_c2_rows, k, k, len(self.wg_taps),
+                                        ky, kx, float(scale), 0, _ptr(tmp), _stream()), "permute_wgrad")
+            if accumulate:
+                dw_out += tmp.transpose(0, 1)
+            else:
+                dw_out.copy_(tmp.transpose(0, 1))
+            return dw_out
+        check(lib.hfc_permute_wgrad(_ptr(cbuf), ncols, self.wg_m, self.wg_c2, self.wg_c2_rows, k, k, len(self.wg_taps), ky, kx,
                                     float(scale), int(accumulate), _ptr(dw_out), _stream()), "permute_wgrad")
         return dw_out
 
     def weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, scale=1.0, dy_act=None):
         """x_act: the forward input act buffer (fp16, with its border); dy_rows fp32 [n*oh*ow][ld].
         Returns dW in the torch layout of the forward weight."""
-        dev = dy_rows.device
         if self.implicit:
             return self._weight_grad_implicit(x_act, dy_rows, dw_out, accumulate, scale, dy_act)
+        assert dy_rows is not None, "the explicit weight-gradient path needs the fp32 gradient rows"
+        dev = dy_rows.device
         ig = self.in_geom
         n, h, w = ig.n, ig.h, ig.w
         hp, wp = h + ig.pt + ig.pb, w + ig.pl + ig.pr

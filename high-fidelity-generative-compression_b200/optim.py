@@ -58,4 +58,8 @@ class Adam(torch.optim.Optimizer):
                 table = torch.tensor(rows, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
                 check(lib.hfc_adam_multi(_ptr(table), _ptr(bm), bm.numel() // 2, float(group["lr"]), float(b1), float(b2),
                                          float(group["eps"]), float(group["weight_decay"]), step, _stream()), "adam_multi")
+            # the kernel wrote the parameters behind torch's back: bump their version counters so that autograd's
+            # saved-tensor checks and the packed-weight caches (ops.Conv.packed_weights) see the update
+            for p in ps:
+                torch.autograd.graph.increment_version(p)
         return loss

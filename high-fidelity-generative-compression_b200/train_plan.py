@@ -16,7 +16,7 @@ import torch
 
 from . import ops
 from ._lib import check, lib
-from .grad import ConvGrad
+from .grad import ConvGrad, Workspace
 from .ops import (ACT_NONE, ACT_RELU, OUT_NCHW_F32, OUT_NHWC_F16, OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO, CN_EPS, Conv,
                   Geom, _ptr, _stream, round_up)
 
@@ -34,16 +34,24 @@ def rows_to_nchw(r, n, c, h, w):
     return r.view(n, h, w, -1)[..., :c].permute(0, 3, 1, 2).contiguous()
 
 
-def norm_bwd(z, g, gamma, beta, act):
+def norm_bwd(z, g, gamma, beta, act, as_operand=True):
     """ChannelNorm(+ReLU) backward on fp32 rows.  Returns (dz, dgamma, dbeta, dbias) with dbias = column sums of dz
-    (the gradient of the bias of the convolution that produced z)."""
+    (the gradient of the bias of the convolution that produced z).  as_operand: dz is written directly as the bf16
+    NHWC operand of the two backward GEMMs of that convolution (pitch round_up(c, 64), shared workspace -- consume it
+    before the next norm_bwd); otherwise as fp32 rows."""
     c = gamma.numel()
     npix = z.shape[0]
-    dz = torch.empty((npix, round_up(c, 4)), dtype=torch.float32, device=z.device)
     dgb = torch.zeros((3, c), dtype=torch.float32, device=z.device)
+    if as_operand:
+        cpad = round_up(c, 64)
+        dz = Workspace.get("dy_act", npix * cpad, torch.int16, z.device).view(npix, cpad)
+        dz_f32, dz_act, ld = None, dz, 0
+    else:
+        dz = torch.empty((npix, round_up(c, 4)), dtype=torch.float32, device=z.device)
+        dz_f32, dz_act, ld, cpad = dz, None, dz.shape[1], 0
     check(lib.hfc_channelnorm_bwd(_ptr(z), z.shape[1], _ptr(g), g.shape[1], _ptr(gamma.detach().reshape(-1)),
-                                  _ptr(beta.detach().reshape(-1)), c, npix, CN_EPS, act, _ptr(dz), dz.shape[1],
-                                  _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _stream()), "channelnorm_bwd")
+                                  _ptr(beta.detach().reshape(-1)), c, npix, CN_EPS, act, _ptr(dz_f32), ld,
+                                  _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _ptr(dz_act), cpad, _stream()), "channelnorm_bwd")
     return dz, dgb[0].view_as(gamma), dgb[1].view_as(beta), dgb[2]
 
 
@@ -91,8 +99,13 @@ class Layer:
         self.x_act = x_act
         return self.conv(x_act, weight, bias)
 
-    def backward(self, dz_rows, weight, need_dx=True, db=None):
-        dy_act = self.grad.dy_to_act(dz_rows)       # one bf16 copy of the gradient serves both GEMMs
+    def backward(self, dz, weight, need_dx=True, db=None):
+        """dz: fp32 gradient rows, or (int16 = bf16 bits) the operand buffer written by norm_bwd(as_operand=True)."""
+        if dz.dtype == torch.int16:
+            dy_act, dz_rows = dz.view(self.grad.dy_geom.shape), None
+            assert db is not None
+        else:
+            dy_act, dz_rows = self.grad.dy_to_act(dz), dz       # one bf16 copy of the gradient serves both GEMMs
         dw = self.grad.weight_grad(self.x_act, dz_rows, dy_act=dy_act)
         if db is None:
             db = self.grad.bias_grad(dz_rows)
@@ -233,7 +246,7 @@ class GeneratorTrainPlan:
             g_head = g_head + g                         # block 0 consumed head; the final `x += head` added it again
         dz0, grads[4], grads[5], db0 = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE)
         ga0, grads[2], grads[3] = self.init.backward(dz0, p[2], db=db0)
-        dy_rows, grads[0], grads[1], _ = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE)
+        dy_rows, grads[0], grads[1], _ = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE, as_operand=False)
         self.zr = self.zu = self.z_init = self.y_rows = None
         return rows_to_nchw(dy_rows, self.n, self.C, self.h, self.w), grads
 

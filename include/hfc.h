@@ -247,8 +247,8 @@ int hfc_permute_wgrad(const float* c, int32_t ldc, int32_t m, int32_t c2, int32_
  * blockmap_dev: 2 x int32 per block {tensor index, chunk index}, one block per hfc_adam_chunk() elements;
  * step: the 1-based step count used for the bias corrections. */
 int32_t hfc_adam_chunk(void);
-int hfc_adam_multi(const int64_t* table_dev, const int32_t* blockmap_dev, int32_t n_blocks, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int64_t step, void* stream);
+int hfc_adam_multi(const int64_t* table_dev, const int32_t* blockmap_dev, int32_t n_blocks, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int64_t step, void* stream);
 /* Implicit weight gradient (autograd of F.conv2d / F.conv_transpose2d w.r.t. the weight, train.py:49-59):
  *   c[m][tap * c2_rows + j] = sum over the pixels p of `plain`  plain[p][m] * shifted[p * stride + tap][j]
  * with c2_rows = round_up(shifted.c, 64).  Both operands are NHWC 16-bit activation buffers (same format: fp16 or
@@ -263,6 +263,8 @@ typedef struct hfc_wgrad_desc {
   int32_t stride;      /* sampling stride in `shifted` (1 or 2) */
   int32_t bf16;        /* operand format: 0 fp16, 1 bf16 */
   int32_t k_splits;    /* 0 = auto; > 1 splits the pixels across CTAs (fp32 atomics into c, which is zeroed first) */
+  int32_t window;      /* 1: `shifted` has an 8-channel pitch; column j of a tap = (pixel offset j / 8, channel j % 8) of the
+                        * 8-pixel window that starts at the tap position (taps then enumerate filter ROWS only) */
   int8_t tap_dh[64];
   int8_t tap_dw[64];
 } hfc_wgrad_desc;
@@ -278,10 +280,12 @@ int hfc_pad_fold(const float* dxp, int32_t ld_in, int32_t hq, int32_t wq, const 
 
 /* ChannelNorm2D (+ReLU) backward: z = saved pre-norm rows, g = gradient w.r.t. the block output (both fp32 rows);
  * writes dz (fp32 rows) and ACCUMULATES dgamma / dbeta (caller zeroes them) and, when dbias != NULL, the column sums
- * of dz (= gradient of the bias of the convolution in front of the norm).  act: HFC_ACT_NONE | HFC_ACT_RELU. */
+ * of dz (= gradient of the bias of the convolution in front of the norm).  dz (fp32 rows) and / or dz_act (bf16,
+ * border-less NHWC with pitch act_cpad, channel padding zeroed: the operand of the backward GEMMs) receive the
+ * result; either may be NULL.  act: HFC_ACT_NONE | HFC_ACT_RELU. */
 int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld_g, const float* gamma,
                         const float* beta, int32_t c, int64_t npix, float eps, int32_t act, float* dz, int32_t ld_dz,
-                        float* dgamma, float* dbeta, float* dbias, void* stream);
+                        float* dgamma, float* dbeta, float* dbias, void* dz_act, int32_t act_cpad, void* stream);
 /* out = g * (y > 0 ? 1 : slope): backward of the fused bias + ReLU (slope 0) / LeakyReLU (slope 0.2) epilogue; y_act
  * is that layer's (bordered) NHWC fp16 output */
 int hfc_relu_mask(const float* g, int32_t ld_g, const void* y_act, const hfc_act_geom* geom, float slope, float* out,

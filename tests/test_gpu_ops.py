@@ -346,7 +346,9 @@ def test_adam_matches_torch():
             if step == 2:
                 ours[1].grad = ref[1].grad = None          # parameters without a gradient are skipped
             l0 = ops.launch_count()
+            ver = ours[0]._version
             oa.step(); ob.step()
+            assert ours[0]._version > ver       # the packed-weight caches key on the version counter
             assert ops.launch_count() - l0 == (2 if step == 3 else 1)   # one launch per distinct step count
         for p, q in zip(ours, ref):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
