@@ -44,7 +44,7 @@ class WgradDesc(ctypes.Structure):
     _fields_ = [
         ("plain", ActGeom), ("shifted", ActGeom),
         ("ntaps", ctypes.c_int32), ("stride", ctypes.c_int32), ("bf16", ctypes.c_int32), ("k_splits", ctypes.c_int32),
-        ("window", ctypes.c_int32),
+        ("pair", ctypes.c_int32), ("window", ctypes.c_int32),
         ("tap_dh", ctypes.c_int8 * 64), ("tap_dw", ctypes.c_int8 * 64),
     ]
 

@@ -54,12 +54,19 @@ struct WgradParams {
   int8_t tap_dw[kWgMaxTaps];
 };
 
+// kPair: CTA pairs (tcgen05 cta_group::2, launched as clusters of 2).  One UMMA then spans M = 256 P-channels (128 in
+// each CTA's TMEM) and the S tile is split in halves between the two CTAs' shared memories, so each SM fetches
+// 16 KB (P) + 16 KB (S) per 64-pixel block instead of 16 + 32 KB: the single-CTA kernel is bound by the L2 -> SM
+// operand traffic (~10 TB/s chip-wide on the 960x960 layers), not by the tensor pipe.
+template <bool kPair>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_s,
                    const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int stage_bytes = (2 + p.nch) * kWgChunkBytes;
+  const int s_chunks = kPair ? p.nch / 2 : p.nch;            // S chunks held by this CTA
+  const int stage_bytes = (2 + s_chunks) * kWgChunkBytes;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;     // 0 = pair leader
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kWgMaxStages;
@@ -77,13 +84,18 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kPair ? 8 : 4);      // pair: the leader waits for the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kWgTmemCols);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_pair(tmem_slot, kWgTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kWgTmemCols);
+      tmem_relinquish();
+    }
   }
   if (p.p_chunks == 1) {
     // P has <= 64 channels: rows 64..127 of the M = 128 tile are never fetched -- zero them once (generic-proxy
@@ -96,17 +108,21 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();     // the peer's barriers exist before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   // work item order: K split fastest, then N tile, tap, M tile -> concurrently running CTAs share P tiles in L2
+  // (pair mode: m_tiles counts 256-channel tiles and one "CTA" of the loops below is a pair)
   const int total_items = p.m_tiles * p.ntaps * p.n_tiles * p.k_splits;
+  const int cta0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int ncta = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      for (int it = cta0; it < total_items; it += ncta) {
         int r = it;
         const int ks = r % p.k_splits; r /= p.k_splits;
         const int nt = r % p.n_tiles; r /= p.n_tiles;
@@ -122,23 +138,34 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
           const int gw = twi * p.bw, gh = thi * p.bh, gn = tni * p.bn;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>((p.p_chunks + p.nch) * kWgChunkBytes));
-          for (int j = 0; j < p.p_chunks; ++j)
-            tma_load_4d(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 2 + j) * 64, gw + p.p_w0, gh + p.p_h0, gn);
           uint8_t* sb = sa + 2 * kWgChunkBytes;
           const int sw0 = gw * p.stride + p.s_w0 + p.tap_dw[tap];
           const int sh0 = gh * p.stride + p.s_h0 + p.tap_dh[tap];
-          for (int j = 0; j < p.nch; ++j)
-            tma_load_4d(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], (nt * p.nch + j) * 64, sw0, sh0, gn);
+          if constexpr (kPair) {
+            // both CTAs fill their own stage; every byte is accounted on the LEADER's barrier
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d_pair(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 4 + crank * 2 + j) * 64, gw + p.p_w0,
+                               gh + p.p_h0, gn);
+            for (int j = 0; j < s_chunks; ++j)
+              tma_load_4d_pair(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], (nt * p.nch + crank * s_chunks + j) * 64, sw0,
+                               sh0, gn);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>((p.p_chunks + p.nch) * kWgChunkBytes));
+            for (int j = 0; j < p.p_chunks; ++j)
+              tma_load_4d(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 2 + j) * 64, gw + p.p_w0, gh + p.p_h0, gn);
+            for (int j = 0; j < p.nch; ++j)
+              tma_load_4d(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], (nt * p.nch + j) * 64, sw0, sh0, gn);
+          }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_f16_mn(p.fmt, 128u, static_cast<uint32_t>(p.nch * 64));
+  } else if (warp == 1 && (!kPair || crank == 0)) {
+    const uint32_t idesc = make_idesc_f16_mn(p.fmt, kPair ? 256u : 128u, static_cast<uint32_t>(p.nch * 64));
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
-    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+    for (int it = cta0; it < total_items; it += ncta) {
       const int ks = it % p.k_splits;
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
@@ -156,29 +183,35 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
             // K = 16 pixels = 16 rows of 128 B = two 1024 B swizzle atoms per step
             const uint64_t a_desc = make_sw128_mnmajor_desc(a_addr + k * 2048, kWgChunkBytes, 1024);
             const uint64_t b_desc = make_sw128_mnmajor_desc(b_addr + k * 2048, kWgChunkBytes, 1024);
-            umma_f16(d_tmem, a_desc, b_desc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            if constexpr (kPair) umma_f16_pair(d_tmem, a_desc, b_desc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            else umma_f16(d_tmem, a_desc, b_desc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+          if constexpr (kPair) {
+            umma_commit_pair_mc(&empty_bar[s], 3);                 // frees the stage in both CTAs
+            if (kb == kb1 - 1) umma_commit_pair_mc(&tfull_bar[as], 3);
+          } else {
+            umma_commit(&empty_bar[s]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue (warps 2..5): thread == row m of the tile =====================
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int ncols = p.nch * 64;
     int as = 0;
     uint32_t aph = 0;
-    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+    for (int it = cta0; it < total_items; it += ncta) {
       int r = it / p.k_splits;
       const int nt = r % p.n_tiles; r /= p.n_tiles;
       const int tap = r % p.ntaps;
       const int mt = r / p.ntaps;
-      const int row = mt * 128 + m;
+      const int row = (kPair ? mt * 2 + static_cast<int>(crank) : mt) * 128 + m;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + as * kWgAccStride + (static_cast<uint32_t>(q * 32) << 16);
@@ -203,14 +236,21 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kWgTmemCols);
+  if constexpr (kPair) cluster_sync_all();     // nobody exits while the peer may still signal its barriers / read its smem
+  if (warp == 1) {
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, kWgTmemCols);
+    else tmem_dealloc(tmem_base, kWgTmemCols);
+  }
 }
 
 typedef CUresult (*PFN_encodeTiledW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -294,13 +334,17 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
                      pg.w, pg.h, kp.bw, kp.bh);
   kp.num_kb = kp.tiles_w * kp.tiles_h * kp.tiles_n;
   const int m_chunks = (pg.c + 63) / 64, n_chunks = window ? 1 : (sg.c + 63) / 64;
-  kp.m_tiles = (m_chunks + 1) / 2;
+  // CTA pairs whenever both operands are wide enough for an M = 256 x N >= 128 tile
+  static const bool env_no_pair = getenv("HFC_NO_WGRAD_PAIR") != nullptr;
+  const bool pair = !window && !env_no_pair && d->pair != 2 && m_chunks >= 3 && n_chunks >= 2 && sms >= 2;
+  kp.m_tiles = pair ? (m_chunks + 3) / 4 : (m_chunks + 1) / 2;
   int best = 1;
   long long best_cost = -1;
   for (int nch = 1; nch <= 4; ++nch) {     // cost ~ tiles x (P chunks + S chunks) of operand traffic / MMA time
     const long long cost = static_cast<long long>((n_chunks + nch - 1) / nch) * (2 + nch);
     if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = nch; }
   }
+  if (pair) best = n_chunks >= 3 ? 4 : 2;   // the S tile is split in halves between the two CTAs
   kp.nch = best;
   kp.n_tiles = (n_chunks + kp.nch - 1) / kp.nch;
   kp.ntaps = d->ntaps;
@@ -310,17 +354,18 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
                      d->ntaps * kp.c2_rows);
   kp.p_chunks = m_chunks == 1 ? 1 : 2;
   const int items = kp.m_tiles * kp.ntaps * kp.n_tiles;
+  const int workers = pair ? sms / 2 : sms;      // CTAs, or CTA pairs
   int ks = d->k_splits;
   if (ks <= 0) {
-    // fill (at most) two full waves of CTAs -- never a partial third one -- but keep >= 8 pixel blocks per item so
+    // fill (at most) two full waves of workers -- never a partial third one -- but keep >= 8 pixel blocks per item so
     // that the pipeline fill and the epilogue amortise
-    ks = std::max(1, std::min((2 * sms) / items, kp.num_kb / 8));
+    ks = std::max(1, std::min((2 * workers) / items, kp.num_kb / 8));
   }
   ks = std::max(1, std::min(ks, kp.num_kb));
   kp.kb_per_split = (kp.num_kb + ks - 1) / ks;
   kp.k_splits = (kp.num_kb + kp.kb_per_split - 1) / kp.kb_per_split;
   kp.atomic = kp.k_splits > 1 ? 1 : 0;
-  const int stage_bytes = (2 + kp.nch) * kWgChunkBytes;
+  const int stage_bytes = (2 + (pair ? kp.nch / 2 : kp.nch)) * kWgChunkBytes;
   kp.stages = std::max(2, std::min((226 * 1024 - 1024 - 512) / stage_bytes, kWgMaxStages));
   kp.stride = d->stride;
   kp.p_h0 = pg.pt; kp.p_w0 = pg.pl; kp.s_h0 = sg.pt; kp.s_w0 = sg.pl;
@@ -343,13 +388,28 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
   const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = std::min(items * kp.k_splits, sms);
-  wgrad_igemm_kernel<<<grid, kWgThreads, smem, st>>>(tmP, tmS, kp);
-  cudaError_t e = cudaGetLastError();
+  const int grid = std::min(items * kp.k_splits, workers) * (pair ? 2 : 1);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kWgThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = pair ? cudaLaunchKernelEx(&cfg, wgrad_igemm_kernel<true>, tmP, tmS, kp)
+                       : cudaLaunchKernelEx(&cfg, wgrad_igemm_kernel<false>, tmP, tmS, kp);
   if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "wgrad_igemm launch: %s", cudaGetErrorString(e));
   note_launch();
   return HFC_OK;

@@ -263,6 +263,7 @@ typedef struct hfc_wgrad_desc {
   int32_t stride;      /* sampling stride in `shifted` (1 or 2) */
   int32_t bf16;        /* operand format: 0 fp16, 1 bf16 */
   int32_t k_splits;    /* 0 = auto; > 1 splits the pixels across CTAs (fp32 atomics into c, which is zeroed first) */
+  int32_t pair;        /* 0 = auto (CTA pairs, cta_group::2, when both operands are wide enough), 2 = never */
   int32_t window;      /* 1: `shifted` has an 8-channel pitch; column j of a tap = (pixel offset j / 8, channel j % 8) of the
                         * 8-pixel window that starts at the tap position (taps then enumerate filter ROWS only) */
   int8_t tap_dh[64];
