@@ -166,6 +166,7 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
     (rate + distortion + LPIPS), backward through the hand-written kernels, gradient all-reduce over NCCL when
     world > 1 (coalesced, after backward), Adam on the amortization and the hyper-latent parameter groups."""
     from hific_b200.config import ModelModes
+    from hific_b200.dist import allreduce_gradients
     from hific_b200.optim import Adam
     B = args.train_batch or args.batch
     model.enable_cuda_graph(False)
@@ -182,11 +183,7 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         losses = model(x, train_generator=True)
         losses['compression'].backward()
         if dist is not None:
-            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
-            dist.all_reduce(flat)
-            flat.div_(world)
-            for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
-                p.grad.copy_(g)
+            allreduce_gradients(params, dist, world)
         opt_a.step()
         opt_a.zero_grad()
         opt_h.step()
@@ -215,6 +212,7 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
     discriminator iterations back-propagate the D loss and step the discriminator's Adam."""
     from hific_b200 import synth
     from hific_b200.config import ModelModes, ModelTypes, hific_args
+    from hific_b200.dist import allreduce_gradients
     from hific_b200.model import Model
     from hific_b200.optim import Adam
     B = args.gan_batch or args.train_batch or args.batch
@@ -230,14 +228,8 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
     x = x_host[:B].to(dev)
 
     def allreduce(params):
-        if dist is None:
-            return
-        gs = [p.grad for p in params if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors(gs)
-        dist.all_reduce(flat)
-        flat.div_(world)
-        for g, f in zip(gs, torch._utils._unflatten_dense_tensors(flat, gs)):
-            g.copy_(f)
+        if dist is not None:
+            allreduce_gradients(params, dist, world)
 
     def g_step():
         losses = model(x, train_generator=True)

@@ -216,14 +216,17 @@ struct FoldParams {
 
 __global__ void __launch_bounds__(256)
 pad_fold_kernel(const float* __restrict__ dxp, float* __restrict__ dx, const __grid_constant__ FoldParams p) {
-  const long long total = static_cast<long long>(p.n) * p.h * p.w * (p.c / 4);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c4 = static_cast<int>(i % (p.c / 4)) * 4;
-    const long long pix = i / (p.c / 4);
-    const int ww = static_cast<int>(pix % p.w);
-    const int hh = static_cast<int>((pix / p.w) % p.h);
-    const int nn = static_cast<int>(pix / (static_cast<long long>(p.w) * p.h));
+  // 32-bit index arithmetic (the launcher checks total < 2^31): this kernel is a pure stream and the 64-bit
+  // div / mod chain was most of its instruction count
+  const unsigned total = static_cast<unsigned>(p.n) * p.h * p.w * (p.c / 4);
+  const unsigned cq = static_cast<unsigned>(p.c / 4);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / cq;
+    const int c4 = static_cast<int>(i - pix * cq) * 4;
+    const unsigned row = pix / static_cast<unsigned>(p.w);
+    const int ww = static_cast<int>(pix - row * static_cast<unsigned>(p.w));
+    const int nn = static_cast<int>(row / static_cast<unsigned>(p.h));
+    const int hh = static_cast<int>(row - static_cast<unsigned>(nn) * static_cast<unsigned>(p.h));
     int rows[3], cols[3];
     const int nr = mirror_targets(hh, p.h, p.pt, p.pb, p.reflect != 0, rows);
     const int nc = mirror_targets(ww, p.w, p.pl, p.pr, p.reflect != 0, cols);
@@ -234,7 +237,7 @@ pad_fold_kernel(const float* __restrict__ dxp, float* __restrict__ dx, const __g
             dxp + ((static_cast<size_t>(nn) * p.hq + rows[ri]) * p.wq + cols[ci]) * p.ld_in + c4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
-    *reinterpret_cast<float4*>(dx + pix * p.ld_out + c4) = acc;
+    *reinterpret_cast<float4*>(dx + static_cast<size_t>(pix) * p.ld_out + c4) = acc;
   }
 }
 
@@ -355,6 +358,8 @@ extern "C" int hfc_pad_fold(const float* dxp, int32_t ld_in, int32_t hq, int32_t
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc != HFC_OK) return rc;
+  if (static_cast<long long>(g->n) * g->h * g->w * (g->c / 4) >= (1LL << 31))
+    return set_error(HFC_ERR_UNSUPPORTED, "pad_fold: more than 2^31 float4 elements");
   FoldParams p;
   p.n = g->n; p.h = g->h; p.w = g->w; p.c = g->c; p.ld_in = ld_in; p.ld_out = ld_out; p.hq = hq; p.wq = wq;
   p.pt = g->pt; p.pl = g->pl; p.pb = g->pb; p.pr = g->pr; p.reflect = reflect;

@@ -185,9 +185,13 @@ channelnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   if (!live) return;
   const float rstd = rsqrtf(q / static_cast<float>(p.c - 1) + p.eps);
 
-  const int ww = static_cast<int>(pix % p.w);
-  const int hh = static_cast<int>((pix / p.w) % p.h);
-  const int nn = static_cast<int>(pix / (static_cast<size_t>(p.w) * p.h));
+  // 32-bit pixel decode (n*h*w < 2^31 is checked by the launcher): 64-bit div / mod cost more than the rest of the
+  // thread's work on the narrow layers
+  const unsigned pix32 = static_cast<unsigned>(pix);
+  const unsigned row32 = pix32 / static_cast<unsigned>(p.w);
+  const int ww = static_cast<int>(pix32 - row32 * static_cast<unsigned>(p.w));
+  const int nn = static_cast<int>(row32 / static_cast<unsigned>(p.h));
+  const int hh = static_cast<int>(row32 - static_cast<unsigned>(nn) * static_cast<unsigned>(p.h));
   int rows[3], cols[3];
   const int nr = mirror_targets(hh, p.h, p.pt, p.pb, p.reflect != 0, rows);
   const int nc = mirror_targets(ww, p.w, p.pl, p.pr, p.reflect != 0, cols);
@@ -498,6 +502,8 @@ extern "C" int hfc_channelnorm(const float* x, int32_t ld, const hfc_act_geom* g
   p.n = g->n; p.c = g->c; p.h = g->h; p.w = g->w; p.cpad = g->cpad; p.ld = ld;
   p.pt = g->pt; p.pl = g->pl; p.pb = g->pb; p.pr = g->pr;
   p.reflect = reflect; p.act = act; p.eps = eps;
+  if (static_cast<long long>(g->n) * g->h * g->w >= (1LL << 31))
+    return set_error(HFC_ERR_UNSUPPORTED, "channelnorm: more than 2^31 pixels");
   // the padded channels (cpad > c) are zero-filled by the lanes past c: capacity must cover cpad
   const int width = std::max(g->c, out_act ? g->cpad : g->c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

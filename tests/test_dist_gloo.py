@@ -1,0 +1,76 @@
+"""world_size-2 test (gloo, CPU) of the multi-GPU plumbing of the training step: batch sharding, the coalesced gradient
+all-reduce and the max-over-ranks timing rule.  The CUDA kernels are not involved (they have no CPU path); the
+helpers are backend-agnostic and run over NCCL on the GPU box (bench.py)."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+from hific_b200.dist import allreduce_gradients, max_over_ranks, shard_range
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _model():
+    torch.manual_seed(3)
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 5, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(5, 2, 1))
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(11)
+        x = torch.randn(8, 3, 6, 6)                       # the global batch, identical on every rank
+        lo, hi = shard_range(x.shape[0], rank, world)
+        m = _model()
+        frozen = list(m.parameters())[-1]
+        loss = m(x[lo:hi]).square().mean()
+        loss.backward()
+        frozen.grad = None                                # a parameter the step did not touch (same on all ranks)
+        nbytes = allreduce_gradients(list(m.parameters()))
+        slow = max_over_ranks(10.0 + rank, torch.device("cpu"))
+        out.put((rank, [None if p.grad is None else p.grad.clone() for p in m.parameters()], nbytes, slow, (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_covers_everything():
+    for n in (1, 7, 8, 32):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_gradient_allreduce_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # reference: the full-batch gradient on one process (equal shards: mean of the shard means == full mean)
+    torch.manual_seed(11)
+    x = torch.randn(8, 3, 6, 6)
+    m = _model()
+    m(x).square().mean().backward()
+    ref = [p.grad for p in m.parameters()]
+    assert [r[4] for r in results] == [(0, 4), (4, 8)]
+    for rank, grads, nbytes, slow, _ in results:
+        assert slow == 11.0                                        # max over ranks of (10 + rank)
+        assert grads[-1] is None                                   # untouched parameter stays without gradient
+        assert nbytes == sum(g.numel() for g in grads[:-1]) * 4    # one flat fp32 buffer
+        for g, r in zip(grads[:-1], ref[:-1]):
+            assert torch.allclose(g, r, rtol=1e-5, atol=1e-7)
