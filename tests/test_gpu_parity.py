@@ -184,12 +184,16 @@ def test_full_size_properties_batch32(model):
         assert torch.allclose(g1[7:8], g_single, rtol=0, atol=1e-4)
 
 
-def test_refuses_cpu_and_grad(model):
+def test_refuses_cpu_and_records_grad(model):
+    """No CPU fallback: a CPU input raises.  With autograd enabled the call is recorded (training plan), without it
+    the fused inference plan runs and nothing is recorded."""
     with pytest.raises(RuntimeError):
         with torch.no_grad():
-            model.Encoder(torch.zeros(1, 3, 64, 64))
-    with pytest.raises(NotImplementedError):
-        model.Encoder(torch.zeros(1, 3, 64, 64, device="cuda"))
+            model.Encoder(torch.zeros(1, 3, 128, 128))
+    x = torch.zeros(1, 3, 128, 128, device="cuda")
+    assert model.Encoder(x).requires_grad
+    with torch.no_grad():
+        assert not model.Encoder(x).requires_grad
 
 
 def test_cuda_graph_replay_matches_eager(sd):
