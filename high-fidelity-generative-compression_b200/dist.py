@@ -13,7 +13,7 @@ def shard_range(n_items, rank, world):
 
 
 def allreduce_gradients(params, dist=None, world=None):
-    """Average `.grad` of `params` over all ranks with ONE all-reduce of a flattened buffer.  Parameters without a
+    """Average `.grad` of `params` over all ranks with ONE collective launch.  Parameters without a
     gradient on this rank are skipped on EVERY rank only if they have none anywhere -- callers pass the parameter group
     that the step back-propagated into, which is the same on all ranks.  Returns the number of bytes reduced."""
     if dist is None:
@@ -23,12 +23,20 @@ def allreduce_gradients(params, dist=None, world=None):
     grads = [p.grad for p in params if p.grad is not None]
     if world == 1 or not grads:
         return 0
-    flat = torch._utils._flatten_dense_tensors(grads)
+    nbytes = sum(g.numel() * g.element_size() for g in grads)
+    if dist.get_backend() == "nccl":
+        # NCCL: one grouped launch over the gradient tensors IN PLACE (ncclGroupStart/End via torch's coalescing
+        # manager) with ncclAvg -- no flatten / unflatten copies (3 extra passes over 726 MB) and no division kernel
+        with dist._coalescing_manager(device=grads[0].device):
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
+        return nbytes
+    flat = torch._utils._flatten_dense_tensors(grads)          # gloo (CPU tests): no AVG, no coalescing fast path
     dist.all_reduce(flat)
     flat.div_(world)
     for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
         g.copy_(f)
-    return flat.numel() * flat.element_size()
+    return nbytes
 
 
 def max_over_ranks(value, device, dist=None):

@@ -213,3 +213,31 @@ def test_cuda_graph_replay_matches_eager(sd):
     assert torch.equal(e1.reconstruction, g1.reconstruction) and torch.equal(e2.reconstruction, g2.reconstruction)
     assert torch.equal(g1.reconstruction, g1b.reconstruction)
     assert float(i1.total_qbpp) == float(j1.total_qbpp) and float(i2.total_qbpp) == float(j2.total_qbpp)
+
+
+def test_pipelined_forward_matches_direct_calls(sd):
+    """hific_b200.pipeline.PipelinedForward (H2D / compute / D2H on three streams, two slots): every submission returns
+    exactly what a plain synchronous Model.forward returns for that batch, also when slots are reused."""
+    from hific_b200.config import ModelModes
+    from hific_b200.pipeline import PipelinedForward
+    m = Model(mse_lpips_args(), logging.getLogger("pipe"), model_mode=ModelModes.EVALUATION)
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    xs = [synth.synth_image(2, 128, 128, 20 + i).pin_memory() for i in range(5)]
+    with torch.no_grad():
+        ref = [tuple(t.cpu().clone() for t in m(x.cuda(), writeout=False)) for x in xs]
+    pipe = PipelinedForward(m, depth=2)
+    tickets, got = [], []
+    for i, x in enumerate(xs):
+        tickets.append(pipe.submit(x))
+        if i >= 1:
+            r, b = pipe.result(tickets[i - 1])
+            got.append((r.clone(), b.clone()))
+    r, b = pipe.result(tickets[-1])
+    got.append((r.clone(), b.clone()))
+    for (r0, b0), (r1, b1) in zip(ref, got):
+        assert torch.equal(r0, r1) and float(b0) == float(b1)
+    with pytest.raises(ValueError):
+        pipe.result(tickets[0])          # slot long reused
+    with pytest.raises(ValueError):
+        pipe.submit(torch.zeros(2, 3, 128, 128))   # not pinned
