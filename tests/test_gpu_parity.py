@@ -236,7 +236,8 @@ def test_pipelined_forward_matches_direct_calls(sd):
     r, b = pipe.result(tickets[-1])
     got.append((r.clone(), b.clone()))
     for (r0, b0), (r1, b1) in zip(ref, got):
-        assert torch.equal(r0, r1) and float(b0) == float(b1)
+        assert torch.equal(r0, r1), "reconstruction differs from the synchronous call"
+        assert abs(float(b0) - float(b1)) <= 1e-6 * abs(float(b0))      # fp64 atomics: summation order may differ
     with pytest.raises(ValueError):
         pipe.result(tickets[0])          # slot long reused
     with pytest.raises(ValueError):
