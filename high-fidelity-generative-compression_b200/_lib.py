@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhfc.so")
+LIB_PATH = os.environ.get("HFC_LIB_PATH") or os.path.join(_HERE, "libhfc.so")   # override: A/B builds
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 
@@ -57,7 +57,7 @@ class ConvInfo(ctypes.Structure):
         ("block_n", ctypes.c_int32), ("n_tiles", ctypes.c_int32), ("m_tiles", ctypes.c_int32),
         ("stages", ctypes.c_int32), ("k_total", ctypes.c_int32),
         ("cluster_m", ctypes.c_int32), ("cluster_n", ctypes.c_int32), ("wide", ctypes.c_int32),
-        ("pair", ctypes.c_int32), ("tapn", ctypes.c_int32),
+        ("pair", ctypes.c_int32), ("tapn", ctypes.c_int32), ("nsub", ctypes.c_int32),
         ("flops", ctypes.c_double),
     ]
 

@@ -53,6 +53,8 @@ struct ConvKernelParams {
   int32_t cm, cn;                     // cluster extent along M tiles / N tiles (1 or 2 each)
   int32_t pair;                       // 1: CTA pairs (cta_group::2 UMMA, M = 256 across two SMs); needs cm == 2
   int32_t b_rows;                     // rows of the B tile held by one CTA (block_n, or block_n/2 in pair mode)
+  int32_t nsub;                       // pair mode: N tiles per work item (2: both 256-column TMEM halves accumulate
+                                      // against ONE fetch of the A tile; no accumulator double buffering then)
   int32_t a_split_n;                  // A slice split: 1 = along the batch dim of the box, 0 = along rows
   int32_t tapn, w_step;               // 'tap-in-N' mode (tiny cout): N = kw*cout, shifted sum in the epilogue;
                                       // tiles advance by w_step = 128-kw+1 output pixels
@@ -97,7 +99,9 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // kPair = true is the CTA-pair (cta_group::2) instantiation; it must be launched with clusters of 2 or 4
 // (ptxas marks a kernel that contains cta_group::2 instructions as cluster-only), so the single-CTA path
 // is a separate instantiation.
-template <bool kPair>
+// kNsub: N tiles per work item (2 only with kPair: one N tile in each 256-column TMEM half, see tile_and_stages); a
+// template parameter so that the single-tile instantiations keep their fully unrolled issue / epilogue loops
+template <bool kPair, int kNsub>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b,
@@ -107,7 +111,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int b_bytes = p.b_rows * kBlockK * 2;
-  const int stage_bytes = p.wide ? p.a_region : kABytes + b_bytes;
+  const int stage_bytes = p.wide ? p.a_region : kABytes + kNsub * b_bytes;
   // wide mode: every weight sub-tile (num_kb * kw of them) stays resident behind the A ring
   uint8_t* w_res = smem + p.stages * stage_bytes;
   const int w_res_bytes = p.wide ? p.num_kb * p.kw * b_bytes : 0;
@@ -171,7 +175,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int m_groups = (tiles_m + p.cm - 1) / p.cm;
-  const int n_groups = (p.n_tiles + p.cn - 1) / p.cn;
+  const int n_groups = (p.n_tiles + p.cn * kNsub - 1) / (p.cn * kNsub);
   const int total_ctiles = m_groups * n_groups * p.k_splits;   // work items per cluster (x K splits in gemm mode)
   const int cid = blockIdx.x / csize;
   const int ncl = gridDim.x / csize;
@@ -207,7 +211,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int ct = cid; ct < total_ctiles; ct += ncl) {
         const int ks = ct % p.k_splits;          // K split (gemm mode), else 0
         const int ctile = ct / p.k_splits;
-        const int nt = (ctile % n_groups) * p.cn + n_idx;
+        const int nt = ((ctile % n_groups) * p.cn + n_idx) * kNsub;
         int mt = (ctile / n_groups) * p.cm + m_idx;
         const int twi = mt % p.tiles_w;
         mt /= p.tiles_w;
@@ -232,7 +236,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else
               tma_load_4d_pair(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
                                h_base + p.tap_dh[tap], n_base);
-            tma_load_2d_pair(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, nt * p.block_n + m_idx * p.b_rows);
+            for (int j = 0; j < kNsub; ++j)
+              tma_load_2d_pair(sb + j * b_bytes, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK,
+                               (nt + j) * p.block_n + m_idx * p.b_rows);
             if (p.gemm) ++chunk; else if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
             if (++s == p.stages) { s = 0; ph ^= 1; }
             continue;
@@ -263,6 +269,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
+      const int acc_stages = kNsub == 2 ? 1 : 2;   // nsub == 2: both TMEM halves belong to one work item
       for (int ct = cid; ct < total_ctiles; ct += ncl) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
@@ -273,17 +280,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (lane == 0) {
             const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
             const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
-            const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
+            for (int j = 0; j < kNsub; ++j) {
+              const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes + j * b_bytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16_pair(d_tmem + j * kAccStride, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             umma_commit_pair_mc(&empty_bar[s], mask_all);   // every CTA that writes into this pair's stages
             if (kb == p.num_kb - 1) umma_commit_pair_mc(&tfull_bar[as], mask_pair);
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        if (++as == 2) { as = 0; aph ^= 1; }
+        if (++as == acc_stages) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -355,7 +364,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int cur_nt = -1, pbuf = 1;
     for (int ct = cid; ct < total_ctiles; ct += ncl) {
       const int ctile = ct / p.k_splits;
-      const int nt = (ctile % n_groups) * p.cn + n_idx;
+      const int nt0 = ((ctile % n_groups) * p.cn + n_idx) * kNsub;
       int mt = (ctile / n_groups) * p.cm + m_idx;
       const int twi = mt % p.tiles_w;
       mt /= p.tiles_w;
@@ -366,8 +375,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n = tni * p.tn + tni_in;
       const int oh = gh * p.osh + p.ooh;
       const int ow = gw * p.osw + p.oow;
-      const bool valid = (tni_in < p.tn) && (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
-                         (ow < p.out_w) && (nt < p.n_tiles) && (!p.tapn || m < p.w_step);
+      const bool valid_px = (tni_in < p.tn) && (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
+                            (ow < p.out_w) && (!p.tapn || m < p.w_step);
+      // nsub == 2 (CTA pairs): the work item owns both TMEM halves, one N tile in each
+      for (int jsub = 0; jsub < kNsub; ++jsub) {
+      const int nt = nt0 + jsub;
+      const bool valid = valid_px && (nt < p.n_tiles);
       const int c_base = nt * p.block_n;
       const bool last_nt = (nt == p.n_tiles - 1);
 
@@ -391,9 +404,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const float* s_gamma = s_bias + kParamStride;
       const float* s_beta = s_bias + 2 * kParamStride;
 
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + as * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      if (jsub == 0) {     // after the parameter staging, which thereby overlaps the tail of the main loop
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after();
+      }
+      const uint32_t t_row = tmem_base + (kNsub == 2 ? jsub : as) * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
       // Walks this warp's 16-column chunks (alternate chunks belong to the partner warp of the quadrant);
       // the TMEM load of the next chunk is in flight while the current one is processed.
@@ -576,13 +591,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      }  // jsub
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (kPair) mbar_arrive_leader(&tempty_bar[as]);
         else mbar_arrive(&tempty_bar[as]);
       }
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == (kNsub == 2 ? 1 : 2)) { as = 0; aph ^= 1; }
     }
   }
 
@@ -985,8 +1001,24 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   kp->pair = (cm == 2 && !kp->wide && !env_no_pair && d->pair != 2 && (pl.block_n / 2) % 8 == 0 &&
               (d->pair == 1 || ph.ntaps * pl.c_chunks >= 8)) ? 1 : 0;
   kp->b_rows = kp->pair ? pl.block_n / 2 : pl.block_n;
+  kp->nsub = 1;
   if (kp->pair) {
-    stage_bytes = kABytes + kp->b_rows * kBlockK * 2;
+    // Two N tiles per work item (one in each 256-column TMEM half) share ONE fetch of the A tile: the pair kernel is
+    // bound by the L2 -> SM operand traffic (~85 % of the 6.3 KB/clk LTS cap in ncu), which this cuts from
+    // 16 + 15 KB to (16 + 30) / 2 = 23 KB per tile and K block.  Costs the accumulator double buffering, so it is taken
+    // only when the wave count says it wins: waves x (1 | 1.8; measured: one wave of 64 double items 100.6 us vs two
+    // waves of single items 111.6 us on the 960x960 layer).
+    static const bool env_no_nsub = getenv("HFC_NO_NSUB") != nullptr;
+    const int pairs = 74;
+    const long long items1 = static_cast<long long>((tiles_m + 1) / 2) * pl.n_tiles;
+    const long long items2 = static_cast<long long>((tiles_m + 1) / 2) * (pl.n_tiles / 2);
+    if (!env_no_nsub && (cn == 1 || d->cluster_n == 0) && !d->norm && pl.n_tiles % 2 == 0 && ph.ntaps * pl.c_chunks >= 16 &&
+        ((items2 + pairs - 1) / pairs) * 180 < ((items1 + pairs - 1) / pairs) * 100) {
+      kp->nsub = 2;
+      kp->cn = cn = 1;          // an auto-chosen N multicast gives way: it does not reduce the LTS traffic (csz <= 4)
+      kp->a_split_n = 0;
+    }
+    stage_bytes = kABytes + kp->nsub * kp->b_rows * kBlockK * 2;
     kp->stages = std::max(2, std::min(budget / stage_bytes, kMaxStages));
   }
   return stage_bytes;
@@ -1035,6 +1067,7 @@ extern "C" int hfc_conv_query(const hfc_conv_desc* d, hfc_conv_info* info) {
   info->wide = kp.wide;
   info->pair = kp.pair;
   info->tapn = kp.tapn;
+  info->nsub = kp.nsub;
   info->cluster_m = kp.cm;
   info->cluster_n = kp.cn;
   info->k_total = 0;
@@ -1214,7 +1247,7 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
 
     const int tiles_m = kp.tiles_w * kp.tiles_h * kp.tiles_n;
     const int csize = kp.cm * kp.cn;
-    const int ctiles = ((tiles_m + kp.cm - 1) / kp.cm) * ((kp.n_tiles + kp.cn - 1) / kp.cn);
+    const int ctiles = ((tiles_m + kp.cm - 1) / kp.cm) * ((kp.n_tiles + kp.cn * kp.nsub - 1) / (kp.cn * kp.nsub));
     // clusters of 2 can use all 148 SMs; clusters of 4 only 132 (GPCs of 16/18/20 SMs)
     const int max_clusters = csize == 4 ? (sm_count * 132 / 148) / 4 : sm_count / csize;
     const int grid = std::min(ctiles, std::max(1, max_clusters)) * csize;
@@ -1222,10 +1255,13 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
                         (kp.tapn ? kTapnBytes : 0) + (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false>,
+      cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, 1>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(conv_igemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_igemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024);
       if (e != cudaSuccess)
         return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1244,8 +1280,9 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = kp.pair ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmA, tmB, kp)
-                            : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmA, tmB, kp);
+    cudaError_t e = !kp.pair ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1>, tmA, tmB, kp)
+                    : kp.nsub == 2 ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 2>, tmA, tmB, kp)
+                                   : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 1>, tmA, tmB, kp);
     if (e != cudaSuccess)
       return set_error(HFC_ERR_LAUNCH, "conv_igemm launch: %s", cudaGetErrorString(e));
     note_launch();
@@ -1290,7 +1327,7 @@ extern "C" int hfc_gemm_nt(const void* a, int32_t a_bf16, const void* b, int32_t
   kp.num_kb = kp.kb_per_split;
   kp.out_atomic = kp.k_splits > 1;
   kp.gemm = 1;
-  kp.cm = kp.cn = 1; kp.b_rows = kp.block_n;
+  kp.cm = kp.cn = 1; kp.b_rows = kp.block_n; kp.nsub = 1;
   kp.grid_h = 1; kp.grid_w = m; kp.batch = 1; kp.sh = kp.sw = 1;
   kp.out_mode = HFC_OUT_NHWC_F32; kp.osh = kp.osw = 1;
   kp.out_h = 1; kp.out_w = m; kp.out_cpad = ldc; kp.cout = n;
@@ -1324,7 +1361,7 @@ extern "C" int hfc_gemm_nt(const void* a, int32_t a_bf16, const void* b, int32_t
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -1339,7 +1376,7 @@ extern "C" int hfc_gemm_nt(const void* a, int32_t a_bf16, const void* b, int32_t
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmA, tmB, kp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1>, tmA, tmB, kp);
   if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "gemm_nt launch: %s", cudaGetErrorString(e));
   note_launch();
   return HFC_OK;

@@ -107,6 +107,7 @@ typedef struct hfc_conv_info {
   int32_t wide;                 /* 1 if the row-resident 'wide' mode is used */
   int32_t pair;                 /* 1 if CTA pairs (cta_group::2) are used */
   int32_t tapn;                 /* 1 if the tap-in-N mode is used */
+  int32_t nsub;                 /* N tiles per work item (2: CTA pairs with one N tile in each TMEM half) */
   double flops;                 /* algorithmic 2*MACs of the layer (real channels) */
 } hfc_conv_info;
 

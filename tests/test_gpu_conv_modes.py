@@ -89,3 +89,15 @@ def test_tap_in_n_other_shapes():
     run_conv_case(1, 64, 16, 128, 4, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, expect=dict(tapn=1))       # 3x3, cout 4
     run_conv_case(2, 128, 9, 130, 2, 5, pad=(2, 2, 2, 2), pad_mode=PAD_ZERO, expect=dict(tapn=1))          # 2 K chunks, zero pad
     run_conv_case(1, 60, 16, 128, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, wide=1, expect=dict(tapn=0, wide=1))
+
+
+def test_cta_pair_two_n_tiles_per_item():
+    """Bench-size residual conv (batch 32: 64 M tiles x 4 N tiles): the planner gives every CTA pair two N tiles (one
+    per TMEM half) against one fetch of the A tile; same numbers as the single-tile schedule."""
+    run_conv_case(32, 960, 16, 16, 960, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F32,
+                  expect=dict(pair=1, nsub=2))
+    run_conv_case(32, 960, 16, 16, 960, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F16,
+                  out_border=(1, 1, 1, 1), act=ACT_RELU, expect=dict(pair=1, nsub=2))
+    # odd number of N-tile pairs is impossible (n_tiles must be even); 480 = 2 x 240 -> one group
+    run_conv_case(32, 960, 16, 16, 480, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F32,
+                  expect=dict(pair=1))

@@ -242,3 +242,31 @@ def test_pipelined_forward_matches_direct_calls(sd):
         pipe.result(tickets[0])          # slot long reused
     with pytest.raises(ValueError):
         pipe.submit(torch.zeros(2, 3, 128, 128))   # not pinned
+
+
+def test_c5_size_1024_properties_and_oracle(model, sd):
+    """Config c5 (compress.py inference, 8 x 3 x 1024 x 1024): size-independent properties at the full size --
+    determinism, batch independence, crop consistency (a latent whose receptive field lies inside a 512-pixel crop
+    must not depend on what is outside it) -- plus one full-size sample against the CPU oracle."""
+    model.eval()
+    x = synth.synth_image(8, 1024, 1024, 9).cuda()
+    with torch.no_grad():
+        y = model.Encoder(x)
+        assert y.shape == (8, 220, 64, 64) and torch.isfinite(y).all()
+        assert torch.equal(y, model.Encoder(x)), "encoder is not deterministic at 1024 x 1024"
+        y3 = model.Encoder(x[3:4].contiguous())
+        assert torch.allclose(y[3:4], y3, rtol=0, atol=1e-5), "sample 3 depends on its batch neighbours"
+        crop = x[3:4, :, 256:768, 256:768].contiguous()
+        yc = model.Encoder(crop)                                   # latents 16..47 of the full image
+        m = 8                                                      # > receptive-field radius (in latent pixels)
+        a, b = y[3:4, :, 16 + m:48 - m, 16 + m:48 - m], yc[:, :, m:32 - m, m:32 - m]
+        assert rel_l2(b, a) < 1e-5, "interior latents depend on pixels outside their receptive field"
+        y_hat = torch.round(y[3:4])
+        g = model.Generator(y_hat)
+        assert g.shape == (1, 3, 1024, 1024) and torch.isfinite(g).all()
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        y_o = O.encoder_forward(sd, x[3:4].cpu())
+        g_o = O.generator_forward(sd, y_hat.cpu())
+    assert rel_l2(y3, y_o) < 1e-3
+    assert rel_l2(g, g_o) < 2e-3

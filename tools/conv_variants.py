@@ -42,7 +42,7 @@ for name, kw in [("1x1", dict(cluster=(1, 1))), ("2x1 multicast", dict(cluster=(
             torch.cuda.synchronize()
             tot += e0.elapsed_time(e1)
         us = 100.0 * tot
-        print(f"{name:18s} stages {conv.info.stages} bn {conv.info.block_n:3d}x{conv.info.n_tiles}  {us:7.1f} us  "
+        print(f"{name:18s} stages {conv.info.stages} bn {conv.info.block_n:3d}x{conv.info.n_tiles} nsub {conv.info.nsub}  {us:7.1f} us  "
               f"{conv.flops / us / 1e6:7.1f} TFLOP/s  rel.diff vs 1x1 {err:.1e}")
     except Exception as e:  # keep going: one broken mode must not hide the others
         print(f"{name:18s} FAILED: {e}")
