@@ -58,14 +58,17 @@ struct WgradParams {
 // each CTA's TMEM) and the S tile is split in halves between the two CTAs' shared memories, so each SM fetches
 // 16 KB (P) + 16 KB (S) per 64-pixel block instead of 16 + 32 KB: the single-CTA kernel is bound by the L2 -> SM
 // operand traffic (~10 TB/s chip-wide on the 960x960 layers), not by the tensor pipe.
-template <bool kPair>
+// kNsub (2 only with kPair): N tiles per work item -- one in each 256-column TMEM half, both accumulating against ONE
+// fetch of the P tile (16 + 2 x 16 KB per pixel block for two tiles instead of 2 x (16 + 16)); no accumulator double
+// buffering then.  Same trade as conv_igemm_kernel<true, 2>.
+template <bool kPair, int kNsub>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_s,
                    const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int s_chunks = kPair ? p.nch / 2 : p.nch;            // S chunks held by this CTA
-  const int stage_bytes = (2 + s_chunks) * kWgChunkBytes;
+  const int stage_bytes = (2 + kNsub * s_chunks) * kWgChunkBytes;
   const uint32_t crank = kPair ? cluster_ctarank() : 0u;     // 0 = pair leader
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* full_bar = bars;
@@ -114,7 +117,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
 
   // work item order: K split fastest, then N tile, tap, M tile -> concurrently running CTAs share P tiles in L2
   // (pair mode: m_tiles counts 256-channel tiles and one "CTA" of the loops below is a pair)
-  const int total_items = p.m_tiles * p.ntaps * p.n_tiles * p.k_splits;
+  const int n_groups = p.n_tiles / kNsub;      // the host makes n_tiles a multiple of kNsub
+  const int total_items = p.m_tiles * p.ntaps * n_groups * p.k_splits;
   const int cta0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int ncta = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
@@ -125,7 +129,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
       for (int it = cta0; it < total_items; it += ncta) {
         int r = it;
         const int ks = r % p.k_splits; r /= p.k_splits;
-        const int nt = r % p.n_tiles; r /= p.n_tiles;
+        const int nt = (r % n_groups) * kNsub; r /= n_groups;
         const int tap = r % p.ntaps;
         const int mt = r / p.ntaps;
         const int kb0 = ks * p.kb_per_split;
@@ -147,9 +151,10 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
             for (int j = 0; j < 2; ++j)
               tma_load_4d_pair(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 4 + crank * 2 + j) * 64, gw + p.p_w0,
                                gh + p.p_h0, gn);
-            for (int j = 0; j < s_chunks; ++j)
-              tma_load_4d_pair(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], (nt * p.nch + crank * s_chunks + j) * 64, sw0,
-                               sh0, gn);
+            for (int js = 0; js < kNsub; ++js)
+              for (int j = 0; j < s_chunks; ++j)
+                tma_load_4d_pair(sb + (js * s_chunks + j) * kWgChunkBytes, &tmap_s, &full_bar[s],
+                                 ((nt + js) * p.nch + crank * s_chunks + j) * 64, sw0, sh0, gn);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>((p.p_chunks + p.nch) * kWgChunkBytes));
             for (int j = 0; j < p.p_chunks; ++j)
@@ -183,8 +188,15 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
             // K = 16 pixels = 16 rows of 128 B = two 1024 B swizzle atoms per step
             const uint64_t a_desc = make_sw128_mnmajor_desc(a_addr + k * 2048, kWgChunkBytes, 1024);
             const uint64_t b_desc = make_sw128_mnmajor_desc(b_addr + k * 2048, kWgChunkBytes, 1024);
-            if constexpr (kPair) umma_f16_pair(d_tmem, a_desc, b_desc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-            else umma_f16(d_tmem, a_desc, b_desc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            if constexpr (kPair) {
+              umma_f16_pair(d_tmem, a_desc, b_desc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              if constexpr (kNsub == 2) {
+                const uint64_t b_desc2 = make_sw128_mnmajor_desc(b_addr + s_chunks * kWgChunkBytes + k * 2048, kWgChunkBytes, 1024);
+                umma_f16_pair(d_tmem + kWgAccStride, a_desc, b_desc2, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              }
+            } else {
+              umma_f16(d_tmem, a_desc, b_desc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            }
           }
           if constexpr (kPair) {
             umma_commit_pair_mc(&empty_bar[s], 3);                 // frees the stage in both CTAs
@@ -197,7 +209,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == (kNsub == 2 ? 1 : 2)) { as = 0; aph ^= 1; }
     }
   } else if (warp >= 2) {
     // ===================== epilogue (warps 2..5): thread == row m of the tile =====================
@@ -208,13 +220,16 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
     uint32_t aph = 0;
     for (int it = cta0; it < total_items; it += ncta) {
       int r = it / p.k_splits;
-      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int nt0 = (r % n_groups) * kNsub; r /= n_groups;
       const int tap = r % p.ntaps;
       const int mt = r / p.ntaps;
       const int row = (kPair ? mt * 2 + static_cast<int>(crank) : mt) * 128 + m;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + as * kWgAccStride + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+      for (int jsub = 0; jsub < kNsub; ++jsub) {
+      const int nt = nt0 + jsub;
+      const uint32_t t_row = tmem_base + (kNsub == 2 ? jsub : as) * kWgAccStride + (static_cast<uint32_t>(q * 32) << 16);
       const int col0 = nt * ncols;
       float* dst = p.out + static_cast<size_t>(row) * p.ldc + static_cast<size_t>(tap) * p.c2_rows + col0;
       for (int c0 = 0; c0 < ncols; c0 += 16) {
@@ -234,13 +249,14 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
           }
         }
       }
+      }  // jsub
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (kPair) mbar_arrive_leader(&tempty_bar[as]);
         else mbar_arrive(&tempty_bar[as]);
       }
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == (kNsub == 2 ? 1 : 2)) { as = 0; aph ^= 1; }
     }
   }
 
@@ -353,7 +369,18 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
     return set_error(HFC_ERR_INVALID, "wgrad: ldc (%d) must be a multiple of 4 and >= ntaps * round_up(c2, 64) = %d", ldc,
                      d->ntaps * kp.c2_rows);
   kp.p_chunks = m_chunks == 1 ? 1 : 2;
-  const int items = kp.m_tiles * kp.ntaps * kp.n_tiles;
+  // pair mode with two N tiles per work item (cf. conv_igemm.cu): correct (tests/test_gpu_grad.py passes with it) but
+  // MEASURED SLOWER here -- 960x960 layers 178 us vs 129 us -- although it moves 25 % fewer bytes: with MN-major
+  // operands the 8 MMAs per pixel block take ~2600 clk, i.e. the kernel stops being L2-bound and becomes bound by the
+  // tensor core's transposed operand fetch.  Opt-in (HFC_WGRAD_NSUB=1) until that is understood.
+  static const bool env_nsub = getenv("HFC_WGRAD_NSUB") != nullptr;
+  int nsub = 1;
+  if (pair && env_nsub && kp.n_tiles % 2 == 0 && kp.nch == 4) {
+    const long long it1 = static_cast<long long>(kp.m_tiles) * kp.ntaps * kp.n_tiles, it2 = it1 / 2;
+    const int prs = std::max(1, sms / 2);
+    if (((it2 + prs - 1) / prs) * 180 < ((it1 + prs - 1) / prs) * 100) nsub = 2;
+  }
+  const int items = kp.m_tiles * kp.ntaps * (kp.n_tiles / nsub);
   const int workers = pair ? sms / 2 : sms;      // CTAs, or CTA pairs
   int ks = d->k_splits;
   if (ks <= 0) {
@@ -365,7 +392,7 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
   kp.kb_per_split = (kp.num_kb + ks - 1) / ks;
   kp.k_splits = (kp.num_kb + kp.kb_per_split - 1) / kp.kb_per_split;
   kp.atomic = kp.k_splits > 1 ? 1 : 0;
-  const int stage_bytes = (2 + (pair ? kp.nch / 2 : kp.nch)) * kWgChunkBytes;
+  const int stage_bytes = (2 + nsub * (pair ? kp.nch / 2 : kp.nch)) * kWgChunkBytes;
   kp.stages = std::max(2, std::min((226 * 1024 - 1024 - 512) / stage_bytes, kWgMaxStages));
   kp.stride = d->stride;
   kp.p_h0 = pg.pt; kp.p_w0 = pg.pl; kp.s_h0 = sg.pt; kp.s_w0 = sg.pl;
@@ -388,9 +415,11 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
   const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(wgrad_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(wgrad_igemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad_igemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -408,8 +437,9 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = pair ? cudaLaunchKernelEx(&cfg, wgrad_igemm_kernel<true>, tmP, tmS, kp)
-                       : cudaLaunchKernelEx(&cfg, wgrad_igemm_kernel<false>, tmP, tmS, kp);
+  cudaError_t e = !pair ? cudaLaunchKernelEx(&cfg, wgrad_igemm_kernel<false, 1>, tmP, tmS, kp)
+                  : nsub == 2 ? cudaLaunchKernelEx(&cfg, wgrad_igemm_kernel<true, 2>, tmP, tmS, kp)
+                              : cudaLaunchKernelEx(&cfg, wgrad_igemm_kernel<true, 1>, tmP, tmS, kp);
   if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "wgrad_igemm launch: %s", cudaGetErrorString(e));
   note_launch();
   return HFC_OK;
