@@ -60,6 +60,8 @@ struct ConvKernelParams {
                                       // tiles advance by w_step = 128-kw+1 output pixels
   int32_t dbg;                        // debugging bits (env HFC_DBG): 1 skip stores, 2 skip norm stats, 4 skip epilogue body
   int32_t wide_boff;                  // debugging: set the descriptor base-offset field for shifted starts
+  int32_t winflat;                    // window packing served from a PLAIN pixel segment (un-swizzled descriptor with
+                                      // overlapping rows) instead of an 8x inflated window tile; tile = 128 px of a row
   int32_t wide, kw;                   // 'wide' mode: row-resident A halo (128+kw-1 pixels), resident weights
   int32_t a_region;                   // bytes per A stage (wide mode: halo row rounded up to 1024)
   int32_t grid_h, grid_w, batch;
@@ -329,7 +331,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);
         } else if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+          // winflat: K = 16 covers two pixels of the window -> the start moves by 2 x 16 B per step, as it does (by
+          // 32 B) inside the 128 B swizzle row of the regular layout
+          const uint64_t a_desc = p.winflat ? make_nosw_window_desc(a_addr) : make_sw128_kmajor_desc(a_addr);
           const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
@@ -954,9 +958,13 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   kp->tapn = pl.tapn;
   kp->w_step = kBlockM - d->kw + 1;
   if (pl.tapn) kp->wide = 0;
-  if (kp->wide || pl.tapn) {
+  // window packing on wide images: 128 consecutive pixels per tile and a plain (128 + 7)-pixel segment per filter
+  // row (2 160 B) instead of 128 inflated windows (16 KB)
+  static const bool env_no_winflat = getenv("HFC_NO_WINFLAT") != nullptr;
+  kp->winflat = (d->window && !env_no_winflat && ph.grid_w >= 96) ? 1 : 0;
+  if (kp->wide || pl.tapn || kp->winflat) {
     kp->tw = kBlockM; kp->th = 1; kp->tn = 1;
-    kp->tx_short = 0;
+    kp->tx_short = kp->winflat ? kABytes - (kBlockM + 7) * 16 : 0;
     free_tile = false;
   }
   kp->tiles_w = pl.tapn ? (ph.grid_w + (kBlockM - d->kw + 1) - 1) / (kBlockM - d->kw + 1)
@@ -985,7 +993,7 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
     cm = (cm == 0) ? ((big && tiles_m % 2 == 0) ? 2 : 1) : cm;
   }
   if (cm < 1 || cm > 2 || cn < 1 || cn > 2) return -1;
-  if (kp->wide || pl.tapn) cm = cn = 1;
+  if (kp->wide || pl.tapn || kp->winflat) cm = cn = 1;
   if (free_tile) cn = 1;                 // the multicast A slices assume a full 128-row tile
   if ((pl.block_n / cm) % 8 != 0 || pl.block_n % cm != 0) cm = 1;
   kp->a_split_n = 0;
@@ -1208,7 +1216,7 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     {
       cuuint64_t dims[4], strides[3];
       cuuint32_t box[4], estr[4];
-      if (d->window) {
+      if (d->window && !kp.winflat) {
         // dim0 = 64 elements = 8 consecutive pixels x 8 channels, dim1 = window start (pixel)
         if (Wp < 8) return set_error(HFC_ERR_INVALID, "conv: window packing needs Wp >= 8");
         dims[0] = 64; dims[1] = static_cast<cuuint64_t>(Wp - 7);
@@ -1224,11 +1232,12 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
       const int tn_box = kp.a_split_n ? kp.tn / kp.cn : kp.tn;
       box[0] = kBlockK; box[1] = kp.tw * ph.sw; box[2] = th_box * ph.sh; box[3] = tn_box;
       if (kp.wide) { box[1] = kBlockM + d->kw - 1; box[2] = 1; box[3] = 1; }
+      if (kp.winflat) { box[0] = 8; box[1] = kBlockM + 7; box[2] = 1; box[3] = 1; }   // plain segment, 16 B per pixel
       estr[0] = 1; estr[1] = ph.sw; estr[2] = ph.sh; estr[3] = 1;
       CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          kp.winflat ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS)
         return set_error(HFC_ERR_LAUNCH, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     }

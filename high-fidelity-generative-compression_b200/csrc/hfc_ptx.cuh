@@ -167,6 +167,18 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
+// K-major operand WITHOUT swizzle whose rows overlap: row r starts 16 B after row r-1 (core matrix = 8 rows x 16 B
+// contiguous, SBO = 128 B between 8-row groups, LBO = 16 B between the two 16-byte K chunks of one MMA).  Over a plain
+// pixel-major buffer with 8 channels (16 B) per pixel, row r of the A matrix is then the 8-pixel x 8-channel WINDOW that
+// starts at pixel r -- the im2col of a filter row, expressed purely in the descriptor.
+__device__ __forceinline__ uint64_t make_nosw_window_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(16 >> 4) << 16;       // LBO: next 8-element K chunk = next pixel
+  d |= static_cast<uint64_t>(128 >> 4) << 32;      // SBO: next group of 8 rows = 8 pixels further
+  d |= static_cast<uint64_t>(1) << 46;             // descriptor version (Blackwell)
+  return d;                                        // layout type 0 = SWIZZLE_NONE
+}
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 // fmt_a / fmt_b: 0 = fp16, 1 = bf16.  Measured on B200: the two operands must use the SAME format (a mixed pair
 // raises an illegal-instruction fault), so the backward GEMMs convert the saved fp16 activations to bf16.

@@ -120,6 +120,7 @@ def test_grad_convT_k5_s2_and_k3_s1():
 def test_grad_first_layer_window_and_tiny_cout_head():
     run_grad_case(2, 3, 32, 32, 60, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, window=True)   # wgrad only (no dx needed)
     run_grad_case(2, 60, 24, 40, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT)               # swap formulation
+    run_grad_case(1, 60, 10, 136, 3, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT)              # wide: flat-segment dgrad
 
 
 def test_grad_conv_4x4_s2_discriminator():

@@ -140,6 +140,14 @@ def test_conv_window_7x7_first_layer():
                   out_border=(1, 0, 0, 1), norm=True, act=ACT_RELU, window=True)
 
 
+@pytest.mark.parametrize("w", [128, 200, 256])
+def test_conv_window_7x7_wide_images_flat_segment(w):
+    """Images >= 96 pixels wide: the window operand is served from a plain pixel segment through an un-swizzled UMMA
+    descriptor with overlapping rows (tile = 128 pixels of one row; ragged last tile at w = 200)."""
+    run_conv_case(2, 3, 12, w, 60, 7, pad=(3, 3, 3, 3), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F16,
+                  out_border=(1, 0, 0, 1), norm=True, act=ACT_RELU, window=True)
+
+
 def test_conv_multi_ntile_nhwc32():
     run_conv_case(2, 64, 16, 16, 320, 3, pad=(1, 1, 1, 1), pad_mode=PAD_ZERO, out_mode=OUT_NHWC_F32, act=ACT_RELU)
 
