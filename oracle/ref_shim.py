@@ -82,3 +82,47 @@ class NoiseFeeder:
     def __exit__(self, *exc):
         import torch
         torch.nn.init.uniform_ = self._orig
+
+
+def install_ans():
+    """Make the reference's vectorised rANS coder (src/compression/entropy_coding.py, ans.py) runnable here.
+    Two workarounds, neither changes its arithmetic:
+      4. NumPy 2 removed value-based casting: `((RANS_L >> precision) << 32) * freqs` (ans.py:64) with uint32
+         `freqs` raises OverflowError (under NumPy 1.x the product is uint64).  `ans.push` is wrapped so that
+         starts / freqs arrive as uint64 -- exactly the dtype NumPy 1.x promoted them to.
+      5. `substack` (entropy_coding.py:418-446) updates the masked lanes of the message head through HIPS
+         autograd's `make_vjp`; without that package the same update is written as a masked assignment.
+    """
+    install()
+    import numpy as np
+    from src.compression import ans as vrans
+    from src.compression import entropy_coding
+    if getattr(vrans, "_hfc_patched", False):
+        return
+    orig_push = vrans.push
+
+    def push_u64(x, starts, freqs, precisions):
+        return orig_push(x, np.asarray(starts, dtype=np.uint64), np.asarray(freqs, dtype=np.uint64), precisions)
+
+    vrans.push = push_u64
+
+    def substack(codec, view_fun):
+        def push(message, start, freq, precision, mask):
+            head, tail = message
+            subhead, tail = vrans.push((view_fun(head, mask), tail), start, freq, precision)
+            head = np.copy(head)
+            head[mask] = subhead
+            return head, tail
+
+        def pop(message, precision, mask, *args, **kwargs):
+            head, tail = message
+            cf, pop_fun = vrans.pop((view_fun(head, mask), tail), precision)
+            subhead, tail = pop_fun(cf, 1)
+            head = np.copy(head)
+            head[mask] = subhead
+            return (head, tail), cf
+
+        return entropy_coding.Codec(push, pop)
+
+    entropy_coding.substack = substack
+    vrans._hfc_patched = True
