@@ -299,7 +299,7 @@ def main():
     cfg = mse_lpips_args()
     cfg.batch_size = args.batch
     model = Model(cfg, logging.getLogger("bench"), model_mode=ModelModes.EVALUATION, model_type=ModelTypes.COMPRESSION)
-    model.load_state_dict(synth.synth_state_dict(0), strict=True)     # identical weights on every rank
+    model.load_state_dict(synth.synth_state_dict(0), strict=False)    # identical weights on every rank; EVALUATION mode adds coder tables
     model.to(dev).eval()
     B = args.batch
     x_host = synth.synth_image(B, 256, 256, seed=1 + rank).pin_memory()  # rank-offset data seed

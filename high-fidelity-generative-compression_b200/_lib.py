@@ -66,6 +66,7 @@ PAD_ZERO, PAD_REFLECT = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY02 = 0, 1, 2
 OUT_NHWC_F16, OUT_NHWC_F32, OUT_NCHW_F32 = 0, 1, 2
 PREC_F16, PREC_BF16X3 = 0, 1
+SYM_BATCH_STEPS, SYM_PIXEL_STEPS = 0, 1
 
 # name -> (restype, argtypes); doubles as the list of symbols the ABI test checks.
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
@@ -111,6 +112,12 @@ SIGNATURES = {
                                        _vp, _vp, _vp, _vp, _vp]),
     "hfc_latent_likelihood": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp]),
     "hfc_hyperlatent_likelihood": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "hfc_quantize_symbols": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hfc_scale_indices": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _f32, _i32, _vp, _vp]),
+    "hfc_dequantize_symbols": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hfc_pmf_to_quantized_cdf_host": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
+    "hfc_rans_encode_host": (_i64, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _i64]),
+    "hfc_rans_decode_host": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
 }
 
 

@@ -1,0 +1,69 @@
+"""Base class of the table-driven entropy models (src/compression/entropy_models.py:21-84)."""
+import abc
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import entropy_coding
+
+MIN_SCALE = 0.11
+MIN_LIKELIHOOD = 1e-9
+MAX_LIKELIHOOD = 1e4
+TAIL_MASS = 2 ** (-8)
+PRECISION_P = 16  # precision of the rANS coder
+
+
+class ContinuousEntropyModel(nn.Module, metaclass=abc.ABCMeta):
+    def __init__(self, distribution, likelihood_bound=MIN_LIKELIHOOD, tail_mass=TAIL_MASS, precision=PRECISION_P):
+        super().__init__()
+        self.distribution = distribution
+        self.likelihood_bound = float(likelihood_bound)
+        self.tail_mass = float(tail_mass)
+        self.precision = int(precision)
+        self._host_tables, self._host_tables_key = None, None
+
+    def quantize_st(self, inputs, offsets=None):
+        """entropy_models.py:49-63 (straight-through rounding; plain torch ops, not on the hot path)."""
+        values = inputs
+        if offsets is not None:
+            offsets = offsets.to(values)
+            values = values - offsets
+        delta = (torch.floor(values + 0.5) - values).detach()
+        values = values + delta
+        if offsets is not None:
+            values = values + offsets
+        return values
+
+    def dequantize(self, x, offsets=None):
+        """entropy_models.py:65-73."""
+        if offsets is not None:
+            return x.type_as(offsets) + offsets
+        return x.to(torch.float32)
+
+    @abc.abstractmethod
+    def build_tables(self, **kwargs):
+        pass
+
+    def _register_tables(self, cdf, cdf_offset, cdf_length):
+        """CDF / CDF_offset / CDF_length as frozen int32 parameters (prior_model.py:109-120): they travel in the
+        state_dict, which is how the decoder gets the encoder's exact tables."""
+        device = self.CDF.device if hasattr(self, "CDF") else None
+        for name, value in (("CDF", cdf), ("CDF_offset", cdf_offset), ("CDF_length", cdf_length)):
+            t = torch.as_tensor(np.asarray(value), dtype=torch.int32)
+            if device is not None:
+                t = t.to(device)
+            if hasattr(self, name):
+                delattr(self, name)
+            self.register_parameter(name, nn.Parameter(t, requires_grad=False))
+        self._host_tables = None
+
+    def host_tables(self):
+        """numpy copy of the tables for the host coder, refreshed when the parameters change (load_state_dict)."""
+        key = tuple((t.data_ptr(), t._version) for t in (self.CDF, self.CDF_length, self.CDF_offset))
+        if self._host_tables is None or self._host_tables_key != key:
+            self._host_tables = entropy_coding.Tables(self.CDF.detach().cpu().numpy(),
+                                                      self.CDF_length.detach().cpu().numpy(),
+                                                      self.CDF_offset.detach().cpu().numpy())
+            self._host_tables_key = key
+        return self._host_tables

@@ -3,6 +3,7 @@
 // All of them are single-pass, vectorised and coalesced; none goes near the tensor cores.
 #include "hfc_internal.h"
 #include "hfc_device_utils.cuh"
+#include "hfc_likelihood.cuh"
 
 #include <cuda_fp16.h>
 
@@ -246,31 +247,6 @@ static void launch_channelnorm(const float* x, const float* gamma, const float* 
 // ------------------------------------------------------------------------------------------------
 // Conditional (mean-scale) likelihood of the latents: hyperprior.py:57-139, maths.py:87-109
 // ------------------------------------------------------------------------------------------------
-// erfc with fractional error < 1.2e-7 everywhere (Chebyshev fit of Numerical Recipes' erfcc): one
-// exp, one reciprocal and a 9-term Horner chain, about half the instructions of erfcf.  The likelihood
-// kernel evaluates four of these per element and is otherwise instruction-bound, not HBM-bound.
-__device__ __forceinline__ float fast_erfc(float x) {
-  const float z = fabsf(x);
-  const float t = __fdividef(1.f, fmaf(0.5f, z, 1.f));
-  float pl = 0.17087277f;
-  pl = fmaf(pl, t, -0.82215223f);
-  pl = fmaf(pl, t, 1.48851587f);
-  pl = fmaf(pl, t, -1.13520398f);
-  pl = fmaf(pl, t, 0.27886807f);
-  pl = fmaf(pl, t, -0.18628806f);
-  pl = fmaf(pl, t, 0.09678418f);
-  pl = fmaf(pl, t, 0.37409196f);
-  pl = fmaf(pl, t, 1.00002368f);
-  pl = fmaf(pl, t, -1.26551223f);
-  const float r = t * __expf(fmaf(-z, z, pl));
-  return x >= 0.f ? r : 2.f - r;
-}
-
-__device__ __forceinline__ float std_cdf(float v, int type) {
-  if (type == 0) return 0.5f * fast_erfc(v * -0.70710678118654752440f);   // maths.py:102-105
-  return __fdividef(1.f, 1.f + __expf(-v));                                 // maths.py:107-109
-}
-
 __device__ __forceinline__ float block_sum_to(float v, float* smem8) {
   v = warp_sum(v);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

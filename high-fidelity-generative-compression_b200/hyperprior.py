@@ -9,7 +9,8 @@ import torch
 import torch.nn as nn
 
 from . import engine, ops
-from .compression import hyperprior_model
+from .compression import hyperprior_model, prior_model
+from .compression.compression_utils import CompressionOutput
 from .network import hyper
 
 MIN_SCALE = 0.11
@@ -61,10 +62,87 @@ class Hyperprior(CodingModel):
         self.amortization_models = [self.analysis_net, self.synthesis_mu, self.synthesis_std]
         self.hyperlatent_likelihood = hyperprior_model.HyperpriorDensity(n_channels=hyperlatent_filters)
         if entropy_code is True:
-            raise NotImplementedError(
-                "entropy_code=True builds the host rANS tables (src/hyperprior.py:183-193): the sequential ANS "
-                "coder is out of scope of the B200 hot path (BASELINE.json north_star); use the reference's "
-                "src/compression for actual bitstreams")
+            # src/hyperprior.py:183-193: integer probability tables for the host rANS coder
+            self.hyperprior_entropy_model = hyperprior_model.HyperpriorEntropyModel(
+                distribution=self.hyperlatent_likelihood)
+            self.prior_density = prior_model.PriorDensity(n_channels=bottleneck_capacity,
+                                                          scale_lower_bound=self.scale_lower_bound,
+                                                          likelihood_type=likelihood_type)
+            self.prior_entropy_model = prior_model.PriorEntropyModel(distribution=self.prior_density,
+                                                                     min_scale=self.scale_lower_bound)
+            self.index_tables = self.prior_entropy_model.scale_table_tensor
+            self.vectorize_encoding = vectorize_encoding
+            self.block_encode = block_encode
+
+    def _latent_statistics(self, hyperlatents_decoded):
+        """(means, raw scales) from the decoded hyper-latents; the 0.11 lower bound of src/hyperprior.py:214,250 is
+        applied inside the kernels that consume the scales.  Both networks are deterministic kernels (no atomics, no
+        split-K), so the encoder and the decoder derive bit-identical statistics from the same hyper-latents."""
+        cur = torch.cuda.current_stream()
+        side = self._side_stream(hyperlatents_decoded.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            latent_scales = self.synthesis_std(hyperlatents_decoded)
+        latent_means = self.synthesis_mu(hyperlatents_decoded)
+        cur.wait_stream(side)
+        latent_scales.record_stream(cur)
+        return latent_means.contiguous(), latent_scales.contiguous()
+
+    def compress_forward(self, latents, spatial_shape, **kwargs):
+        """src/hyperprior.py:195-247: y -> (hyper-latent message, latent message, shapes, Shannon estimates).  GPU:
+        analysis / synthesis networks, symbols + table indices + bit estimates in coder order (csrc/symbols.cu);
+        host: the rANS coder.  As in the reference the hyper-latents are coded, DEcoded again and the latent statistics
+        derived from the decoded values, so that the decoder sees exactly the same (means, scales)."""
+        engine._require_cuda(latents, "Hyperprior.compress_forward")
+        with torch.no_grad():
+            latents = latents.contiguous()
+            hyperlatents = self.analysis_net(latents)
+            hyperlatent_spatial_shape = hyperlatents.size()[2:]
+            batch_shape = latents.size(0)
+            hem, pem = self.hyperprior_entropy_model, self.prior_entropy_model
+            hyperlatent_bits, hyperlatent_bpp, _ = hem._estimate_compression_bits(hyperlatents, spatial_shape)
+            hyperlatents_encoded, hyper_coding_shape, _ = hem.compress(
+                hyperlatents, vectorize=self.vectorize_encoding, block_encode=self.block_encode)
+            hyperlatents_decoded, _ = hem.decompress(
+                hyperlatents_encoded, batch_shape=batch_shape, broadcast_shape=hyperlatent_spatial_shape,
+                coding_shape=hyper_coding_shape, vectorize=self.vectorize_encoding, block_decode=self.block_encode,
+                device=latents.device)
+            latent_means, latent_scales = self._latent_statistics(hyperlatents_decoded)
+            latents_encoded, latent_coding_shape, _, log_sum = pem.compress(
+                latents, means=latent_means, scales=latent_scales, vectorize=self.vectorize_encoding,
+                block_encode=self.block_encode, return_bits=True)
+            latent_bits, latent_bpp, _ = pem._bits(log_sum, batch_shape, spatial_shape)
+        return CompressionOutput(
+            hyperlatents_encoded=hyperlatents_encoded,
+            latents_encoded=latents_encoded,
+            hyperlatent_spatial_shape=hyperlatent_spatial_shape,
+            spatial_shape=spatial_shape,
+            hyper_coding_shape=hyper_coding_shape,
+            latent_coding_shape=latent_coding_shape,
+            batch_shape=batch_shape,
+            hyperlatent_bits=hyperlatent_bits.item(),
+            latent_bits=latent_bits.item(),
+            total_bits=(hyperlatent_bits + latent_bits).item(),
+            hyperlatent_bpp=hyperlatent_bpp.item(),
+            latent_bpp=latent_bpp.item(),
+            total_bpp=(hyperlatent_bpp + latent_bpp).item(),
+        )
+
+    def decompress_forward(self, compression_output, device):
+        """src/hyperprior.py:249-274: messages -> decoded latents (N, C, H, W) on `device`."""
+        co = compression_output
+        with torch.no_grad():
+            hyperlatents_decoded, _ = self.hyperprior_entropy_model.decompress(
+                co.hyperlatents_encoded, batch_shape=co.batch_shape, broadcast_shape=co.hyperlatent_spatial_shape,
+                coding_shape=co.hyper_coding_shape, vectorize=self.vectorize_encoding,
+                block_decode=self.block_encode, device=device)
+            latent_means, latent_scales = self._latent_statistics(hyperlatents_decoded)
+            latent_spatial_shape = latent_scales.size()[2:]
+            latents_decoded, _ = self.prior_entropy_model.decompress(
+                co.latents_encoded, means=latent_means, scales=latent_scales, broadcast_shape=latent_spatial_shape,
+                coding_shape=co.latent_coding_shape, vectorize=self.vectorize_encoding,
+                block_decode=self.block_encode)
+        return latents_decoded.to(device)
 
     def forward(self, latents, spatial_shape, **kwargs):
         engine._require_cuda(latents, "Hyperprior")

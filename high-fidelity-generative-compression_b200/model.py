@@ -6,6 +6,7 @@ differentiable end to end through hand-written backward kernels (hific_b200.trai
 """
 from collections import defaultdict, namedtuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -51,8 +52,8 @@ class Model(nn.Module):
         if not hasattr(ModelModes, self.model_mode.upper()):
             raise ValueError("Invalid model_mode: [{}]".format(self.model_mode))
         self.image_dims, self.batch_size = args.image_dims, args.batch_size
-        # EVALUATION mode in the reference also builds the host rANS tables; those stay with the reference.
-        self.entropy_code = False
+        # src/model.py:64-66: EVALUATION mode builds the integer probability tables of the host rANS coder
+        self.entropy_code = self.model_mode == ModelModes.EVALUATION
         self.Encoder = encoder.Encoder(self.image_dims, self.batch_size, C=args.latent_channels,
                                        channel_norm=args.use_channel_norm)
         self.Generator = generator.Generator(self.image_dims, self.batch_size, C=args.latent_channels,
@@ -60,7 +61,8 @@ class Model(nn.Module):
                                              channel_norm=args.use_channel_norm, sample_noise=args.sample_noise,
                                              noise_dim=args.noise_dim)
         self.Hyperprior = hyperprior.Hyperprior(bottleneck_capacity=args.latent_channels,
-                                                likelihood_type=args.likelihood_type, entropy_code=False)
+                                                likelihood_type=args.likelihood_type,
+                                                entropy_code=self.entropy_code)
         self.amortization_models = [self.Encoder, self.Generator]
         self.amortization_models.extend(self.Hyperprior.amortization_models)
         self.use_discriminator = (self.model_type == ModelTypes.COMPRESSION_GAN
@@ -245,8 +247,45 @@ class Model(nn.Module):
         return D_loss, G_loss
 
     def compress(self, x, silent=False):
-        raise NotImplementedError("Model.compress drives the host rANS coder (src/model.py:262-310), which is out of "
-                                  "scope of the B200 hot path; use the reference's src/compression with this model's weights")
+        """src/model.py:262-310: x -> Encoder -> y -> Hyperprior.compress_forward -> CompressionOutput (two rANS
+        messages + shapes + Shannon estimates)."""
+        assert self.model_mode == ModelModes.EVALUATION and (self.training is False), (
+            f'Set model mode to {ModelModes.EVALUATION} for compression.')
+        spatial_shape = tuple(x.size()[2:])
+        with torch.no_grad():
+            x = pad_factor(x, x.size()[2:], 2 ** self.Encoder.n_downsampling_layers)
+            y = self.Encoder(x)
+            y = pad_factor(y, y.size()[2:], 2 ** self.Hyperprior.analysis_net.n_downsampling_layers)
+            compression_output = self.Hyperprior.compress_forward(y, spatial_shape)
+        n_pixels = np.prod(spatial_shape)
+        attained_hbpp = 32 * len(compression_output.hyperlatents_encoded) / n_pixels
+        attained_lbpp = 32 * len(compression_output.latents_encoded) / n_pixels
+        attained_bpp = 32 * ((len(compression_output.hyperlatents_encoded)
+                              + len(compression_output.latents_encoded)) / n_pixels)
+        if silent is False:
+            self.logger.info('[ESTIMATED]')
+            self.logger.info(f'BPP: {compression_output.total_bpp:.3f}')
+            self.logger.info(f'HL BPP: {compression_output.hyperlatent_bpp:.3f}')
+            self.logger.info(f'L BPP: {compression_output.latent_bpp:.3f}')
+            self.logger.info('[ATTAINED]')
+            self.logger.info(f'BPP: {attained_bpp:.3f}')
+            self.logger.info(f'HL BPP: {attained_hbpp:.3f}')
+            self.logger.info(f'L BPP: {attained_lbpp:.3f}')
+        return compression_output
 
     def decompress(self, compression_output):
-        raise NotImplementedError("Model.decompress drives the host rANS coder (src/model.py:312-344): out of scope")
+        """src/model.py:312-344: CompressionOutput -> reconstruction in [0, 1], cropped to the original size."""
+        assert self.model_mode == ModelModes.EVALUATION and (self.training is False), (
+            f'Set model mode to {ModelModes.EVALUATION} for decompression.')
+        device = next(self.parameters()).device
+        with torch.no_grad():
+            latents_decoded = self.Hyperprior.decompress_forward(compression_output, device=device)
+            reconstruction = self.Generator(latents_decoded)
+            if self.args.normalize_input_image is True:
+                reconstruction = torch.tanh(reconstruction)
+            image_dims = compression_output.spatial_shape
+            reconstruction = reconstruction[:, :, :image_dims[0], :image_dims[1]]
+            if self.args.normalize_input_image is True:
+                reconstruction = (reconstruction + 1.) / 2.
+            reconstruction = torch.clamp(reconstruction, min=0., max=1.)
+        return reconstruction

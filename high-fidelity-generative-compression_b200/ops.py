@@ -403,3 +403,63 @@ class GanLossFn(torch.autograd.Function):
         g = g.to(torch.float32).contiguous()
         check(lib.hfc_gan_grad(_ptr(lg), half, ctx.mode, _ptr(g), _ptr(out), _stream()), "gan_grad")
         return out[:half].view(ctx.shapes[0]), out[half:].view(ctx.shapes[1]), None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# compress / decompress path: the GPU half either side of the host rANS coder (csrc/symbols.cu)
+# ------------------------------------------------------------------------------------------------------------
+def quantize_symbols(x, mean=None, scale_raw=None, scale_table=None, scale_lower_bound=0.11,
+                     likelihood_type="gaussian", layout=_lib.SYM_BATCH_STEPS, want_symbols=True, want_indices=True,
+                     want_dequant=False, want_bits=False):
+    """One pass over the (N, C, H, W) latents: int32 symbols floor(x + .5 - mean) and table indices in coder order
+    (`layout`), optionally the dequantised latents (NCHW fp32) and the natural-log likelihood sum of the quantised
+    values (fp64 device scalar).  Returns a dict with the requested entries."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    for t in (mean, scale_raw):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == x.shape)
+    n, c, h, w = x.shape
+    dev = x.device
+    out = {}
+    if want_symbols:
+        out["symbols"] = torch.empty(n * c * h * w, dtype=torch.int32, device=dev)
+    if want_indices:
+        out["indices"] = torch.empty(n * c * h * w, dtype=torch.int32, device=dev)
+    if want_dequant:
+        out["dequant"] = torch.empty_like(x)
+    if want_bits:
+        assert scale_raw is not None
+        out["bits_sum"] = torch.zeros(1, dtype=torch.float64, device=dev)
+    tbl = None
+    if scale_raw is not None:
+        tbl = scale_table.to(device=dev, dtype=torch.float32).contiguous()
+    lt = {"gaussian": 0, "logistic": 1}[likelihood_type]
+    check(lib.hfc_quantize_symbols(_ptr(x), _ptr(mean), _ptr(scale_raw), n, c, h * w, _ptr(tbl),
+                                   tbl.numel() if tbl is not None else 0, float(scale_lower_bound), lt, int(layout),
+                                   _ptr(out.get("symbols")), _ptr(out.get("indices")), _ptr(out.get("dequant")),
+                                   _ptr(out.get("bits_sum")), _stream()), "quantize_symbols")
+    if want_bits:
+        out["bits_sum"] = out["bits_sum"][0]
+    return out
+
+
+def scale_indices(scale_raw, scale_table, scale_lower_bound=0.11, layout=_lib.SYM_BATCH_STEPS):
+    """Table index of every scale (PriorEntropyModel.compute_indices) as flat int32 in coder order."""
+    assert scale_raw.is_cuda and scale_raw.dtype == torch.float32 and scale_raw.is_contiguous() and scale_raw.dim() == 4
+    n, c, h, w = scale_raw.shape
+    tbl = scale_table.to(device=scale_raw.device, dtype=torch.float32).contiguous()
+    out = torch.empty(n * c * h * w, dtype=torch.int32, device=scale_raw.device)
+    check(lib.hfc_scale_indices(_ptr(scale_raw), n, c, h * w, _ptr(tbl), tbl.numel(), float(scale_lower_bound),
+                                int(layout), _ptr(out), _stream()), "scale_indices")
+    return out
+
+
+def dequantize_symbols(symbols, mean, shape, layout=_lib.SYM_BATCH_STEPS):
+    """int32 symbols in coder order (+ NCHW fp32 mean, may be None) -> NCHW fp32 latents."""
+    n, c, h, w = shape
+    assert symbols.is_cuda and symbols.dtype == torch.int32 and symbols.is_contiguous() and symbols.numel() == n * c * h * w
+    assert mean is None or (mean.is_cuda and mean.dtype == torch.float32 and mean.is_contiguous()
+                            and tuple(mean.shape) == tuple(shape))
+    out = torch.empty(shape, dtype=torch.float32, device=symbols.device)
+    check(lib.hfc_dequantize_symbols(_ptr(symbols), _ptr(mean), n, c, h * w, int(layout), _ptr(out), _stream()),
+          "dequantize_symbols")
+    return out

@@ -320,6 +320,60 @@ int hfc_hyperlatent_likelihood_bwd(const float* z_noisy, const float* dz_in, con
 int hfc_lpips_layer_bwd(const float* f0, const float* f1, const float* lin_w, const float* upstream, int32_t n,
                         int32_t c, int32_t hw, float* df1, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Compress / decompress path (compress.py, src/model.py:262-344, src/hyperprior.py:195-274): the GPU half
+ * (symbols, table indices, Shannon bits, dequantisation) and the HOST half (table quantisation, the rANS coder
+ * -- "the sequential ANS entropy coder stays on the host", BASELINE north_star).  *_host functions take HOST
+ * pointers, do not touch the GPU and work without one.
+ * --------------------------------------------------------------------------------------------------------- */
+/* layout of the symbol arrays the vectorised coder walks, [steps][lanes] (entropy_coding.py:298-316 with
+ * PATCH_SIZE (1, 1)): HFC_SYM_BATCH_STEPS: steps = n, lanes = (c, h, w) (plain NCHW, the reference's batch > 1 case);
+ * HFC_SYM_PIXEL_STEPS: steps = (n, h, w), lanes = c (the reference's batch == 1 case, n must be 1 there). */
+enum { HFC_SYM_BATCH_STEPS = 0, HFC_SYM_PIXEL_STEPS = 1 };
+/*
+ * Encoder side of PriorEntropyModel.compress (src/compression/prior_model.py:148-198) fused with
+ * _estimate_compression_bits (:122-146) -- and of HyperpriorEntropyModel.compress (hyperprior_model.py:141-197)
+ * when mean == NULL and scale_raw == NULL:
+ *   symbols = (int32) floor(x + 0.5 - mean)
+ *   indices = 63 - #{ s in scale_table[0..n_scales-2] : max(scale_raw, scale_lower_bound) <= s }   (compute_indices)
+ *             (scale_raw == NULL: indices = channel)
+ *   dequant = symbols + mean   (what the decoder reconstructs; optional, NCHW fp32)
+ *   *bits_sum += sum ln(max(p, 1e-9) + 1e-9), p = conditional likelihood of the quantised value (optional, fp64,
+ *               caller-zeroed; only with scale_raw; natural log: divide by -ln 2 for bits)
+ * x / mean / scale_raw / dequant: NCHW fp32; symbols / indices: int32 in `layout` order.
+ */
+int hfc_quantize_symbols(const float* x, const float* mean, const float* scale_raw, int32_t n, int32_t c, int32_t hw,
+                         const float* scale_table, int32_t n_scales, float scale_lower_bound, int32_t likelihood_type,
+                         int32_t layout, int32_t* symbols, int32_t* indices, float* dequant, double* bits_sum,
+                         void* stream);
+/* Decoder side (prior_model.py:201-246, entropy_models.py:65-73): symbols (int32, `layout` order) -> NCHW fp32
+ * out = symbols + mean (mean may be NULL). */
+int hfc_dequantize_symbols(const int32_t* symbols, const float* mean, int32_t n, int32_t c, int32_t hw, int32_t layout,
+                           float* out, void* stream);
+/* Decoder side of compute_indices alone (prior_model.py:148-156): indices in `layout` order from NCHW scale_raw. */
+int hfc_scale_indices(const float* scale_raw, int32_t n, int32_t c, int32_t hw, const float* scale_table,
+                      int32_t n_scales, float scale_lower_bound, int32_t layout, int32_t* indices, void* stream);
+
+/* maths.pmf_to_quantized_cdf (src/helpers/maths.py:5-73): n float32 probabilities -> n + 1 integers, cdf[0] = 0,
+ * cdf[n] = 2^precision, every symbol keeps a non-zero frequency. */
+int hfc_pmf_to_quantized_cdf_host(const float* pmf_host, int32_t n, int32_t precision, int32_t* cdf_host);
+/*
+ * The reference's vectorised indexed rANS coder (src/compression/entropy_coding.py:251-476, 555-676 over
+ * src/compression/ans.py): one 64-bit state per lane, `steps` symbols per lane, symbols / indices int32 [steps][lanes];
+ * cdf (cdf_rows x cdf_cols) int32 row-major with cdf_length / cdf_offset per row; symbols outside
+ * [offset, offset + length - 2) are escaped with 4-bit codes exactly as the reference does.
+ * encode: returns the number of 32-bit words written to out_host (the flat message of ans.flatten), or, with
+ * out_host == NULL, the number of words needed; negative hfc_status on error.
+ */
+int64_t hfc_rans_encode_host(const int32_t* symbols_host, const int32_t* indices_host, int64_t steps, int64_t lanes,
+                             const int32_t* cdf_host, int32_t cdf_rows, int32_t cdf_cols,
+                             const int32_t* cdf_length_host, const int32_t* cdf_offset_host, int32_t precision,
+                             uint32_t* out_host, int64_t out_capacity);
+int hfc_rans_decode_host(const uint32_t* encoded_host, int64_t n_words, const int32_t* indices_host, int64_t steps,
+                         int64_t lanes, const int32_t* cdf_host, int32_t cdf_rows, int32_t cdf_cols,
+                         const int32_t* cdf_length_host, const int32_t* cdf_offset_host, int32_t precision,
+                         int32_t* symbols_host);
+
 #ifdef __cplusplus
 }
 #endif
