@@ -127,6 +127,38 @@ def main():
         back = compression_utils.load_compressed_format(p)
         assert np.array_equal(back.latents_encoded, out["prior_b1.encoded"])
 
+    # ---------------------------------------------------------------- whole Model.compress / decompress (CPU reference)
+    import logging
+    from default_config import ModelModes, ModelTypes, mse_lpips_args
+    from src.model import Model
+
+    class A(mse_lpips_args):
+        pass
+    cfg = A()
+    cfg.image_dims, cfg.latent_dims, cfg.batch_size = (3, 256, 256), (cfg.latent_channels, 16, 16), 1
+    with quiet:
+        model = Model(cfg, logging.getLogger("golden"), model_mode=ModelModes.EVALUATION, model_type=ModelTypes.COMPRESSION)
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    model.eval()
+    with quiet:
+        model.Hyperprior.hyperprior_entropy_model.build_tables()
+    assert np.array_equal(model.Hyperprior.hyperprior_entropy_model.CDF.numpy(), out["hyper.CDF"])
+    for name, (b, h, w) in (("m1", (1, 100, 144)), ("m2", (2, 96, 128))):
+        x = synth.synth_image(b, h, w, 30 + b)
+        with torch.no_grad(), quiet:
+            co = model.compress(x, silent=True)
+            rec = model.decompress(co)
+        out[f"model_{name}.hyperlatents_encoded"] = np.asarray(co.hyperlatents_encoded, dtype=np.uint32)
+        out[f"model_{name}.latents_encoded"] = np.asarray(co.latents_encoded, dtype=np.uint32)
+        out[f"model_{name}.shapes"] = np.array(list(co.hyperlatent_spatial_shape) + list(co.spatial_shape)
+                                               + list(co.hyper_coding_shape) + list(co.latent_coding_shape)
+                                               + [co.batch_shape], dtype=np.int64)
+        out[f"model_{name}.bpp"] = np.array([co.hyperlatent_bpp, co.latent_bpp, co.total_bpp, co.hyperlatent_bits,
+                                             co.latent_bits, co.total_bits], dtype=np.float64)
+        out[f"model_{name}.reconstruction"] = rec.numpy()
+        print("model", name, "words", len(co.hyperlatents_encoded), len(co.latents_encoded), "bpp", co.total_bpp)
+
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     path = os.path.join(GOLDEN_DIR, "entropy_coding.npz")
     np.savez_compressed(path, **out)
