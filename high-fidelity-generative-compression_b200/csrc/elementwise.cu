@@ -6,6 +6,11 @@
 #include "hfc_likelihood.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdlib>
+
+#ifndef HFC_LIKELIHOOD_DEFAULT_VARIANT
+#define HFC_LIKELIHOOD_DEFAULT_VARIANT 1
+#endif
 
 namespace hfc {
 
@@ -496,6 +501,11 @@ extern "C" int hfc_channelnorm(const float* x, int32_t ld, const hfc_act_geom* g
   return HFC_OK;
 }
 
+static int likelihood_variant() {
+  const char* v = getenv("HFC_LIKELIHOOD_V");
+  return (v && v[0] == '2') ? 2 : HFC_LIKELIHOOD_DEFAULT_VARIANT;
+}
+
 extern "C" int hfc_latent_likelihood(const float* y, const float* mean, const float* scale_raw,
                                      const float* noise, int64_t count, float scale_lower_bound,
                                      int32_t likelihood_type, float* decoded, double* sums,
@@ -507,6 +517,16 @@ extern "C" int hfc_latent_likelihood(const float* y, const float* mean, const fl
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc != HFC_OK) return rc;
+  // Gaussian likelihood: schedule 2 (packed fp32 + balanced persistent grid, likelihood_v2.cu) when selected with
+  // HFC_LIKELIHOOD_V=2 (A/B switch while both schedules are being measured; read per call)
+  if (likelihood_type == 0 && likelihood_variant() == 2) {
+    rc = launch_latent_likelihood_v2(y, mean, scale_raw, noise, count, scale_lower_bound, decoded, sums, sms,
+                                     static_cast<cudaStream_t>(stream));
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "latent_likelihood (v2) launch: %s", cudaGetErrorString(e2));
+    note_launch();
+    return rc;
+  }
   // one float4 per thread up to 16 resident blocks of 128 threads per SM, grid-stride beyond that
   const long long want = (count / 4 + 127) / 128;
   const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(want, sms * 32LL)));
