@@ -261,6 +261,84 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
                     "backward of the D loss + Adam; gradient all-reduce (NCCL) when n_gpus > 1"}
 
 
+
+def run_likelihood_roofline(dev, peaks, batch):
+    """HBM roofline of the conditional-likelihood kernel at this batch's latent size (north_star: >= 60 % of HBM peak at
+    batch 32): 20 B/element algorithmic traffic, CUDA events around single launches on the launching
+    stream, L2 flushed (256 MiB memset) before every launch.  Both schedules of the kernel are timed; `schedule` is the
+    one hfc_latent_likelihood uses by default."""
+    from hific_b200 import ops
+    n = batch * 220 * 16 * 16
+    g = torch.Generator(device=dev).manual_seed(0)
+    y = torch.randn(n, device=dev, generator=g).view(batch, 220, 16, 16) * 2
+    mu = torch.randn(n, device=dev, generator=g).view_as(y)
+    s = torch.rand(n, device=dev, generator=g).view_as(y) * 2
+    nz = torch.rand(n, device=dev, generator=g).view_as(y) - 0.5
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    default = os.environ.get("HFC_LIKELIHOOD_V")
+    res = {}
+    try:
+        for v in ("1", "2"):
+            os.environ["HFC_LIKELIHOOD_V"] = v
+            sums = torch.zeros(2, dtype=torch.float64, device=dev)
+            for _ in range(3):
+                ops.latent_likelihood(y, mu, s, nz, sums=sums)
+            ts = []
+            for _ in range(20):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ops.latent_likelihood(y, mu, s, nz, sums=sums)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sum(ts) / len(ts)
+            gbs = 20.0 * n / (ms * 1e-3) / 1e9
+            res[v] = {"ms_per_launch": ms, "achieved": gbs, "frac": gbs / peaks["hbm"]}
+    finally:
+        if default is None:
+            os.environ.pop("HFC_LIKELIHOOD_V", None)
+        else:
+            os.environ["HFC_LIKELIHOOD_V"] = default
+    used = default if default in ("1", "2") else "1"
+    return {"kernel": "latent_likelihood_kernel (y, mean, scale, noise -> y_hat, 2 log-likelihood sums), %d elements" % n,
+            "bound": "hbm", "achieved": res[used]["achieved"], "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": res[used]["frac"], "traffic": None, "ms_per_launch": res[used]["ms_per_launch"],
+            "algorithmic_bytes_per_launch": 20 * n, "schedule": used, "schedules": res,
+            "peak_source": peaks["source"] + ", HBM copy bandwidth", "l2": "flushed (256 MiB memset) before every timed launch"}
+
+
+def run_compress_path(model, dev, x_host):
+    """compress.py's path through the public API (Model.compress -> CompressionOutput -> Model.decompress): GPU networks
+    and symbol kernels + the host rANS coder; wall clock with a device synchronisation on both sides."""
+    model.enable_cuda_graph(False)
+    t0 = time.perf_counter()
+    model.Hyperprior.hyperprior_entropy_model.build_tables()          # compress.py:61,122 (host, once per checkpoint)
+    out = {"hyper_table_build_s": time.perf_counter() - t0}
+    for b in sorted({1, min(8, x_host.shape[0])}):
+        x = x_host[:b].to(dev)
+        co = model.compress(x, silent=True)
+        model.decompress(co)
+        torch.cuda.synchronize()
+        n = 3
+        t0 = time.perf_counter()
+        for _ in range(n):
+            co = model.compress(x, silent=True)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(n):
+            rec = model.decompress(co)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        out[f"batch{b}"] = {"compress_ms": 1e3 * (t1 - t0) / n, "decompress_ms": 1e3 * (t2 - t1) / n,
+                            "message_bytes": 4 * (len(co.hyperlatents_encoded) + len(co.latents_encoded)),
+                            "estimated_bits": co.total_bits, "coder_lanes": "channels" if b == 1 else "C*H*W"}
+    out["what"] = ("Model.compress / Model.decompress on b x 3x256x256 (random-init weights: ~10 bpp, far above a trained "
+                   "model's rate): Encoder/Hyperprior/Generator kernels + hfc_quantize_symbols / hfc_scale_indices / "
+                   "hfc_dequantize_symbols on the GPU, rANS coder (bit-compatible with the reference's) on one host core")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,6 +351,7 @@ def main():
     ap.add_argument("--train-batch", type=int, default=0, help="per-GPU batch of the training step (default: --batch)")
     ap.add_argument("--gan-batch", type=int, default=0, help="per-GPU batch of the GAN iterations (default: the training batch)")
     ap.add_argument("--no-gan", action="store_true", help="skip the COMPRESSION_GAN alternating-iteration measurement")
+    ap.add_argument("--no-compress", action="store_true", help="skip the Model.compress / decompress measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true",
                     help="profiling mode (ncu): device-resident steps only, no e2e / roofline / CPU legs")
@@ -425,6 +504,19 @@ def main():
         cpu = {"value": sb * n / dt, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": f"{n} forward passes of {sb}x3x256x256 through the CPU oracle (torch fp32, best of probed thread counts: {cores} of {os.cpu_count()} cores)"}
 
+    # --- compress / decompress through the public API, then the HBM roofline of the likelihood kernel (rank 0) ---
+    comp, lik = None, None
+    if rank == 0 and world == 1 and not args.no_compress:
+        try:
+            comp = run_compress_path(model, dev, x_host)
+        except Exception as e:          # never lose the headline line to an auxiliary measurement
+            comp = {"unavailable": repr(e)[:300]}
+    if rank == 0:
+        try:
+            lik = run_likelihood_roofline(dev, measured_peaks(), B)
+        except Exception as e:
+            lik = {"unavailable": repr(e)[:300]}
+
     if rank == 0:
         per_step = ms / args.steps
         print(json.dumps({
@@ -440,6 +532,7 @@ def main():
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "tflops_per_step_algorithmic": E_H_G_FLOPS_PER_IMAGE * B / 1e12,
             "train_step": train, "gan_train_iteration": gan,
+            "roofline_hbm": lik, "compress_path": comp,
         }))
     if dist is not None:
         dist.destroy_process_group()
