@@ -262,10 +262,30 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
 
 
 
+def ncu_dram_traffic(profile, kernel_substr):
+    """DRAM bytes (read + write) per launch of a kernel from a committed `ncu --set full` summary under profiles/
+    (tools/ncu_summary.py format); None when the file or the kernel is missing."""
+    path = os.path.join(ROOT, "profiles", profile)
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        for rec in json.load(open(path)):
+            if kernel_substr in rec.get("Kernel Name", ""):
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    val, u = rec[k].split()
+                    tot += float(val) * unit[u]
+                return tot
+    except (KeyError, ValueError, OSError):
+        return None
+    return None
+
+
 def run_likelihood_roofline(dev, peaks, batch):
     """HBM roofline of the conditional-likelihood kernel at this batch's latent size (north_star: >= 60 % of HBM peak at
     batch 32): 20 B/element algorithmic traffic, CUDA events around single launches on the launching
-    stream, L2 flushed (256 MiB memset) before every launch.  Both schedules of the kernel are timed; `schedule` is the
+    stream, L2 flushed (256 MiB memset) before every launch.  All three schedules of the kernel are timed; `schedule` is the
     one hfc_latent_likelihood uses by default."""
     from hific_b200 import ops
     n = batch * 220 * 16 * 16
@@ -278,7 +298,7 @@ def run_likelihood_roofline(dev, peaks, batch):
     default = os.environ.get("HFC_LIKELIHOOD_V")
     res = {}
     try:
-        for v in ("1", "2"):
+        for v in ("1", "2", "3"):
             os.environ["HFC_LIKELIHOOD_V"] = v
             sums = torch.zeros(2, dtype=torch.float64, device=dev)
             for _ in range(3):
@@ -300,7 +320,7 @@ def run_likelihood_roofline(dev, peaks, batch):
             os.environ.pop("HFC_LIKELIHOOD_V", None)
         else:
             os.environ["HFC_LIKELIHOOD_V"] = default
-    used = default if default in ("1", "2") else "1"
+    used = default if default in ("1", "2", "3") else "2"         # HFC_LIKELIHOOD_DEFAULT_VARIANT in csrc/elementwise.cu
     return {"kernel": "latent_likelihood_kernel (y, mean, scale, noise -> y_hat, 2 log-likelihood sums), %d elements" % n,
             "bound": "hbm", "achieved": res[used]["achieved"], "peak": peaks["hbm"], "unit": "GB/s",
             "frac": res[used]["frac"], "traffic": None, "ms_per_launch": res[used]["ms_per_launch"],
@@ -477,7 +497,11 @@ def main():
         achieved = flops / (k_ms * 1e-3) / 1e12
         roof = {"kernel": "conv_igemm_kernel (Generator residual conv 960->960 3x3, M=%d N=960 K=8640)" % (B * 256),
                 "bound": "tensor", "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["burst"], "traffic": None, "ms_per_launch": k_ms,
+                "frac": achieved / peaks["burst"],
+                "traffic": ncu_dram_traffic("r01_ncu_resconv_v9.json", "conv_igemm_kernel<1, 2>"),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_resconv_v9.json "
+                                  "(ncu --set full; the operands of this GEMM are L2-resident re-reads, DRAM sees the weights once)",
+                "ms_per_launch": k_ms,
                 "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", bf16 burst",
                 "l2": "flushed (256 MiB memset) before every timed launch",
                 "step_tensor_frac": (E_H_G_FLOPS_PER_IMAGE * B / (ms / args.steps * 1e-3) / 1e12) / peaks["sustained"]}

@@ -112,8 +112,8 @@ SIGNATURES = {
                                        _vp, _vp, _vp, _vp, _vp]),
     "hfc_latent_likelihood": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp]),
     "hfc_hyperlatent_likelihood": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
-    "hfc_quantize_symbols": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "hfc_scale_indices": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _f32, _i32, _vp, _vp]),
+    "hfc_quantize_symbols": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hfc_scale_indices": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _f32, _i32, _i32, _vp, _vp]),
     "hfc_dequantize_symbols": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "hfc_pmf_to_quantized_cdf_host": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "hfc_rans_encode_host": (_i64, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _i64]),

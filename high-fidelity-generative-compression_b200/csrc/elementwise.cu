@@ -9,7 +9,7 @@
 #include <cstdlib>
 
 #ifndef HFC_LIKELIHOOD_DEFAULT_VARIANT
-#define HFC_LIKELIHOOD_DEFAULT_VARIANT 1
+#define HFC_LIKELIHOOD_DEFAULT_VARIANT 2
 #endif
 
 namespace hfc {
@@ -503,7 +503,7 @@ extern "C" int hfc_channelnorm(const float* x, int32_t ld, const hfc_act_geom* g
 
 static int likelihood_variant() {
   const char* v = getenv("HFC_LIKELIHOOD_V");
-  return (v && v[0] == '2') ? 2 : HFC_LIKELIHOOD_DEFAULT_VARIANT;
+  return (v && v[0] >= '1' && v[0] <= '3') ? v[0] - '0' : HFC_LIKELIHOOD_DEFAULT_VARIANT;
 }
 
 extern "C" int hfc_latent_likelihood(const float* y, const float* mean, const float* scale_raw,
@@ -517,11 +517,13 @@ extern "C" int hfc_latent_likelihood(const float* y, const float* mean, const fl
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc != HFC_OK) return rc;
-  // Gaussian likelihood: schedule 2 (packed fp32 + balanced persistent grid, likelihood_v2.cu) when selected with
-  // HFC_LIKELIHOOD_V=2 (A/B switch while both schedules are being measured; read per call)
-  if (likelihood_type == 0 && likelihood_variant() == 2) {
+  // Gaussian likelihood: schedule 2 (packed fp32 + balanced persistent grid, likelihood_v2.cu) by default -- measured
+  // 20.5 -> 16.4 us at the c2 size, 47.1 -> 36.9 us at c5 (profiles/r01_likelihood_ab.json); HFC_LIKELIHOOD_V=1|2|3
+  // selects a schedule explicitly (1: latent_likelihood_kernel below, 3: schedule 2 + register-double-buffered loads)
+  const int variant = likelihood_variant();
+  if (likelihood_type == 0 && variant >= 2) {
     rc = launch_latent_likelihood_v2(y, mean, scale_raw, noise, count, scale_lower_bound, decoded, sums, sms,
-                                     static_cast<cudaStream_t>(stream));
+                                     variant == 3, static_cast<cudaStream_t>(stream));
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "latent_likelihood (v2) launch: %s", cudaGetErrorString(e2));
     note_launch();

@@ -21,6 +21,7 @@ int device_sm_count(int* sm_count);
 void note_launch();
 // Second schedule of the Gaussian latent-likelihood kernel (likelihood_v2.cu); same contract as hfc_latent_likelihood.
 int launch_latent_likelihood_v2(const float* y, const float* mean, const float* scale_raw, const float* noise,
-                                int64_t count, float lb, float* decoded, double* sums, int sms, cudaStream_t st);
+                                int64_t count, float lb, float* decoded, double* sums, int sms, bool prefetch,
+                                cudaStream_t st);
 
 }  // namespace hfc

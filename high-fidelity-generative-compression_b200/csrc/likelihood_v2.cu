@@ -117,8 +117,8 @@ __device__ __forceinline__ f2 element(float y, float mu, float sraw, float nz, f
   return pk(lg2(fmaxf(p0, 1e-9f) + 1e-9f), lg2(fmaxf(p1, 1e-9f) + 1e-9f));
 }
 
-template <bool HAS_NOISE>
-__global__ void __launch_bounds__(256, 5)
+template <bool HAS_NOISE, bool PREFETCH>
+__global__ void __launch_bounds__(256, PREFETCH ? 4 : 5)
 latent_likelihood_v2_kernel(const float* __restrict__ y, const float* __restrict__ mean,
                             const float* __restrict__ scale, const float* __restrict__ noise, int64_t count, float lb,
                             float* __restrict__ decoded, double* __restrict__ sums) {
@@ -127,18 +127,50 @@ latent_likelihood_v2_kernel(const float* __restrict__ y, const float* __restrict
   // equal contiguous slices of the float4 vectors per block
   const int64_t v0 = nvec * blockIdx.x / gridDim.x, v1 = nvec * (blockIdx.x + 1) / gridDim.x;
   f2 acc = pk1(0.f);                                                   // (quantised, noisy) in log2 units
-  for (int64_t i = v0 + threadIdx.x; i < v1; i += 256) {
-    const float4 yy = reinterpret_cast<const float4*>(y)[i];
-    const float4 mm = reinterpret_cast<const float4*>(mean)[i];
-    const float4 ss = reinterpret_cast<const float4*>(scale)[i];
-    float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (HAS_NOISE) nz = reinterpret_cast<const float4*>(noise)[i];
-    float4 dd;
-    acc = add2(acc, element(yy.x, mm.x, ss.x, nz.x, lb, dd.x));
-    acc = add2(acc, element(yy.y, mm.y, ss.y, nz.y, lb, dd.y));
-    acc = add2(acc, element(yy.z, mm.z, ss.z, nz.z, lb, dd.z));
-    acc = add2(acc, element(yy.w, mm.w, ss.w, nz.w, lb, dd.w));
-    if (decoded) reinterpret_cast<float4*>(decoded)[i] = dd;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (PREFETCH) {
+    // schedule 3: the loads of vector i + 256 are in flight while vector i is evaluated (register double buffer), so
+    // that DRAM does not idle during the arithmetic phase of a thread's 1-3 iterations
+    int64_t i = v0 + threadIdx.x;
+    float4 yy = zero4, mm = zero4, ss = zero4, nz = zero4;
+    if (i < v1) {
+      yy = reinterpret_cast<const float4*>(y)[i];
+      mm = reinterpret_cast<const float4*>(mean)[i];
+      ss = reinterpret_cast<const float4*>(scale)[i];
+      if (HAS_NOISE) nz = reinterpret_cast<const float4*>(noise)[i];
+    }
+    while (i < v1) {
+      const int64_t in = i + 256;
+      float4 yn = zero4, mn = zero4, sn = zero4, nn = zero4;
+      if (in < v1) {
+        yn = reinterpret_cast<const float4*>(y)[in];
+        mn = reinterpret_cast<const float4*>(mean)[in];
+        sn = reinterpret_cast<const float4*>(scale)[in];
+        if (HAS_NOISE) nn = reinterpret_cast<const float4*>(noise)[in];
+      }
+      float4 dd;
+      acc = add2(acc, element(yy.x, mm.x, ss.x, nz.x, lb, dd.x));
+      acc = add2(acc, element(yy.y, mm.y, ss.y, nz.y, lb, dd.y));
+      acc = add2(acc, element(yy.z, mm.z, ss.z, nz.z, lb, dd.z));
+      acc = add2(acc, element(yy.w, mm.w, ss.w, nz.w, lb, dd.w));
+      if (decoded) reinterpret_cast<float4*>(decoded)[i] = dd;
+      yy = yn; mm = mn; ss = sn; nz = nn;
+      i = in;
+    }
+  } else {
+    for (int64_t i = v0 + threadIdx.x; i < v1; i += 256) {
+      const float4 yy = reinterpret_cast<const float4*>(y)[i];
+      const float4 mm = reinterpret_cast<const float4*>(mean)[i];
+      const float4 ss = reinterpret_cast<const float4*>(scale)[i];
+      float4 nz = zero4;
+      if (HAS_NOISE) nz = reinterpret_cast<const float4*>(noise)[i];
+      float4 dd;
+      acc = add2(acc, element(yy.x, mm.x, ss.x, nz.x, lb, dd.x));
+      acc = add2(acc, element(yy.y, mm.y, ss.y, nz.y, lb, dd.y));
+      acc = add2(acc, element(yy.z, mm.z, ss.z, nz.z, lb, dd.z));
+      acc = add2(acc, element(yy.w, mm.w, ss.w, nz.w, lb, dd.w));
+      if (decoded) reinterpret_cast<float4*>(decoded)[i] = dd;
+    }
   }
   if (blockIdx.x == 0) {                                              // ragged tail (count % 4 elements)
     const int64_t i = nvec * 4 + threadIdx.x;
@@ -169,15 +201,24 @@ latent_likelihood_v2_kernel(const float* __restrict__ y, const float* __restrict
 
 }  // namespace
 
-// Gaussian likelihood only (the logistic variant stays on latent_likelihood_kernel).
+// Gaussian likelihood only (the logistic variant stays on latent_likelihood_kernel).  prefetch: schedule 3.
 int launch_latent_likelihood_v2(const float* y, const float* mean, const float* scale_raw, const float* noise,
-                                int64_t count, float lb, float* decoded, double* sums, int sms, cudaStream_t st) {
+                                int64_t count, float lb, float* decoded, double* sums, int sms, bool prefetch,
+                                cudaStream_t st) {
   const int64_t nvec = count / 4;
-  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((nvec + 255) / 256, sms * 5LL)));
-  if (noise)
-    latent_likelihood_v2_kernel<true><<<blocks, 256, 0, st>>>(y, mean, scale_raw, noise, count, lb, decoded, sums);
-  else
-    latent_likelihood_v2_kernel<false><<<blocks, 256, 0, st>>>(y, mean, scale_raw, noise, count, lb, decoded, sums);
+  const int per_sm = prefetch ? 4 : 5;
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((nvec + 255) / 256, static_cast<int64_t>(sms) * per_sm)));
+  if (prefetch) {
+    if (noise)
+      latent_likelihood_v2_kernel<true, true><<<blocks, 256, 0, st>>>(y, mean, scale_raw, noise, count, lb, decoded, sums);
+    else
+      latent_likelihood_v2_kernel<false, true><<<blocks, 256, 0, st>>>(y, mean, scale_raw, noise, count, lb, decoded, sums);
+  } else {
+    if (noise)
+      latent_likelihood_v2_kernel<true, false><<<blocks, 256, 0, st>>>(y, mean, scale_raw, noise, count, lb, decoded, sums);
+    else
+      latent_likelihood_v2_kernel<false, false><<<blocks, 256, 0, st>>>(y, mean, scale_raw, noise, count, lb, decoded, sums);
+  }
   return HFC_OK;
 }
 

@@ -23,6 +23,7 @@ struct SymParams {
   int32_t n_scales;
   float lb;
   int32_t type;
+  int32_t sorted;      // scale table is non-decreasing: binary search instead of the linear count
 };
 
 struct SymOut {
@@ -40,9 +41,22 @@ __device__ __forceinline__ SymOut sym_one(float x, float mu, float sraw, bool ha
     // LowerBoundToward forward = clamp(min) (maths.py:92-96); NaN propagates as in torch.clamp
     scale = (sraw >= p.lb || sraw != sraw) ? sraw : p.lb;
     // compute_indices (prior_model.py:148-156): (n_scales - 1) - #{ s in table[:-1] : scale <= s }
-    int below = p.n_scales - 1;
-    for (int k = 0; k < p.n_scales - 1; ++k) below -= (scale <= table[k]) ? 1 : 0;
-    o.idx = below;
+    //   = #{ s in table[:-1] : s < scale } (NaN: n_scales - 1).
+    if (p.sorted) {
+      // non-decreasing table (the reference's log-spaced one; checked on the host): the count is the lower bound of
+      // `scale`, found in ceil(log2(n_scales)) probes instead of the reference's n_scales - 1 full-tensor compares.
+      // (first ncu capture of the linear count at the c5 size: 113 M warp instructions, 118 us, sm 83 % -- compute-bound)
+      int lo = 0, hi = p.n_scales - 1;                     // answer in [lo, hi]
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (table[mid] < scale) lo = mid + 1; else hi = mid;
+      }
+      o.idx = (scale != scale) ? p.n_scales - 1 : lo;
+    } else {
+      int below = p.n_scales - 1;
+      for (int k = 0; k < p.n_scales - 1; ++k) below -= (scale <= table[k]) ? 1 : 0;
+      o.idx = below;
+    }
   }
   if (has_x) {
     const float m = has_mean ? mu : 0.f;
@@ -193,7 +207,7 @@ static int flat_blocks(int64_t count, int sms) {
 static int launch_quantize(const float* x, const float* mean, const float* scale_raw, int32_t n, int32_t c, int32_t hw,
                            const float* scale_table, int32_t n_scales, float lb, int32_t likelihood_type, int32_t layout,
                            int32_t* symbols, int32_t* indices, float* dequant, double* bits_sum, void* stream,
-                           const char* who) {
+                           int32_t table_sorted, const char* who) {
   if (n <= 0 || c <= 0 || hw <= 0) return set_error(HFC_ERR_INVALID, "%s: empty tensor", who);
   if (!x && !scale_raw) return set_error(HFC_ERR_INVALID, "%s: neither values nor scales given", who);
   if (scale_raw && (!scale_table || n_scales < 2 || n_scales > kMaxScales))
@@ -208,6 +222,7 @@ static int launch_quantize(const float* x, const float* mean, const float* scale
   if (rc != HFC_OK) return rc;
   SymParams p;
   p.n = n; p.c = c; p.hw = hw; p.n_scales = scale_raw ? n_scales : 0; p.lb = lb; p.type = likelihood_type;
+  p.sorted = table_sorted;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (layout == HFC_SYM_BATCH_STEPS) {
     const int64_t count = static_cast<int64_t>(n) * c * hw;
@@ -231,20 +246,20 @@ using namespace hfc;
 
 extern "C" int hfc_quantize_symbols(const float* x, const float* mean, const float* scale_raw, int32_t n, int32_t c,
                                     int32_t hw, const float* scale_table, int32_t n_scales, float scale_lower_bound,
-                                    int32_t likelihood_type, int32_t layout, int32_t* symbols, int32_t* indices,
-                                    float* dequant, double* bits_sum, void* stream) {
+                                    int32_t likelihood_type, int32_t layout, int32_t table_sorted, int32_t* symbols,
+                                    int32_t* indices, float* dequant, double* bits_sum, void* stream) {
   if (!x || (!symbols && !bits_sum))
     return set_error(HFC_ERR_INVALID, "quantize_symbols: values and a symbol buffer (or a bit-sum target) required");
   return launch_quantize(x, mean, scale_raw, n, c, hw, scale_table, n_scales, scale_lower_bound, likelihood_type, layout,
-                         symbols, indices, dequant, bits_sum, stream, "quantize_symbols");
+                         symbols, indices, dequant, bits_sum, stream, table_sorted, "quantize_symbols");
 }
 
 extern "C" int hfc_scale_indices(const float* scale_raw, int32_t n, int32_t c, int32_t hw, const float* scale_table,
-                                 int32_t n_scales, float scale_lower_bound, int32_t layout, int32_t* indices,
-                                 void* stream) {
+                                 int32_t n_scales, float scale_lower_bound, int32_t layout, int32_t table_sorted,
+                                 int32_t* indices, void* stream) {
   if (!scale_raw || !indices) return set_error(HFC_ERR_INVALID, "scale_indices: scales and index buffer required");
   return launch_quantize(nullptr, nullptr, scale_raw, n, c, hw, scale_table, n_scales, scale_lower_bound, 0, layout,
-                         nullptr, indices, nullptr, nullptr, stream, "scale_indices");
+                         nullptr, indices, nullptr, nullptr, stream, table_sorted, "scale_indices");
 }
 
 extern "C" int hfc_dequantize_symbols(const int32_t* symbols, const float* mean, int32_t n, int32_t c, int32_t hw,

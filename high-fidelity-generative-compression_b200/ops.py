@@ -408,6 +408,24 @@ class GanLossFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------------
 # compress / decompress path: the GPU half either side of the host rANS coder (csrc/symbols.cu)
 # ------------------------------------------------------------------------------------------------------------
+_TABLE_CACHE = {}
+
+
+def _scale_table(scale_table, device):
+    """Device copy of the scale table + whether it is non-decreasing (then the kernels binary-search it); cached per
+    (storage, version, device) so the check and the copy cost nothing per call."""
+    key = (scale_table.data_ptr(), scale_table._version, scale_table.device, device)
+    hit = _TABLE_CACHE.get(key)
+    if hit is None:
+        host = scale_table.detach().to(dtype=torch.float32, device="cpu").reshape(-1)
+        is_sorted = int(bool((host[1:] >= host[:-1]).all()))
+        hit = (scale_table.detach().to(device=device, dtype=torch.float32).contiguous(), is_sorted, scale_table)
+        if len(_TABLE_CACHE) > 16:
+            _TABLE_CACHE.clear()
+        _TABLE_CACHE[key] = hit
+    return hit[0], hit[1]
+
+
 def quantize_symbols(x, mean=None, scale_raw=None, scale_table=None, scale_lower_bound=0.11,
                      likelihood_type="gaussian", layout=_lib.SYM_BATCH_STEPS, want_symbols=True, want_indices=True,
                      want_dequant=False, want_bits=False):
@@ -429,13 +447,13 @@ def quantize_symbols(x, mean=None, scale_raw=None, scale_table=None, scale_lower
     if want_bits:
         assert scale_raw is not None
         out["bits_sum"] = torch.zeros(1, dtype=torch.float64, device=dev)
-    tbl = None
+    tbl, is_sorted = None, 0
     if scale_raw is not None:
-        tbl = scale_table.to(device=dev, dtype=torch.float32).contiguous()
+        tbl, is_sorted = _scale_table(scale_table, dev)
     lt = {"gaussian": 0, "logistic": 1}[likelihood_type]
     check(lib.hfc_quantize_symbols(_ptr(x), _ptr(mean), _ptr(scale_raw), n, c, h * w, _ptr(tbl),
                                    tbl.numel() if tbl is not None else 0, float(scale_lower_bound), lt, int(layout),
-                                   _ptr(out.get("symbols")), _ptr(out.get("indices")), _ptr(out.get("dequant")),
+                                   is_sorted, _ptr(out.get("symbols")), _ptr(out.get("indices")), _ptr(out.get("dequant")),
                                    _ptr(out.get("bits_sum")), _stream()), "quantize_symbols")
     if want_bits:
         out["bits_sum"] = out["bits_sum"][0]
@@ -446,10 +464,10 @@ def scale_indices(scale_raw, scale_table, scale_lower_bound=0.11, layout=_lib.SY
     """Table index of every scale (PriorEntropyModel.compute_indices) as flat int32 in coder order."""
     assert scale_raw.is_cuda and scale_raw.dtype == torch.float32 and scale_raw.is_contiguous() and scale_raw.dim() == 4
     n, c, h, w = scale_raw.shape
-    tbl = scale_table.to(device=scale_raw.device, dtype=torch.float32).contiguous()
+    tbl, is_sorted = _scale_table(scale_table, scale_raw.device)
     out = torch.empty(n * c * h * w, dtype=torch.int32, device=scale_raw.device)
     check(lib.hfc_scale_indices(_ptr(scale_raw), n, c, h * w, _ptr(tbl), tbl.numel(), float(scale_lower_bound),
-                                int(layout), _ptr(out), _stream()), "scale_indices")
+                                int(layout), is_sorted, _ptr(out), _stream()), "scale_indices")
     return out
 
 

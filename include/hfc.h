@@ -341,18 +341,21 @@ enum { HFC_SYM_BATCH_STEPS = 0, HFC_SYM_PIXEL_STEPS = 1 };
  *   *bits_sum += sum ln(max(p, 1e-9) + 1e-9), p = conditional likelihood of the quantised value (optional, fp64,
  *               caller-zeroed; only with scale_raw; natural log: divide by -ln 2 for bits)
  * x / mean / scale_raw / dequant: NCHW fp32; symbols / indices: int32 in `layout` order.
+ * table_sorted: 1 if scale_table is non-decreasing (the caller checks; the reference's log-spaced table is): the
+ * index is then found by binary search -- same integers as the reference's compare loop -- else by the linear count.
  */
 int hfc_quantize_symbols(const float* x, const float* mean, const float* scale_raw, int32_t n, int32_t c, int32_t hw,
                          const float* scale_table, int32_t n_scales, float scale_lower_bound, int32_t likelihood_type,
-                         int32_t layout, int32_t* symbols, int32_t* indices, float* dequant, double* bits_sum,
-                         void* stream);
+                         int32_t layout, int32_t table_sorted, int32_t* symbols, int32_t* indices, float* dequant,
+                         double* bits_sum, void* stream);
 /* Decoder side (prior_model.py:201-246, entropy_models.py:65-73): symbols (int32, `layout` order) -> NCHW fp32
  * out = symbols + mean (mean may be NULL). */
 int hfc_dequantize_symbols(const int32_t* symbols, const float* mean, int32_t n, int32_t c, int32_t hw, int32_t layout,
                            float* out, void* stream);
 /* Decoder side of compute_indices alone (prior_model.py:148-156): indices in `layout` order from NCHW scale_raw. */
 int hfc_scale_indices(const float* scale_raw, int32_t n, int32_t c, int32_t hw, const float* scale_table,
-                      int32_t n_scales, float scale_lower_bound, int32_t layout, int32_t* indices, void* stream);
+                      int32_t n_scales, float scale_lower_bound, int32_t layout, int32_t table_sorted, int32_t* indices,
+                      void* stream);
 
 /* maths.pmf_to_quantized_cdf (src/helpers/maths.py:5-73): n float32 probabilities -> n + 1 integers, cdf[0] = 0,
  * cdf[n] = 2^precision, every symbol keeps a non-zero frequency. */

@@ -1,5 +1,5 @@
-"""GPU: second schedule of the Gaussian latent-likelihood kernel (csrc/likelihood_v2.cu: packed fp32, balanced
-persistent grid), selected with HFC_LIKELIHOOD_V=2, against a float64 restatement of src/hyperprior.py:124-139 and
+"""GPU: schedules 2 (the default: packed fp32, balanced persistent grid) and 3 (2 + register-double-buffered loads) of the
+Gaussian latent-likelihood kernel (csrc/likelihood_v2.cu), selected with HFC_LIKELIHOOD_V, against a float64 restatement of src/hyperprior.py:124-139 and
 against the first schedule on the same inputs.  Tolerance: 2e-5 relative on the log-likelihood sums (as for schedule 1),
 straight-through latents bit-identical to schedule 1."""
 import math
@@ -61,7 +61,8 @@ def inputs(shape, seed, scale=2.0):
 
 @pytest.mark.parametrize("shape", [(4, 220, 16, 16), (32, 220, 16, 16), (1, 3, 5, 7), (1, 1, 1, 2), (3, 7, 11, 13)])
 @pytest.mark.parametrize("with_noise", [True, False])
-def test_schedule2_matches_float64_and_schedule1(shape, with_noise):
+@pytest.mark.parametrize("schedule", [2, 3])
+def test_schedule2_matches_float64_and_schedule1(shape, with_noise, schedule):
     y, mu, sraw, noise = inputs(shape, seed=sum(shape))
     if not with_noise:
         noise = None
@@ -70,7 +71,7 @@ def test_schedule2_matches_float64_and_schedule1(shape, with_noise):
     with Schedule(1):
         dec1, sums1 = ops.latent_likelihood(*dev, 0.11, "gaussian")
     l0 = ops.launch_count()
-    with Schedule(2):
+    with Schedule(schedule):
         dec2, sums2 = ops.latent_likelihood(*dev, 0.11, "gaussian")
     assert ops.launch_count() - l0 == 1
     torch.cuda.synchronize()
@@ -84,7 +85,8 @@ def test_schedule2_matches_float64_and_schedule1(shape, with_noise):
         assert sums2[0].item() == 0.0
 
 
-def test_schedule2_far_tails_and_tiny_scales():
+@pytest.mark.parametrize("schedule", [2, 3])
+def test_schedule2_far_tails_and_tiny_scales(schedule):
     """|y - mu| up to 1e4 at scale 0.11 (p underflows to the 1e-9 bound), large scales (p ~ 4e-3 from the difference of two values near 1), exact half-integers."""
     g = torch.Generator().manual_seed(3)
     n = 4096
@@ -95,7 +97,7 @@ def test_schedule2_far_tails_and_tiny_scales():
     shape = (1, 3, 64, 64)
     y, mu, sraw, noise = (t.view(shape).contiguous() for t in (y, mu, sraw, noise))
     dec64, sn, sq = ref64(y, mu, sraw, noise)
-    with Schedule(2):
+    with Schedule(schedule):
         dec, sums = ops.latent_likelihood(y.cuda(), mu.cuda(), sraw.cuda(), noise.cuda(), 0.11, "gaussian")
     assert torch.equal(dec.cpu(), dec64)
     assert torch.isfinite(sums).all()

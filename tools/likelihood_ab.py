@@ -1,4 +1,4 @@
-"""A/B timing of the two schedules of the Gaussian latent-likelihood kernel (HFC_LIKELIHOOD_V=1|2) at the c2
+"""A/B timing of the three schedules of the Gaussian latent-likelihood kernel (HFC_LIKELIHOOD_V=1|2|3) at the c2
 (1 802 240 elements) and c5 (7 208 960) sizes: CUDA events on the launching stream, L2 flushed before every launch,
 20 B/element algorithmic traffic against the measured HBM peak.  GPU box only; prints one JSON line."""
 import json
@@ -27,7 +27,7 @@ def main():
         s = torch.rand(n, device="cuda", generator=g).view_as(y) * 2
         nz = torch.rand(n, device="cuda", generator=g).view_as(y) - 0.5
         res = {}
-        for v in ("1", "2"):
+        for v in ("1", "2", "3"):
             os.environ["HFC_LIKELIHOOD_V"] = v
             sums = torch.zeros(2, dtype=torch.float64, device="cuda")
             for _ in range(5):

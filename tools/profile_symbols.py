@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 n = 1802240
 y = torch.randn(n, device="cuda").view(1, 1, 1, n) * 2
 mu, s, nz = torch.randn_like(y), torch.rand_like(y) * 2, torch.rand_like(y) - 0.5
-for v in ("1", "2", "1", "2"):
+for v in ("1", "2", "3", "1", "2", "3"):
     os.environ["HFC_LIKELIHOOD_V"] = v
     ops.latent_likelihood(y, mu, s, nz)
 torch.cuda.synchronize()
