@@ -83,10 +83,29 @@ class PerceptualLoss(nn.Module):
             outs.append(h)
         return outs
 
+    def native_trunk(self):
+        """HFC_LPIPS_TRUNK=native runs the AlexNet trunk on the tcgen05 conv kernel (loss/lpips_trunk.py) instead of
+        cuDNN.  Opt-in until its GPU parity tests have run on hardware (written without GPU time left in round 1)."""
+        return os.environ.get("HFC_LPIPS_TRUNK", "cudnn") == "native"
+
+    def _native(self, pred, target, normalize):
+        from .. import engine
+        from . import lpips_trunk
+        if getattr(self, "_native_plans", None) is None:
+            self._native_plans = engine.PlanCache(
+                lambda x: lpips_trunk.LpipsTrunkPlan(x.shape[0], x.shape[2], x.shape[3], x.device))
+        plan = self._native_plans.get(pred)
+        if torch.is_grad_enabled() and pred.requires_grad:
+            return lpips_trunk.LpipsTrunkFn.apply(pred, target.detach(), plan, self, bool(normalize)).view(-1, 1, 1, 1)
+        with torch.no_grad():
+            return plan.forward(self, target, pred, bool(normalize)).view(-1, 1, 1, 1)
+
     def forward(self, pred, target, normalize=False):
         """Returns (N, 1, 1, 1) like the reference."""
         if not pred.is_cuda:
             raise RuntimeError("PerceptualLoss: hific_b200 has no CPU path")
+        if self.native_trunk():
+            return self._native(pred, target, normalize)
         if normalize:
             target = 2 * target - 1
             pred = 2 * pred - 1

@@ -481,3 +481,71 @@ def dequantize_symbols(symbols, mean, shape, layout=_lib.SYM_BATCH_STEPS):
     check(lib.hfc_dequantize_symbols(_ptr(symbols), _ptr(mean), n, c, h * w, int(layout), _ptr(out), _stream()),
           "dequantize_symbols")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# LPIPS trunk pieces in the activation format (csrc/lpips_trunk.cu)
+# ------------------------------------------------------------------------------------------------------------
+def lpips_prep(target, pred, geom, normalize, shift, scale, out=None):
+    """(n, 3, h, w) target / pred -> (2n, hs, ws, 64) fp16 scaled space-to-depth buffer `geom` (n = 2n images)."""
+    assert target.shape == pred.shape and target.is_cuda and pred.is_cuda
+    target, pred = target.contiguous(), pred.contiguous()
+    n, c, h, w = target.shape
+    assert c == 3 and geom.n == 2 * n and geom.cpad == 64
+    if out is None:
+        out = geom.alloc(target.device)
+    check(lib.hfc_lpips_prep(_ptr(target), _ptr(pred), n, h, w, geom.h, geom.w, int(bool(normalize)),
+                             _ptr(shift.reshape(-1).contiguous()), _ptr(scale.reshape(-1).contiguous()), _ptr(out),
+                             _stream()), "lpips_prep")
+    return out
+
+
+def lpips_prep_bwd(g_rows, n, h, w, hs, ws, normalize, scale):
+    assert g_rows.dtype == torch.float32 and g_rows.is_contiguous() and g_rows.shape[0] == n * hs * ws
+    dpred = torch.empty((n, 3, h, w), dtype=torch.float32, device=g_rows.device)
+    check(lib.hfc_lpips_prep_bwd(_ptr(g_rows), g_rows.shape[1], n, h, w, hs, ws, int(bool(normalize)),
+                                 _ptr(scale.reshape(-1).contiguous()), _ptr(dpred), _stream()), "lpips_prep_bwd")
+    return dpred
+
+
+def maxpool3s2(x_act, geom, out_geom, out=None):
+    """nn.MaxPool2d(3, 2) on a border-less NHWC fp16 buffer."""
+    assert tuple(x_act.shape) == geom.shape and x_act.dtype == torch.float16
+    assert (out_geom.h, out_geom.w) == ((geom.h - 3) // 2 + 1, (geom.w - 3) // 2 + 1) and out_geom.cpad == geom.cpad
+    if out is None:
+        out = out_geom.alloc(x_act.device)
+    g = geom.c_struct()
+    check(lib.hfc_maxpool3s2(_ptr(x_act), ctypes.byref(g), _ptr(out), _stream()), "maxpool3s2")
+    return out
+
+
+def maxpool3s2_bwd(g_out_rows, x_act, geom):
+    """Adjoint of maxpool3s2 for the images described by `geom` (x_act = the pooled layer's input for those images):
+    fp32 rows [n*oh*ow][ld] -> fp32 rows [n*h*w][c]."""
+    assert g_out_rows.dtype == torch.float32 and g_out_rows.is_contiguous() and x_act.dtype == torch.float16
+    g_in = torch.zeros((geom.n * geom.h * geom.w, geom.c), dtype=torch.float32, device=g_out_rows.device)
+    g = geom.c_struct()
+    check(lib.hfc_maxpool3s2_bwd(_ptr(g_out_rows), g_out_rows.shape[1], _ptr(x_act), ctypes.byref(g), _ptr(g_in),
+                                 g_in.shape[1], _stream()), "maxpool3s2_bwd")
+    return g_in
+
+
+def lpips_nhwc(feat_act, geom, lin_w, out):
+    """out[i] += LPIPS distance of one layer; feat_act (2n, h, w, cpad) holds target [0, n) and reconstruction [n, 2n)."""
+    assert tuple(feat_act.shape) == geom.shape and geom.n % 2 == 0 and out.numel() == geom.n // 2
+    check(lib.hfc_lpips_nhwc(_ptr(feat_act), geom.n // 2, geom.h * geom.w, geom.c, geom.cpad,
+                             _ptr(lin_w.reshape(-1).contiguous()), _ptr(out), _stream()), "lpips_nhwc")
+    return out
+
+
+def lpips_nhwc_bwd(feat_act, geom, lin_w, upstream, g_in_rows=None):
+    """fp32 rows [n*h*w][c]: gradient w.r.t. the pre-ReLU features of the reconstruction half (see hfc.h)."""
+    n = geom.n // 2
+    out = torch.empty((n * geom.h * geom.w, geom.c), dtype=torch.float32, device=feat_act.device)
+    assert g_in_rows is None or (g_in_rows.dtype == torch.float32 and g_in_rows.is_contiguous()
+                                 and g_in_rows.shape[0] == out.shape[0])
+    check(lib.hfc_lpips_nhwc_bwd(_ptr(feat_act), n, geom.h * geom.w, geom.c, geom.cpad,
+                                 _ptr(lin_w.reshape(-1).contiguous()), _ptr(upstream.contiguous()), _ptr(g_in_rows),
+                                 g_in_rows.shape[1] if g_in_rows is not None else 0, _ptr(out), out.shape[1], _stream()),
+          "lpips_nhwc_bwd")
+    return out

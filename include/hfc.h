@@ -377,6 +377,36 @@ int hfc_rans_decode_host(const uint32_t* encoded_host, int64_t n_words, const in
                          const int32_t* cdf_length_host, const int32_t* cdf_offset_host, int32_t precision,
                          int32_t* symbols_host);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * LPIPS (AlexNet) trunk in the internal activation format: the non-convolution pieces of
+ * src/loss/perceptual_similarity/{perceptual_loss.py:26-46, networks_basic.py:61-98, pretrained_networks.py:56-94}.
+ * The trunk's five convolutions are hfc_conv_forward launches (the 11x11 stride-4 head as a 3x3 conv over the 4x4
+ * space-to-depth image that hfc_lpips_prep writes); the frozen trunk needs data gradients only.
+ * --------------------------------------------------------------------------------------------------------- */
+/* target, pred: (n, 3, h, w) fp32 NCHW -> out_act (2n, hs, ws, 64) fp16 border-less, images [0, n) = target, [n, 2n) =
+ * pred; channel (dy * 4 + dx) * 3 + c of s2d pixel (I, J) = ((normalize ? 2x - 1 : x) - shift3[c]) / scale3[c] at image
+ * position (4I + dy - 2, 4J + dx - 2), zero outside the image; channels 48..63 zero.  hs = ((h + 4 - 11) / 4 + 1) + 2. */
+int hfc_lpips_prep(const float* target, const float* pred, int32_t n, int32_t h, int32_t w, int32_t hs, int32_t ws,
+                   int32_t normalize, const float* shift3, const float* scale3, void* out_act, void* stream);
+/* adjoint for the pred half: g_rows fp32 [n * hs * ws][ld >= 48] -> dpred (n, 3, h, w) */
+int hfc_lpips_prep_bwd(const float* g_rows, int32_t ld, int32_t n, int32_t h, int32_t w, int32_t hs, int32_t ws,
+                       int32_t normalize, const float* scale3, float* dpred, void* stream);
+/* nn.MaxPool2d(kernel_size=3, stride=2) on a border-less NHWC fp16 buffer g -> (n, (h-3)/2+1, (w-3)/2+1, cpad) */
+int hfc_maxpool3s2(const void* in_act, const hfc_act_geom* g, void* out_act, void* stream);
+/* its adjoint: g_out_rows fp32 [n * oh * ow][ld_out] -> ADDED into g_in_rows fp32 [n * h * w][ld_in] (caller zeroes) at
+ * the first maximum of every window (ATen semantics); in_act / g describe the pooled layer's input */
+int hfc_maxpool3s2_bwd(const float* g_out_rows, int32_t ld_out, const void* in_act, const hfc_act_geom* g,
+                       float* g_in_rows, int32_t ld_in, void* stream);
+/* hfc_lpips_layer on one NHWC fp16 feature buffer (2n, hw, cpad) holding target [0, n) and reconstruction [n, 2n):
+ * out_per_image[i] += mean_hw sum_c lin_w[c] (f0/|f0| - f1/|f1|)^2 */
+int hfc_lpips_nhwc(const void* feat_act, int32_t n, int32_t hw, int32_t c, int32_t cpad, const float* lin_w,
+                   float* out_per_image, void* stream);
+/* gradient w.r.t. the PRE-ReLU value of the reconstruction's features: g_out_rows[p][k] = (f1 > 0) *
+ * (upstream[img] * d dist / d f1 + g_in_rows[p][k]) ; g_in_rows (the gradient arriving from deeper layers) may be NULL */
+int hfc_lpips_nhwc_bwd(const void* feat_act, int32_t n, int32_t hw, int32_t c, int32_t cpad, const float* lin_w,
+                       const float* upstream, const float* g_in_rows, int32_t ld_g, float* g_out_rows, int32_t ld_out,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
