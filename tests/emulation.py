@@ -95,3 +95,140 @@ def cpu_emulation():
     finally:
         for obj, name, value in reversed(saved):
             setattr(obj, name, value)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# LPIPS trunk plan (hific_b200.loss.lpips_trunk): CPU stand-ins for the entry points it calls, written independently of
+# the CUDA code (plain torch ops on NCHW tensors), so that the PLAN (geometry, weight re-indexing, batching of the two
+# images, order of the adjoints) can be checked against torchvision's AlexNet + autograd without a GPU.  The `-m gpu`
+# tests then compare the real kernels with these same functions.
+# ----------------------------------------------------------------------------------------------------------------------
+import torch.nn.functional as F
+
+from hific_b200 import grad as _grad
+from hific_b200._lib import ACT_RELU, OUT_NHWC_F16, PAD_ZERO
+
+
+def _act_to_nchw(x_act, geom):
+    return x_act.view(geom.shape)[..., :geom.c].permute(0, 3, 1, 2).float()
+
+
+def _nchw_to_act(t, geom, out):
+    out.view(geom.shape).zero_()
+    out.view(geom.shape)[..., :geom.c] = t.permute(0, 2, 3, 1).to(torch.float16)
+    return out
+
+
+def conv_call(self, x_act, weight, bias=None, gamma=None, beta=None, out=None, scale=None, scale_key=None):
+    """ops.Conv.__call__ for the configuration the LPIPS plan uses: stride-1 conv2d, zero padding, bias + ReLU,
+    border-less NHWC fp16 in and out, fp16 operands with fp32 accumulation."""
+    d = self.desc
+    if d.stride != 1 or d.transposed or d.pad_mode != PAD_ZERO or d.out_mode != OUT_NHWC_F16 or d.norm or d.window \
+            or d.act != ACT_RELU or any((self.in_geom.pt, self.in_geom.pl, self.out_geom.pt, self.out_geom.pl)):
+        raise NotImplementedError("emulation covers the LPIPS trunk's conv configuration only")
+    x = _act_to_nchw(x_act, self.in_geom)
+    w = weight.detach().to(torch.float16).float()
+    y = F.conv2d(F.pad(x, (d.pad_l, d.pad_r, d.pad_t, d.pad_b)), w, bias.detach().float() if bias is not None else None)
+    y = torch.relu(y)
+    if out is None:
+        out = self.out_geom.alloc(x_act.device)
+    return _nchw_to_act(y, self.out_geom, out)
+
+
+def convgrad_data_grad(self, dy_rows, weight, out=None, scale=None, dy_act=None):
+    """grad.ConvGrad.data_grad for a stride-1 zero-padded conv2d: bf16 operands, fp32 accumulation, fp32 rows out."""
+    if self.transposed or self.stride != 1 or self.pad_mode != PAD_ZERO:
+        raise NotImplementedError
+    n = self.in_geom.n
+    dy = dy_rows[:, :self.cout].reshape(n, self.oh, self.ow, self.cout).permute(0, 3, 1, 2)
+    dy = dy.to(torch.bfloat16).float()
+    w = weight.detach().to(torch.bfloat16).float()
+    dx = F.conv_transpose2d(dy, w, stride=1, padding=self.pad[0])
+    rows = torch.zeros((n * self.in_geom.h * self.in_geom.w, self.cin4), dtype=torch.float32)
+    rows[:, :self.cin] = dx.permute(0, 2, 3, 1).reshape(-1, self.cin)
+    return rows
+
+
+def lpips_prep(target, pred, geom, normalize, shift, scale, out=None):
+    x = torch.cat([target, pred], 0).float()
+    if normalize:
+        x = 2 * x - 1
+    x = (x - shift.view(1, 3, 1, 1)) / scale.view(1, 3, 1, 1)
+    n2, _, h, w = x.shape
+    xp = torch.zeros((n2, 3, 4 * geom.h, 4 * geom.w))
+    hh, ww = min(h, 4 * geom.h - 2), min(w, 4 * geom.w - 2)
+    xp[:, :, 2:2 + hh, 2:2 + ww] = x[:, :, :hh, :ww]
+    s2d = xp.view(n2, 3, geom.h, 4, geom.w, 4).permute(0, 3, 5, 1, 2, 4).reshape(n2, 48, geom.h, geom.w)
+    if out is None:
+        out = geom.alloc(x.device)
+    return _nchw_to_act(s2d, geom, out)
+
+
+def lpips_prep_bwd(g_rows, n, h, w, hs, ws, normalize, scale):
+    g = g_rows[:, :48].reshape(n, hs, ws, 4, 4, 3).permute(0, 5, 1, 3, 2, 4).reshape(n, 3, 4 * hs, 4 * ws)
+    d = torch.zeros((n, 3, h, w))
+    hh, ww = min(h, 4 * hs - 2), min(w, 4 * ws - 2)
+    d[:, :, :hh, :ww] = g[:, :, 2:2 + hh, 2:2 + ww]
+    return d * (2.0 if normalize else 1.0) / scale.view(1, 3, 1, 1)
+
+
+def maxpool3s2(x_act, geom, out_geom, out=None):
+    y = F.max_pool2d(_act_to_nchw(x_act, geom), 3, 2)
+    if out is None:
+        out = out_geom.alloc(x_act.device)
+    return _nchw_to_act(y, out_geom, out)
+
+
+def maxpool3s2_bwd(g_out_rows, x_act, geom):
+    with torch.enable_grad():                 # called from inside an autograd Function's backward (grad mode off)
+        x = _act_to_nchw(x_act, geom).requires_grad_(True)
+        y = F.max_pool2d(x, 3, 2)
+        g = g_out_rows[:, :geom.c].reshape(geom.n, y.shape[2], y.shape[3], geom.c).permute(0, 3, 1, 2)
+        y.backward(g)
+    return x.grad.permute(0, 2, 3, 1).reshape(-1, geom.c).contiguous()
+
+
+def _lpips_dist(f, lin_w, n):
+    f0, f1 = f[:n], f[n:]
+    n0 = f0 / torch.sqrt((f0 ** 2).sum(1, keepdim=True) + 1e-10)
+    n1 = f1 / torch.sqrt((f1 ** 2).sum(1, keepdim=True) + 1e-10)
+    return (((n0 - n1) ** 2) * lin_w.view(1, -1, 1, 1)).sum(1).mean(dim=(1, 2))
+
+
+def lpips_nhwc(feat_act, geom, lin_w, out):
+    out += _lpips_dist(_act_to_nchw(feat_act, geom), lin_w.detach().float(), geom.n // 2)
+    return out
+
+
+def lpips_nhwc_bwd(feat_act, geom, lin_w, upstream, g_in_rows=None):
+    n = geom.n // 2
+    f = _act_to_nchw(feat_act, geom)
+    with torch.enable_grad():
+        f1 = f[n:].clone().requires_grad_(True)
+        d = _lpips_dist(torch.cat([f[:n], f1], 0), lin_w.detach().float(), n)
+        d.backward(upstream.float())
+    g = f1.grad
+    if g_in_rows is not None:
+        g = g + g_in_rows[:, :geom.c].reshape(n, geom.h, geom.w, geom.c).permute(0, 3, 1, 2)
+    g = g * (f[n:] > 0)
+    return g.permute(0, 2, 3, 1).reshape(-1, geom.c).contiguous()
+
+
+@contextlib.contextmanager
+def lpips_cpu_emulation():
+    saved = []
+
+    def patch(obj, name, value):
+        saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, value)
+
+    patch(ops.Conv, "__call__", conv_call)
+    patch(_grad.ConvGrad, "data_grad", convgrad_data_grad)
+    for name, fn in (("lpips_prep", lpips_prep), ("lpips_prep_bwd", lpips_prep_bwd), ("maxpool3s2", maxpool3s2),
+                     ("maxpool3s2_bwd", maxpool3s2_bwd), ("lpips_nhwc", lpips_nhwc), ("lpips_nhwc_bwd", lpips_nhwc_bwd)):
+        patch(ops, name, fn)
+    try:
+        yield
+    finally:
+        for obj, name, value in reversed(saved):
+            setattr(obj, name, value)

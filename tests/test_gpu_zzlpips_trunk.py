@@ -1,0 +1,102 @@
+"""GPU: the native LPIPS trunk (csrc/lpips_trunk.cu + loss/lpips_trunk.py), kernel by kernel against
+the independent torch stand-ins in tests/emulation.py and end to end against the cuDNN trunk + torch autograd.
+
+NOT YET RUN ON HARDWARE: written after round 1's GPU minutes were spent, so the file only runs when
+HFC_LPIPS_TRUNK=native is set (the same switch that selects the native trunk in the product); the plan logic is
+covered on the CPU by tests/test_lpips_plan.py.  Tolerances: fp16 features -> 2e-3 relative on the distances; bf16
+gradient operands + ReLU / arg-max flips -> 5e-2 relative L2 on d loss / d pred (the bar of tests/test_gpu_train.py).
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+if os.environ.get("HFC_LPIPS_TRUNK") != "native":
+    pytest.skip("native LPIPS trunk is opt-in until verified on hardware (set HFC_LPIPS_TRUNK=native)",
+                allow_module_level=True)
+
+import emulation as E  # noqa: E402
+from hific_b200 import ops  # noqa: E402
+from hific_b200.loss import lpips_trunk  # noqa: E402
+from hific_b200.loss.perceptual import PerceptualLoss  # noqa: E402
+from hific_b200.ops import Geom  # noqa: E402
+
+
+def test_prep_and_its_adjoint():
+    g = torch.Generator().manual_seed(0)
+    n, h, w = 2, 100, 144
+    target, pred = torch.rand((n, 3, h, w), generator=g), torch.rand((n, 3, h, w), generator=g)
+    shift, scale = torch.tensor([-.030, -.088, -.188]), torch.tensor([.458, .448, .450])
+    hs, ws = (h + 4 - 11) // 4 + 3, (w + 4 - 11) // 4 + 3
+    geom = Geom(2 * n, hs, ws, 48, 64)
+    for normalize in (True, False):
+        want = E.lpips_prep(target, pred, geom, normalize, shift, scale)
+        got = ops.lpips_prep(target.cuda(), pred.cuda(), geom, normalize, shift.cuda(), scale.cuda())
+        assert torch.equal(got.cpu(), want)
+        rows = torch.randn((n * hs * ws, 48), generator=g)
+        want_b = E.lpips_prep_bwd(rows, n, h, w, hs, ws, normalize, scale)
+        got_b = ops.lpips_prep_bwd(rows.cuda(), n, h, w, hs, ws, normalize, scale.cuda())
+        assert torch.allclose(got_b.cpu(), want_b, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 31, 31, 64), (3, 15, 17, 192), (1, 63, 63, 64)])
+def test_maxpool_and_its_adjoint(n, h, w, c):
+    g = torch.Generator().manual_seed(c)
+    geom = Geom(n, h, w, c, c)
+    x = torch.relu(torch.randn(geom.shape, generator=g)).to(torch.float16)      # ReLU output: many exact ties at 0
+    og = Geom(n, (h - 3) // 2 + 1, (w - 3) // 2 + 1, c, c)
+    want = E.maxpool3s2(x, geom, og)
+    got = ops.maxpool3s2(x.cuda(), geom, og)
+    assert torch.equal(got.cpu(), want)
+    rows = torch.randn((n * og.h * og.w, c), generator=g)
+    want_b = E.maxpool3s2_bwd(rows, x, geom)
+    got_b = ops.maxpool3s2_bwd(rows.cuda(), x.cuda(), geom)
+    assert torch.allclose(got_b.cpu(), want_b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 15, 15, 256), (1, 31, 29, 192), (3, 7, 9, 384), (2, 63, 63, 64)])
+def test_lpips_nhwc_and_its_adjoint(n, h, w, c):
+    g = torch.Generator().manual_seed(h)
+    geom = Geom(2 * n, h, w, c, c)
+    f = torch.relu(torch.randn(geom.shape, generator=g)).to(torch.float16)
+    lin = torch.rand(c, generator=g) * 0.02
+    want = E.lpips_nhwc(f, geom, lin, torch.zeros(n))
+    got = ops.lpips_nhwc(f.cuda(), geom, lin.cuda(), torch.zeros(n).cuda())
+    assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-8)
+    up = torch.rand(n, generator=g) + 0.5
+    g_in = torch.randn((n * h * w, c), generator=g) * 1e-4
+    for gi in (None, g_in):
+        want_b = E.lpips_nhwc_bwd(f, geom, lin, up, gi)
+        got_b = ops.lpips_nhwc_bwd(f.cuda(), geom, lin.cuda(), up.cuda(), gi.cuda() if gi is not None else None)
+        assert torch.allclose(got_b.cpu(), want_b, rtol=2e-3, atol=1e-7 * float(want_b.abs().max()) + 1e-12)
+
+
+@pytest.mark.parametrize("n,h,w,normalize", [(2, 128, 128, True), (1, 100, 144, False), (4, 256, 256, True)])
+def test_native_trunk_matches_cudnn_trunk(n, h, w, normalize):
+    loss = PerceptualLoss().cuda()
+    g = torch.Generator().manual_seed(n + h)
+    target = torch.rand((n, 3, h, w), generator=g).cuda()
+    pred = (target + 0.1 * torch.randn((n, 3, h, w), generator=g).cuda()).clamp(0, 1)
+    up = torch.linspace(0.5, 1.5, n).cuda()
+    os.environ["HFC_LPIPS_TRUNK"] = "cudnn"
+    try:
+        p0 = pred.clone().requires_grad_(True)
+        want = loss(p0, target, normalize=normalize).view(-1)
+        (want * up).sum().backward()
+    finally:
+        os.environ["HFC_LPIPS_TRUNK"] = "native"
+    l0 = ops.launch_count()
+    p1 = pred.clone().requires_grad_(True)
+    got = loss(p1, target, normalize=normalize).view(-1)
+    (got * up).sum().backward()
+    torch.cuda.synchronize()
+    assert ops.launch_count() - l0 >= 5 + 2 + 1 + 5 + 5 + 5, "the native trunk did not run"
+    assert torch.allclose(got, want.detach(), rtol=2e-3, atol=1e-6), (got, want)
+    rel = ((p1.grad - p0.grad).norm() / p0.grad.norm()).item()
+    assert rel < 5e-2, rel
+    with torch.no_grad():                                        # evaluation path (no autograd)
+        again = loss(pred, target, normalize=normalize).view(-1)
+    assert torch.allclose(again, got.detach(), rtol=1e-6)
