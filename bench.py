@@ -239,11 +239,28 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         opt_h.step()
         opt_h.zero_grad()
 
+    native = None
     try:
         for _ in range(3):
             step()
         steps = max(3, args.steps // 4)
         ms = timed(step, steps)
+        # the same step with the LPIPS AlexNet trunk on the tcgen05 conv kernel instead of cuDNN (opt-in switch,
+        # parity-tested in tests/test_gpu_zzlpips_trunk.py): recorded so that the default can be chosen on evidence
+        old_trunk = os.environ.get("HFC_LPIPS_TRUNK")
+        try:
+            if world == 1:                       # single-GPU runs only: keeps the multi-rank collectives in lock step
+                os.environ["HFC_LPIPS_TRUNK"] = "native"
+                for _ in range(2):
+                    step()
+                native = {"ms_per_step": timed(step, steps) / steps}
+        except Exception as e:
+            native = {"unavailable": repr(e)[:200]}
+        finally:
+            if old_trunk is None:
+                os.environ.pop("HFC_LPIPS_TRUNK", None)
+            else:
+                os.environ["HFC_LPIPS_TRUNK"] = old_trunk
     except NotImplementedError as e:      # a piece of the backward is missing: report it, do not fake a number
         return {"unavailable": str(e)[:200]}
     finally:
@@ -253,6 +270,7 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         model.eval()
     return {"ms_per_step": ms / steps, "images_per_s": world * B * steps / (ms * 1e-3), "steps": steps,
             "per_gpu_batch": B, "n_gpus": world, "gradient_allreduce": reduce_mode,
+            "lpips_trunk": os.environ.get("HFC_LPIPS_TRUNK", "cudnn"), "with_native_lpips_trunk": native,
             "what": "compression model (no GAN): fwd + rate/distortion/LPIPS losses + bwd + 2x Adam (hific_b200.optim.Adam, one launch each); bf16 backward GEMMs; "
                     "LPIPS AlexNet trunk on cuDNN; gradient all-reduce (NCCL, coalesced after backward) when n_gpus > 1"}
 
@@ -372,7 +390,7 @@ def run_likelihood_roofline(dev, peaks, batch):
             os.environ.pop("HFC_LIKELIHOOD_V", None)
         else:
             os.environ["HFC_LIKELIHOOD_V"] = default
-    used = default if default in ("1", "2", "3") else "2"         # HFC_LIKELIHOOD_DEFAULT_VARIANT in csrc/elementwise.cu
+    used = default if default in ("1", "2", "3") else "3"         # HFC_LIKELIHOOD_DEFAULT_VARIANT in csrc/elementwise.cu
     return {"kernel": "latent_likelihood_kernel (y, mean, scale, noise -> y_hat, 2 log-likelihood sums), %d elements" % n,
             "bound": "hbm", "achieved": res[used]["achieved"], "peak": peaks["hbm"], "unit": "GB/s",
             "frac": res[used]["frac"], "traffic": None, "ms_per_launch": res[used]["ms_per_launch"],

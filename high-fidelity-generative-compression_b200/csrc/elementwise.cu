@@ -9,7 +9,7 @@
 #include <cstdlib>
 
 #ifndef HFC_LIKELIHOOD_DEFAULT_VARIANT
-#define HFC_LIKELIHOOD_DEFAULT_VARIANT 2
+#define HFC_LIKELIHOOD_DEFAULT_VARIANT 3
 #endif
 
 namespace hfc {
@@ -517,9 +517,9 @@ extern "C" int hfc_latent_likelihood(const float* y, const float* mean, const fl
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc != HFC_OK) return rc;
-  // Gaussian likelihood: schedule 2 (packed fp32 + balanced persistent grid, likelihood_v2.cu) by default -- measured
-  // 20.5 -> 16.4 us at the c2 size, 47.1 -> 36.9 us at c5 (profiles/r01_likelihood_ab.json); HFC_LIKELIHOOD_V=1|2|3
-  // selects a schedule explicitly (1: latent_likelihood_kernel below, 3: schedule 2 + register-double-buffered loads)
+  // Gaussian likelihood: schedule 3 by default (likelihood_v2.cu: packed fp32 + balanced persistent grid + register-
+  // double-buffered loads) -- measured at c2 / c5 sizes with a cold L2 (profiles/r01_likelihood_ab.json): schedule 1
+  // 20.5 / 49.2 us, schedule 2 16.4 / 36.9 us, schedule 3 14.3 / 35.8 us.  HFC_LIKELIHOOD_V=1|2|3 selects one explicitly.
   const int variant = likelihood_variant();
   if (likelihood_type == 0 && variant >= 2) {
     rc = launch_latent_likelihood_v2(y, mean, scale_raw, noise, count, scale_lower_bound, decoded, sums, sms,

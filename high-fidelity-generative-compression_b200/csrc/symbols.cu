@@ -106,7 +106,9 @@ quantize_symbols_flat_kernel(const float* __restrict__ x, const float* __restric
   const bool want_bits = bits_sum != nullptr;
   float acc = 0.f;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
-    const int ch = static_cast<int>((i / p.hw) % p.c);
+    // the channel is only the table row of the hyper-latents (no scales); the latent path skips the two 64-bit
+    // divisions (second ncu capture: 280 issued instructions per element, most of them this emulated division)
+    const int ch = scale ? 0 : static_cast<int>((i / p.hw) % p.c);
     const SymOut o = sym_one(x ? x[i] : 0.f, mean ? mean[i] : 0.f, scale ? scale[i] : 0.f, x != nullptr,
                              mean != nullptr, scale != nullptr, ch, table, p, want_bits);
     if (symbols) symbols[i] = o.sym;

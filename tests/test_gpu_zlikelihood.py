@@ -1,4 +1,4 @@
-"""GPU: schedules 2 (the default: packed fp32, balanced persistent grid) and 3 (2 + register-double-buffered loads) of the
+"""GPU: schedules 2 (packed fp32, balanced persistent grid) and 3 (the default: 2 + register-double-buffered loads) of the
 Gaussian latent-likelihood kernel (csrc/likelihood_v2.cu), selected with HFC_LIKELIHOOD_V, against a float64 restatement of src/hyperprior.py:124-139 and
 against the first schedule on the same inputs.  Tolerance: 2e-5 relative on the log-likelihood sums (as for schedule 1),
 straight-through latents bit-identical to schedule 1."""
