@@ -232,3 +232,129 @@ def lpips_cpu_emulation():
     finally:
         for obj, name, value in reversed(saved):
             setattr(obj, name, value)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# General CPU stand-ins for the activation-format entry points the inference plans (hific_b200.engine) call, so that
+# the plans' geometry -- materialised reflect borders, asymmetric pads, stride-2 / transposed layers, channel padding,
+# fused ChannelNorm, residual adds, row pitches -- can be checked against the oracle without a GPU.  They model the
+# numerics of the kernels only to first order (operands rounded to fp16, fp32 accumulation in torch's order).
+# ----------------------------------------------------------------------------------------------------------------------
+from hific_b200._lib import ACT_LEAKY02, ACT_NONE, OUT_NCHW_F32, OUT_NHWC_F32, PAD_REFLECT
+
+CN_EPS = 1e-3
+
+
+def _apply_act(y, act):
+    if act == ACT_RELU:
+        return torch.relu(y)
+    if act == ACT_LEAKY02:
+        return F.leaky_relu(y, 0.2)
+    return y
+
+
+def _channel_norm(y, gamma, beta):
+    mean = y.mean(dim=1, keepdim=True)
+    var = y.var(dim=1, keepdim=True)                       # unbiased, as torch.var in channel.py:48-59
+    return gamma.view(1, -1, 1, 1) * (y - mean) * torch.rsqrt(var + CN_EPS) + beta.view(1, -1, 1, 1)
+
+
+def _write_act(y, geom, out, reflect):
+    """(n, c, h, w) fp32 -> bordered NHWC fp16 buffer; the border by reflection of the interior (ReflectionPad2d
+    semantics) when `reflect`, otherwise left at zero."""
+    buf = out.view(geom.shape)
+    buf.zero_()
+    t = y
+    if reflect and any((geom.pt, geom.pl, geom.pb, geom.pr)):
+        t = F.pad(y, (geom.pl, geom.pr, geom.pt, geom.pb), mode="reflect")
+        buf[..., :geom.c] = t.permute(0, 2, 3, 1).to(torch.float16)
+    else:
+        buf[:, geom.pt:geom.pt + geom.h, geom.pl:geom.pl + geom.w, :geom.c] = t.permute(0, 2, 3, 1).to(torch.float16)
+    return out
+
+
+def conv_call_general(self, x_act, weight, bias=None, gamma=None, beta=None, out=None, scale=None, scale_key=None):
+    d, gi = self.desc, self.in_geom
+    buf = x_act.view(gi.shape).float()
+    w = weight.detach().float()
+    if scale is not None:
+        w = w * scale.float().reshape(())
+    w = (w.to(torch.bfloat16) if d.b_bf16 else w.to(torch.float16)).float()
+    if d.dgrad:
+        w = w.flip(2, 3).transpose(0, 1)
+    interior = buf[:, gi.pt:gi.pt + gi.h, gi.pl:gi.pl + gi.w, :gi.c].permute(0, 3, 1, 2)
+    if d.transposed:
+        assert not any((gi.pt, gi.pl, gi.pb, gi.pr))
+        y = F.conv_transpose2d(interior, w, stride=d.stride, padding=d.pad_t, output_padding=d.stride - 1)
+    else:
+        if d.pad_mode == PAD_REFLECT:
+            assert gi.pt >= d.pad_t and gi.pl >= d.pad_l and gi.pb >= d.pad_b and gi.pr >= d.pad_r
+            region = buf[:, gi.pt - d.pad_t:gi.pt + gi.h + d.pad_b, gi.pl - d.pad_l:gi.pl + gi.w + d.pad_r, :gi.c]
+            region = region.permute(0, 3, 1, 2)             # reads the MATERIALISED border the producer wrote
+        else:
+            region = F.pad(interior, (d.pad_l, d.pad_r, d.pad_t, d.pad_b))
+        y = F.conv2d(region, w, stride=d.stride)
+    if bias is not None:
+        y = y + bias.detach().float().view(1, -1, 1, 1)
+    if d.norm:
+        y = _channel_norm(y, gamma.detach().float().reshape(-1), beta.detach().float().reshape(-1))
+    y = _apply_act(y, d.act)
+    go = self.out_geom
+    assert tuple(y.shape[2:]) == (go.h, go.w), (y.shape, go)
+    if out is None:
+        out = self.alloc_out(x_act.device)
+    if d.out_mode == OUT_NHWC_F16:
+        return _write_act(y, go, out, bool(d.out_reflect))
+    if d.out_mode == OUT_NHWC_F32:
+        out.zero_()
+        out.view(-1, go.cpad)[:, :self.cout] = y.permute(0, 2, 3, 1).reshape(-1, self.cout)
+        return out
+    out.copy_(y)
+    return out
+
+
+def nchw_to_act(x, geom, reflect=False, norm=False, gamma=None, beta=None, out=None):
+    y = x.float()
+    if norm:
+        y = _channel_norm(y, gamma.detach().float().reshape(-1), beta.detach().float().reshape(-1))
+    if out is None:
+        out = geom.alloc(x.device)
+    return _write_act(y, geom, out, reflect)
+
+
+def channelnorm(x_rows, geom, gamma, beta, act=ACT_NONE, reflect=False, res1=None, res2=None, want_f32=False,
+                want_act=True, out_act=None, out_f32=None):
+    n, h, w, c = geom.n, geom.h, geom.w, geom.c
+    y = x_rows.view(n * h * w, -1)[:, :c].reshape(n, h, w, c).permute(0, 3, 1, 2)
+    y = _apply_act(_channel_norm(y, gamma.detach().float().reshape(-1), beta.detach().float().reshape(-1)), act)
+    for r in (res1, res2):
+        if r is not None:
+            y = y + r.view(n, h, w, -1)[..., :c].permute(0, 3, 1, 2)
+    if want_f32:
+        if out_f32 is None:
+            out_f32 = torch.empty((n * h * w, c), dtype=torch.float32)
+        out_f32.copy_(y.permute(0, 2, 3, 1).reshape(n * h * w, c))
+    if want_act:
+        if out_act is None:
+            out_act = geom.alloc(x_rows.device)
+        _write_act(y, geom, out_act, reflect)
+    return out_act, out_f32
+
+
+@contextlib.contextmanager
+def plan_cpu_emulation():
+    saved = []
+
+    def patch(obj, name, value):
+        saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, value)
+
+    patch(ops.Conv, "__call__", conv_call_general)
+    patch(ops, "nchw_to_act", nchw_to_act)
+    patch(ops, "channelnorm", channelnorm)
+    patch(engine, "_require_cuda", lambda x, who: None)
+    try:
+        yield
+    finally:
+        for obj, name, value in reversed(saved):
+            setattr(obj, name, value)
