@@ -183,12 +183,14 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
     # plain after-backward all-reduce runs once before timing; on any mismatch / error the plain path is used.
     reducer, reduce_mode = None, "none (single GPU)"
     if dist is not None:
+        reduce_mode = "after backward, one coalesced NCCL all-reduce"
+    # opt-in (HFC_OVERLAP_ALLREDUCE=1) until it has run over NCCL once: it was written with no multi-GPU minutes left
+    if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE") == "1":
         from hific_b200.dist import OverlappedGradientReducer
         hp = model.Hyperprior
         buckets = [list(model.Generator.parameters()),
                    [p for m in (hp.synthesis_mu, hp.synthesis_std, hp.analysis_net) for p in m.parameters()] + hyper,
                    list(model.Encoder.parameters())]
-        reduce_mode = "after backward, one coalesced NCCL all-reduce"
         try:
             reducer = OverlappedGradientReducer(buckets, dist, world)
             probe = [b[0] for b in reducer.buckets] + [b[-1] for b in reducer.buckets]
