@@ -358,3 +358,81 @@ def plan_cpu_emulation():
     finally:
         for obj, name, value in reversed(saved):
             setattr(obj, name, value)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Whole `Model.forward` on the CPU: the plan stand-ins above + the two likelihood entry points + inert CUDA streams.
+# ----------------------------------------------------------------------------------------------------------------------
+def latent_likelihood(y, mean, scale_raw, noise=None, scale_lower_bound=0.11, likelihood_type="gaussian", sums=None):
+    scale = torch.clamp(scale_raw, min=scale_lower_bound)
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float64)
+    qy = torch.floor(y - mean + 0.5) + mean
+    sums[1] += torch.log(O.latent_likelihood(qy, mean, scale, likelihood_type) + 1e-9).double().sum()
+    if noise is not None:
+        sums[0] += torch.log(O.latent_likelihood(y + noise, mean, scale, likelihood_type) + 1e-9).double().sum()
+    return O.quantize_st(y, mean), sums
+
+
+def _density_logits_packed(x, p):
+    """x (n, c, hw), p (c, 64) packed as documented in include/hfc.h (softplus / tanh already applied)."""
+    c = p.shape[0]
+    P = lambda lo, hi, *shape: p[:, lo:hi].reshape(c, *shape)
+    h = x.permute(1, 0, 2).reshape(c, 1, -1)                               # (c, 1, N)
+    layers = ((P(0, 3, 3, 1), P(3, 6, 3, 1), P(6, 9, 3, 1)), (P(9, 18, 3, 3), P(18, 21, 3, 1), P(21, 24, 3, 1)),
+              (P(24, 33, 3, 3), P(33, 36, 3, 1), P(36, 39, 3, 1)), (P(39, 42, 1, 3), P(42, 43, 1, 1), P(43, 44, 1, 1)))
+    for H, b, a in layers:
+        h = torch.bmm(H, h) + b
+        h = h + a * torch.tanh(h)
+    return h.reshape(c, x.shape[0], -1).permute(1, 0, 2)
+
+
+def hyperlatent_likelihood(z, params64, noise=None, sums=None):
+    n, c, hh, ww = z.shape
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float64)
+
+    def loglik(v):
+        x = v.reshape(n, c, -1)
+        up, lo = _density_logits_packed(x + 0.5, params64), _density_logits_packed(x - 0.5, params64)
+        sign = -torch.sign(up + lo)
+        p = torch.clamp(torch.abs(torch.sigmoid(sign * up) - torch.sigmoid(sign * lo)), min=1e-9)
+        return torch.log(p + 1e-9).double().sum()
+
+    z_quant = torch.floor(z + 0.5)
+    sums[1] += loglik(z_quant)
+    z_noisy = None
+    if noise is not None:
+        z_noisy = z + noise
+        sums[0] += loglik(z_noisy)
+    return z_noisy, z_quant, sums
+
+
+class _InertStream:
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+
+@contextlib.contextmanager
+def model_cpu_emulation():
+    saved = []
+
+    def patch(obj, name, value):
+        saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, value)
+
+    with plan_cpu_emulation():
+        patch(ops, "latent_likelihood", latent_likelihood)
+        patch(ops, "hyperlatent_likelihood", hyperlatent_likelihood)
+        patch(torch.cuda, "current_stream", lambda *a, **k: _InertStream())
+        patch(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+        patch(hyperprior.Hyperprior, "_side_stream", lambda self, device: _InertStream())
+        patch(torch.Tensor, "record_stream", lambda self, s: None)
+        try:
+            yield
+        finally:
+            for obj, name, value in reversed(saved):
+                setattr(obj, name, value)

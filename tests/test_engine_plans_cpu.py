@@ -65,3 +65,37 @@ def test_hyper_plans(sd, n, h, w):
     assert z.shape == want_z.shape == (n, 320, h // 4, w // 4) and rel_l2(z, want_z) < REL
     want_mu = O.hyper_synthesis(sd, torch.round(z), "Hyperprior.synthesis_mu.")
     assert mu.shape == want_mu.shape == (n, 220, h, w) and rel_l2(mu, want_mu) < REL
+
+
+@pytest.mark.parametrize("b,h,w,evaluation", [(2, 128, 128, False), (1, 100, 144, True)])
+def test_model_forward_eval_on_cpu(sd, b, h, w, evaluation):
+    """`Model.forward` / `compression_forward` in eval mode through the emulated entry points: padding to multiples of
+    16 / 4 and cropping (EVALUATION mode, ragged 100 x 144), hyperprior glue, bpp bookkeeping -- against the oracle."""
+    import logging
+    from emulation import model_cpu_emulation
+    from hific_b200.config import ModelModes, mse_lpips_args
+    from hific_b200.model import Model
+    m = Model(mse_lpips_args(), logging.getLogger("cpu"),
+              model_mode=ModelModes.EVALUATION if evaluation else ModelModes.TRAINING)
+    assert not m.load_state_dict(sd, strict=False).unexpected_keys
+    m.eval()
+    x = synth.synth_image(b, h, w, 0)
+    want_rec, want_hyp, _ = O.compression_forward(sd, x, training=False, evaluation_mode=evaluation)
+    with torch.no_grad(), model_cpu_emulation():
+        inter, info = m.compression_forward(x)
+        if evaluation:
+            rec, q_bpp = m(x, writeout=False)
+            assert tuple(rec.shape) == (b, 3, h, w) and float(rec.min()) >= 0 and float(rec.max()) <= 1
+            assert abs(float(q_bpp) - float(want_hyp.total_qbpp)) < 5e-3 * float(want_hyp.total_qbpp)
+    assert tuple(inter.reconstruction.shape) == tuple(want_rec.shape)
+    flips = ((inter.latents_quantized - want_hyp.decoded).abs() > 0.5).float().mean().item()
+    # whole chain (encoder error reaches the rounding, unlike the stage-wise GPU protocol that feeds the oracle's y):
+    # |y - mu| within ~1e-3 |y| of a rounding boundary flips -- a percent or two of the latents with random weights
+    assert flips < 3e-2
+    assert abs(float(info.total_qbpp) - float(want_hyp.total_qbpp)) < 5e-3 * float(want_hyp.total_qbpp)
+    assert abs(float(info.hyperlatent_qbpp) - float(want_hyp.hyperlatent_qbpp)) < 5e-3 * float(want_hyp.hyperlatent_qbpp)
+    # the generator amplifies the flipped latents: compare it on the oracle's latents instead (stage-wise protocol)
+    with torch.no_grad(), model_cpu_emulation():
+        xh = m.Generator(want_hyp.decoded)
+    crop = xh[:, :, :want_rec.shape[2], :want_rec.shape[3]]
+    assert rel_l2(crop, want_rec) < REL
