@@ -24,22 +24,16 @@ class ContinuousEntropyModel(nn.Module, metaclass=abc.ABCMeta):
         self._host_tables, self._host_tables_key = None, None
 
     def quantize_st(self, inputs, offsets=None):
-        """entropy_models.py:49-63 (straight-through rounding; plain torch ops, not on the hot path)."""
-        values = inputs
-        if offsets is not None:
-            offsets = offsets.to(values)
-            values = values - offsets
-        delta = (torch.floor(values + 0.5) - values).detach()
-        values = values + delta
-        if offsets is not None:
-            values = values + offsets
-        return values
+        """Straight-through rounding about `offsets` (entropy_models.py:49-63): forward floor(v + .5), identity gradient.
+        Plain tensor ops -- API parity only; the hot path rounds inside hfc_latent_likelihood / hfc_quantize_symbols."""
+        shift = 0 if offsets is None else offsets.to(inputs)
+        centred = inputs - shift
+        rounded = centred + (torch.floor(centred + 0.5) - centred).detach()
+        return rounded if offsets is None else rounded + shift
 
     def dequantize(self, x, offsets=None):
-        """entropy_models.py:65-73."""
-        if offsets is not None:
-            return x.type_as(offsets) + offsets
-        return x.to(torch.float32)
+        """Symbols -> latents (entropy_models.py:65-73)."""
+        return x.to(torch.float32) if offsets is None else x.type_as(offsets) + offsets
 
     @abc.abstractmethod
     def build_tables(self, **kwargs):
