@@ -99,3 +99,29 @@ def test_model_forward_eval_on_cpu(sd, b, h, w, evaluation):
         xh = m.Generator(want_hyp.decoded)
     crop = xh[:, :, :want_rec.shape[2], :want_rec.shape[3]]
     assert rel_l2(crop, want_rec) < REL
+
+
+@pytest.mark.parametrize("C", [64, 100])
+def test_plans_with_other_latent_channels(C):
+    """train.py exposes `--latent_channels` (train.py:240): the plans must follow any C, not only HiFIC's 220."""
+    torch.manual_seed(C)
+    enc = encoder.Encoder((3, 64, 64), 1, C=C).eval()
+    gen = generator.Generator((C, 4, 4), 1, C=C, n_residual_blocks=2).eval()
+    ana = hyper.HyperpriorAnalysis(C=C, N=320).eval()
+    syn = hyper.HyperpriorSynthesis(C=C, N=320).eval()
+    sd = {}
+    for prefix, m in (("Encoder.", enc), ("Generator.", gen), ("Hyperprior.analysis_net.", ana),
+                      ("Hyperprior.synthesis_mu.", syn)):
+        sd.update({prefix + k: v.detach() for k, v in m.state_dict().items()})
+    x = synth.synth_image(1, 64, 64, 1)
+    g = torch.Generator().manual_seed(2)
+    y16 = torch.randn((1, C, 16, 16), generator=g)
+    with torch.no_grad(), plan_cpu_emulation():
+        y = enc(x)
+        x_hat = gen(torch.round(y))
+        z = ana(y16)
+        mu = syn(torch.round(z))
+    assert rel_l2(y, O.encoder_forward(sd, x)) < REL
+    assert rel_l2(x_hat, O.generator_forward(sd, torch.round(y), n_residual_blocks=2)) < REL
+    assert rel_l2(z, O.hyper_analysis(sd, y16)) < REL
+    assert rel_l2(mu, O.hyper_synthesis(sd, torch.round(z), "Hyperprior.synthesis_mu.")) < REL
