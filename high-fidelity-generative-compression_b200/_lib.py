@@ -118,6 +118,8 @@ SIGNATURES = {
     "hfc_pmf_to_quantized_cdf_host": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "hfc_rans_encode_host": (_i64, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _i64]),
     "hfc_rans_decode_host": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "hfc_dlmm_likelihood": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hfc_dlmm_likelihood_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hfc_lpips_prep": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "hfc_lpips_prep_bwd": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hfc_maxpool3s2": (ctypes.c_int, [_vp, ctypes.POINTER(ActGeom), _vp, _vp]),

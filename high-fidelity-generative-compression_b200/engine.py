@@ -213,6 +213,30 @@ class HyperSynthesisPlan:
         return self.c3(h, mod.conv3.weight, mod.conv3.bias)
 
 
+class HyperSynthesisDLMMPlan:
+    """HyperpriorSynthesisDLMM.forward (src/network/hyper.py:121-130)."""
+
+    def __init__(self, n, h, w, C, N, n_out, device):
+        self.g_in = Geom(n, h, w, N, round_up(N, 64))
+        self.in_act = self.g_in.alloc(device)
+        g1 = Geom(n, 2 * h, 2 * w, N, round_up(N, 64))
+        g2 = Geom(n, 4 * h, 4 * w, N, round_up(N, 64))
+        g3 = Geom(n, 4 * h, 4 * w, C, round_up(C, 64))
+        self.c1 = Conv(self.g_in, N, 5, stride=2, transposed=True, pad=(2, 2, 2, 2), out_geom=g1, act=ACT_RELU)
+        self.c2 = Conv(g1, N, 5, stride=2, transposed=True, pad=(2, 2, 2, 2), out_geom=g2, act=ACT_RELU)
+        self.c3 = Conv(g2, C, 3, stride=1, transposed=True, pad=(1, 1, 1, 1), out_geom=g3, act=ACT_NONE)
+        self.c4 = Conv(g3, n_out, 1, out_mode=OUT_NCHW_F32)
+        self.b1, self.b2, self.b3 = self.c1.alloc_out(device), self.c2.alloc_out(device), self.c3.alloc_out(device)
+        self.flops = self.c1.flops + self.c2.flops + self.c3.flops + self.c4.flops
+
+    def run(self, mod, z):
+        ops.nchw_to_act(z, self.g_in, out=self.in_act)
+        h = self.c1(self.in_act, mod.conv1.weight, mod.conv1.bias, out=self.b1)
+        h = self.c2(h, mod.conv2.weight, mod.conv2.bias, out=self.b2)
+        h = self.c3(h, mod.conv3.weight, mod.conv3.bias, out=self.b3)
+        return self.c4(h, mod.conv_out.weight, mod.conv_out.bias)
+
+
 class DiscriminatorPlan:
     """Discriminator.forward (src/network/discriminator.py:66-86) for n = 2B stacked real / generated images."""
     FILTERS = (64, 128, 256, 512)

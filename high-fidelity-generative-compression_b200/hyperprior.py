@@ -212,3 +212,49 @@ class Hyperprior(CodingModel):
         if getattr(self, "_side", None) is None or self._side[0] != key:
             self._side = (key, torch.cuda.Stream(device=device))
         return self._side[1]
+
+
+class HyperpriorDLMM(CodingModel):
+    """`-LMM` variant (src/hyperprior.py:340-458): the latents are modelled by a K-component discretised mixture whose
+    logits / means / log-scales come from one synthesis network; no compress path exists for it in the reference either."""
+
+    def __init__(self, bottleneck_capacity=64, hyperlatent_filters=LARGE_HYPERLATENT_FILTERS, mode='large',
+                 likelihood_type='gaussian', scale_lower_bound=MIN_SCALE, mixture_components=4, entropy_code=False):
+        super().__init__(n_channels=bottleneck_capacity)
+        assert bottleneck_capacity <= 128, 'Will probably run out of memory!'        # hyperprior.py:354
+        self.bottleneck_capacity = bottleneck_capacity
+        self.scale_lower_bound = scale_lower_bound
+        self.mixture_components = mixture_components
+        if mode == 'small':
+            hyperlatent_filters = SMALL_HYPERLATENT_FILTERS
+        if likelihood_type not in ('gaussian', 'logistic'):
+            raise ValueError('Unknown likelihood model: {}'.format(likelihood_type))
+        self.likelihood_type = likelihood_type
+        self.analysis_net = hyper.HyperpriorAnalysis(C=bottleneck_capacity, N=hyperlatent_filters)
+        self.synthesis_DLMM_params = hyper.HyperpriorSynthesisDLMM(C=bottleneck_capacity, N=hyperlatent_filters)
+        self.amortization_models = [self.analysis_net, self.synthesis_DLMM_params]
+        self.hyperlatent_likelihood = hyperprior_model.HyperpriorDensity(n_channels=hyperlatent_filters)
+
+    def forward(self, latents, spatial_shape, **kwargs):
+        engine._require_cuda(latents, "HyperpriorDLMM")
+        grad = engine.wants_grad(self, latents)
+        latents = latents.contiguous()
+        batch = latents.shape[0]
+        hyperlatents = self.analysis_net(latents)
+        noise_z = torch.nn.init.uniform_(torch.zeros_like(hyperlatents), -0.5, 0.5)       # hyperprior.py:65 via :409
+        d = self.hyperlatent_likelihood
+        if grad:
+            packed = ops.pack_density_params_autograd(*d._tensors())
+            z_noisy, z_quant, sums_z = ops.HyperlatentLikelihoodFn.apply(hyperlatents.contiguous(), packed, noise_z)
+        else:
+            z_noisy, z_quant, sums_z = ops.hyperlatent_likelihood(hyperlatents, d.packed_params(), noise_z)
+        hyperlatents_decoded = z_noisy if self.training else z_quant                    # hyperprior.py:421-424
+        dlmm_params = self.synthesis_DLMM_params(hyperlatents_decoded).contiguous()
+        noise_y = torch.nn.init.uniform_(torch.zeros_like(latents), -0.5, 0.5)           # hyperprior.py:429
+        if grad:
+            decoded, sums_y = ops.DlmmLikelihoodFn.apply(latents, dlmm_params, noise_y, self.likelihood_type,
+                                                         bool(self.training))
+        else:
+            decoded, sums_y = ops.dlmm_likelihood(latents, dlmm_params, noise_y, self.likelihood_type,
+                                                  straight_through=bool(self.training))
+        return Hyperprior._hyperinfo(self, decoded, torch.cat([sums_z, sums_y]), batch, spatial_shape)

@@ -45,8 +45,6 @@ class Model(nn.Module):
         self.log_interval = args.log_interval
         self.storage_train, self.storage_test = storage_train, storage_test
         self.step_counter = 0
-        if getattr(args, "use_latent_mixture_model", False):
-            raise NotImplementedError("HyperpriorDLMM is a non-default variant (SURVEY.md 8f), not built")
         if not hasattr(ModelTypes, self.model_type.upper()):
             raise ValueError("Invalid model_type: [{}]".format(self.model_type))
         if not hasattr(ModelModes, self.model_mode.upper()):
@@ -60,9 +58,15 @@ class Model(nn.Module):
                                              n_residual_blocks=args.n_residual_blocks,
                                              channel_norm=args.use_channel_norm, sample_noise=args.sample_noise,
                                              noise_dim=args.noise_dim)
-        self.Hyperprior = hyperprior.Hyperprior(bottleneck_capacity=args.latent_channels,
-                                                likelihood_type=args.likelihood_type,
-                                                entropy_code=self.entropy_code)
+        if getattr(args, "use_latent_mixture_model", False) is True:                   # src/model.py:76-78 (`-LMM`)
+            self.Hyperprior = hyperprior.HyperpriorDLMM(bottleneck_capacity=args.latent_channels,
+                                                        likelihood_type=args.likelihood_type,
+                                                        mixture_components=args.mixture_components,
+                                                        entropy_code=self.entropy_code)
+        else:
+            self.Hyperprior = hyperprior.Hyperprior(bottleneck_capacity=args.latent_channels,
+                                                    likelihood_type=args.likelihood_type,
+                                                    entropy_code=self.entropy_code)
         self.amortization_models = [self.Encoder, self.Generator]
         self.amortization_models.extend(self.Hyperprior.amortization_models)
         self.use_discriminator = (self.model_type == ModelTypes.COMPRESSION_GAN

@@ -549,3 +549,53 @@ def lpips_nhwc_bwd(feat_act, geom, lin_w, upstream, g_in_rows=None):
                                  g_in_rows.shape[1] if g_in_rows is not None else 0, _ptr(out), out.shape[1], _stream()),
           "lpips_nhwc_bwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# discretised mixture likelihood of the latents (csrc/dlmm.cu; HyperpriorDLMM, src/hyperprior.py:340-458)
+# ------------------------------------------------------------------------------------------------------------
+def dlmm_likelihood(x, dlmm_params, noise=None, likelihood_type="gaussian", straight_through=True, sums=None):
+    """x (N, C, H, W), dlmm_params (N, 3*C*K, H, W) -> (decoded, sums[2]) with sums = [sum L(x + noise), sum L(round x)]
+    (natural log, fp64, on device)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, c, h, w = x.shape
+    assert dlmm_params.is_cuda and dlmm_params.dtype == torch.float32 and dlmm_params.is_contiguous()
+    assert dlmm_params.shape[0] == n and tuple(dlmm_params.shape[2:]) == (h, w) and dlmm_params.shape[1] % (3 * c) == 0
+    k = dlmm_params.shape[1] // (3 * c)
+    assert noise is None or (noise.is_cuda and noise.is_contiguous() and noise.shape == x.shape)
+    decoded = torch.empty_like(x)
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float64, device=x.device)
+    lt = {"gaussian": 0, "logistic": 1}[likelihood_type]
+    check(lib.hfc_dlmm_likelihood(_ptr(x), _ptr(noise), _ptr(dlmm_params), n, c, k, h * w, lt, int(bool(straight_through)),
+                                  _ptr(decoded), _ptr(sums), _stream()), "dlmm_likelihood")
+    return decoded, sums
+
+
+def dlmm_likelihood_bwd(x, dlmm_params, noise, d_decoded, g_nbpp, likelihood_type="gaussian"):
+    n, c, h, w = x.shape
+    k = dlmm_params.shape[1] // (3 * c)
+    dx, dparams = torch.empty_like(x), torch.empty_like(dlmm_params)
+    lt = {"gaussian": 0, "logistic": 1}[likelihood_type]
+    check(lib.hfc_dlmm_likelihood_bwd(_ptr(x), _ptr(noise), _ptr(dlmm_params), _ptr(d_decoded), _ptr(g_nbpp), 1.0, n, c,
+                                      k, h * w, lt, _ptr(dx), _ptr(dparams), _stream()), "dlmm_likelihood_bwd")
+    return dx, dparams
+
+
+class DlmmLikelihoodFn(torch.autograd.Function):
+    """(x, dlmm_params, noise) -> (decoded, sums[2]); gradient through decoded (straight-through to x) and sums[0]."""
+
+    @staticmethod
+    def forward(ctx, x, dlmm_params, noise, kind, straight_through):
+        decoded, sums = dlmm_likelihood(x, dlmm_params, noise, kind, straight_through)
+        ctx.save_for_backward(x, dlmm_params, noise)
+        ctx.kind = kind
+        return decoded, sums
+
+    @staticmethod
+    def backward(ctx, d_decoded, d_sums):
+        x, dlmm_params, noise = ctx.saved_tensors
+        g = d_sums[0:1].to(torch.float32).contiguous() if d_sums is not None else torch.zeros(1, device=x.device)
+        dd = d_decoded.contiguous() if d_decoded is not None else None
+        dx, dparams = dlmm_likelihood_bwd(x, dlmm_params, noise, dd, g, ctx.kind)
+        return dx, dparams, None, None, None

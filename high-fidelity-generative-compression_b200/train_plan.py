@@ -71,14 +71,14 @@ class Layer:
     """One conv / transposed conv of a training plan with its forward kernel, its backward and its saved tensors."""
 
     def __init__(self, in_geom, cout, k, stride=1, transposed=False, pad_mode=PAD_ZERO, pad=(0, 0, 0, 0), window=False,
-                 fused_relu_geom=None, nchw_out=False):
+                 fused_relu_geom=None, nchw_out=False, fused_act=ACT_RELU):
         self.in_geom, self.cout = in_geom, cout
         kw = dict(stride=stride, transposed=transposed, pad_mode=pad_mode, pad=pad, window=window)
         if nchw_out:
             self.conv = Conv(in_geom, cout, k, out_mode=OUT_NCHW_F32, **kw)
         elif fused_relu_geom is not None:    # bias + ReLU in the epilogue, bordered fp16 output (hyper networks)
             self.conv = Conv(in_geom, cout, k, out_geom=fused_relu_geom, out_reflect=any(
-                (fused_relu_geom.pt, fused_relu_geom.pl, fused_relu_geom.pb, fused_relu_geom.pr)), act=ACT_RELU, **kw)
+                (fused_relu_geom.pt, fused_relu_geom.pl, fused_relu_geom.pb, fused_relu_geom.pr)), act=fused_act, **kw)
         else:
             og = self.conv_out_geom(in_geom, cout, k, stride, transposed, pad)
             self.conv = Conv(in_geom, cout, k, out_mode=OUT_NHWC_F32, out_geom=og, **kw)
@@ -302,6 +302,41 @@ class HyperSynthesisTrainPlan:
     def backward(self, dout, p):
         grads = [None] * 6
         g, grads[4], grads[5] = self.l3.backward(nchw_to_rows(dout), p[4])
+        g = relu_mask(g, self.a2, self.g2)
+        g, grads[2], grads[3] = self.l2.backward(g, p[2])
+        g = relu_mask(g, self.a1, self.g1)
+        g, grads[0], grads[1] = self.l1.backward(g, p[0])
+        self.a1 = self.a2 = None
+        return rows_to_nchw(g, self.n, self.N, self.h, self.w), grads
+
+
+class HyperSynthesisDLMMTrainPlan:
+    """HyperpriorSynthesisDLMM (src/network/hyper.py:100-130): two ReLU transposed convs, a LINEAR transposed conv kept as
+    an fp16 activation buffer, and the linear 1x1 conv to the 3*K*C mixture parameters (NCHW fp32)."""
+
+    def __init__(self, n, h, w, C, N, n_out, device):
+        self.n, self.h, self.w, self.C, self.N = n, h, w, C, N
+        self.g_in = Geom(n, h, w, N, round_up(N, 64))
+        self.g1 = Geom(n, 2 * h, 2 * w, N, round_up(N, 64))
+        self.g2 = Geom(n, 4 * h, 4 * w, N, round_up(N, 64))
+        self.g3 = Geom(n, 4 * h, 4 * w, C, round_up(C, 64))
+        self.l1 = Layer(self.g_in, N, 5, stride=2, transposed=True, pad=(2, 2, 2, 2), fused_relu_geom=self.g1)
+        self.l2 = Layer(self.g1, N, 5, stride=2, transposed=True, pad=(2, 2, 2, 2), fused_relu_geom=self.g2)
+        self.l3 = Layer(self.g2, C, 3, stride=1, transposed=True, pad=(1, 1, 1, 1), fused_relu_geom=self.g3,
+                        fused_act=ACT_NONE)
+        self.l4 = Layer(self.g3, n_out, 1, nchw_out=True)
+
+    def forward(self, z, p):
+        a0 = ops.nchw_to_act(z, self.g_in)
+        self.a1 = self.l1.forward(a0, p[0], p[1])
+        self.a2 = self.l2.forward(self.a1, p[2], p[3])
+        a3 = self.l3.forward(self.a2, p[4], p[5])
+        return self.l4.forward(a3, p[6], p[7])
+
+    def backward(self, dout, p):
+        grads = [None] * 8
+        g, grads[6], grads[7] = self.l4.backward(nchw_to_rows(dout), p[6])
+        g, grads[4], grads[5] = self.l3.backward(g, p[4])                      # linear layer: no mask
         g = relu_mask(g, self.a2, self.g2)
         g, grads[2], grads[3] = self.l2.backward(g, p[2])
         g = relu_mask(g, self.a1, self.g1)

@@ -407,6 +407,23 @@ int hfc_lpips_nhwc_bwd(const void* feat_act, int32_t n, int32_t hw, int32_t c, i
                        const float* upstream, const float* g_in_rows, int32_t ld_g, float* g_out_rows, int32_t ld_out,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Discretised mixture likelihood of the latents (`-LMM`; HyperpriorDLMM, src/hyperprior.py:340-458,
+ * unpack_likelihood_params src/network/hyper.py:19-35).  x, noise, decoded: (n, c, hw) fp32; dlmm_params: the
+ * synthesis network's output (n, 3*c*k, hw), plane (s*c + ch)*k + j with s = 0 mixture logits, 1 means, 2 log-scales.
+ *   L(v) = logsumexp_j [log_softmax(logit)_j + log max(Phi(e^{-ls_j}(.5-|v-mu_j|)) - Phi(e^{-ls_j}(-.5-|v-mu_j|)), 1e-9)],
+ *   ls_j = max(log-scale_j, -3);  sums[0] += sum L(x + noise) (skipped when noise == NULL), sums[1] += sum L(floor(x+.5));
+ *   decoded = straight_through ? x + (floor(x+.5) - x) : floor(x+.5)   (hyperprior.py:443-446).
+ * --------------------------------------------------------------------------------------------------------- */
+int hfc_dlmm_likelihood(const float* x, const float* noise, const float* dlmm_params, int32_t n, int32_t c, int32_t k,
+                        int32_t hw, int32_t likelihood_type, int32_t straight_through, float* decoded, double* sums,
+                        void* stream);
+/* gradient of (*g_nbpp) * coef * sum L(x + noise) w.r.t. x (dx = d_decoded + ...; d_decoded may be NULL) and w.r.t.
+ * dlmm_params (dparams, same layout, overwritten), with both LowerBoundToward gates (pmf >= 1e-9, log-scale >= -3) */
+int hfc_dlmm_likelihood_bwd(const float* x, const float* noise, const float* dlmm_params, const float* d_decoded,
+                            const float* g_nbpp, float coef, int32_t n, int32_t c, int32_t k, int32_t hw,
+                            int32_t likelihood_type, float* dx, float* dparams, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -389,3 +389,63 @@ def round_fp16(t):
 
 def round_bf16(t):
     return t.bfloat16().float()
+
+
+# ------------------------------------------------------------------------------------------------
+# HyperpriorDLMM -- src/hyperprior.py:340-458 with HyperpriorSynthesisDLMM src/network/hyper.py:100-130 and
+# unpack_likelihood_params hyper.py:19-35 (discretised mixture likelihood of the latents; `-LMM` in train.py:227).
+# Pinned against the real reference by tests/golden/dlmm_c8.npz (oracle/make_golden_dlmm.py).
+# ------------------------------------------------------------------------------------------------
+LOG_SCALES_MIN = -3.0
+
+
+def hyper_synthesis_dlmm(sd, z, prefix="Hyperprior.synthesis_DLMM_params.", rnd=_ident):
+    """HyperpriorSynthesisDLMM.forward -- hyper.py:121-130: two ReLU transposed convs, a linear transposed conv and a
+    linear 1x1 conv to 3*K*C channels."""
+    h = F.relu(_convT(sd, prefix + "conv1", z, 2, 2, 1, rnd))
+    h = F.relu(_convT(sd, prefix + "conv2", h, 2, 2, 1, rnd))
+    h = _convT(sd, prefix + "conv3", h, 1, 1, 0, rnd)
+    return F.conv2d(rnd(h), rnd(sd[prefix + "conv_out.weight"]), sd[prefix + "conv_out.bias"])
+
+
+def dlmm_log_likelihood(x, dlmm_params, likelihood_type="gaussian"):
+    """HyperpriorDLMM.latent_log_likelihood_DLMM -- hyperprior.py:379-401.  x (N, C, H, W), dlmm_params (N, 3*C*K, H, W)
+    -> log-likelihood (N, C, H, W)."""
+    n, c, h, w = x.shape
+    k = dlmm_params.shape[1] // (3 * c)
+    p = dlmm_params.reshape(n, 3, c, k, h, w)
+    logit_pis, means = p[:, 0], p[:, 1]
+    log_scales = lower_bound(p[:, 2], LOG_SCALES_MIN)
+    xc = torch.abs(x.reshape(n, c, 1, h, w) - means)
+    inv_stds = torch.exp(-log_scales)
+    upper = standardized_cdf(inv_stds * (0.5 - xc), likelihood_type)
+    lower = standardized_cdf(inv_stds * (-0.5 - xc), likelihood_type)
+    pmf = lower_bound(upper - lower, MIN_LIKELIHOOD)
+    return torch.logsumexp(F.log_softmax(logit_pis, dim=2) + torch.log(pmf), dim=2)
+
+
+def estimate_entropy_log(log_likelihood, spatial_shape):
+    """CodingModel._estimate_entropy_log -- hyperprior.py:95-106."""
+    batch = log_likelihood.shape[0]
+    n_bits = torch.sum(log_likelihood) / (batch * -math.log(2.0))
+    return n_bits, n_bits / (spatial_shape[0] * spatial_shape[1])
+
+
+def hyperprior_dlmm_forward(sd, y, spatial_shape, training, noise_z=None, noise_y=None, likelihood_type="gaussian",
+                            prefix="Hyperprior.", rnd=_ident):
+    """HyperpriorDLMM.forward -- hyperprior.py:403-458 (noise tensors as in hyperprior_forward)."""
+    p = prefix
+    z = hyper_analysis(sd, y, p + "analysis_net.", rnd=rnd)
+    nz = z + (noise_z if noise_z is not None else torch.zeros_like(z))
+    _, hl_nbpp = estimate_entropy(density_likelihood(sd, nz, p + "hyperlatent_likelihood."), spatial_shape)
+    qz = torch.floor(z + 0.5)
+    _, hl_qbpp = estimate_entropy(density_likelihood(sd, qz, p + "hyperlatent_likelihood."), spatial_shape)
+    z_dec = nz if training else qz
+    params = hyper_synthesis_dlmm(sd, z_dec, p + "synthesis_DLMM_params.", rnd=rnd)
+    ny = y + (noise_y if noise_y is not None else torch.zeros_like(y))
+    _, l_nbpp = estimate_entropy_log(dlmm_log_likelihood(ny, params, likelihood_type), spatial_shape)
+    qy = torch.floor(y + 0.5)
+    _, l_qbpp = estimate_entropy_log(dlmm_log_likelihood(qy, params, likelihood_type), spatial_shape)
+    decoded = (y + (torch.floor(y + 0.5) - y).detach()) if training else qy          # hyperprior.py:443-446
+    return HyperOut(z, nz, qz, params, None, decoded, l_nbpp, hl_nbpp, l_nbpp + hl_nbpp, l_qbpp, hl_qbpp,
+                    l_qbpp + hl_qbpp)

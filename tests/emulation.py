@@ -436,3 +436,165 @@ def model_cpu_emulation():
         finally:
             for obj, name, value in reversed(saved):
                 setattr(obj, name, value)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Discretised mixture likelihood (csrc/dlmm.cu): the forward through the oracle, the backward as the SAME closed-form
+# expressions the kernel evaluates (so that the formulas themselves are checked against torch autograd on the CPU).
+# ----------------------------------------------------------------------------------------------------------------------
+def dlmm_likelihood(x, dlmm_params, noise=None, likelihood_type="gaussian", straight_through=True, sums=None):
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float64)
+    q = torch.floor(x + 0.5)
+    sums[1] += O.dlmm_log_likelihood(q, dlmm_params, likelihood_type).double().sum()
+    if noise is not None:
+        sums[0] += O.dlmm_log_likelihood(x + noise, dlmm_params, likelihood_type).double().sum()
+    return (x + (q - x)) if straight_through else q, sums
+
+
+def dlmm_likelihood_bwd(x, dlmm_params, noise, d_decoded, g_nbpp, likelihood_type="gaussian"):
+    n, c, h, w = x.shape
+    k = dlmm_params.shape[1] // (3 * c)
+    p = dlmm_params.reshape(n, 3, c, k, h, w)
+    logit, mu, ls_raw = p[:, 0], p[:, 1], p[:, 2]
+    g = float(g_nbpp.reshape(-1)[0])
+    cdf = (lambda t: 0.5 * torch.erfc(t * (-1.0 / 2 ** 0.5))) if likelihood_type == "gaussian" else torch.sigmoid
+    if likelihood_type == "gaussian":
+        pdf = lambda t: 0.39894228040143267794 * torch.exp(-0.5 * t * t)
+    else:
+        pdf = lambda t: torch.sigmoid(t) * (1 - torch.sigmoid(t))
+    v = (x + noise).reshape(n, c, 1, h, w)
+    inv = torch.exp(-torch.clamp(ls_raw, min=-3.0))
+    d = torch.abs(v - mu)
+    tu, tl = inv * (0.5 - d), inv * (-0.5 - d)
+    praw = cdf(tu) - cdf(tl)
+    lse = torch.logsumexp(logit, dim=2, keepdim=True)
+    a = (logit - lse) + torch.log(torch.clamp(praw, min=1e-9))
+    wgt = torch.softmax(a, dim=2)
+    pi = torch.exp(logit - lse)
+    d_logit = g * (wgt - pi)
+    gp = g * wgt / torch.clamp(praw, min=1e-9)
+    gp = torch.where((praw >= 1e-9) | (gp < 0), gp, torch.zeros_like(gp))
+    fu, fl = pdf(tu), pdf(tl)
+    dp_dd = -inv * (fu - fl)
+    dp_dinv = fu * (0.5 - d) - fl * (-0.5 - d)
+    sgn = torch.sign(v - mu)
+    dv = (gp * dp_dd * sgn).sum(dim=2)
+    d_mu = -gp * dp_dd * sgn
+    gls = gp * dp_dinv * -inv
+    gls = torch.where((ls_raw >= -3.0) | (gls < 0), gls, torch.zeros_like(gls))
+    dparams = torch.stack([d_logit, d_mu, gls], dim=1).reshape(dlmm_params.shape)
+    dx = dv + (d_decoded if d_decoded is not None else 0)
+    return dx, dparams
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Training path on the CPU: grad.ConvGrad through torch autograd of the same convolution (bf16-rounded operands, as the
+# backward GEMMs use), train_plan.relu_mask, and a differentiable stand-in of the hyper-latent likelihood Function.
+# ----------------------------------------------------------------------------------------------------------------------
+from hific_b200 import train_plan as _train_plan
+
+
+def _convgrad_apply(cg, x, w):
+    if cg.transposed:
+        return F.conv_transpose2d(x, w, stride=cg.stride, padding=cg.pad[0], output_padding=cg.stride - 1)
+    pt, pl, pb, pr = cg.pad
+    xp = F.pad(x, (pl, pr, pt, pb), mode="reflect" if cg.pad_mode == PAD_REFLECT else "constant")
+    return F.conv2d(xp, w, stride=cg.stride)
+
+
+def _rows_to_nchw(rows, n, h, w, c):
+    return rows[:, :c].reshape(n, h, w, c).permute(0, 3, 1, 2)
+
+
+def convgrad_data_grad_general(self, dy_rows, weight, out=None, scale=None, dy_act=None):
+    assert dy_rows is not None, "emulation needs the fp32 gradient rows"
+    g = self.in_geom
+    dy = _rows_to_nchw(dy_rows, g.n, self.oh, self.ow, self.cout).to(torch.bfloat16).float()
+    w = weight.detach().float()
+    if scale is not None:
+        w = w * scale.float().reshape(())
+    w = w.to(torch.bfloat16).float()
+    with torch.enable_grad():
+        x = torch.zeros((g.n, self.cin, g.h, g.w), requires_grad=True)
+        _convgrad_apply(self, x, w).backward(dy)
+    rows = torch.zeros((g.n * g.h * g.w, self.cin4))
+    rows[:, :self.cin] = x.grad.permute(0, 2, 3, 1).reshape(-1, self.cin)
+    return rows
+
+
+def convgrad_weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, scale=1.0, dy_act=None):
+    assert dy_rows is not None, "emulation needs the fp32 gradient rows"
+    g = self.in_geom
+    x = x_act.view(g.shape)[:, g.pt:g.pt + g.h, g.pl:g.pl + g.w, :g.c].permute(0, 3, 1, 2).float()
+    x = x.to(torch.bfloat16).float()
+    dy = _rows_to_nchw(dy_rows, g.n, self.oh, self.ow, self.cout).to(torch.bfloat16).float()
+    shape = (self.cin, self.cout, self.k, self.k) if self.transposed else (self.cout, self.cin, self.k, self.k)
+    with torch.enable_grad():
+        w = torch.zeros(shape, requires_grad=True)
+        _convgrad_apply(self, x, w).backward(dy)
+    dw = w.grad * scale
+    if dw_out is None:
+        return dw
+    if accumulate:
+        dw_out += dw
+    else:
+        dw_out.copy_(dw)
+    return dw_out
+
+
+def convgrad_bias_grad(self, dy_rows, db_out=None, accumulate=False, scale=1.0):
+    db = dy_rows[:, :self.cout].sum(0) * scale
+    if db_out is None:
+        return db
+    if accumulate:
+        db_out += db
+    else:
+        db_out.copy_(db)
+    return db_out
+
+
+def relu_mask(g, y_act, geom, slope=0.0):
+    y = y_act.view(geom.shape)[:, geom.pt:geom.pt + geom.h, geom.pl:geom.pl + geom.w, :geom.c].reshape(-1, geom.c).float()
+    out = torch.zeros((g.shape[0], (geom.c + 3) // 4 * 4))
+    out[:, :geom.c] = g[:, :geom.c] * torch.where(y > 0, torch.ones_like(y), torch.full_like(y, slope))
+    return out
+
+
+def hyperlatent_likelihood_fn(z, params64, noise):
+    """Differentiable stand-in of ops.HyperlatentLikelihoodFn.apply."""
+    n, c = z.shape[:2]
+
+    def loglik(v):
+        x = v.reshape(n, c, -1)
+        up, lo = _density_logits_packed(x + 0.5, params64), _density_logits_packed(x - 0.5, params64)
+        sign = -torch.sign(up + lo).detach()
+        p = O.lower_bound(torch.abs(torch.sigmoid(sign * up) - torch.sigmoid(sign * lo)), 1e-9)
+        return torch.log(p + 1e-9).double().sum()
+
+    z_noisy, z_quant = z + noise, torch.floor(z + 0.5).detach()
+    return z_noisy, z_quant, torch.stack([loglik(z_noisy), loglik(z_quant).detach()])
+
+
+@contextlib.contextmanager
+def training_cpu_emulation():
+    saved = []
+
+    def patch(obj, name, value):
+        saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, value)
+
+    with model_cpu_emulation():
+        patch(_grad.ConvGrad, "data_grad", convgrad_data_grad_general)
+        patch(_grad.ConvGrad, "weight_grad", convgrad_weight_grad)
+        patch(_grad.ConvGrad, "bias_grad", convgrad_bias_grad)
+        patch(_grad.ConvGrad, "dy_to_act", lambda self, dy_rows: None)     # the stand-ins work from the fp32 rows
+        patch(_train_plan, "relu_mask", relu_mask)
+        patch(ops, "dlmm_likelihood", dlmm_likelihood)
+        patch(ops, "dlmm_likelihood_bwd", dlmm_likelihood_bwd)
+        patch(ops.HyperlatentLikelihoodFn, "apply", staticmethod(hyperlatent_likelihood_fn))
+        try:
+            yield
+        finally:
+            for obj, name, value in reversed(saved):
+                setattr(obj, name, value)

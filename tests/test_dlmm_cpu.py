@@ -1,0 +1,104 @@
+"""CPU: the `-LMM` variant (HyperpriorDLMM, src/hyperprior.py:340-458).
+
+  * the oracle restatement against tests/golden/dlmm_c8.npz, produced by the REAL reference module under seed 21
+    (oracle/make_golden_dlmm.py): forward and gradients bit-exact -- with the weights taken from the PRODUCT's mirror module
+    built under the same seed, which also proves the constructor draws its parameters in the reference's order;
+  * the closed-form backward the CUDA kernel evaluates (tests/emulation.py: dlmm_likelihood_bwd mirrors csrc/dlmm.cu line
+    by line) against torch autograd, both gate directions;
+  * the product's host logic (module, inference + training plans, autograd Functions) through emulated entry points
+    against the same golden values.  The kernels themselves are checked by tests/test_gpu_zzdlmm.py on a GPU.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import emulation as E
+from hific_b200 import hyperprior
+from oracle import hific_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dlmm_c8.npz")
+FIELDS = ("decoded", "latent_nbpp", "hyperlatent_nbpp", "total_nbpp", "latent_qbpp", "hyperlatent_qbpp", "total_qbpp")
+GRAD_KEYS = ("analysis_net.conv1.weight", "synthesis_DLMM_params.conv_out.weight", "synthesis_DLMM_params.conv3.bias",
+             "synthesis_DLMM_params.conv3.weight", "hyperlatent_likelihood.H_1")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLDEN)
+
+
+def mirror():
+    torch.manual_seed(21)
+    return hyperprior.HyperpriorDLMM(bottleneck_capacity=8)
+
+
+def test_oracle_and_constructor_parity_with_the_reference(gold):
+    hp = mirror()
+    sd = {"Hyperprior." + k: v.detach() for k, v in hp.state_dict().items()}
+    y, nz, ny = (torch.from_numpy(gold[k]) for k in ("y", "noise_z", "noise_y"))
+    for training in (True, False):
+        tag = "train" if training else "eval"
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        yy = y.clone().requires_grad_(True)
+        o = O.hyperprior_dlmm_forward(sdg, yy, (256, 256), training, nz, ny)
+        for f in FIELDS:
+            assert np.array_equal(getattr(o, f).detach().numpy(), gold[f"{tag}.{f}"]), (tag, f)
+        if training:
+            (o.total_nbpp * 1000.0 + o.decoded.square().mean()).backward()
+            assert np.array_equal(yy.grad.numpy(), gold["train.grad.y"])
+            for k in GRAD_KEYS:
+                assert np.array_equal(sdg["Hyperprior." + k].grad.numpy(), gold["train.grad." + k]), k
+
+
+@pytest.mark.parametrize("kind", ["gaussian", "logistic"])
+@pytest.mark.parametrize("upstream", [-0.37, 0.8])
+def test_closed_form_backward_matches_autograd(kind, upstream):
+    g = torch.Generator().manual_seed(3)
+    n, c, k, h, w = 2, 5, 4, 6, 7
+    x = (torch.randn((n, c, h, w), generator=g) * 6).requires_grad_(True)      # far tails: pmf below the 1e-9 bound
+    params = torch.randn((n, 3 * c * k, h, w), generator=g)
+    params[:, 2 * c * k:] = params[:, 2 * c * k:] * 2 - 2.5                     # log-scales on both sides of -3
+    params[:, c * k:2 * c * k] *= 3
+    params = params.requires_grad_(True)
+    noise = torch.rand((n, c, h, w), generator=g) - 0.5
+    dd = torch.randn((n, c, h, w), generator=g)
+    L = O.dlmm_log_likelihood(x + noise, params, kind)
+    dec = x + (torch.floor(x + 0.5) - x).detach()
+    (upstream * L.sum() + (dec * dd).sum()).backward()
+    dx, dp = E.dlmm_likelihood_bwd(x.detach(), params.detach(), noise, dd, torch.tensor([upstream]), kind)
+    assert ((dx - x.grad).norm() / x.grad.norm()).item() < 1e-5
+    assert ((dp - params.grad).norm() / params.grad.norm()).item() < 1e-5
+    clamped = (params[:, 2 * c * k:] < -3).float().mean().item()
+    assert 0.2 < clamped < 0.8
+
+
+def test_product_host_logic_matches_the_reference(gold):
+    """HyperpriorDLMM of the product under emulated entry points: train-mode forward + backward and eval-mode forward
+    against the reference's values.  Tolerances: fp16 activations / bf16 gradient operands of the emulated kernels."""
+    y, nz, ny = (torch.from_numpy(gold[k]) for k in ("y", "noise_z", "noise_y"))
+    with E.training_cpu_emulation():
+        from oracle.ref_shim import NoiseFeeder
+        hp = mirror().train()
+        yy = y.clone().requires_grad_(True)
+        with NoiseFeeder([nz, ny]):
+            info = hp(yy, spatial_shape=(256, 256))
+        (info.total_nbpp * 1000.0 + info.decoded.square().mean()).backward()
+        grads = {k: v.grad for k, v in hp.named_parameters()}
+        for f in FIELDS[1:]:
+            assert abs(float(getattr(info, f)) - float(gold[f"train.{f}"])) < 5e-3 * abs(float(gold[f"train.{f}"])), f
+        assert torch.equal(info.decoded.detach(), torch.from_numpy(gold["train.decoded"]))
+        rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+        assert rel(yy.grad, torch.from_numpy(gold["train.grad.y"])) < 5e-2
+        for k in GRAD_KEYS:
+            assert rel(grads[k], torch.from_numpy(gold["train.grad." + k])) < 5e-2, k
+        hp.eval()
+        with torch.no_grad(), NoiseFeeder([nz, ny]):
+            info = hp(y, spatial_shape=(256, 256))
+        for f in FIELDS[1:]:
+            assert abs(float(getattr(info, f)) - float(gold[f"eval.{f}"])) < 5e-3 * abs(float(gold[f"eval.{f}"])), f
+        assert torch.equal(info.decoded, torch.from_numpy(gold["eval.decoded"]))
+        params = hp.synthesis_DLMM_params(torch.floor(hp.analysis_net(y) + 0.5))
+        want = torch.from_numpy(gold["eval.dlmm_params"])
+        assert rel(params, want) < 3e-3
