@@ -590,6 +590,7 @@ def training_cpu_emulation():
         patch(_grad.ConvGrad, "bias_grad", convgrad_bias_grad)
         patch(_grad.ConvGrad, "dy_to_act", lambda self, dy_rows: None)     # the stand-ins work from the fp32 rows
         patch(_train_plan, "relu_mask", relu_mask)
+        patch(_train_plan, "norm_bwd", norm_bwd)
         patch(ops, "dlmm_likelihood", dlmm_likelihood)
         patch(ops, "dlmm_likelihood_bwd", dlmm_likelihood_bwd)
         patch(ops.HyperlatentLikelihoodFn, "apply", staticmethod(hyperlatent_likelihood_fn))
@@ -598,3 +599,20 @@ def training_cpu_emulation():
         finally:
             for obj, name, value in reversed(saved):
                 setattr(obj, name, value)
+
+
+def norm_bwd(z, g, gamma, beta, act, as_operand=True):
+    """train_plan.norm_bwd through torch autograd of ChannelNorm(+ReLU) on fp32 rows; always returns fp32 rows (the
+    emulated ConvGrad works from rows, so the bf16 operand form of the real kernel is not modelled)."""
+    c = gamma.numel()
+    with torch.enable_grad():
+        zz = z[:, :c].detach().clone().requires_grad_(True)
+        gm = gamma.detach().reshape(-1).clone().requires_grad_(True)
+        bt = beta.detach().reshape(-1).clone().requires_grad_(True)
+        mean = zz.mean(dim=1, keepdim=True)
+        var = zz.var(dim=1, keepdim=True)
+        y = _apply_act(gm * (zz - mean) * torch.rsqrt(var + CN_EPS) + bt, act)
+        y.backward(g[:, :c])
+    dz = torch.zeros((z.shape[0], (c + 3) // 4 * 4))
+    dz[:, :c] = zz.grad
+    return dz, gm.grad.view_as(gamma), bt.grad.view_as(beta), zz.grad.sum(0)

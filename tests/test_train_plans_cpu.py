@@ -1,0 +1,69 @@
+"""CPU: the TRAINING plans of hific_b200.train_plan (what is saved in the forward pass, the order of the adjoints, which
+gradient lands in which parameter slot, the residual / head fan-out of the Generator) against torch autograd of the
+oracle, with the kernels replaced by torch stand-ins (tests/emulation.py).  Host logic only; the kernels are checked by
+tests/test_gpu_grad.py / test_gpu_train.py on a GPU.  Tolerance: bf16 gradient operands, fp16 activations, ReLU flips of
+those activations -> 5e-2 relative L2 per tensor (the bar of the GPU tests)."""
+import pytest
+import torch
+
+from emulation import training_cpu_emulation
+from hific_b200 import synth
+from hific_b200.network import encoder, generator, hyper
+from oracle import hific_oracle as O
+
+TOL = 8e-2          # small maps: ReLU-flip noise averages over fewer pixels than in the GPU tests (5e-2 on 128 x 128 x 2)
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synth.synth_state_dict(0)
+
+
+def check(module, prefix, sd, x, oracle_fn, out_weight, input_grad=True):
+    module.load_state_dict({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, strict=True)
+    module.train()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(prefix)}
+    xo = x.clone().requires_grad_(True)
+    (oracle_fn(sdg, xo) * out_weight).sum().backward()
+    xp = x.clone().requires_grad_(True)
+    with training_cpu_emulation():
+        (module(xp) * out_weight).sum().backward()
+    if input_grad:
+        assert rel(xp.grad, xo.grad) < TOL, "input gradient"
+    else:
+        assert xp.grad is None                   # the image needs no gradient: the plan skips the first data gradient
+    worst = ("", 0.0)
+    for name, p in module.named_parameters():
+        r = rel(p.grad, sdg[prefix + name].grad)
+        worst = max(worst, (name, r), key=lambda t: t[1])
+    assert worst[1] < TOL, worst
+
+
+def test_encoder_training_plan(sd):
+    g = torch.Generator().manual_seed(0)
+    x = synth.synth_image(1, 64, 64, 2)
+    wgt = torch.randn((1, 220, 4, 4), generator=g)
+    check(encoder.Encoder((3, 64, 64), 1, C=220), "Encoder.", sd, x, lambda s, t: O.encoder_forward(s, t), wgt,
+          input_grad=False)
+
+
+def test_generator_training_plan(sd):
+    g = torch.Generator().manual_seed(1)
+    y = torch.round(torch.randn((1, 220, 2, 3), generator=g) * 2)
+    wgt = torch.randn((1, 3, 32, 48), generator=g)
+    check(generator.Generator((220, 2, 3), 1, C=220, n_residual_blocks=9), "Generator.", sd, y,
+          lambda s, t: O.generator_forward(s, t), wgt)
+
+
+def test_hyper_training_plans(sd):
+    g = torch.Generator().manual_seed(2)
+    y = torch.randn((2, 220, 16, 16), generator=g)
+    check(hyper.HyperpriorAnalysis(C=220, N=320), "Hyperprior.analysis_net.", sd, y,
+          lambda s, t: O.hyper_analysis(s, t), torch.randn((2, 320, 4, 4), generator=g))
+    z = torch.round(torch.randn((2, 320, 2, 3), generator=g) * 3)
+    check(hyper.HyperpriorSynthesis(C=220, N=320), "Hyperprior.synthesis_std.", sd, z,
+          lambda s, t: O.hyper_synthesis(s, t, "Hyperprior.synthesis_std."), torch.randn((2, 220, 8, 12), generator=g))
