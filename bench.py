@@ -10,6 +10,10 @@ no data-path collective: samples are independent).  Prints ONE JSON line (rank 0
   e2e       the same through the public API with HOST buffers (pinned H2D of x, D2H of x_hat + q_bpp)
   roofline  the dominant kernel (960->960 3x3 residual conv, tcgen05 implicit GEMM) timed alone, live
   cpu_baseline  the CPU oracle (port of the reference path) on a bounded sample, rank 0 at N=1 only
+  roofline_hbm  the conditional-likelihood kernel against the measured HBM peak (20 B/element), all three schedules
+  train_step / gan_train_iteration  the training half of BASELINE.json's metric (fwd + losses + bwd + Adam; NCCL
+                gradient all-reduce at N > 1), plus the same step with the native LPIPS trunk (single GPU)
+  compress_path Model.compress / Model.decompress through the public API (GPU networks + symbol kernels + host rANS)
 `--impl reference` times the reference's CPU implementation of the path (oracle port) instead.
 """
 import argparse
