@@ -387,6 +387,41 @@ def run_likelihood_roofline(dev, peaks, batch):
             "peak_source": peaks["source"] + ", HBM copy bandwidth", "l2": "flushed (256 MiB memset) before every timed launch"}
 
 
+def run_symbols_roofline(dev, peaks):
+    """HBM roofline of the compress-path kernel at the c5 latent size (8 x 220 x 64 x 64): hfc_quantize_symbols with
+    symbols + table indices + Shannon estimate = 12 B read + 8 B written per element; CUDA events, L2
+    flushed before every launch."""
+    from hific_b200 import ops
+    from hific_b200._lib import SYM_BATCH_STEPS, SYM_PIXEL_STEPS
+    from hific_b200.compression.prior_model import prior_scale_table
+    table = torch.clamp(prior_scale_table(), 0.11).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, shape, layout in (("batch_steps_8x220x64x64", (8, 220, 64, 64), SYM_BATCH_STEPS),
+                                ("pixel_steps_1x220x64x64", (1, 220, 64, 64), SYM_PIXEL_STEPS)):
+        g = torch.Generator(device=dev).manual_seed(0)
+        y = torch.randn(shape, device=dev, generator=g) * 3
+        mu = torch.randn(shape, device=dev, generator=g)
+        sc = torch.rand(shape, device=dev, generator=g) * 3
+        for _ in range(3):
+            ops.quantize_symbols(y, mu, sc, table, 0.11, "gaussian", layout, want_bits=True)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.quantize_symbols(y, mu, sc, table, 0.11, "gaussian", layout, want_bits=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]          # median: the output allocations inside the wrapper add jitter
+        gbs = 20.0 * y.numel() / (ms * 1e-3) / 1e9
+        out[name] = {"ms_per_launch": ms, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                     "algorithmic_bytes_per_launch": 20 * y.numel()}
+    out["kernel"] = "quantize_symbols_{flat,transposed}_kernel (symbols, table indices, Shannon estimate), bound: hbm"
+    return out
+
+
 def run_compress_path(model, dev, x_host):
     """compress.py's path through the public API (Model.compress -> CompressionOutput -> Model.decompress): GPU networks
     and symbol kernels + the host rANS coder; wall clock with a device synchronisation on both sides."""
@@ -599,6 +634,11 @@ def main():
             lik = run_likelihood_roofline(dev, measured_peaks(), B)
         except Exception as e:
             lik = {"unavailable": repr(e)[:300]}
+        if isinstance(comp, dict) and "unavailable" not in comp:
+            try:
+                comp["symbols_kernel"] = run_symbols_roofline(dev, measured_peaks())
+            except Exception as e:
+                comp["symbols_kernel"] = {"unavailable": repr(e)[:300]}
 
     # --- the training step once more with the LPIPS AlexNet trunk on the tcgen05 conv kernel instead of cuDNN (opt-in
     # switch HFC_LPIPS_TRUNK=native, parity-tested in tests/test_gpu_zzlpips_trunk.py): recorded so that the default
