@@ -225,3 +225,37 @@ def test_evaluation_model_has_the_reference_state_dict_keys():
     assert sd["Hyperprior.hyperprior_entropy_model.distribution.H_0"].data_ptr() == \
         sd["Hyperprior.hyperlatent_likelihood.H_0"].data_ptr()
     assert tuple(sd["Hyperprior.prior_entropy_model.CDF"].shape) == (64, 1481)
+
+
+def _random_tables(rng, rows, max_len, precision=16):
+    """Valid quantised CDF rows of ragged lengths built with the product's own quantiser from random PMFs."""
+    lengths = rng.integers(1, max_len + 1, size=rows)                 # pmf_length >= 1 -> cdf_length = pmf_length + 2 >= 3
+    cdf = np.zeros((rows, max_len + 2), dtype=np.int32)
+    for r in range(rows):
+        pmf = rng.random(lengths[r] + 1).astype(np.float32) ** 4 + 1e-7   # + the overflow / tail bin
+        pmf /= pmf.sum()
+        cdf[r, :lengths[r] + 2] = entropy_coding.pmf_to_quantized_cdf(pmf, precision)
+    offset = -rng.integers(0, max_len, size=rows).astype(np.int32)
+    return entropy_coding.Tables(cdf, (lengths + 2).astype(np.int32), offset)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_host_coder_property_random_tables(seed):
+    """Random ragged tables (1..40 symbols per row, including single-symbol rows), random shapes, symbols inside and far
+    outside every row: the C coder equals the oracle word for word, decodes what the oracle decodes, and every in-table
+    symbol round-trips exactly."""
+    rng = np.random.default_rng(100 + seed)
+    rows = int(rng.integers(1, 9))
+    T = _random_tables(rng, rows, int(rng.integers(1, 41)))
+    steps, lanes = int(rng.integers(1, 20)), int(rng.integers(1, 70))
+    idx = rng.integers(0, rows, size=(steps, lanes)).astype(np.int32)
+    span = (T.length[idx] - 2).astype(np.int64)
+    sym = (T.offset[idx] + rng.integers(0, np.maximum(span, 1))).astype(np.int32)
+    wild = rng.random((steps, lanes)) < 0.15
+    sym[wild] += rng.integers(-300, 300, size=int(wild.sum())).astype(np.int32)
+    enc = entropy_coding.vec_ans_index_encoder(sym, idx, T)
+    assert np.array_equal(enc, EO.vec_encode(sym, idx, T.cdf, T.length, T.offset))
+    dec = entropy_coding.vec_ans_index_decoder(enc, idx, T)
+    assert np.array_equal(dec, EO.vec_decode(enc, idx, T.cdf, T.length, T.offset))
+    inside = (sym - T.offset[idx] >= 0) & (sym - T.offset[idx] < span)
+    assert np.array_equal(dec[inside], sym[inside])
