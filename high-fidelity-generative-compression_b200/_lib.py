@@ -107,6 +107,9 @@ SIGNATURES = {
     "hfc_hyperlatent_likelihood_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hfc_lpips_layer_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "hfc_conv_forward": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hfc_conv_widenorm_supported": (ctypes.c_int, [ctypes.POINTER(ConvDesc)]),
+    "hfc_conv_forward_widenorm": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
+                                                 _vp, _vp]),
     "hfc_nchw_to_act": (ctypes.c_int, [_vp, ctypes.POINTER(ActGeom), _i32, _i32, _vp, _vp, _f32, _vp, _vp]),
     "hfc_channelnorm": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _vp, _f32, _i32,
                                        _vp, _vp, _vp, _vp, _vp]),

@@ -79,6 +79,13 @@ struct ConvKernelParams {
   int32_t gemm;                       // plain GEMM mode: A rows = 128 consecutive rows of a [M][K] matrix
   int32_t k_splits, kb_per_split;     // split-K (gemm mode): tile index carries the K range; fp32 atomics out
   int32_t out_atomic;                 // NHWC_F32 output accumulated with atomicAdd
+  // norm == 2 ("wide" fused ChannelNorm, pair + nsub 2 + cn 2): the channel row of a pixel is spread over the four TMEM
+  // halves of two CTAs; statistics are exchanged through distributed shared memory, then y = act(norm(x)) + res1 + res2
+  // goes to fp32 rows (out_f32, optional) and to the bordered fp16 buffer (out, optional)
+  const float* res1;
+  const float* res2;
+  float* out_f32;
+  int32_t ld_res, ld_f32;
   const float* bias;
   const float* gamma;
   const float* beta;
@@ -103,7 +110,9 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // is a separate instantiation.
 // kNsub: N tiles per work item (2 only with kPair: one N tile in each 256-column TMEM half, see tile_and_stages); a
 // template parameter so that the single-tile instantiations keep their fully unrolled issue / epilogue loops
-template <bool kPair, int kNsub>
+// kWideNorm (only with kPair, kNsub == 2 and a 2 x 2 cluster): the epilogue of the "wide" fused ChannelNorm (norm == 2); a
+// separate instantiation so that the hot <true, 2, false> kernel keeps its register allocation (162, no spills).
+template <bool kPair, int kNsub, bool kWideNorm = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b,
@@ -123,6 +132,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint64_t* wfull_bar = tempty_bar + 2;          // [1] resident weights landed (wide mode)
+  uint64_t* xchg_bar = bars + 24;                // [1] statistics of the peer CTA landed (norm == 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   float* s_par = reinterpret_cast<float*>(bars + 32);  // [2][3][kParamStride] bias / gamma / beta
   float* s_red = s_par + 2 * 3 * kParamStride;         // [2 acc stages][2 (sum, ssq)][2 warps][128 rows]
@@ -158,6 +168,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(&tempty_bar[s], (kPair ? 2 : 1) * (kEpiThreads / 32));
     }
     mbar_init(wfull_bar, 1);
+    if constexpr (kWideNorm) mbar_init(xchg_bar, kBlockM);       // one remote arrival per pixel row of the peer CTA
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -366,6 +377,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int as = 0;
     uint32_t aph = 0;
     int cur_nt = -1, pbuf = 1;
+    [[maybe_unused]] uint32_t xph = 0; // phase of xchg_bar == index of the exchange buffer (norm == 2)
     for (int ct = cid; ct < total_ctiles; ct += ncl) {
       const int ctile = ct / p.k_splits;
       const int nt0 = ((ctile % n_groups) * p.cn + n_idx) * kNsub;
@@ -381,7 +393,178 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int ow = gw * p.osw + p.oow;
       const bool valid_px = (tni_in < p.tn) && (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
                             (ow < p.out_w) && (!p.tapn || m < p.w_step);
+      bool wide_norm_done = false;
+      if constexpr (kWideNorm && kNsub == 2) {
+        if (p.norm == 2) {
+          // ============ ChannelNorm over a channel row held by TWO CTAs (4 N tiles: 2 TMEM halves here, 2 in the peer
+          // pair of the 4-CTA cluster) -- replaces conv -> fp32 rows -> hfc_channelnorm for the 960-channel layers ======
+          wide_norm_done = true;
+          auto stage_params = [&](int nt) {
+            if (nt != cur_nt) {
+              cur_nt = nt;
+              pbuf ^= 1;
+              float* sp = s_par + pbuf * (3 * kParamStride);
+              for (int i = et; i < p.block_n; i += kEpiThreads) {
+                const int c = nt * p.block_n + i;
+                const bool real = c < p.cout;
+                sp[i] = (real && p.bias) ? __ldg(p.bias + c) : 0.f;
+                sp[kParamStride + i] = real ? __ldg(p.gamma + c) : 0.f;
+                sp[2 * kParamStride + i] = real ? __ldg(p.beta + c) : 0.f;
+              }
+              asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+            }
+          };
+          auto walk = [&](uint32_t t_row, auto&& body) {      // this warp's alternate 16-column chunks of one TMEM half
+            uint32_t va[16], vb[16];
+            int c0 = 16 * hsel;
+            if (c0 < p.block_n) tmem_ld16(t_row + c0, va);
+            while (c0 < p.block_n) {
+              tmem_ld_wait();
+              if (c0 + 32 < p.block_n) tmem_ld16(t_row + c0 + 32, vb);
+              body(va, c0);
+              c0 += 32;
+              if (c0 >= p.block_n) break;
+              tmem_ld_wait();
+              if (c0 + 32 < p.block_n) tmem_ld16(t_row + c0 + 32, va);
+              body(vb, c0);
+              c0 += 32;
+            }
+          };
+          // ---- phase 1: (count, mean, M2) of the channels this CTA holds, per pixel row
+          float cnt_a = 0.f, mean_a = 0.f, m2_a = 0.f;
+          for (int jsub = 0; jsub < 2; ++jsub) {
+            const int nt = nt0 + jsub;
+            stage_params(nt);
+            const float* s_bias = s_par + pbuf * (3 * kParamStride);
+            if (jsub == 0) {
+              mbar_wait(&tfull_bar[as], aph);
+              tc_fence_after();
+            }
+            const uint32_t t_row = tmem_base + jsub * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+            uint32_t first;
+            tmem_ld1(t_row, first);
+            tmem_ld_wait();
+            const float shift = __uint_as_float(first) + s_bias[0];
+            float sd = 0.f, sq = 0.f;
+            walk(t_row, [&](const uint32_t (&v)[16], int c0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float dlt = (__uint_as_float(v[j]) + s_bias[c0 + j]) - shift;
+                sd += dlt;
+                sq = fmaf(dlt, dlt, sq);
+              }
+            });
+            float* red = s_red;                          // first half of s_red (nsub == 2 has one accumulator stage)
+            red[hsel * 128 + m] = sd;
+            red[256 + hsel * 128 + m] = sq;
+            asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");
+            const int real = max(0, min(p.block_n, p.cout - nt * p.block_n));
+            const float npad = static_cast<float>(p.block_n - real);   // padding columns hold exact zeros: d = -shift
+            const float sd_t = red[m] + red[128 + m] + npad * shift;
+            const float sq_t = red[256 + m] + red[384 + m] - npad * shift * shift;
+            asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");   // red is rewritten by the next half
+            const float cj = static_cast<float>(real);
+            if (real > 0) {
+              const float mean_j = shift + sd_t / cj;
+              const float m2_j = fmaxf(sq_t - sd_t * sd_t / cj, 0.f);
+              if (cnt_a == 0.f) {
+                cnt_a = cj; mean_a = mean_j; m2_a = m2_j;
+              } else {                                   // Chan et al.: merge two (count, mean, M2) summaries
+                const float tot = cnt_a + cj, dl = mean_j - mean_a;
+                m2_a = m2_a + m2_j + dl * dl * (cnt_a * cj / tot);
+                mean_a = mean_a + dl * (cj / tot);
+                cnt_a = tot;
+              }
+            }
+          }
+          // ---- exchange with the CTA of the other pair that holds the same pixel rows (same m_idx, other n_idx)
+          float* xbuf = s_red + 512 + static_cast<int>(xph) * 256;     // [2 (mean, M2)][128], double-buffered by phase
+          const uint32_t peer = crank ^ static_cast<uint32_t>(p.cm);
+          if (hsel == 0) {
+            st_cluster_f32(mapa_u32(smem_u32(xbuf + m), peer), mean_a);
+            st_cluster_f32(mapa_u32(smem_u32(xbuf + 128 + m), peer), m2_a);
+            mbar_arrive_remote_release(mapa_u32(smem_u32(xchg_bar), peer));
+          }
+          mbar_wait_acquire_cluster(xchg_bar, xph);
+          const float mean_b = xbuf[m], m2_b = xbuf[128 + m];
+          xph ^= 1u;
+          const float ctot = static_cast<float>(p.cout), cnt_b = ctot - cnt_a;
+          const float dl = mean_b - mean_a;
+          const float mean = mean_a + dl * (cnt_b / ctot);
+          const float m2 = m2_a + m2_b + dl * dl * (cnt_a * cnt_b / ctot);
+          const float rstd = rsqrtf(fmaxf(m2, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
+          // ---- phase 2: normalise, activate, add the residual streams, write fp32 rows and / or the fp16 buffer
+          int rows[3], cols[3];
+          int nr = 0, nc = 0;
+          rows[nr++] = oh + p.out_pt;
+          cols[nc++] = ow + p.out_pl;
+          if (p.out_reflect) {
+            if (oh >= 1 && oh <= p.out_pt) rows[nr++] = p.out_pt - oh;
+            if (oh <= p.out_h - 2 && oh >= p.out_h - 1 - p.out_pb) rows[nr++] = p.out_pt + 2 * (p.out_h - 1) - oh;
+            if (ow >= 1 && ow <= p.out_pl) cols[nc++] = p.out_pl - ow;
+            if (ow <= p.out_w - 2 && ow >= p.out_w - 1 - p.out_pr) cols[nc++] = p.out_pl + 2 * (p.out_w - 1) - ow;
+          }
+          const int Hp = p.out_h + p.out_pt + p.out_pb;
+          const int Wp = p.out_w + p.out_pl + p.out_pr;
+          const size_t pix = (static_cast<size_t>(n) * p.out_h + oh) * p.out_w + ow;
+          for (int jsub = 0; jsub < 2; ++jsub) {
+            const int nt = nt0 + jsub;
+            stage_params(nt);
+            const float* s_bias = s_par + pbuf * (3 * kParamStride);
+            const float* s_gamma = s_bias + kParamStride;
+            const float* s_beta = s_bias + 2 * kParamStride;
+            const uint32_t t_row = tmem_base + jsub * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+            const int c_base = nt * p.block_n;
+            walk(t_row, [&](const uint32_t (&v)[16], int c0) {
+              const int cc = c_base + c0;
+              if (!valid_px || cc >= p.cout) return;       // cout is a multiple of 16 in this mode (checked on the host)
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float x = __uint_as_float(v[j]) + s_bias[c0 + j];
+                f[j] = apply_act(fmaf(s_gamma[c0 + j] * rstd, x - mean, s_beta[c0 + j]), p.act);
+              }
+              if (p.res1) {
+                const float4* r = reinterpret_cast<const float4*>(p.res1 + pix * p.ld_res + cc);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 t = r[j4];
+                  f[4 * j4] += t.x; f[4 * j4 + 1] += t.y; f[4 * j4 + 2] += t.z; f[4 * j4 + 3] += t.w;
+                }
+              }
+              if (p.res2) {
+                const float4* r = reinterpret_cast<const float4*>(p.res2 + pix * p.ld_res + cc);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 t = r[j4];
+                  f[4 * j4] += t.x; f[4 * j4 + 1] += t.y; f[4 * j4 + 2] += t.z; f[4 * j4 + 3] += t.w;
+                }
+              }
+              if (p.out_f32) {
+                float4* dst = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_f32 + cc);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+              }
+              if (p.out) {
+                uint4 lo, hi;
+                lo.x = pack_half2(f[0], f[1]);   lo.y = pack_half2(f[2], f[3]);
+                lo.z = pack_half2(f[4], f[5]);   lo.w = pack_half2(f[6], f[7]);
+                hi.x = pack_half2(f[8], f[9]);   hi.y = pack_half2(f[10], f[11]);
+                hi.z = pack_half2(f[12], f[13]); hi.w = pack_half2(f[14], f[15]);
+                for (int ri = 0; ri < nr; ++ri)
+                  for (int ci = 0; ci < nc; ++ci) {
+                    __half* dst = reinterpret_cast<__half*>(p.out) +
+                                  ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) * p.out_cpad + cc;
+                    reinterpret_cast<uint4*>(dst)[0] = lo;
+                    reinterpret_cast<uint4*>(dst)[1] = hi;
+                  }
+              }
+            });
+          }
+        }
+      }
       // nsub == 2 (CTA pairs): the work item owns both TMEM halves, one N tile in each
+      if (!wide_norm_done)
       for (int jsub = 0; jsub < kNsub; ++jsub) {
       const int nt = nt0 + jsub;
       const bool valid = valid_px && (nt < p.n_tiles);
@@ -771,7 +954,7 @@ static int next_pow2(int v) {
   return r;
 }
 
-static int make_plan(const hfc_conv_desc* d, Plan* pl) {
+static int make_plan(const hfc_conv_desc* d, Plan* pl, bool widenorm = false) {
   if (!d) return set_error(HFC_ERR_INVALID, "conv: null descriptor");
   const hfc_act_geom& in = d->in;
   if (in.n <= 0 || in.h <= 0 || in.w <= 0 || in.c <= 0 || d->cout <= 0)
@@ -870,7 +1053,12 @@ static int make_plan(const hfc_conv_desc* d, Plan* pl) {
   pl->block_n = bn;
   pl->n_tiles = (n_cols + bn - 1) / bn;
   pl->rows = pl->n_tiles * bn;
-  if (d->norm && pl->n_tiles != 1)
+  if (widenorm) {
+    if (pl->n_tiles != 4 || d->cout % 16 != 0 || !d->norm || d->transposed || d->window || pl->tapn ||
+        d->out_mode != HFC_OUT_NHWC_F16)
+      return set_error(HFC_ERR_INVALID, "conv: the wide fused ChannelNorm needs a conv2d with exactly 4 N tiles "
+                                        "(768 < cout <= 1024, cout %% 16 == 0), norm = 1 and an NHWC fp16 output geometry");
+  } else if (d->norm && pl->n_tiles != 1)
     return set_error(HFC_ERR_INVALID,
                      "conv: fused ChannelNorm needs cout <= 256 (use NHWC_F32 + hfc_channelnorm)");
   if (d->norm && d->cout < 2) return set_error(HFC_ERR_INVALID, "conv: ChannelNorm needs cout >= 2");
@@ -907,7 +1095,7 @@ static int make_plan(const hfc_conv_desc* d, Plan* pl) {
 }
 
 static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& ph, int batch,
-                           ConvKernelParams* kp) {
+                           ConvKernelParams* kp, bool widenorm = false) {
   kp->tw = std::min(16, next_pow2(ph.grid_w));
   kp->th = std::min(kBlockM / kp->tw, next_pow2(ph.grid_h));
   kp->tn = kBlockM / (kp->tw * kp->th);
@@ -1027,6 +1215,18 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
       kp->a_split_n = 0;
     }
     stage_bytes = kABytes + kp->nsub * kp->b_rows * kBlockK * 2;
+    kp->stages = std::max(2, std::min(budget / stage_bytes, kMaxStages));
+  }
+  if (widenorm) {
+    // the channel row of a pixel = 4 N tiles = 2 TMEM halves in each of the two pairs of a 2 x 2 cluster
+    if (free_tile || kp->wide || kp->winflat || tiles_m % 2 != 0 || (pl.block_n / 2) % 8 != 0)
+      return -2;
+    kp->cm = 2; kp->cn = 2; kp->pair = 1; kp->nsub = 2;
+    kp->a_split_n = 0;
+    if (kp->tn % 2 == 0) kp->a_split_n = 1;
+    else if (kp->th % 2 != 0) return -2;
+    kp->b_rows = pl.block_n / 2;
+    stage_bytes = kABytes + 2 * kp->b_rows * kBlockK * 2;
     kp->stages = std::max(2, std::min(budget / stage_bytes, kMaxStages));
   }
   return stage_bytes;
@@ -1153,13 +1353,20 @@ static int pack_weights_impl(const hfc_conv_desc* d, const float* w, const float
   return HFC_OK;
 }
 
-extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const void* packed,
-                                const float* bias, const float* gamma, const float* beta, void* out,
-                                void* stream) {
+struct WideNormArgs {
+  const float* res1;
+  const float* res2;
+  int32_t ld_res;
+  float* out_f32;
+  int32_t ld_f32;
+};
+
+static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void* packed, const float* bias,
+                             const float* gamma, const float* beta, void* out, void* stream, const WideNormArgs* wn) {
   Plan pl;
-  int rc = make_plan(d, &pl);
+  int rc = make_plan(d, &pl, wn != nullptr);
   if (rc != HFC_OK) return rc;
-  if (!in || !packed || !out) return set_error(HFC_ERR_INVALID, "conv_forward: null pointer");
+  if (!in || !packed || (!out && !(wn && wn->out_f32))) return set_error(HFC_ERR_INVALID, "conv_forward: null pointer");
   if (d->norm && (!gamma || !beta))
     return set_error(HFC_ERR_INVALID, "conv_forward: fused norm needs gamma and beta");
   int sm_count = 0;
@@ -1177,7 +1384,10 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     const Phase& ph = pl.ph[i];
     ConvKernelParams kp;
     memset(&kp, 0, sizeof(kp));
-    const int stage_bytes = tile_and_stages(d, pl, ph, ig.n, &kp);
+    const int stage_bytes = tile_and_stages(d, pl, ph, ig.n, &kp, wn != nullptr);
+    if (stage_bytes == -2)
+      return set_error(HFC_ERR_UNSUPPORTED, "conv: the wide fused ChannelNorm needs power-of-two pixel tiles that pair up "
+                                            "along M and split in two (this geometry does not)");
     if (stage_bytes < 0)
       return set_error(HFC_ERR_INVALID, "conv: cluster_m / cluster_n must be 0 (auto), 1 or 2");
     kp.n_tiles = pl.n_tiles;
@@ -1202,6 +1412,11 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     kp.fmt_b = d->b_bf16 ? 1u : 0u;
     kp.bias = bias; kp.gamma = gamma; kp.beta = beta;
     kp.out = out;
+    if (wn) {
+      kp.norm = 2;
+      kp.res1 = wn->res1; kp.res2 = wn->res2; kp.ld_res = wn->ld_res;
+      kp.out_f32 = wn->out_f32; kp.ld_f32 = wn->ld_f32;
+    }
     memcpy(kp.tap_dh, ph.dh, sizeof(kp.tap_dh));
     memcpy(kp.tap_dw, ph.dw, sizeof(kp.tap_dw));
     if (kp.wide) {  // one entry per filter row: (ky - pad_t, -pad_l)
@@ -1272,6 +1487,9 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(conv_igemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_igemm_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024);
       if (e != cudaSuccess)
         return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       attr_set = true;
@@ -1289,7 +1507,8 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = !kp.pair ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1>, tmA, tmB, kp)
+    cudaError_t e = wn ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 2, true>, tmA, tmB, kp)
+                    : !kp.pair ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1>, tmA, tmB, kp)
                     : kp.nsub == 2 ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 2>, tmA, tmB, kp)
                                    : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 1>, tmA, tmB, kp);
     if (e != cudaSuccess)
@@ -1297,6 +1516,40 @@ extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const vo
     note_launch();
   }
   return HFC_OK;
+}
+
+extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const void* packed,
+                                const float* bias, const float* gamma, const float* beta, void* out,
+                                void* stream) {
+  return conv_forward_impl(d, in, packed, bias, gamma, beta, out, stream, nullptr);
+}
+
+extern "C" int hfc_conv_widenorm_supported(const hfc_conv_desc* d) {
+  Plan pl;
+  int rc = make_plan(d, &pl, true);
+  if (rc != HFC_OK) return rc;
+  if (d->out.cpad != d->cout)
+    return set_error(HFC_ERR_UNSUPPORTED, "conv: the wide fused ChannelNorm writes no channel padding (out.cpad must equal cout)");
+  ConvKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int sb = tile_and_stages(d, pl, pl.ph[0], d->in.n, &kp, true);
+  if (sb < 0) return set_error(HFC_ERR_UNSUPPORTED, "conv: pixel tiles of this geometry do not pair up for the wide fused ChannelNorm");
+  return HFC_OK;
+}
+
+extern "C" int hfc_conv_forward_widenorm(const hfc_conv_desc* d, const void* in, const void* packed, const float* bias,
+                                         const float* gamma, const float* beta, const float* res1, const float* res2,
+                                         int32_t ld_res, float* out_f32, int32_t ld_f32, void* out_act, void* stream) {
+  if (!d || !gamma || !beta) return set_error(HFC_ERR_INVALID, "conv_forward_widenorm: descriptor, gamma and beta required");
+  if (!out_f32 && !out_act) return set_error(HFC_ERR_INVALID, "conv_forward_widenorm: no output requested");
+  if ((res1 || res2) && (ld_res < d->cout || ld_res % 4 != 0))
+    return set_error(HFC_ERR_INVALID, "conv_forward_widenorm: residual row pitch must be a multiple of 4 and >= cout");
+  if (out_f32 && (ld_f32 < d->cout || ld_f32 % 4 != 0))
+    return set_error(HFC_ERR_INVALID, "conv_forward_widenorm: fp32 row pitch must be a multiple of 4 and >= cout");
+  if (d->out.cpad != d->cout)
+    return set_error(HFC_ERR_UNSUPPORTED, "conv_forward_widenorm: out.cpad must equal cout (no channel padding is written)");
+  WideNormArgs wn{res1, res2, ld_res, out_f32, ld_f32};
+  return conv_forward_impl(d, in, packed, bias, gamma, beta, out_act, stream, &wn);
 }
 
 

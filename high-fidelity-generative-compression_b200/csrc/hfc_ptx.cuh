@@ -308,6 +308,45 @@ __device__ __forceinline__ void tma_load_4d_pair_mc(void* smem_dst, const CUtens
       "r"(c3), "h"(cta_mask)
       : "memory");
 }
+// ---- distributed shared memory: exchange of per-row statistics between two CTAs of a cluster ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+// arrive (release at cluster scope: the arriving thread's earlier st.shared::cluster stores become visible to whoever
+// acquires the phase) on an mbarrier of ANOTHER CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_acquire_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_acquire_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("hfc: cluster mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+             parity);
+      __trap();
+    }
+  }
+}
+
 // arrive on the mbarrier at this smem offset in the pair LEADER (works from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & kPeerBitMask)

@@ -11,6 +11,8 @@ Layer lists follow the reference networks:
   HyperpriorAnalysis src/network/hyper.py:52-63
   HyperpriorSynthesis src/network/hyper.py:83-97
 """
+import os
+
 import torch
 
 from . import ops
@@ -110,6 +112,20 @@ class GeneratorPlan:
         self.res_convs = [(Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows960),
                            Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows960))
                           for _ in range(n_residual_blocks)]
+        # HFC_FUSE_RESNORM=1: every residual conv runs fused with the ChannelNorm (+ReLU / + residual adds) behind it
+        # (hfc_conv_forward_widenorm: the 960-channel row of a pixel is normalised across a 4-CTA cluster), which removes
+        # the stand-alone ChannelNorm launch and the fp32 round trip of the conv output.  Opt-in: not yet run on hardware.
+        self.fused = None
+        if os.environ.get("HFC_FUSE_RESNORM") == "1" and n_residual_blocks > 0:
+            fused = []
+            for i in range(n_residual_blocks):
+                last = i == n_residual_blocks - 1
+                c1 = Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_geom=self.g_b1, out_reflect=True, act=ACT_RELU)
+                c2 = Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_geom=self.g_flat if last else self.g_b1,
+                          out_reflect=not last, act=ACT_NONE)
+                fused.append((c1, c2))
+            if all(c.widenorm_supported() for pair in fused for c in pair):
+                self.fused = fused
         m = n * h * w
         self.rows = torch.empty((m, 960), dtype=torch.float32, device=device)
         self.head_f32 = torch.empty((m, 960), dtype=torch.float32, device=device)
@@ -145,7 +161,17 @@ class GeneratorPlan:
         ops.channelnorm(self.rows, self.g_b1, init[3].gamma, init[3].beta, act=ACT_NONE, reflect=True,
                         want_f32=True, out_f32=self.head_f32, out_act=self.act_a)
         x_f32, x_act = self.head_f32, self.act_a
-        for m in range(self.n_res):
+        for m in range(self.n_res if self.fused is not None else 0):
+            blk = getattr(mod, f"resblock_{m}")
+            c1, c2 = self.fused[m]
+            last = m == self.n_res - 1
+            nxt = self.x_f32[m % 2]
+            c1.call_widenorm(x_act, blk.conv1.weight, blk.conv1.bias, blk.norm1.gamma, blk.norm1.beta, out_act=self.act_b)
+            c2.call_widenorm(self.act_b, blk.conv2.weight, blk.conv2.bias, blk.norm2.gamma, blk.norm2.beta, res1=x_f32,
+                             res2=self.head_f32 if last else None, out_f32=None if last else nxt,
+                             out_act=self.act_flat if last else self.act_a)
+            x_f32, x_act = nxt, (self.act_flat if last else self.act_a)
+        for m in range(self.n_res if self.fused is None else 0):
             blk = getattr(mod, f"resblock_{m}")
             c1, c2 = self.res_convs[m]
             c1(x_act, blk.conv1.weight, blk.conv1.bias, out=self.rows)

@@ -146,6 +146,37 @@ class Conv:
         self._packed_key = None
         self._packed_src = None
 
+    def widenorm_supported(self):
+        """True if this conv (NHWC fp16 output geometry, 768 < cout <= 1024) can run fused with the ChannelNorm that
+        follows it through hfc_conv_forward_widenorm (host-side check)."""
+        d = _lib.ConvDesc.from_buffer_copy(self.desc)
+        d.norm = 1
+        return lib.hfc_conv_widenorm_supported(ctypes.byref(d)) == 0
+
+    def call_widenorm(self, x_act, weight, bias, gamma, beta, res1=None, res2=None, out_f32=None, out_act=None):
+        """conv + bias + ChannelNorm over the whole (wide) channel row + activation [+ res1] [+ res2] in ONE launch:
+        fp32 rows into `out_f32` (pitch = its row length) and / or the bordered fp16 buffer `out_act` (self.out_geom)."""
+        assert x_act.is_cuda and x_act.dtype == torch.float16 and tuple(x_act.shape) == self.in_geom.shape
+        assert self.out_mode == OUT_NHWC_F16 and (out_f32 is not None or out_act is not None)
+        packed = self.packed_weights(weight)
+        d = _lib.ConvDesc.from_buffer_copy(self.desc)
+        d.norm = 1
+        ld_res = 0
+        for r in (res1, res2):
+            if r is not None:
+                assert r.dtype == torch.float32 and r.is_contiguous()
+                ld_res = r.shape[-1]
+        assert res1 is None or res2 is None or res1.shape[-1] == res2.shape[-1]
+        if out_act is not None:
+            assert tuple(out_act.shape) == self.out_geom.shape and out_act.dtype == torch.float16
+        check(lib.hfc_conv_forward_widenorm(ctypes.byref(d), _ptr(x_act), _ptr(packed),
+                                            _ptr(bias.detach().reshape(-1) if bias is not None else None),
+                                            _ptr(gamma.detach().reshape(-1)), _ptr(beta.detach().reshape(-1)),
+                                            _ptr(res1), _ptr(res2), ld_res, _ptr(out_f32),
+                                            out_f32.shape[-1] if out_f32 is not None else 0, _ptr(out_act), _stream()),
+              "conv_forward_widenorm")
+        return out_act, out_f32
+
     def alloc_out(self, device):
         g = self.out_geom
         if self.out_mode == OUT_NHWC_F16:

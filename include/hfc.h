@@ -130,6 +130,21 @@ int hfc_conv_pack_weights_scaled(const hfc_conv_desc* d, const float* w, const f
  * out: buffer of d->out_mode/d->out */
 int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const void* packed, const float* bias,
                      const float* gamma, const float* beta, void* out, void* stream);
+/*
+ * Convolution fused with a ChannelNorm2D over a channel row that does NOT fit one accumulator tile (768 < cout <= 1024:
+ * the Generator's 960-channel residual trunk, src/network/generator.py:33-44): the row of a pixel lives in the four TMEM
+ * halves of two CTA pairs of a 4-CTA cluster, which exchange per-pixel (mean, M2) through distributed shared memory;
+ * y = act(gamma * (x - mean) * rsqrt(var_unbiased + eps) + beta) [+ res1] [+ res2] is written as fp32 rows (out_f32,
+ * pitch ld_f32; optional) and into the bordered NHWC fp16 buffer described by d->out (out_act; optional) -- i.e.
+ * hfc_conv_forward(NHWC_F32) + hfc_channelnorm in one launch.  d: a stride-1 / stride-2 conv2d descriptor with norm = 1,
+ * out_mode = HFC_OUT_NHWC_F16, cout % 16 == 0; res1 / res2: fp32 rows of pitch ld_res (may be NULL).
+ * Returns HFC_ERR_UNSUPPORTED for geometries whose pixel tiles do not pair up (callers then use the two-launch path).
+ */
+/* HFC_OK if hfc_conv_forward_widenorm can run this descriptor (host-only check, works without a GPU) */
+int hfc_conv_widenorm_supported(const hfc_conv_desc* d);
+int hfc_conv_forward_widenorm(const hfc_conv_desc* d, const void* in, const void* packed, const float* bias,
+                              const float* gamma, const float* beta, const float* res1, const float* res2,
+                              int32_t ld_res, float* out_f32, int32_t ld_f32, void* out_act, void* stream);
 
 /*
  * Layout conversion at module boundaries (the reference modules exchange NCHW fp32):

@@ -273,6 +273,45 @@ def _write_act(y, geom, out, reflect):
     return out
 
 
+def conv_call_widenorm(self, x_act, weight, bias, gamma, beta, res1=None, res2=None, out_f32=None, out_act=None):
+    """ops.Conv.call_widenorm: conv + ChannelNorm over the whole channel row + act [+ res1] [+ res2]."""
+    go = self.out_geom
+    y = _conv_linear(self, x_act, weight, bias)
+    y = _apply_act(_channel_norm(y, gamma.detach().float().reshape(-1), beta.detach().float().reshape(-1)), self.desc.act)
+    for r in (res1, res2):
+        if r is not None:
+            y = y + r.view(go.n, go.h, go.w, -1)[..., :self.cout].permute(0, 3, 1, 2)
+    if out_f32 is not None:
+        out_f32.view(go.n * go.h * go.w, -1)[:, :self.cout] = y.permute(0, 2, 3, 1).reshape(-1, self.cout)
+    if out_act is not None:
+        _write_act(y, go, out_act, bool(self.desc.out_reflect))
+    return out_act, out_f32
+
+
+def _conv_linear(self, x_act, weight, bias=None, scale=None):
+    d, gi = self.desc, self.in_geom
+    buf = x_act.view(gi.shape).float()
+    w = weight.detach().float()
+    if scale is not None:
+        w = w * scale.float().reshape(())
+    w = (w.to(torch.bfloat16) if d.b_bf16 else w.to(torch.float16)).float()
+    if d.dgrad:
+        w = w.flip(2, 3).transpose(0, 1)
+    interior = buf[:, gi.pt:gi.pt + gi.h, gi.pl:gi.pl + gi.w, :gi.c].permute(0, 3, 1, 2)
+    if d.transposed:
+        y = F.conv_transpose2d(interior, w, stride=d.stride, padding=d.pad_t, output_padding=d.stride - 1)
+    else:
+        if d.pad_mode == PAD_REFLECT:
+            region = buf[:, gi.pt - d.pad_t:gi.pt + gi.h + d.pad_b, gi.pl - d.pad_l:gi.pl + gi.w + d.pad_r, :gi.c]
+            region = region.permute(0, 3, 1, 2)
+        else:
+            region = F.pad(interior, (d.pad_l, d.pad_r, d.pad_t, d.pad_b))
+        y = F.conv2d(region, w, stride=d.stride)
+    if bias is not None:
+        y = y + bias.detach().float().view(1, -1, 1, 1)
+    return y
+
+
 def conv_call_general(self, x_act, weight, bias=None, gamma=None, beta=None, out=None, scale=None, scale_key=None):
     d, gi = self.desc, self.in_geom
     buf = x_act.view(gi.shape).float()
@@ -350,6 +389,7 @@ def plan_cpu_emulation():
         setattr(obj, name, value)
 
     patch(ops.Conv, "__call__", conv_call_general)
+    patch(ops.Conv, "call_widenorm", conv_call_widenorm)
     patch(ops, "nchw_to_act", nchw_to_act)
     patch(ops, "channelnorm", channelnorm)
     patch(engine, "_require_cuda", lambda x, who: None)

@@ -125,3 +125,19 @@ def test_plans_with_other_latent_channels(C):
     assert rel_l2(x_hat, O.generator_forward(sd, torch.round(y), n_residual_blocks=2)) < REL
     assert rel_l2(z, O.hyper_analysis(sd, y16)) < REL
     assert rel_l2(mu, O.hyper_synthesis(sd, torch.round(z), "Hyperprior.synthesis_mu.")) < REL
+
+
+def test_generator_plan_with_fused_residual_norms(sd, monkeypatch):
+    """HFC_FUSE_RESNORM=1: the residual trunk through `Conv.call_widenorm` (conv + ChannelNorm + ReLU / residual adds in
+    one launch) -- same result as the two-launch plan, i.e. as the oracle; ragged maps fall back to the two-launch plan."""
+    from hific_b200 import engine
+    monkeypatch.setenv("HFC_FUSE_RESNORM", "1")
+    g = torch.Generator().manual_seed(5)
+    for n, h, w, fused in ((2, 16, 16, True), (1, 3, 5, False)):
+        gen = load(generator.Generator((220, h, w), n, C=220, n_residual_blocks=9), sd, "Generator.")
+        y_hat = torch.round(torch.randn((n, 220, h, w), generator=g) * 2)
+        with torch.no_grad(), plan_cpu_emulation():
+            x_hat = gen(y_hat)
+            plan = gen._plans.get(y_hat)
+        assert (plan.fused is not None) == fused
+        assert rel_l2(x_hat, O.generator_forward(sd, y_hat)) < REL

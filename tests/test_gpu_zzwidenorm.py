@@ -1,0 +1,84 @@
+"""GPU: convolution fused with the ChannelNorm of a 960-channel row (hfc_conv_forward_widenorm: pair kernel, two N tiles
+per CTA, 2 x 2 cluster, per-pixel (mean, M2) exchanged through distributed shared memory) against the two-launch path it
+replaces (hfc_conv_forward -> fp32 rows -> hfc_channelnorm), and the Generator plan with HFC_FUSE_RESNORM=1 against the
+default plan.
+
+NOT YET RUN ON HARDWARE (written after round 1's GPU minutes were spent): runs only with HFC_RUN_UNVERIFIED=1
+(tools/next_round_checks.sh).  The plan logic is covered on the CPU by tests/test_engine_plans_cpu.py.  Tolerances: the
+statistics are merged in a different order (Chan's pairwise update instead of one two-pass sweep), so fp32 rows agree to
+1e-4 relative and the fp16 buffers to one fp16 ulp (2e-3 relative)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+if os.environ.get("HFC_RUN_UNVERIFIED") != "1":
+    pytest.skip("the wide fused ChannelNorm has not run on hardware yet (set HFC_RUN_UNVERIFIED=1)", allow_module_level=True)
+
+from hific_b200 import ops, synth  # noqa: E402
+from hific_b200.network import generator  # noqa: E402
+from hific_b200.ops import ACT_NONE, ACT_RELU, OUT_NHWC_F32, PAD_REFLECT, Conv, Geom  # noqa: E402
+
+
+@pytest.mark.parametrize("n,h,w", [(32, 16, 16), (2, 16, 16), (8, 32, 32)])
+@pytest.mark.parametrize("variant", ["relu_act_only", "residual_f32_and_act", "last_block"])
+def test_widenorm_matches_two_launch_path(n, h, w, variant):
+    g = torch.Generator().manual_seed(n + h)
+    b1 = (1, 1, 1, 1)
+    g_in = Geom(n, h, w, 960, 960, *b1)
+    last = variant == "last_block"
+    g_out = Geom(n, h, w, 960, 960) if last else Geom(n, h, w, 960, 960, *b1)
+    act = ACT_RELU if variant == "relu_act_only" else ACT_NONE
+    x = torch.randn((n, 960, h, w), generator=g).cuda() * 0.5
+    x_act = ops.nchw_to_act(x, g_in, reflect=True)
+    wgt = (torch.randn((960, 960, 3, 3), generator=g) * 0.01).cuda()
+    bias, gamma, beta = (torch.randn(960, generator=g).cuda() for _ in range(3))
+    res1 = res2 = None
+    if variant != "relu_act_only":
+        res1 = torch.randn((n * h * w, 960), generator=g).cuda()
+    if last:
+        res2 = torch.randn((n * h * w, 960), generator=g).cuda()
+    # reference: conv -> fp32 rows -> stand-alone ChannelNorm
+    rows_conv = Conv(g_in, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, 960, 960))
+    rows = rows_conv(x_act, wgt, bias)
+    want_act, want_f32 = ops.channelnorm(rows, g_out, gamma, beta, act=act, reflect=not last, res1=res1, res2=res2,
+                                         want_f32=True)
+    fused = Conv(g_in, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_geom=g_out, out_reflect=not last, act=act)
+    assert fused.widenorm_supported()
+    out_act = torch.full(g_out.shape, float("nan"), dtype=torch.float16, device="cuda")
+    out_f32 = torch.full((n * h * w, 960), float("nan"), device="cuda")
+    l0 = ops.launch_count()
+    fused.call_widenorm(x_act, wgt, bias, gamma, beta, res1=res1, res2=res2, out_f32=out_f32, out_act=out_act)
+    torch.cuda.synchronize()
+    assert ops.launch_count() - l0 == 1
+    assert torch.isfinite(out_f32).all() and torch.isfinite(out_act.float()).all()          # every element written
+    assert torch.allclose(out_f32, want_f32, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(out_act.float(), want_act.float(), rtol=2e-3, atol=2e-3)
+
+
+def test_generator_plan_fused_equals_default(monkeypatch):
+    sd = synth.synth_state_dict(0)
+    gen = generator.Generator((220, 16, 16), 4, C=220, n_residual_blocks=9)
+    gen.load_state_dict({k[len("Generator."):]: v for k, v in sd.items() if k.startswith("Generator.")}, strict=True)
+    gen.cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    y_hat = torch.round(torch.randn((4, 220, 16, 16), generator=g) * 2).cuda()
+    with torch.no_grad():
+        want = gen(y_hat)
+    monkeypatch.setenv("HFC_FUSE_RESNORM", "1")
+    gen._plans.clear()
+    with torch.no_grad():
+        l0 = ops.launch_count()
+        got = gen(y_hat)
+        fused_launches = ops.launch_count() - l0
+    assert gen._plans.get(y_hat).fused is not None
+    assert ((got - want).norm() / want.norm()).item() < 2e-4
+    monkeypatch.delenv("HFC_FUSE_RESNORM")
+    gen._plans.clear()
+    with torch.no_grad():
+        l0 = ops.launch_count()
+        gen(y_hat)
+        assert fused_launches == (ops.launch_count() - l0) - 18          # one launch fewer per residual conv

@@ -9,6 +9,10 @@ if [ "$N" = "1" ]; then
   HFC_RUN_UNVERIFIED=1 timeout 420 python -m pytest tests -m gpu -x -q > gpurun_out/nr_tests.log 2>&1; echo "tests rc=$?" > gpurun_out/nr_status.txt   # incl. tests/test_gpu_zzdlmm.py (DLMM kernels: first run on hardware)
   # 2. bench: train_step.with_native_lpips_trunk vs train_step.ms_per_step decides HFC_LPIPS_TRUNK's default
   timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/nr_bench.json 2> gpurun_out/nr_bench.err; echo "bench rc=$?" >> gpurun_out/nr_status.txt
+  # 2b. forward with the residual convs fused with their ChannelNorm (hfc_conv_forward_widenorm; parity: tests/test_gpu_zzwidenorm.py
+  #     in step 1): compare "value" / "ms_per_step" with nr_bench.json -- expected ~0.5 ms less per forward if it works
+  HFC_FUSE_RESNORM=1 timeout 120 python bench.py --steps 20 --warmup 5 --no-train --no-cpu-baseline --no-compress \
+      > gpurun_out/nr_bench_fused_resnorm.json 2> gpurun_out/nr_bench_fused_resnorm.err; echo "bench fused rc=$?" >> gpurun_out/nr_status.txt
   # 3. re-profile the compress-path kernels (64-bit divisions removed after the last capture)
   timeout 120 ncu --set full --clock-control none --import-source on -k regex:"symbols" -c 12 -f -o gpurun_out/nr_symbols \
       python tools/profile_symbols.py > gpurun_out/nr_ncu.log 2>&1; echo "ncu rc=$?" >> gpurun_out/nr_status.txt
