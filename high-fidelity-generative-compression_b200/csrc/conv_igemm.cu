@@ -430,6 +430,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               c0 += 32;
             }
           };
+          auto walk1 = [&](uint32_t t_row, auto&& body) {     // same chunks, no TMEM prefetch (fewer live registers)
+            uint32_t va[16];
+            for (int c0 = 16 * hsel; c0 < p.block_n; c0 += 32) {
+              tmem_ld16(t_row + c0, va);
+              tmem_ld_wait();
+              body(va, c0);
+            }
+          };
           // ---- phase 1: (count, mean, M2) of the channels this CTA holds, per pixel row
           float cnt_a = 0.f, mean_a = 0.f, m2_a = 0.f;
           for (int jsub = 0; jsub < 2; ++jsub) {
@@ -515,7 +523,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const float* s_beta = s_bias + 2 * kParamStride;
             const uint32_t t_row = tmem_base + jsub * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
             const int c_base = nt * p.block_n;
-            walk(t_row, [&](const uint32_t (&v)[16], int c0) {
+            walk1(t_row, [&](const uint32_t (&v)[16], int c0) {
               const int cc = c_base + c0;
               if (!valid_px || cc >= p.cout) return;       // cout is a multiple of 16 in this mode (checked on the host)
               float f[16];
