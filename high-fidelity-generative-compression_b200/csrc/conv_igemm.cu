@@ -112,7 +112,11 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // template parameter so that the single-tile instantiations keep their fully unrolled issue / epilogue loops
 // kWideNorm (only with kPair, kNsub == 2 and a 2 x 2 cluster): the epilogue of the "wide" fused ChannelNorm (norm == 2); a
 // separate instantiation so that the hot <true, 2, false> kernel keeps its register allocation (162, no spills).
-template <bool kPair, int kNsub, bool kWideNorm = false>
+// kThin (single-CTA MMA, one N tile of <= 64 columns, NHWC fp16 output): the two groups of four epilogue warps serve
+// DIFFERENT accumulator stages concurrently, each thread holds its pixel's whole channel row in registers (one TMEM pass, no
+// cross-warp exchange, no named barrier) and frees the TMEM stage right after the load -- for the big-map 60-channel layers
+// whose tiles are epilogue-latency-bound (E1 355 us, G.up4 384 us against ~50 us of HBM time).  Own instantiation.
+template <bool kPair, int kNsub, bool kWideNorm = false, bool kThin = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b,
@@ -165,7 +169,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       // pair mode: the leader's MMA warp waits for the epilogue warps of BOTH CTAs
-      mbar_init(&tempty_bar[s], (kPair ? 2 : 1) * (kEpiThreads / 32));
+      mbar_init(&tempty_bar[s], kThin ? 4u : (kPair ? 2 : 1) * (kEpiThreads / 32));
     }
     mbar_init(wfull_bar, 1);
     if constexpr (kWideNorm) mbar_init(xchg_bar, kBlockM);       // one remote arrival per pixel row of the peer CTA
@@ -365,6 +369,119 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // Two warps per TMEM lane quadrant: both own the same 32 pixel rows and take alternate 16-column
     // chunks, so every scheduler has two epilogue warps to interleave (a lone warp issues one dependent
     // instruction every ~5 cycles, which made the 128-wide epilogues the bottleneck of the big-map layers).
+    if constexpr (kThin) {
+      const int q = warp & 3;            // TMEM lane quadrant this warp may access
+      const int grp = (warp - 2) >> 2;   // epilogue group == the accumulator stage it serves (items alternate stages)
+      const int m = q * 32 + lane;
+      const int et = threadIdx.x - 64;
+      for (int i = et; i < p.block_n; i += kEpiThreads) {     // one N tile: parameters staged once
+        const bool real = i < p.cout;
+        s_par[i] = (real && p.bias) ? __ldg(p.bias + i) : 0.f;
+        s_par[kParamStride + i] = (real && p.norm) ? __ldg(p.gamma + i) : 0.f;
+        s_par[2 * kParamStride + i] = (real && p.norm) ? __ldg(p.beta + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+      const float* s_bias = s_par;
+      const float* s_gamma = s_par + kParamStride;
+      const float* s_beta = s_par + 2 * kParamStride;
+      const int twi_in = m % p.tw;
+      const int thi_in = (m / p.tw) % p.th;
+      const int tni_in = m / (p.tw * p.th);
+      const int Hp = p.out_h + p.out_pt + p.out_pb;
+      const int Wp = p.out_w + p.out_pl + p.out_pr;
+      const float inv_c = 1.f / static_cast<float>(p.cout);
+      int it = 0;
+      for (int ct = cid; ct < total_ctiles; ct += ncl, ++it) {
+        if ((it & 1) != grp) continue;
+        const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+        int mt = (ct / n_groups) * p.cm + m_idx;
+        const int twi = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int thi = mt % p.tiles_h;
+        const int tni = mt / p.tiles_h;
+        const int gw = twi * p.tw + twi_in;
+        const int gh = thi * p.th + thi_in;
+        const int n = tni * p.tn + tni_in;
+        const int oh = gh * p.osh + p.ooh;
+        const int ow = gw * p.osw + p.oow;
+        const bool valid = (tni_in < p.tn) && (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
+                           (ow < p.out_w);
+        mbar_wait(&tfull_bar[grp], aph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + grp * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (16 * c < p.block_n) tmem_ld16(t_row + 16 * c, v[c]);
+        tmem_ld_wait();
+        tc_fence_before();                 // the row is in registers: hand the accumulator stage back to the MMA warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+        // in place: v holds the bit patterns of x = acc + bias, then of the normalised values
+#define HFC_X(c, j) __uint_as_float(v[c][j])
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[c][j] = (16 * c < p.block_n) ? __float_as_uint(HFC_X(c, j) + s_bias[16 * c + j]) : 0u;
+        if (p.norm) {                      // two-pass mean / unbiased variance over the real channels, all in registers
+          float sum = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (16 * c + j < p.cout) sum += HFC_X(c, j);
+          const float mean = sum * inv_c;
+          float ssq = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (16 * c + j < p.cout) { const float dlt = HFC_X(c, j) - mean; ssq = fmaf(dlt, dlt, ssq); }
+          const float rstd = rsqrtf(ssq / static_cast<float>(p.cout - 1) + p.eps);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (16 * c < p.block_n)   // padding columns: gamma = beta = 0 -> exactly 0
+                v[c][j] = __float_as_uint(fmaf(s_gamma[16 * c + j] * rstd, HFC_X(c, j) - mean, s_beta[16 * c + j]));
+        }
+        if (!valid) continue;
+        int rows[3], cols[3];
+        int nr = 0, nc = 0;
+        rows[nr++] = oh + p.out_pt;
+        cols[nc++] = ow + p.out_pl;
+        if (p.out_reflect) {
+          if (oh >= 1 && oh <= p.out_pt) rows[nr++] = p.out_pt - oh;
+          if (oh <= p.out_h - 2 && oh >= p.out_h - 1 - p.out_pb) rows[nr++] = p.out_pt + 2 * (p.out_h - 1) - oh;
+          if (ow >= 1 && ow <= p.out_pl) cols[nc++] = p.out_pl - ow;
+          if (ow <= p.out_w - 2 && ow >= p.out_w - 1 - p.out_pr) cols[nc++] = p.out_pl + 2 * (p.out_w - 1) - ow;
+        }
+        for (int ri = 0; ri < nr; ++ri)
+          for (int ci = 0; ci < nc; ++ci) {
+            __half* dst = reinterpret_cast<__half*>(p.out) +
+                          ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) * p.out_cpad;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (16 * c >= p.block_n || 16 * c >= p.out_cpad) continue;
+              uint4 lo, hi;
+              lo.x = pack_half2(apply_act(HFC_X(c, 0), p.act), apply_act(HFC_X(c, 1), p.act));
+              lo.y = pack_half2(apply_act(HFC_X(c, 2), p.act), apply_act(HFC_X(c, 3), p.act));
+              lo.z = pack_half2(apply_act(HFC_X(c, 4), p.act), apply_act(HFC_X(c, 5), p.act));
+              lo.w = pack_half2(apply_act(HFC_X(c, 6), p.act), apply_act(HFC_X(c, 7), p.act));
+              hi.x = pack_half2(apply_act(HFC_X(c, 8), p.act), apply_act(HFC_X(c, 9), p.act));
+              hi.y = pack_half2(apply_act(HFC_X(c, 10), p.act), apply_act(HFC_X(c, 11), p.act));
+              hi.z = pack_half2(apply_act(HFC_X(c, 12), p.act), apply_act(HFC_X(c, 13), p.act));
+              hi.w = pack_half2(apply_act(HFC_X(c, 14), p.act), apply_act(HFC_X(c, 15), p.act));
+              reinterpret_cast<uint4*>(dst + 16 * c)[0] = lo;
+              if (16 * c + 8 < p.out_cpad) reinterpret_cast<uint4*>(dst + 16 * c)[1] = hi;
+            }
+            for (int c = p.block_n; c < p.out_cpad; c += 8)      // channel padding the N tile does not cover
+              *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+          }
+#undef HFC_X
+      }
+    } else {
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
     const int hsel = (warp - 2) >> 2;  // which of the two warps of the quadrant
     const int m = q * 32 + lane;
@@ -795,6 +912,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       if (++as == (kNsub == 2 ? 1 : 2)) { as = 0; aph ^= 1; }
     }
+    }  // !kThin
   }
 
   tc_fence_before();
@@ -1498,6 +1616,9 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(conv_igemm_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_igemm_kernel<false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024);
       if (e != cudaSuccess)
         return set_error(HFC_ERR_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       attr_set = true;
@@ -1515,7 +1636,12 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = wn ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 2, true>, tmA, tmB, kp)
+    // thin epilogue (opt-in, HFC_THIN_EPILOGUE=1): single-CTA MMA, one N tile of <= 64 columns, NHWC fp16 output
+    static const bool env_thin = getenv("HFC_THIN_EPILOGUE") != nullptr && getenv("HFC_THIN_EPILOGUE")[0] == '1';
+    const bool thin = env_thin && !wn && !kp.pair && kp.cn == 1 && kp.n_tiles == 1 && kp.block_n <= 64 && !kp.tapn &&
+                      !kp.wide && d->out_mode == HFC_OUT_NHWC_F16 && kp.k_splits == 1;
+    cudaError_t e = thin ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1, false, true>, tmA, tmB, kp)
+                    : wn ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 2, true>, tmA, tmB, kp)
                     : !kp.pair ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1>, tmA, tmB, kp)
                     : kp.nsub == 2 ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 2>, tmA, tmB, kp)
                                    : cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 1>, tmA, tmB, kp);

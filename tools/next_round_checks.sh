@@ -13,6 +13,14 @@ if [ "$N" = "1" ]; then
   #     in step 1): compare "value" / "ms_per_step" with nr_bench.json -- expected ~0.5 ms less per forward if it works
   HFC_FUSE_RESNORM=1 timeout 120 python bench.py --steps 20 --warmup 5 --no-train --no-cpu-baseline --no-compress \
       > gpurun_out/nr_bench_fused_resnorm.json 2> gpurun_out/nr_bench_fused_resnorm.err; echo "bench fused rc=$?" >> gpurun_out/nr_status.txt
+  # 2c. thin epilogue for the 60-channel big-map layers (own kernel instantiation; the switch is read once per process):
+  #     parity through the existing op / model tests, then the forward time
+  HFC_THIN_EPILOGUE=1 timeout 200 python -m pytest tests/test_gpu_ops.py tests/test_gpu_parity.py tests/test_gpu_conv_modes.py -x -q \
+      > gpurun_out/nr_tests_thin.log 2>&1; echo "tests thin rc=$?" >> gpurun_out/nr_status.txt
+  HFC_THIN_EPILOGUE=1 timeout 120 python bench.py --steps 20 --warmup 5 --no-train --no-cpu-baseline --no-compress \
+      > gpurun_out/nr_bench_thin.json 2> gpurun_out/nr_bench_thin.err; echo "bench thin rc=$?" >> gpurun_out/nr_status.txt
+  HFC_THIN_EPILOGUE=1 HFC_FUSE_RESNORM=1 timeout 120 python bench.py --steps 20 --warmup 5 --no-train --no-cpu-baseline --no-compress \
+      > gpurun_out/nr_bench_thin_fused.json 2> gpurun_out/nr_bench_thin_fused.err; echo "bench thin+fused rc=$?" >> gpurun_out/nr_status.txt
   # 3. re-profile the compress-path kernels (64-bit divisions removed after the last capture)
   timeout 120 ncu --set full --clock-control none --import-source on -k regex:"symbols" -c 12 -f -o gpurun_out/nr_symbols \
       python tools/profile_symbols.py > gpurun_out/nr_ncu.log 2>&1; echo "ncu rc=$?" >> gpurun_out/nr_status.txt
