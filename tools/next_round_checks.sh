@@ -21,6 +21,8 @@ if [ "$N" = "1" ]; then
       > gpurun_out/nr_bench_thin.json 2> gpurun_out/nr_bench_thin.err; echo "bench thin rc=$?" >> gpurun_out/nr_status.txt
   HFC_THIN_EPILOGUE=1 HFC_FUSE_RESNORM=1 timeout 120 python bench.py --steps 20 --warmup 5 --no-train --no-cpu-baseline --no-compress \
       > gpurun_out/nr_bench_thin_fused.json 2> gpurun_out/nr_bench_thin_fused.err; echo "bench thin+fused rc=$?" >> gpurun_out/nr_status.txt
+  timeout 60 python tools/profile_thin_layers.py > gpurun_out/nr_thin_layers_off.txt 2>&1
+  HFC_THIN_EPILOGUE=1 timeout 60 python tools/profile_thin_layers.py > gpurun_out/nr_thin_layers_on.txt 2>&1
   # 3. re-profile the compress-path kernels (64-bit divisions removed after the last capture)
   timeout 120 ncu --set full --clock-control none --import-source on -k regex:"symbols" -c 12 -f -o gpurun_out/nr_symbols \
       python tools/profile_symbols.py > gpurun_out/nr_ncu.log 2>&1; echo "ncu rc=$?" >> gpurun_out/nr_status.txt
