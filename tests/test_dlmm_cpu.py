@@ -102,3 +102,47 @@ def test_product_host_logic_matches_the_reference(gold):
         params = hp.synthesis_DLMM_params(torch.floor(hp.analysis_net(y) + 0.5))
         want = torch.from_numpy(gold["eval.dlmm_params"])
         assert rel(params, want) < 3e-3
+
+
+@pytest.fixture(scope="module")
+def host_kernels(tmp_path_factory):
+    """The per-element code of csrc/dlmm.cu (csrc/dlmm_math.cuh) compiled for the HOST with g++."""
+    import ctypes
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path_factory.mktemp("dlmm") / "dlmm_math_host.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-x", "c++",
+                    os.path.join(here, "dlmm_math_host.cpp"), "-o", so], check=True)
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize("kind", ["gaussian", "logistic"])
+@pytest.mark.parametrize("shape", [(2, 5, 4, 6, 7), (1, 8, 2, 1, 3), (3, 16, 8, 4, 4)])
+def test_kernel_element_code_on_the_host(host_kernels, kind, shape):
+    """The functions every CUDA thread runs, executed on the CPU: forward sums / decoded against the oracle, gradients
+    against torch autograd (through the closed-form stand-in, itself checked above) -- float32 libm vs torch: 1e-5."""
+    import ctypes
+    n, c, k, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn((n, c, h, w), generator=g) * 5
+    params = torch.randn((n, 3 * c * k, h, w), generator=g)
+    params[:, 2 * c * k:] = params[:, 2 * c * k:] * 2 - 2.5
+    params[:, c * k:2 * c * k] *= 3
+    noise = torch.rand((n, c, h, w), generator=g) - 0.5
+    dd = torch.randn((n, c, h, w), generator=g)
+    lt = {"gaussian": 0, "logistic": 1}[kind]
+    fp = lambda t: ctypes.c_void_p(t.data_ptr())
+    for st in (1, 0):
+        dec = torch.empty_like(x)
+        sums = torch.zeros(2, dtype=torch.float64)
+        host_kernels.dlmm_forward_host(fp(x), fp(noise), fp(params), n, c, k, h * w, lt, st, fp(dec), fp(sums))
+        want_dec, want = E.dlmm_likelihood(x, params, noise, kind, bool(st))
+        assert torch.equal(dec, want_dec)
+        assert torch.allclose(sums, want, rtol=1e-5)
+    for upstream in (-0.37, 0.8):
+        dx, dp = torch.empty_like(x), torch.empty_like(params)
+        host_kernels.dlmm_backward_host(fp(x), fp(noise), fp(params), fp(dd), ctypes.c_float(upstream), n, c, k, h * w, lt,
+                                        fp(dx), fp(dp))
+        want_dx, want_dp = E.dlmm_likelihood_bwd(x, params, noise, dd, torch.tensor([upstream]), kind)
+        assert ((dx - want_dx).norm() / want_dx.norm()).item() < 1e-5
+        assert ((dp - want_dp).norm() / want_dp.norm()).item() < 1e-5
