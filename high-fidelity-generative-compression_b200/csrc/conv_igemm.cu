@@ -374,9 +374,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int grp = (warp - 2) >> 2;   // epilogue group == the accumulator stage it serves (items alternate stages)
       const int m = q * 32 + lane;
       const int et = threadIdx.x - 64;
+      float* s_bias_raw = s_par + 3 * kParamStride;            // tap-in-N: bias per output channel (cout <= 32 there)
       for (int i = et; i < p.block_n; i += kEpiThreads) {     // one N tile: parameters staged once
         const bool real = i < p.cout;
-        s_par[i] = (real && p.bias) ? __ldg(p.bias + i) : 0.f;
+        s_bias_raw[i] = (real && p.bias) ? __ldg(p.bias + i) : 0.f;
+        s_par[i] = (real && p.bias && !p.tapn) ? __ldg(p.bias + i) : 0.f;
         s_par[kParamStride + i] = (real && p.norm) ? __ldg(p.gamma + i) : 0.f;
         s_par[2 * kParamStride + i] = (real && p.norm) ? __ldg(p.beta + i) : 0.f;
       }
@@ -399,13 +401,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mt /= p.tiles_w;
         const int thi = mt % p.tiles_h;
         const int tni = mt / p.tiles_h;
-        const int gw = twi * p.tw + twi_in;
+        const int gw = (p.tapn ? twi * p.w_step : twi * p.tw) + twi_in;
         const int gh = thi * p.th + thi_in;
         const int n = tni * p.tn + tni_in;
         const int oh = gh * p.osh + p.ooh;
         const int ow = gw * p.osw + p.oow;
         const bool valid = (tni_in < p.tn) && (n < p.batch) && (gh < p.grid_h) && (gw < p.grid_w) && (oh < p.out_h) &&
-                           (ow < p.out_w);
+                           (ow < p.out_w) && (!p.tapn || m < p.w_step);
         mbar_wait(&tfull_bar[grp], aph);
         tc_fence_after();
         const uint32_t t_row = tmem_base + grp * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
@@ -417,6 +419,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tc_fence_before();                 // the row is in registers: hand the accumulator stage back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+        if (p.tapn) {
+          // 'tap-in-N' (7x7 60 -> 3 head): column t*cout + co of pixel row m is the partial product of filter column t;
+          // out[w][co] = bias[co] + sum_t D[w + t][t*cout + co].  The group stages its tile in ITS half of s_tapn and
+          // synchronises on its own named barrier, so the two groups work on two tiles at the same time.
+          float* st = s_tapn + grp * (kBlockM * kTapnLd);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (16 * c < p.block_n) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) st[m * kTapnLd + 16 * c + j] = __uint_as_float(v[c][j]);
+            }
+          if (grp == 0) asm volatile("bar.sync 3, 128;\n" ::: "memory");
+          else asm volatile("bar.sync 4, 128;\n" ::: "memory");
+          if (valid) {
+            float* dst = reinterpret_cast<float*>(p.out);
+            const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
+            for (int co = 0; co < p.cout; ++co) {
+              float acc = p.bias ? s_bias_raw[co] : 0.f;
+              for (int t = 0; t < p.kw; ++t) acc += st[(m + t) * kTapnLd + t * p.cout + co];
+              dst[(static_cast<size_t>(n) * p.cout + co) * plane + static_cast<size_t>(oh) * p.out_w + ow] =
+                  apply_act(acc, p.act);
+            }
+          }
+          // the next tile of this group overwrites the staging buffer: everyone must be done reading it
+          if (grp == 0) asm volatile("bar.sync 3, 128;\n" ::: "memory");
+          else asm volatile("bar.sync 4, 128;\n" ::: "memory");
+          continue;
+        }
         // in place: v holds the bit patterns of x = acc + bias, then of the normalised values
 #define HFC_X(c, j) __uint_as_float(v[c][j])
 #pragma unroll
@@ -1638,8 +1668,9 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     cfg.numAttrs = 1;
     // thin epilogue (opt-in, HFC_THIN_EPILOGUE=1): single-CTA MMA, one N tile of <= 64 columns, NHWC fp16 output
     static const bool env_thin = getenv("HFC_THIN_EPILOGUE") != nullptr && getenv("HFC_THIN_EPILOGUE")[0] == '1';
-    const bool thin = env_thin && !wn && !kp.pair && kp.cn == 1 && kp.n_tiles == 1 && kp.block_n <= 64 && !kp.tapn &&
-                      !kp.wide && d->out_mode == HFC_OUT_NHWC_F16 && kp.k_splits == 1;
+    const bool thin = env_thin && !wn && !kp.pair && kp.cn == 1 && kp.n_tiles == 1 && kp.block_n <= 64 && !kp.wide &&
+                      kp.k_splits == 1 &&
+                      (kp.tapn ? (d->out_mode == HFC_OUT_NCHW_F32 && kp.block_n <= 32) : d->out_mode == HFC_OUT_NHWC_F16);
     cudaError_t e = thin ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1, false, true>, tmA, tmB, kp)
                     : wn ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 2, true>, tmA, tmB, kp)
                     : !kp.pair ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1>, tmA, tmB, kp)
