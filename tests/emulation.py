@@ -656,3 +656,40 @@ def norm_bwd(z, g, gamma, beta, act, as_operand=True):
     dz = torch.zeros((z.shape[0], (c + 3) // 4 * 4))
     dz[:, :c] = zz.grad
     return dz, gm.grad.view_as(gamma), bt.grad.view_as(beta), zz.grad.sum(0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Differentiable stand-ins of the remaining autograd Functions of the compression model's training step, so that
+# `Model.compression_forward` + losses + `backward()` run end to end on the CPU (host logic of the whole step).
+# ----------------------------------------------------------------------------------------------------------------------
+def latent_likelihood_fn(y, mean, scale_raw, noise, lb, kind):
+    """ops.LatentLikelihoodFn.apply: (decoded, sums[2]) with LowerBoundToward gates and straight-through latents."""
+    scale = O.lower_bound(scale_raw, lb)
+    qy = torch.floor(y - mean + 0.5).detach() + mean.detach()
+    s_n = torch.log(O.latent_likelihood(y + noise, mean, scale, kind) + 1e-9).double().sum()
+    s_q = torch.log(O.latent_likelihood(qy, mean.detach(), scale.detach(), kind) + 1e-9).double().sum().detach()
+    # quantize_latents_st (hyperprior.py:108-122): d decoded / d y = 1, the mean carries no gradient
+    decoded = O.quantize_st(y, mean.detach())
+    return decoded, torch.stack([s_n, s_q])
+
+
+def sqdiff_mean_fn(a, b, scale):
+    return torch.mean((a * scale - b * scale) ** 2)
+
+
+@contextlib.contextmanager
+def train_step_cpu_emulation():
+    saved = []
+
+    def patch(obj, name, value):
+        saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, value)
+
+    with training_cpu_emulation():
+        patch(ops.LatentLikelihoodFn, "apply", staticmethod(latent_likelihood_fn))
+        patch(ops.SqDiffMeanFn, "apply", staticmethod(sqdiff_mean_fn))
+        try:
+            yield
+        finally:
+            for obj, name, value in reversed(saved):
+                setattr(obj, name, value)

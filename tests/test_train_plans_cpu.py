@@ -67,3 +67,44 @@ def test_hyper_training_plans(sd):
     z = torch.round(torch.randn((2, 320, 2, 3), generator=g) * 3)
     check(hyper.HyperpriorSynthesis(C=220, N=320), "Hyperprior.synthesis_std.", sd, z,
           lambda s, t: O.hyper_synthesis(s, t, "Hyperprior.synthesis_std."), torch.randn((2, 220, 8, 12), generator=g))
+
+
+def test_whole_training_step_on_cpu():
+    """CPU mirror of tests/test_gpu_train.py::test_full_training_step_vs_oracle: `Model.compression_forward` in training
+    mode (noise fed as the reference draws it), rate + distortion loss, `backward()` through every training plan and
+    autograd Function -- every parameter gradient against autograd of the oracle.  Same tolerances as on the GPU: the rate
+    side strictly, the image side loosely (rounding flips of y_hat make the loss only piecewise smooth)."""
+    import logging
+    from emulation import train_step_cpu_emulation
+    from hific_b200.config import mse_lpips_args
+    from hific_b200.model import Model
+    from oracle.ref_shim import NoiseFeeder
+    cfg = mse_lpips_args()
+    cfg.n_residual_blocks = 2
+    sd2 = synth.synth_state_dict(0, n_residual_blocks=2)
+    m = Model(cfg, logging.getLogger("cpu-train"))
+    m.load_state_dict(sd2, strict=True)
+    m.train()
+    x = synth.synth_image(2, 128, 128, 0)
+    nz = synth.synth_noise((2, 320, 2, 2), "zt", 0)
+    ny = synth.synth_noise((2, 220, 8, 8), "yt", 0)
+    with train_step_cpu_emulation():
+        with NoiseFeeder([nz, ny]):
+            inter, info = m.compression_forward(x)
+        loss = 2.0 * inter.n_bpp + cfg.k_M * m.distortion_loss(inter.reconstruction, inter.input_image)
+        loss.backward()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd2.items()}
+    recon, hyp, _ = O.compression_forward(sdg, x, True, False, nz, ny, n_residual_blocks=2)
+    out = 2.0 * hyp.total_nbpp + cfg.k_M * O.distortion_loss(recon, x)
+    out.backward()
+    assert abs(float(loss) - float(out)) < 0.05 * abs(float(out))
+
+    def worst(module, prefix):
+        w = ("", 0.0)
+        for name, p in module.named_parameters():
+            assert p.grad is not None, prefix + name
+            w = max(w, (name, rel(p.grad, sdg[prefix + name].grad)), key=lambda t: t[1])
+        return w
+    assert worst(m.Hyperprior, "Hyperprior.")[1] < 0.1
+    assert worst(m.Encoder, "Encoder.")[1] < 0.3
+    assert worst(m.Generator, "Generator.")[1] < 0.3
