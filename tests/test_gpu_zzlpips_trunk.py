@@ -16,6 +16,23 @@ if not torch.cuda.is_available():
     pytest.skip("needs a CUDA device", allow_module_level=True)
 
 
+# the comparator is the cuDNN trunk in FULL fp32 (TF32 off): the bar below is the native trunk's own error
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+GRAD_TOL = 5e-2
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "lpips_trunk_errors.txt")
+
+
+def _report(line):
+    print(line)
+    try:
+        os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+        with open(REPORT, "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+
+
 @pytest.fixture(autouse=True)
 def native_trunk_selected():
     old = os.environ.get("HFC_LPIPS_TRUNK")
@@ -105,7 +122,9 @@ def test_native_trunk_matches_cudnn_trunk(n, h, w, normalize):
     assert ops.launch_count() - l0 >= 5 + 2 + 1 + 5 + 5 + 5, "the native trunk did not run"
     assert torch.allclose(got, want.detach(), rtol=2e-3, atol=1e-6), (got, want)
     rel = ((p1.grad - p0.grad).norm() / p0.grad.norm()).item()
-    assert rel < 5e-2, rel
+    _report(f"native vs cuDNN-fp32 trunk  n={n} {h}x{w} normalize={normalize}: d loss/d pred rel-L2 {rel:.3e}, "
+            f"distances max rel {((got - want.detach()).abs() / want.detach().abs()).max().item():.3e}")
+    assert rel < GRAD_TOL, rel
     with torch.no_grad():                                        # evaluation path (no autograd)
         again = loss(pred, target, normalize=normalize).view(-1)
     assert torch.allclose(again, got.detach(), rtol=1e-6)
