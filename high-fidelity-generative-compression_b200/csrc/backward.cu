@@ -18,6 +18,12 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float v) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
+// fp16 gradient operands saturate (a stale loss scale clips outliers instead of turning the step into inf / nan)
+__device__ __forceinline__ uint16_t f32_to_f16_bits(float v) {
+  __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp32 rows [P][ld] -> border-less 16-bit act buffer [P][cpad] (bf16 or fp16), padding channels = 0
 // ------------------------------------------------------------------------------------------------
@@ -35,7 +41,7 @@ rows_to_act_kernel(const float* __restrict__ rows, int ld, int c, int cpad, long
       const int ch = g * 8 + j;
       const float f = ch < c ? rows[pix * ld + ch] : 0.f;
       if (to_bf16) v[j] = f32_to_bf16_bits(f);
-      else { __half h = __float2half_rn(f); v[j] = *reinterpret_cast<uint16_t*>(&h); }
+      else v[j] = f32_to_f16_bits(f);
     }
     *reinterpret_cast<uint4*>(out + pix * cpad + g * 8) = *reinterpret_cast<const uint4*>(v);
   }
@@ -60,7 +66,7 @@ rows_to_act_geom_kernel(const float* __restrict__ rows, uint16_t* __restrict__ o
       const int ch = g * 8 + j;
       const float f = ch < p.c ? rows[pix * p.ld + ch] : 0.f;
       if (p.to_bf16) v[j] = f32_to_bf16_bits(f);
-      else { __half h = __float2half_rn(f); v[j] = *reinterpret_cast<uint16_t*>(&h); }
+      else v[j] = f32_to_f16_bits(f);
     }
     *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(nn) * Hp + hh + p.pt) * Wp + ww + p.pl) * p.cpad + g * 8) =
         *reinterpret_cast<const uint4*>(v);
@@ -78,7 +84,7 @@ struct ColTParams {
   int32_t gh, gw;                   // pixel grid
   int32_t stride, oh0, ow0;         // source coordinate = g*stride + d + o0
   int32_t ntaps, c_rows, c_src;     // channels emitted per tap (multiple of 64), real source channels
-  int32_t src_f32;                  // 0: 16-bit copied verbatim, 1: fp32 -> bf16, 2: fp16 -> bf16
+  int32_t src_f32;                  // 0: 16-bit copied verbatim, 1: fp32 -> bf16, 2: fp16 -> bf16, 3: fp32 -> fp16
   long long p_total, p_pad;
   int8_t dh[64], dw[64];
 };
@@ -111,6 +117,7 @@ im2col_t_kernel(const void* __restrict__ src, uint16_t* __restrict__ out, const 
       if (ok && ch < p.c_src) {
         if (p.src_f32 == 1) v = f32_to_bf16_bits(reinterpret_cast<const float*>(src)[base + ch]);
         else if (p.src_f32 == 2) v = f32_to_bf16_bits(__half2float(reinterpret_cast<const __half*>(src)[base + ch]));
+        else if (p.src_f32 == 3) v = f32_to_f16_bits(reinterpret_cast<const float*>(src)[base + ch]);
         else v = reinterpret_cast<const uint16_t*>(src)[base + ch];
       }
       tile[cg + j][px] = v;
@@ -149,6 +156,7 @@ im2col_t_c8_kernel(const void* __restrict__ src, uint16_t* __restrict__ out, con
         if (j < p.c_src)
           v[j] = p.src_f32 == 1 ? f32_to_bf16_bits(reinterpret_cast<const float*>(src)[base + j])
                  : p.src_f32 == 2 ? f32_to_bf16_bits(__half2float(reinterpret_cast<const __half*>(src)[base + j]))
+                 : p.src_f32 == 3 ? f32_to_f16_bits(reinterpret_cast<const float*>(src)[base + j])
                                   : reinterpret_cast<const uint16_t*>(src)[base + j];
     }
   }

@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256, MINB)
 channelnorm_bwd_kernel(const float* __restrict__ z, int ld_z, const float* __restrict__ g, int ld_g,
                        const float* __restrict__ gamma, const float* __restrict__ beta, int c, long long npix,
                        float eps, int act, float* __restrict__ dz, int ld_dz, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, float* __restrict__ dbias, uint16_t* __restrict__ dz_act, int act_cpad) {
+                       float* __restrict__ dbeta, float* __restrict__ dbias, uint16_t* __restrict__ dz_act, int act_cpad,
+                       int act_bf16) {
   constexpr int kPix = 32 / GROUP;
   constexpr int kCap = GROUP * VEC * 4;
   __shared__ float s_acc[3][kCap];
@@ -130,11 +131,19 @@ channelnorm_bwd_kernel(const float* __restrict__ z, int ld_z, const float* __res
         o.x = r * (gg[i].x - s1 - v[i].x * s2); o.y = r * (gg[i].y - s1 - v[i].y * s2);
         o.z = r * (gg[i].z - s1 - v[i].z * s2); o.w = r * (gg[i].w - s1 - v[i].w * s2);
         if (dz) *reinterpret_cast<float4*>(dr + ch) = o;
-        if (dz_act) {     // bf16 copy in the operand layout of the backward GEMMs (border-less NHWC, pitch act_cpad)
-          const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        if (dz_act) {     // 16-bit copy in the operand layout of the backward GEMMs (border-less NHWC, pitch act_cpad)
           uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          if (act_bf16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          } else {        // fp16 (loss-scaled gradients, see grad.py): overflow becomes inf and is caught by the optimizer
+            const float kMax = 65504.f;   // saturate: see grad.py
+            const __half2 lo = __floats2half2_rn(fminf(fmaxf(o.x, -kMax), kMax), fminf(fmaxf(o.y, -kMax), kMax));
+            const __half2 hi = __floats2half2_rn(fminf(fmaxf(o.z, -kMax), kMax), fminf(fmaxf(o.w, -kMax), kMax));
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          }
           *reinterpret_cast<uint2*>(dz_act + pix * act_cpad + ch) = pk;
         }
         ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
@@ -167,13 +176,13 @@ channelnorm_bwd_kernel(const float* __restrict__ z, int ld_z, const float* __res
 template <int VEC, int GROUP, int MINB>
 static void launch_channelnorm_bwd(const float* z, int ld_z, const float* g, int ld_g, const float* gamma,
                                    const float* beta, int c, long long npix, float eps, int act, float* dz, int ld_dz,
-                                   float* dgamma, float* dbeta, float* dbias, uint16_t* dz_act, int act_cpad, int sms,
+                                   float* dgamma, float* dbeta, float* dbias, uint16_t* dz_act, int act_cpad, int act_bf16, int sms,
                                    cudaStream_t st) {
   const long long per_block = 8LL * (32 / GROUP);
   const long long blocks = std::max<long long>(1, std::min<long long>((npix + per_block - 1) / per_block,
                                                                        static_cast<long long>(sms) * MINB));
   channelnorm_bwd_kernel<VEC, GROUP, MINB><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, dbeta, dbias, dz_act, act_cpad);
+      z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, dbeta, dbias, dz_act, act_cpad, act_bf16);
 }
 
 // g_out[p][c] = g[p][c] * (y_act[p][c] > 0)   (y_act: bordered NHWC fp16 output of a bias+ReLU conv)
@@ -424,7 +433,7 @@ using namespace hfc;
 extern "C" int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld_g, const float* gamma,
                                    const float* beta, int32_t c, int64_t npix, float eps, int32_t act, float* dz,
                                    int32_t ld_dz, float* dgamma, float* dbeta, float* dbias, void* dz_act,
-                                   int32_t act_cpad, void* stream) {
+                                   int32_t act_cpad, int32_t act_bf16, void* stream) {
   if (!z || !g || !gamma || !beta || (!dz && !dz_act) || !dgamma || !dbeta || npix <= 0)
     return set_error(HFC_ERR_INVALID, "channelnorm_bwd: null pointer or empty input");
   if (dz_act && (act_cpad % 4 != 0 || act_cpad < c || act_cpad > kCnbVec * 128))
@@ -438,7 +447,7 @@ extern "C" int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g,
   if (rc != HFC_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define HFC_CNB(V, G, B) launch_channelnorm_bwd<V, G, B>(z, ld_z, g, ld_g, gamma, beta, c, npix, eps, act, dz, ld_dz, dgamma, \
-                                                        dbeta, dbias, reinterpret_cast<uint16_t*>(dz_act), act_cpad, sms, st)
+                                                        dbeta, dbias, reinterpret_cast<uint16_t*>(dz_act), act_cpad, act_bf16, sms, st)
   if (width <= 32) HFC_CNB(1, 8, 4);
   else if (width <= 64) HFC_CNB(1, 16, 4);
   else if (width <= 128) HFC_CNB(1, 32, 4);

@@ -11,9 +11,16 @@ F.conv_transpose2d as issued by the reference's training step, train.py:49-59).
                    implicit wgrad kernel is the obvious next optimisation)
   bias gradient    column sums of the gradient rows
 
-Gradients travel as fp32 rows [pixels][channels]; GEMM operands derived from them are bf16 (fp32 exponent range, so
-no loss scaling); the fp16 activations saved by the forward pass and the weights are converted to bf16 on the fly
-so that every backward GEMM is bf16 x bf16 with fp32 accumulation.
+Gradients travel as fp32 rows [pixels][channels].  Operand format of the backward GEMMs (process-wide, HFC_GRAD_FMT):
+
+  fp16 (default)  the gradient operand is rounded to fp16 -- the 10-bit mantissa of the TF32 path cuDNN gives the reference
+                  on a GPU -- and meets the fp16 activations saved by the forward pass and the fp16 weights as they are
+                  (no conversion pass).  fp16's narrow exponent is handled by a power-of-two LOSS SCALE per backward
+                  Function (`GradScale`): the incoming gradient is multiplied by S, everything in between is linear, the
+                  parameter / input gradients are divided by S on the way out (exact).  Conversions saturate at +-65504
+                  instead of producing inf, so a stale scale clips outliers rather than poisoning the step.
+  bf16            round 1's path: bf16 gradients (fp32 exponent range, no scaling, 8-bit mantissa) against activations and
+                  weights converted to bf16 on the fly; kept for the side-by-side precision study (tools/grad_precision.py).
 """
 import ctypes
 import os
@@ -23,6 +30,79 @@ import torch
 from . import _lib, ops
 from ._lib import check, lib
 from .ops import OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO, Conv, Geom, _ptr, _stream, round_up
+
+
+GRAD_BF16 = os.environ.get("HFC_GRAD_FMT", "fp16").strip().lower() == "bf16"
+_FMT = int(GRAD_BF16)          # the `to_bf16` / `bf16` flags of the C ABI
+_K_ROWS = 1 if GRAD_BF16 else 3    # hfc_im2col_t source kinds: fp32 rows -> bf16 | fp16
+_K_ACT = 2 if GRAD_BF16 else 0     #                           fp16 act buffer -> bf16 | verbatim
+
+
+# calibration only: device scalars max|operand| of every gradient operand written while a GradScale calibrates
+_amax_log = None
+
+
+def _log_operand(buf):
+    if _amax_log is not None and not GRAD_BF16:
+        _amax_log.append(buf.view(torch.float16).abs().amax().float())
+
+
+class GradScale:
+    """Power-of-two loss scale of ONE backward Function (fp16 gradient operands; a no-op with HFC_GRAD_FMT=bf16).
+
+    `run(plan_backward, dout)` multiplies the incoming gradient by S, calls `plan_backward(scaled)` -> (dx, grads) and
+    divides every result by S (exact).  S is calibrated on the first call and then every HFC_GRAD_RECAL calls (default
+    200) from the largest operand magnitude seen anywhere in that backward chain (one device->host read per
+    calibration, none in between): it is placed near 2^PEAK_LOG2, i.e. 5 binades below fp16's saturation and 24
+    above its smallest normal.  Between calibrations the conversions saturate, so a gradient that grew > 32 x clips."""
+    PEAK_LOG2 = 11
+    RECAL = int(os.environ.get("HFC_GRAD_RECAL", "200"))
+
+    def __init__(self):
+        self.scale, self.calls, self.peak = None, 0, None
+
+    @staticmethod
+    def _pow2_at_most(v):
+        import math
+        return 2.0 ** math.floor(math.log2(v))
+
+    def run(self, plan_backward, dout):
+        global _amax_log
+        if GRAD_BF16:
+            return plan_backward(dout)
+        self.calls += 1
+        if self.scale is None or (self.RECAL > 0 and self.calls % self.RECAL == 0):
+            amax_in = float(dout.detach().abs().amax())
+            if not (amax_in > 0.0) or amax_in == float("inf"):
+                return plan_backward(dout)                  # all-zero (or broken) upstream gradient: nothing to place
+            s = self.scale if self.scale is not None else self._pow2_at_most(1.0 / amax_in)
+            res = None
+            for _ in range(4):
+                _amax_log = []
+                try:
+                    res = plan_backward(dout * s)
+                    peak = float(torch.stack(_amax_log).max()) if _amax_log else 0.0
+                finally:
+                    _amax_log = None
+                self.scale, self.peak = s, peak
+                if peak <= 0.0:
+                    break                                   # no 16-bit gradient operand on this path
+                want = 2.0 ** self.PEAK_LOG2
+                if peak < 65504.0 and want / 8 <= peak <= want * 4:
+                    break
+                # saturated: the true peak is unknown, step down far; else move the measured peak onto the target
+                s = s / 4096.0 if peak >= 65504.0 else s * self._pow2_at_most(want / peak)
+        else:
+            s = self.scale
+            res = plan_backward(dout * s)
+        dx, grads = res
+        inv = 1.0 / s
+        live = [g for g in grads if g is not None]
+        if live:
+            torch._foreach_mul_(live, inv)
+        if dx is not None:
+            dx = dx * inv
+        return dx, grads
 
 
 class Workspace:
@@ -99,26 +179,26 @@ class ConvGrad:
             b = kh - 1
             self.dy_window_geom = Geom(n, self.oh, self.ow, cout, 8, b, b, b, b + 1)
             self.dgrad = Conv(self.dy_window_geom, self.cin, kh, stride=1, pad_mode=PAD_REFLECT, pad=(b,) * 4, window=True,
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, b_bf16=True, dgrad=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=GRAD_BF16, b_bf16=GRAD_BF16, dgrad=True)
             self.fold = (hq, wq)
         elif not transposed and stride == 1:
             hq, wq = h + pt + pb, w + pl + pr
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=1, pad_mode=PAD_ZERO, pad=(kh - 1,) * 4,
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, b_bf16=True, dgrad=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=GRAD_BF16, b_bf16=GRAD_BF16, dgrad=True)
             self.fold = (hq, wq)
         elif not transposed:
             hq = 2 * self.oh + kh - 1
             wq = 2 * self.ow + kw - 1
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=2, transposed=True, pad=(0, 0, 0, 0),
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=True, b_bf16=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, hq, wq, self.cin, cin4), a_bf16=GRAD_BF16, b_bf16=GRAD_BF16)
             self.fold = (hq, wq)
         elif stride == 2:
             hi = kh - 2 - pt
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=2, pad_mode=PAD_ZERO, pad=(pt, pl, hi, hi),
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=True, b_bf16=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=GRAD_BF16, b_bf16=GRAD_BF16)
         else:
             self.dgrad = Conv(self.dy_geom, self.cin, kh, stride=1, pad_mode=PAD_ZERO, pad=(pt, pl, pt, pl),
-                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=True, b_bf16=True)
+                              out_mode=OUT_NHWC_F32, out_geom=Geom(n, h, w, self.cin, cin4), a_bf16=GRAD_BF16, b_bf16=GRAD_BF16)
         self.cin4 = cin4
         self.taps = [(ky, kx) for ky in range(kh) for kx in range(kw)]
         # weight-gradient GEMM operands: which side is transposed plainly (A1) and which is im2col'ed (A2).
@@ -142,7 +222,7 @@ class ConvGrad:
                 d.plain, d.shifted = self.dy_geom.c_struct(), in_geom.c_struct()
                 self.wg_m, self.wg_c2 = cout, self.cin
             offs = [(ky - pt, kx - pl) for ky, kx in self.taps]
-            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = len(self.taps), stride, 1, 0, 0
+            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = len(self.taps), stride, _FMT, 0, 0
             self.wg_c2_rows = round_up(self.wg_c2, 64)
             self.wg_taps = self.taps
         elif (not self.swap) and (not transposed) and stride == 1 and in_geom.cpad == 8 and k <= 8:
@@ -152,7 +232,7 @@ class ConvGrad:
             d.plain, d.shifted = self.dy_geom.c_struct(), in_geom.c_struct()
             self.wg_m, self.wg_c2 = cout, self.cin
             offs = [(ky - pt, -pl) for ky in range(k)]
-            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = k, 1, 1, 0, 1
+            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = k, 1, _FMT, 0, 1
             self.wg_c2_rows = 8
             self.wg_taps = [(t // 8, t % 8) if t % 8 < k else (-1, -1) for t in range(8 * k)]
         elif self.swap and self.dy_window_geom is not None and pad_mode == PAD_REFLECT and \
@@ -164,7 +244,7 @@ class ConvGrad:
             d.plain, d.shifted = Geom(n, hp, wp, self.cin, in_geom.cpad).c_struct(), self.dy_window_geom.c_struct()
             self.wg_m, self.wg_c2 = self.cin, cout
             offs = [(-ky, -(k - 1)) for ky in range(k)]
-            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = k, 1, 1, 0, 1
+            d.ntaps, d.stride, d.bf16, d.k_splits, d.window = k, 1, _FMT, 0, 1
             self.wg_c2_rows = 8
             self.wg_taps = [(t // 8, k - 1 - t % 8) if t % 8 < k else (-1, -1) for t in range(8 * k)]
         if self.implicit:
@@ -207,21 +287,26 @@ class ConvGrad:
             g = self.dy_window_geom
             buf = Workspace.named(("dy_window",) + g.shape, g.shape, torch.int16, dy_rows.device, zero=True)
             gs = g.c_struct()      # the border is zeroed once; only the interior is rewritten
-            check(lib.hfc_rows_to_act_geom(_ptr(dy_rows), dy_rows.shape[-1], ctypes.byref(gs), 1, _ptr(buf), _stream()),
+            check(lib.hfc_rows_to_act_geom(_ptr(dy_rows), dy_rows.shape[-1], ctypes.byref(gs), _FMT, _ptr(buf), _stream()),
                   "rows_to_act_geom")
+            _log_operand(buf)
             return buf
         g = self.dy_geom
         dy_act = Workspace.get("dy_act", g.n * g.h * g.w * g.cpad, torch.int16, dy_rows.device).view(g.shape)
-        check(lib.hfc_rows_to_act(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, g.cpad, 1, _ptr(dy_act),
+        check(lib.hfc_rows_to_act(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, g.cpad, _FMT, _ptr(dy_act),
                                   _stream()), "rows_to_act")
+        _log_operand(dy_act)
         return dy_act
 
     def _weight_grad_implicit(self, x_act, dy_rows, dw_out, accumulate, scale, dy_act=None):
         dev = x_act.device
         if dy_act is None:
             dy_act = self.dy_to_act(dy_rows)
-        x_bf = Workspace.get("x_bf16", x_act.numel(), torch.int16, dev)
-        check(lib.hfc_act_to_bf16(_ptr(x_act), _ptr(x_bf), x_act.numel(), _stream()), "act_to_bf16")
+        if GRAD_BF16:
+            x_bf = Workspace.get("x_bf16", x_act.numel(), torch.int16, dev)
+            check(lib.hfc_act_to_bf16(_ptr(x_act), _ptr(x_bf), x_act.numel(), _stream()), "act_to_bf16")
+        else:
+            x_bf = x_act              # fp16 x fp16: the saved activation buffer is the operand
         ncols = self.wg_cols
         cbuf = Workspace.get("wgrad_c", self.wg_m * ncols, torch.float32, dev).view(self.wg_m, ncols)
         x_is_plain = self.transposed or self.implicit == "window_dy"
@@ -264,11 +349,11 @@ class ConvGrad:
             p_pad = round_up(self.p_out, 64)
             c1_rows, c2_rows = round_up(self.cout, 64), (8 if ig.cpad == 8 else round_up(self.cin, 64))
             a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
-            im2col_t(dy_rows, 1, n, self.oh, self.ow, ld_dy, self.cout, self.oh, self.ow, 1, 0, 0, [(0, 0)], c1_rows, a1)
+            im2col_t(dy_rows, _K_ROWS, n, self.oh, self.ow, ld_dy, self.cout, self.oh, self.ow, 1, 0, 0, [(0, 0)], c1_rows, a1)
             col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
-            im2col_t(x_act, 2, n, hp, wp, ig.cpad, self.cin, self.oh, self.ow, s, ig.pt - pt, ig.pl - pl, self.taps,
+            im2col_t(x_act, _K_ACT, n, hp, wp, ig.cpad, self.cin, self.oh, self.ow, s, ig.pt - pt, ig.pl - pl, self.taps,
                      c2_rows, col)
-            m, c2, a_bf, b_bf = self.cout, self.cin, True, True
+            m, c2, a_bf, b_bf = self.cout, self.cin, GRAD_BF16, GRAD_BF16
             shape = (self.cout, self.cin, k, k)
         elif not self.transposed:
             # tiny cout: pixels = padded input pixels q; A1 = x^T (fp16), COLT[(tap, co)][q] = dy[q - tap] (bf16)
@@ -280,21 +365,21 @@ class ConvGrad:
             p_pad = round_up(n * gh * gw, 64)
             c1_rows, c2_rows = round_up(self.cin, 64), 8
             a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
-            im2col_t(x_act, 2, n, hp, wp, ig.cpad, self.cin, gh, gw, 1, o0h, o0w, [(0, 0)], c1_rows, a1)
+            im2col_t(x_act, _K_ACT, n, hp, wp, ig.cpad, self.cin, gh, gw, 1, o0h, o0w, [(0, 0)], c1_rows, a1)
             col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
-            im2col_t(dy_rows, 1, n, self.oh, self.ow, ld_dy, self.cout, gh, gw, 1, 0, 0,
+            im2col_t(dy_rows, _K_ROWS, n, self.oh, self.ow, ld_dy, self.cout, gh, gw, 1, 0, 0,
                      [(-ky, -kx) for ky, kx in self.taps], c2_rows, col)
-            m, c2, a_bf, b_bf = self.cin, self.cout, True, True
+            m, c2, a_bf, b_bf = self.cin, self.cout, GRAD_BF16, GRAD_BF16
             shape = (self.cout, self.cin, k, k)
         else:
             # transposed conv: pixels = input pixels i; A1 = x^T (fp16), COLT[(tap, co)][i] = dy[i*s - p + tap] (bf16)
             p_pad = round_up(self.p_in, 64)
             c1_rows, c2_rows = round_up(self.cin, 64), round_up(self.cout, 64)
             a1 = Workspace.get("a1t", c1_rows * p_pad, torch.int16, dev).view(c1_rows, p_pad)
-            im2col_t(x_act, 2, n, hp, wp, ig.cpad, self.cin, h, w, 1, ig.pt, ig.pl, [(0, 0)], c1_rows, a1)
+            im2col_t(x_act, _K_ACT, n, hp, wp, ig.cpad, self.cin, h, w, 1, ig.pt, ig.pl, [(0, 0)], c1_rows, a1)
             col = Workspace.get("colt", len(self.taps) * c2_rows * p_pad, torch.int16, dev).view(-1, p_pad)
-            im2col_t(dy_rows, 1, n, self.oh, self.ow, ld_dy, self.cout, h, w, s, -pt, -pl, self.taps, c2_rows, col)
-            m, c2, a_bf, b_bf = self.cin, self.cout, True, True
+            im2col_t(dy_rows, _K_ROWS, n, self.oh, self.ow, ld_dy, self.cout, h, w, s, -pt, -pl, self.taps, c2_rows, col)
+            m, c2, a_bf, b_bf = self.cin, self.cout, GRAD_BF16, GRAD_BF16
             shape = (self.cin, self.cout, k, k)
         ncols = len(self.taps) * c2_rows
         cbuf = Workspace.get("wgrad_c", m * round_up(ncols, 4), torch.float32, dev).view(m, round_up(ncols, 4))

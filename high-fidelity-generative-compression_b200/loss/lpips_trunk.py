@@ -14,7 +14,7 @@ fused "layer gradient + incoming gradient + ReLU mask" kernel, for the reconstru
 import torch
 
 from .. import ops
-from ..grad import ConvGrad
+from ..grad import ConvGrad, GradScale
 from ..ops import ACT_RELU, PAD_ZERO, Conv, Geom
 
 _CONV_IDX = (0, 3, 6, 8, 10)           # conv layers inside torchvision's alexnet.features
@@ -107,5 +107,9 @@ class LpipsTrunkFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
-        dpred = ctx.plan.backward(ctx.owner, d_out.to(torch.float32).contiguous(), ctx.normalize)
+        plan = ctx.plan
+        if not hasattr(plan, "grad_scale"):
+            plan.grad_scale = GradScale()
+        dpred, _ = plan.grad_scale.run(
+            lambda d: (plan.backward(ctx.owner, d.to(torch.float32).contiguous(), ctx.normalize), []), d_out)
         return dpred, None, None, None, None

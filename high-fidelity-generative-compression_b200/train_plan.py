@@ -16,7 +16,8 @@ import torch
 
 from . import ops
 from ._lib import check, lib
-from .grad import ConvGrad, Workspace
+from . import grad as _grad
+from .grad import GRAD_BF16, ConvGrad, GradScale, Workspace
 from .ops import (ACT_NONE, ACT_RELU, OUT_NCHW_F32, OUT_NHWC_F16, OUT_NHWC_F32, PAD_REFLECT, PAD_ZERO, CN_EPS, Conv,
                   Geom, _ptr, _stream, round_up)
 
@@ -51,7 +52,9 @@ def norm_bwd(z, g, gamma, beta, act, as_operand=True):
         dz_f32, dz_act, ld, cpad = dz, None, dz.shape[1], 0
     check(lib.hfc_channelnorm_bwd(_ptr(z), z.shape[1], _ptr(g), g.shape[1], _ptr(gamma.detach().reshape(-1)),
                                   _ptr(beta.detach().reshape(-1)), c, npix, CN_EPS, act, _ptr(dz_f32), ld,
-                                  _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _ptr(dz_act), cpad, _stream()), "channelnorm_bwd")
+                                  _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _ptr(dz_act), cpad, int(GRAD_BF16), _stream()), "channelnorm_bwd")
+    if as_operand:
+        _grad._log_operand(dz)
     return dz, dgb[0].view_as(gamma), dgb[1].view_as(beta), dgb[2]
 
 
@@ -158,8 +161,10 @@ class EncoderTrainPlan:
             w, b, gm, bt = p[4 * i:4 * i + 4]
             dz, grads[4 * i + 2], grads[4 * i + 3], db = norm_bwd(self.z[i], g, gm, bt, ACT_RELU)
             g, grads[4 * i], grads[4 * i + 1] = self.layers[i].backward(dz, w, need_dx=i > 0, db=db)
-        self.z = None
         return grads
+
+    def release(self):
+        self.z = None
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -247,8 +252,10 @@ class GeneratorTrainPlan:
         dz0, grads[4], grads[5], db0 = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE)
         ga0, grads[2], grads[3] = self.init.backward(dz0, p[2], db=db0)
         dy_rows, grads[0], grads[1], _ = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE, as_operand=False)
-        self.zr = self.zu = self.z_init = self.y_rows = None
         return rows_to_nchw(dy_rows, self.n, self.C, self.h, self.w), grads
+
+    def release(self):
+        self.zr = self.zu = self.z_init = self.y_rows = None
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -279,8 +286,10 @@ class HyperAnalysisTrainPlan:
         g, grads[2], grads[3] = self.l2.backward(g, p[2])
         g = relu_mask(g, self.a1, self.g1)
         g, grads[0], grads[1] = self.l1.backward(g, p[0])
-        self.a1 = self.a2 = None
         return rows_to_nchw(g, self.n, self.C, self.h, self.w), grads
+
+    def release(self):
+        self.a1 = self.a2 = None
 
 
 class HyperSynthesisTrainPlan:
@@ -306,8 +315,10 @@ class HyperSynthesisTrainPlan:
         g, grads[2], grads[3] = self.l2.backward(g, p[2])
         g = relu_mask(g, self.a1, self.g1)
         g, grads[0], grads[1] = self.l1.backward(g, p[0])
-        self.a1 = self.a2 = None
         return rows_to_nchw(g, self.n, self.N, self.h, self.w), grads
+
+    def release(self):
+        self.a1 = self.a2 = None
 
 
 class HyperSynthesisDLMMTrainPlan:
@@ -341,8 +352,10 @@ class HyperSynthesisDLMMTrainPlan:
         g, grads[2], grads[3] = self.l2.backward(g, p[2])
         g = relu_mask(g, self.a1, self.g1)
         g, grads[0], grads[1] = self.l1.backward(g, p[0])
-        self.a1 = self.a2 = None
         return rows_to_nchw(g, self.n, self.N, self.h, self.w), grads
+
+    def release(self):
+        self.a1 = self.a2 = None
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -402,8 +415,10 @@ class DiscriminatorTrainPlan:
         dctx = relu_mask(dctx, f.ctx_act, gc, self.SLOPE)
         grads[0] = self.g_ctx.weight_grad(f.y_act, dctx)
         grads[1] = self.g_ctx.bias_grad(dctx)
-        self.sn = None
         return dx, grads
+
+    def release(self):
+        self.sn = None
 
     @staticmethod
     def _layer_bwd(cg, x_act, dz_rows, weight, inv_sigma, need_dx=True):
@@ -425,8 +440,13 @@ class DiscriminatorFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
+        plan = ctx.plan
+        if not hasattr(plan, "grad_scale"):
+            plan.grad_scale = GradScale()
         with torch.no_grad():
-            dx, grads = ctx.plan.backward(dlogits.contiguous(), [q.detach() for q in ctx.params], ctx.needs_dx)
+            params = [q.detach() for q in ctx.params]
+            dx, grads = plan.grad_scale.run(lambda d: plan.backward(d.contiguous(), params, ctx.needs_dx), dlogits)
+            plan.release()
         grads = [g.reshape(q.shape) if g is not None else None for g, q in zip(grads, ctx.params)]
         return (None, None, dx, None, *grads)
 
@@ -447,12 +467,17 @@ class PlanFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        plan = ctx.plan
+        if not hasattr(plan, "grad_scale"):
+            plan.grad_scale = GradScale()
+
+        def walk(d):
+            res = plan.backward(d.contiguous(), params)
+            return res if isinstance(res, tuple) else (None, res)
         with torch.no_grad():
-            res = ctx.plan.backward(dout.contiguous(), [q.detach() for q in ctx.params])
-        if isinstance(res, tuple):
-            dx, grads = res
-        else:
-            dx, grads = None, res
+            params = [q.detach() for q in ctx.params]
+            dx, grads = plan.grad_scale.run(walk, dout)
+            plan.release()
         grads = [g.reshape(q.shape) if g is not None else None for g, q in zip(grads, ctx.params)]
         return (None, dx if ctx.needs_dx else None, *grads)
 

@@ -248,7 +248,7 @@ int hfc_rows_to_act(const float* rows, int32_t ld, int64_t npix, int32_t c, int3
 int hfc_rows_to_act_geom(const float* rows, int32_t ld, const hfc_act_geom* g, int32_t to_bf16, void* out, void* stream);
 /* transposed im2col (see csrc/backward.cu): out[(tap*c_rows + ch)][p], p over the (n, gh, gw) pixel grid, source
  * coordinate (g*stride + d[tap] + o0) in a physical buffer of n x hp x wp pixels with cpad channels (pitch, for fp32
- * rows), zero outside; src_f32: 0 = 16-bit source copied verbatim, 1 = fp32 rows converted to bf16, 2 = fp16 act
+ * rows), zero outside; src_f32: 0 = 16-bit source copied verbatim, 1 = fp32 rows converted to bf16 (3: to fp16), 2 = fp16 act
  * buffer converted to bf16 (the backward GEMMs run bf16 x bf16).
  * dh_host / dw_host are HOST arrays of ntaps offsets. */
 int hfc_im2col_t(const void* src, int32_t src_f32, int32_t n, int32_t hp, int32_t wp, int32_t cpad, int32_t c_src,
@@ -297,12 +297,13 @@ int hfc_pad_fold(const float* dxp, int32_t ld_in, int32_t hq, int32_t wq, const 
 
 /* ChannelNorm2D (+ReLU) backward: z = saved pre-norm rows, g = gradient w.r.t. the block output (both fp32 rows);
  * writes dz (fp32 rows) and ACCUMULATES dgamma / dbeta (caller zeroes them) and, when dbias != NULL, the column sums
- * of dz (= gradient of the bias of the convolution in front of the norm).  dz (fp32 rows) and / or dz_act (bf16,
- * border-less NHWC with pitch act_cpad, channel padding zeroed: the operand of the backward GEMMs) receive the
- * result; either may be NULL.  act: HFC_ACT_NONE | HFC_ACT_RELU. */
+ * of dz (= gradient of the bias of the convolution in front of the norm).  dz (fp32 rows) and / or dz_act (16-bit:
+ * bf16 if act_bf16 else fp16; border-less NHWC with pitch act_cpad, channel padding zeroed: the operand of the backward
+ * GEMMs) receive the result; either may be NULL.  act: HFC_ACT_NONE | HFC_ACT_RELU. */
 int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld_g, const float* gamma,
                         const float* beta, int32_t c, int64_t npix, float eps, int32_t act, float* dz, int32_t ld_dz,
-                        float* dgamma, float* dbeta, float* dbias, void* dz_act, int32_t act_cpad, void* stream);
+                        float* dgamma, float* dbeta, float* dbias, void* dz_act, int32_t act_cpad, int32_t act_bf16,
+                        void* stream);
 /* out = g * (y > 0 ? 1 : slope): backward of the fused bias + ReLU (slope 0) / LeakyReLU (slope 0.2) epilogue; y_act
  * is that layer's (bordered) NHWC fp16 output */
 int hfc_relu_mask(const float* g, int32_t ld_g, const void* y_act, const hfc_act_geom* geom, float slope, float* out,

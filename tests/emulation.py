@@ -78,7 +78,7 @@ def cpu_emulation():
     patch(ops, "dequantize_symbols", dequantize_symbols)
     patch(engine, "_require_cuda", lambda x, who: None)
     patch(encoder.Encoder, "forward", lambda self, x: O.encoder_forward(_sd(self), x, prefix=""))
-    patch(generator.Generator, "forward", lambda self, y: O.generator_forward(_sd(self), y, prefix=""))
+    patch(generator.Generator, "forward", lambda self, y: O.generator_forward(_sd(self), y, n_residual_blocks=self.n_residual_blocks, prefix=""))
     patch(hyper.HyperpriorAnalysis, "forward", lambda self, y: O.hyper_analysis(_sd(self), y, prefix=""))
     patch(hyper.HyperpriorSynthesis, "forward", lambda self, z: O.hyper_synthesis(_sd(self), z, prefix=""))
     patch(hyperprior.Hyperprior, "_latent_statistics",
@@ -141,8 +141,8 @@ def convgrad_data_grad(self, dy_rows, weight, out=None, scale=None, dy_act=None)
         raise NotImplementedError
     n = self.in_geom.n
     dy = dy_rows[:, :self.cout].reshape(n, self.oh, self.ow, self.cout).permute(0, 3, 1, 2)
-    dy = dy.to(torch.bfloat16).float()
-    w = weight.detach().to(torch.bfloat16).float()
+    dy = dy.to(_GFMT).float()
+    w = weight.detach().to(_GFMT).float()
     dx = F.conv_transpose2d(dy, w, stride=1, padding=self.pad[0])
     rows = torch.zeros((n * self.in_geom.h * self.in_geom.w, self.cin4), dtype=torch.float32)
     rows[:, :self.cin] = dx.permute(0, 2, 3, 1).reshape(-1, self.cin)
@@ -535,6 +535,9 @@ def dlmm_likelihood_bwd(x, dlmm_params, noise, d_decoded, g_nbpp, likelihood_typ
 from hific_b200 import train_plan as _train_plan
 
 
+_GFMT = torch.bfloat16 if _grad.GRAD_BF16 else torch.float16     # gradient operand format of the product (grad.py)
+
+
 def _convgrad_apply(cg, x, w):
     if cg.transposed:
         return F.conv_transpose2d(x, w, stride=cg.stride, padding=cg.pad[0], output_padding=cg.stride - 1)
@@ -550,11 +553,11 @@ def _rows_to_nchw(rows, n, h, w, c):
 def convgrad_data_grad_general(self, dy_rows, weight, out=None, scale=None, dy_act=None):
     assert dy_rows is not None, "emulation needs the fp32 gradient rows"
     g = self.in_geom
-    dy = _rows_to_nchw(dy_rows, g.n, self.oh, self.ow, self.cout).to(torch.bfloat16).float()
+    dy = _rows_to_nchw(dy_rows, g.n, self.oh, self.ow, self.cout).to(_GFMT).float()
     w = weight.detach().float()
     if scale is not None:
         w = w * scale.float().reshape(())
-    w = w.to(torch.bfloat16).float()
+    w = w.to(_GFMT).float()
     with torch.enable_grad():
         x = torch.zeros((g.n, self.cin, g.h, g.w), requires_grad=True)
         _convgrad_apply(self, x, w).backward(dy)
@@ -567,8 +570,8 @@ def convgrad_weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, sc
     assert dy_rows is not None, "emulation needs the fp32 gradient rows"
     g = self.in_geom
     x = x_act.view(g.shape)[:, g.pt:g.pt + g.h, g.pl:g.pl + g.w, :g.c].permute(0, 3, 1, 2).float()
-    x = x.to(torch.bfloat16).float()
-    dy = _rows_to_nchw(dy_rows, g.n, self.oh, self.ow, self.cout).to(torch.bfloat16).float()
+    x = x.to(_GFMT).float()
+    dy = _rows_to_nchw(dy_rows, g.n, self.oh, self.ow, self.cout).to(_GFMT).float()
     shape = (self.cin, self.cout, self.k, self.k) if self.transposed else (self.cout, self.cin, self.k, self.k)
     with torch.enable_grad():
         w = torch.zeros(shape, requires_grad=True)
@@ -693,3 +696,38 @@ def train_step_cpu_emulation():
         finally:
             for obj, name, value in reversed(saved):
                 setattr(obj, name, value)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Drop-in test (tests/test_dropin_reference.py): the reference's train.py / src/model.py drive the mirror's networks on the
+# CPU.  Encoder / Generator / hyper networks / Hyperprior run their REAL host code (training plans, autograd Functions)
+# over the stand-ins above; the Discriminator's plan has no CPU stand-ins for its layout / spectral-norm entry points, so
+# its forward is the oracle's with torch autograd -- including torch.nn.utils.spectral_norm's in-place u / v update.
+# ----------------------------------------------------------------------------------------------------------------------
+from hific_b200.network import discriminator as _discriminator
+
+
+def discriminator_forward(self, x, y):
+    """Discriminator.forward (src/network/discriminator.py:66-86) on fp16-rounded conv operands."""
+    if x.shape[0] != y.shape[0]:
+        raise ValueError("Discriminator: image and context batch sizes differ")
+    sd = dict(self.named_parameters())
+    sd.update(dict(self.named_buffers()))
+    out, logits, new_uv = O.discriminator_forward(sd, x, y, prefix="", training=self.training, rnd=O.round_fp16)
+    if self.training:
+        with torch.no_grad():
+            for name, (u, v) in new_uv.items():
+                getattr(self, name).weight_u.copy_(u)
+                getattr(self, name).weight_v.copy_(v)
+    return out, logits
+
+
+@contextlib.contextmanager
+def dropin_cpu_emulation():
+    with train_step_cpu_emulation():
+        old = _discriminator.Discriminator.forward
+        _discriminator.Discriminator.forward = discriminator_forward
+        try:
+            yield
+        finally:
+            _discriminator.Discriminator.forward = old

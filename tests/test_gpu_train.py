@@ -95,9 +95,11 @@ def test_channelnorm_backward_kernel(c, n, h, w):
         assert rel(dz.view(n, h, w, c).permute(0, 3, 1, 2), z.grad) < 1e-4
         # the same result written directly as the bf16 GEMM operand (pitch round_up(c, 64), zero channel padding)
         op, dg2, _, dbias2 = norm_bwd(nchw_to_rows(z.detach()), nchw_to_rows(up), gamma.detach(), beta.detach(), act)
-        op = op.clone().view(torch.bfloat16)
+        from hific_b200.grad import GRAD_BF16
+        fmt = torch.bfloat16 if GRAD_BF16 else torch.float16
+        op = op.clone().view(fmt)
         assert op.shape == (n * h * w, ops.round_up(c, 64))
-        assert torch.equal(op[:, :c], dz[:, :c].bfloat16())
+        assert torch.equal(op[:, :c], dz[:, :c].to(fmt))
         assert float(op[:, c:].float().abs().max() if op.shape[1] > c else 0.0) == 0.0
         assert rel(dg2, dg) < 1e-6 and rel(dbias2, dbias) < 1e-5
         assert rel(dg, gamma.grad) < 1e-4 and rel(db, beta.grad) < 1e-4
