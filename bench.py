@@ -28,6 +28,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("HFC_LPIPS_SYNTHETIC", "1")   # synthetic weights everywhere (no checkpoints offline): "data": "synthetic"
 
 import torch  # noqa: E402
 
@@ -146,7 +147,8 @@ def run_reference(args, rank):
         step()
     dt = time.perf_counter() - t0
     val = sample_b * args.steps / dt
-    sample = f"{args.steps} forward passes of {sample_b}x3x256x256 (bounded sample of the B={args.batch} workload)"
+    sample = (f"{args.steps} forward passes of {sample_b}x3x256x256 (bounded sample of the B={args.batch} workload: the CPU arm "
+              f"runs batch {sample_b}, the GPU arm batch {args.batch}; images/s is per image)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -182,52 +184,49 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
     opt_h = Adam(hyper, lr=1e-4)
     x = x_host[:B].to(dev)
     params = amort + hyper
-    # multi-GPU: the all-reduce of a network's gradients starts as soon as its backward is done (grad-ready hooks) and
-    # overlaps the backward of the networks in front of it; buckets in completion order.  A self-check against the
-    # plain after-backward all-reduce runs once before timing; on any mismatch / error the plain path is used.
+    # multi-GPU: the training plans hand every layer's parameter gradients to an in-backward reducer
+    # (hific_b200.dist.InBackwardGradientReducer): 32 MB buckets all-reduced (ncclAvg, in place) on a side stream while the
+    # backward keeps walking; only the hyper-latent density parameters (14 080) go through the plain call afterwards.  A
+    # self-check against the plain after-backward all-reduce runs once before timing; on any mismatch the plain path is used.
     reducer, reduce_mode = None, "none (single GPU)"
     if dist is not None:
         reduce_mode = "after backward, one coalesced NCCL all-reduce"
-    # opt-in (HFC_OVERLAP_ALLREDUCE=1) until it has run over NCCL once: it was written with no multi-GPU minutes left
-    if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE") == "1":
-        from hific_b200.dist import OverlappedGradientReducer
-        hp = model.Hyperprior
-        buckets = [list(model.Generator.parameters()),
-                   [p for m in (hp.synthesis_mu, hp.synthesis_std, hp.analysis_net) for p in m.parameters()] + hyper,
-                   list(model.Encoder.parameters())]
+    if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE", "1") == "1":
+        from hific_b200.dist import InBackwardGradientReducer
         try:
-            reducer = OverlappedGradientReducer(buckets, dist, world)
-            probe = [b[0] for b in reducer.buckets] + [b[-1] for b in reducer.buckets]
+            reducer = InBackwardGradientReducer(dist, world)
+            probe = [amort[0], amort[len(amort) // 2], amort[-1], hyper[0]]
 
             def grads_once(overlapped):
                 for p in params:
                     p.grad = None
                 torch.manual_seed(1234)
-                reducer.enabled = overlapped
-                model(x, train_generator=True)['compression'].backward()
+                loss = model(x, train_generator=True)['compression']
                 if overlapped:
-                    reducer.finish()
+                    with reducer:
+                        loss.backward()
+                    reducer.reduce_rest(hyper)
                 else:
+                    loss.backward()
                     allreduce_gradients(params, dist, world)
                 torch.cuda.synchronize()
                 return [p.grad.detach().clone() for p in probe]
 
             try:
+                grads_once(True)                                    # calibrates the loss scales (per-Function hand-over)
                 ref, got = grads_once(False), grads_once(True)
-                ok = all(torch.allclose(a, b, rtol=5e-2, atol=1e-3 * float(a.abs().max()) + 1e-12)
-                         for a, b in zip(ref, got))
+                ok = all(torch.allclose(a, b, rtol=2e-2, atol=1e-3 * float(a.abs().max()) + 1e-12)
+                         for a, b in zip(ref, got)) and reducer.buckets_launched >= 20
             except Exception:                        # every rank must still reach the agreement collective below
                 ok = False
             flag = torch.tensor([1.0 if ok else 0.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if flag.item() < 1.0:
-                raise RuntimeError("overlapped all-reduce disagrees with the plain one")
-            reducer.enabled = True
-            reduce_mode = ("overlapped with backward: 3 buckets (Generator | Hyperprior | Encoder) all-reduced on a side "
-                           "stream from grad-ready hooks (self-check against the plain all-reduce passed)")
+                raise RuntimeError("in-backward all-reduce disagrees with the plain one")
+            reduce_mode = (f"overlapped with backward: {reducer.buckets_launched} buckets of <= 32 MB handed over layer by layer from "
+                           "inside the network Functions, all-reduced (ncclAvg, in place) on a side stream (self-check against "
+                           "the plain all-reduce passed)")
         except Exception as e:                       # keep the measurement alive on the proven path
-            if reducer is not None:
-                reducer.remove()
             reducer = None
             reduce_mode += f" (overlap disabled: {repr(e)[:120]})"
         for p in params:
@@ -235,11 +234,14 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
 
     def step():
         losses = model(x, train_generator=True)
-        losses['compression'].backward()
         if reducer is not None:
-            reducer.finish()
-        elif dist is not None:
-            allreduce_gradients(params, dist, world)
+            with reducer:
+                losses['compression'].backward()
+            reducer.reduce_rest(hyper)
+        else:
+            losses['compression'].backward()
+            if dist is not None:
+                allreduce_gradients(params, dist, world)
         opt_a.step()
         opt_a.zero_grad()
         opt_h.step()
@@ -253,18 +255,19 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
     except NotImplementedError as e:      # a piece of the backward is missing: report it, do not fake a number
         return {"unavailable": str(e)[:200]}
     finally:
-        if reducer is not None:
-            reducer.remove()
         model.model_mode = ModelModes.EVALUATION
         model.eval()
     return {"ms_per_step": ms / steps, "images_per_s": world * B * steps / (ms * 1e-3), "steps": steps,
             "per_gpu_batch": B, "n_gpus": world, "gradient_allreduce": reduce_mode,
-            "lpips_trunk": os.environ.get("HFC_LPIPS_TRUNK", "cudnn"),
-            "what": "compression model (no GAN): fwd + rate/distortion/LPIPS losses + bwd + 2x Adam (hific_b200.optim.Adam, one launch each); bf16 backward GEMMs; "
-                    f"LPIPS AlexNet trunk: {os.environ.get('HFC_LPIPS_TRUNK', 'cudnn')}; gradient all-reduce over NCCL when n_gpus > 1"}
+            "lpips_trunk": os.environ.get("HFC_LPIPS_TRUNK", "native"),
+            "dtype": ("bf16 x bf16 backward GEMMs (HFC_GRAD_FMT=bf16)" if os.environ.get("HFC_GRAD_FMT", "fp16").lower() == "bf16" else
+                      "fp16 x fp16 backward GEMMs (10-bit mantissa as TF32; power-of-two loss scale per backward Function), "
+                      "fp16-operand forward, fp32 accumulate, fp32 elementwise / Adam"),
+            "what": "compression model (no GAN): fwd + rate/distortion/LPIPS losses + bwd + 2x Adam (hific_b200.optim.Adam, one launch each); "
+                    f"LPIPS AlexNet trunk: {os.environ.get('HFC_LPIPS_TRUNK', 'native')}; gradient all-reduce over NCCL when n_gpus > 1"}
 
 
-def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
+def run_gan_steps(args, dev, dist, rank, world, x_host, timed, batch=None, regime="low", label="c4 shapes"):
     """The alternating generator / discriminator iterations of COMPRESSION_GAN training (configs c3 / c4;
     train.py:137-141): every iteration runs the full forward (E, H, G, D, all losses); generator iterations
     back-propagate the compression loss (+ beta * G loss, through D into G) and step the two Adam optimizers,
@@ -274,9 +277,11 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
     from hific_b200.dist import allreduce_gradients
     from hific_b200.model import Model
     from hific_b200.optim import Adam
-    B = args.gan_batch or args.train_batch or args.batch
+    B = batch or args.gan_batch or args.train_batch or args.batch
     cfg = hific_args()
     cfg.batch_size = B
+    cfg.regime = regime                                   # default_config.py: target rate / lambda_A follow the regime
+    cfg.target_rate, cfg.lambda_A = cfg.target_rate_map[regime], cfg.lambda_A_map[regime]
     model = Model(cfg, logging.getLogger("bench-gan"), model_mode=ModelModes.TRAINING, model_type=ModelTypes.COMPRESSION_GAN)
     model.load_state_dict(synth.synth_state_dict(0, gan=True), strict=True)
     model.to(dev).train()
@@ -290,10 +295,20 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
         if dist is not None:
             allreduce_gradients(params, dist, world)
 
+    reducer = None
+    if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE", "1") == "1":
+        from hific_b200.dist import InBackwardGradientReducer
+        reducer = InBackwardGradientReducer(dist, world)
+
     def g_step():
         losses = model(x, train_generator=True)
-        losses['compression'].backward()
-        allreduce(amort + hyper)
+        if reducer is not None:                 # E / H / G gradients reduced from inside their backward; the discriminator's
+            with reducer:                       # (stale, un-stepped on G iterations: train.py:54-59) stay local as before
+                losses['compression'].backward()
+            reducer.reduce_rest(hyper)
+        else:
+            losses['compression'].backward()
+            allreduce(amort + hyper)
         opt_a.step(); opt_a.zero_grad()
         opt_h.step(); opt_h.zero_grad()
 
@@ -304,21 +319,159 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed):
         opt_d.step(); opt_d.zero_grad()
 
     try:
-        for _ in range(2):
+        for _ in range(5):                                  # >= 5 warm-up pairs: cuDNN autotune (LPIPS trunk), allocator, plans
             g_step(); d_step()
-        steps = max(3, args.steps // 4)
-        ms_g = timed(g_step, steps)
-        ms_d = timed(d_step, steps)
+        steps = max(10, args.steps // 2)
+        # every iteration is timed on its own (barrier + events, max over ranks) and the MEDIAN is reported: a 5-step mean
+        # let one allocator / autotune hiccup move the figure by 60 % in round 1 (56.8 vs 34.7 ms)
+        tg = sorted(timed(g_step, 1) for _ in range(steps))
+        td = sorted(timed(d_step, 1) for _ in range(steps))
+        ms_g, ms_d = tg[len(tg) // 2] * steps, td[len(td) // 2] * steps
     except NotImplementedError as e:
         return {"unavailable": str(e)[:200]}
     pair = (ms_g + ms_d) / steps
-    return {"ms_per_generator_iteration": ms_g / steps, "ms_per_discriminator_iteration": ms_d / steps,
+    return {"config": f"{label}: compression_gan regime={regime} batch={B}/GPU 3x256x256",
+            "ms_per_generator_iteration": ms_g / steps, "ms_per_discriminator_iteration": ms_d / steps,
+            "ms_per_generator_iteration_min_max": [tg[0], tg[-1]], "ms_per_discriminator_iteration_min_max": [td[0], td[-1]],
+            "timing": f"median of {steps} individually timed iterations after 5 warm-up pairs",
             "ms_per_iteration": pair / 2, "images_per_s": world * B * 2 / (pair * 1e-3), "steps": steps, "per_gpu_batch": B,
             "n_gpus": world,
             "what": "COMPRESSION_GAN alternating iterations (train.py:137-141): full forward incl. discriminator and "
                     "LPIPS every iteration; G iterations: backward of the compression loss + 2x Adam; D iterations: "
                     "backward of the D loss + Adam; gradient all-reduce (NCCL) when n_gpus > 1"}
 
+
+
+def _event_times(fn, warmup, reps):
+    """Per-call CUDA-event times (ms) of `fn` on the current stream, after `warmup` untimed calls."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return ts
+
+
+def run_eager_cudnn(args, dev, x_host, ours_fwd_ms, ours_train_ms):
+    """The real bar: the reference's modules under torch-eager + cuDNN on THIS GPU.
+    /root/reference does not exist on the GPU box, so the arithmetic is the oracle's functional restatement of
+    Encoder / Hyperprior / Generator (src/network/encoder.py:104-111, src/hyperprior.py:277-330,
+    src/network/generator.py:145-169; pinned bit-exactly to the real modules, tests/test_oracle_golden.py) run on `cuda`:
+    the same F.conv2d / F.conv_transpose2d / elementwise calls the reference issues, dispatched to cuDNN by torch.
+    Timed with cuDNN's TF32 convolutions (torch's default, what the reference gets on an Ampere+ GPU; cudnn.benchmark on
+    as train.py:29 sets it) and with TF32 off (strict fp32).  c2 forward (eval) and the c2 training step
+    (rate + distortion + LPIPS, backward, 2 x torch.optim.Adam as train.py:287-300)."""
+    import torchvision
+    from hific_b200 import synth
+    from hific_b200.config import mse_lpips_args
+    from oracle import hific_oracle as O
+    B = args.batch
+    cfgc = mse_lpips_args()
+    cfg = dict(lambda_A=cfgc.lambda_A, lambda_B=cfgc.lambda_B, lambda_schedule=cfgc.lambda_schedule,
+               target_rate=cfgc.target_rate, target_schedule=cfgc.target_schedule, k_M=cfgc.k_M, k_P=cfgc.k_P)
+    sd = {k: v.to(dev) for k, v in synth.synth_state_dict(0).items()}
+    x = x_host[:B].to(dev)
+    state = torch.random.get_rng_state()
+    torch.manual_seed(1234)
+    trunk = torchvision.models.alexnet(weights=None).features.to(dev).eval()
+    torch.random.set_rng_state(state)
+    for p in trunk.parameters():
+        p.requires_grad = False
+    lins = [torch.rand(c, device=dev) * 0.02 for c in (64, 192, 384, 256, 256)]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    out = {"what": "oracle restatement of the reference modules on cuda (torch eager + cuDNN), same synthetic weights / "
+                   f"inputs, batch {B}; cudnn.benchmark = True (train.py:29)", "per_gpu_batch": B}
+    try:
+        torch.backends.cudnn.benchmark = True
+        for tag, tf32 in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
+            def fwd():
+                with torch.no_grad():
+                    return O.compression_forward(sd, x, training=False)
+            ts = _event_times(fwd, 3, 10)
+            ms = statistics.median(ts)
+            out[f"forward_{tag}"] = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3),
+                                     "ours_speedup": (ms / ours_fwd_ms) if ours_fwd_ms else None}
+            if args.no_train:
+                continue
+            sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+            amort = [v for k, v in sdg.items() if v.requires_grad and "hyperlatent_likelihood" not in k]
+            hyper = [v for k, v in sdg.items() if v.requires_grad and "hyperlatent_likelihood" in k]
+            opt_a, opt_h = torch.optim.Adam(amort, lr=1e-4), torch.optim.Adam(hyper, lr=1e-4)
+
+            def train():
+                nz = torch.rand((B, 320, 4, 4), device=dev) - 0.5
+                ny = torch.rand((B, 220, 16, 16), device=dev) - 0.5
+                recon, hyp, _ = O.compression_forward(sdg, x, True, False, nz, ny)
+                rate, _ = O.weighted_rate_loss(cfg, hyp.total_nbpp, hyp.total_qbpp, 1)       # .item() sync, as losses.py:21
+                loss = rate + cfg["k_M"] * O.distortion_loss(recon, x) + \
+                    cfg["k_P"] * O.lpips_forward(trunk, lins, recon, x).mean()
+                loss.backward()
+                opt_a.step(); opt_h.step()
+                opt_a.zero_grad(); opt_h.zero_grad()
+            ts = _event_times(train, 3, 8)
+            ms = statistics.median(ts)
+            out[f"train_step_{tag}"] = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3),
+                                        "ours_speedup": (ms / ours_train_ms) if ours_train_ms else None}
+            del sdg, amort, hyper, opt_a, opt_h
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    return out
+
+
+def run_c5_inference(model, dev, peaks, rank):
+    """Config c5 (BASELINE.json): compress.py's inference path at batch 8 x 3 x 1024 x 1024, encode -> latents -> decode
+    with the entropy coder bypassed (compress.py:143-150, `model(data, writeout=False)` in EVALUATION mode)."""
+    B5 = 8
+    from hific_b200 import synth
+    x = synth.synth_image(B5, 1024, 1024, seed=7 + rank).to(dev)
+
+    def step():
+        with torch.no_grad():
+            return model(x, writeout=False)
+    ts = _event_times(step, 3, 10)
+    ms = statistics.median(ts)
+    flops = E_H_G_FLOPS_PER_IMAGE * 16 * B5
+    return {"workload": "c5: compress.py inference path, batch 8 x 3x1024x1024, E + H + G forward, eval mode, ANS bypassed",
+            "ms_per_step": ms, "images_per_s": B5 / (ms * 1e-3), "images_256_equiv_per_s": 16 * B5 / (ms * 1e-3),
+            "tflops_per_step_algorithmic": flops / 1e12, "step_tensor_frac": flops / (ms * 1e-3) / 1e12 / peaks["sustained"],
+            "timing": "median of 10 CUDA-event-timed steps after 3 warm-ups; inputs resident in HBM; working set >> L2"}
+
+
+def cpu_c1_train_step(cores):
+    """Config c1 (BASELINE.json configs[0]): compression (no GAN), regime low, batch 4 x 3x256x256,
+    ONE forward + backward step on the host cores through the oracle (rate + distortion loss; torch CPU autograd)."""
+    from hific_b200 import synth
+    from oracle import hific_oracle as O
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(0)
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    x = synth.synth_image(4, 256, 256, 0)
+    nz, ny = torch.rand((4, 320, 4, 4)) - 0.5, torch.rand((4, 220, 16, 16)) - 0.5
+    k_M = 0.075 * 2 ** (-5)
+
+    def step():
+        for v in sdg.values():
+            v.grad = None
+        recon, hyp, _ = O.compression_forward(sdg, x, True, False, nz, ny)
+        (2.0 * hyp.total_nbpp + k_M * O.distortion_loss(recon, x)).backward()
+    step()
+    n, t0 = 0, time.perf_counter()
+    while n < 2 or (time.perf_counter() - t0 < 8 and n < 10):
+        step()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"ms_per_step": 1e3 * dt, "images_per_s": 4 / dt, "cores": cores, "steps": n,
+            "what": "c1: batch 4 x 3x256x256 forward + backward (rate + distortion) through the CPU oracle, torch fp32"}
 
 
 def ncu_dram_traffic(profile, kernel_substr):
@@ -466,6 +619,7 @@ def main():
     ap.add_argument("--gan-batch", type=int, default=0, help="per-GPU batch of the GAN iterations (default: the training batch)")
     ap.add_argument("--no-gan", action="store_true", help="skip the COMPRESSION_GAN alternating-iteration measurement")
     ap.add_argument("--no-compress", action="store_true", help="skip the Model.compress / decompress measurement")
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager + cuDNN comparison and the c5 inference leg")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true",
                     help="profiling mode (ncu): device-resident steps only, no e2e / roofline / CPU legs")
@@ -605,9 +759,13 @@ def main():
     if not args.no_train:
         train = run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed)
 
-    gan = None
+    gan = gan_c3 = None
     if not args.no_train and not args.no_gan:
-        gan = run_gan_steps(args, dev, dist, rank, world, x_host, timed)
+        # c4 shapes (regime low, batch 32 per GPU) at every N: the weak-scaling series of the GAN step; at N = 1 also c3
+        # exactly as BASELINE.json states it (regime med, batch 16)
+        gan = run_gan_steps(args, dev, dist, rank, world, x_host, timed, regime="low", label="c4 shapes")
+        if world == 1 and not args.gan_batch:
+            gan_c3 = run_gan_steps(args, dev, dist, rank, world, x_host, timed, batch=16, regime="med", label="c3")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -620,7 +778,12 @@ def main():
             n += 1
         dt = time.perf_counter() - t0
         cpu = {"value": sb * n / dt, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{n} forward passes of {sb}x3x256x256 through the CPU oracle (torch fp32, best of probed thread counts: {cores} of {os.cpu_count()} cores)"}
+               "sample": f"{n} forward passes of {sb}x3x256x256 through the CPU oracle (torch fp32, best of probed thread counts: {cores} of {os.cpu_count()} cores)",
+               "batch_note": f"CPU sample batch {sb} vs GPU batch {B}: throughput in images/s is per image, the batch differs"}
+        try:
+            cpu["c1_train_step"] = cpu_c1_train_step(cores)
+        except Exception as e:
+            cpu["c1_train_step"] = {"unavailable": repr(e)[:200]}
 
     # --- compress / decompress through the public API, then the HBM roofline of the likelihood kernel (rank 0) ---
     comp, lik = None, None
@@ -640,18 +803,31 @@ def main():
             except Exception as e:
                 comp["symbols_kernel"] = {"unavailable": repr(e)[:300]}
 
-    # --- the training step once more with the LPIPS AlexNet trunk on the tcgen05 conv kernel instead of cuDNN (opt-in
-    # switch HFC_LPIPS_TRUNK=native, parity-tested in tests/test_gpu_zzlpips_trunk.py): recorded so that the default
-    # can be chosen on evidence.  Single-GPU runs only, and after every other measurement (last thing before the line is printed).
+    # --- the training step once more with the LPIPS AlexNet trunk on cuDNN + torch autograd (HFC_LPIPS_TRUNK=cudnn; the
+    # native tcgen05 trunk is the default since round 2): kept so that the choice stays backed by a number.  Single GPU.
     if world == 1 and isinstance(train, dict) and "ms_per_step" in train and os.environ.get("HFC_LPIPS_TRUNK") is None:
         try:
-            os.environ["HFC_LPIPS_TRUNK"] = "native"
+            os.environ["HFC_LPIPS_TRUNK"] = "cudnn"
             t2 = run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed)
-            train["with_native_lpips_trunk"] = {k: t2[k] for k in ("ms_per_step", "images_per_s") if k in t2} or t2
+            train["with_cudnn_lpips_trunk"] = {k: t2[k] for k in ("ms_per_step", "images_per_s") if k in t2} or t2
         except Exception as e:
-            train["with_native_lpips_trunk"] = {"unavailable": repr(e)[:200]}
+            train["with_cudnn_lpips_trunk"] = {"unavailable": repr(e)[:200]}
         finally:
             os.environ.pop("HFC_LPIPS_TRUNK", None)
+
+    eager = c5 = None
+    if rank == 0 and world == 1 and not args.no_eager:
+        model.enable_cuda_graph(use_graph)
+        try:
+            c5 = run_c5_inference(model, dev, measured_peaks(), rank)
+        except Exception as e:
+            c5 = {"unavailable": repr(e)[:300]}
+        torch.cuda.empty_cache()
+        try:
+            eager = run_eager_cudnn(args, dev, x_host, ms / args.steps,
+                                    train.get("ms_per_step") if isinstance(train, dict) else None)
+        except Exception as e:
+            eager = {"unavailable": repr(e)[:300]}
 
     if rank == 0:
         per_step = ms / args.steps
@@ -667,7 +843,12 @@ def main():
             "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "cuda_graph": use_graph,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "tflops_per_step_algorithmic": E_H_G_FLOPS_PER_IMAGE * B / 1e12,
-            "train_step": train, "gan_train_iteration": gan,
+            "train_step_ms": train.get("ms_per_step") if isinstance(train, dict) else None,
+            "train_step_dtype": train.get("dtype") if isinstance(train, dict) else None,
+            "gan_generator_iteration_ms": gan.get("ms_per_generator_iteration") if isinstance(gan, dict) else None,
+            "gan_discriminator_iteration_ms": gan.get("ms_per_discriminator_iteration") if isinstance(gan, dict) else None,
+            "eager_cudnn": eager, "c5_inference": c5,
+            "train_step": train, "gan_train_iteration": gan, "c3_gan_train_iteration": gan_c3,
             "roofline_hbm": lik, "compress_path": comp,
         }))
     if dist is not None:

@@ -139,3 +139,105 @@ class OverlappedGradientReducer:
         self.launched = [False] * len(self.buckets)
         self.bytes_reduced = 0
         return nbytes
+
+
+class InBackwardGradientReducer:
+    """Gradient all-reduce issued from INSIDE the backward of the network Functions.
+
+    Each network of the hot path is ONE autograd Function, so grad-ready hooks (`OverlappedGradientReducer`) only fire
+    when a whole network is done -- and the Generator, 87 % of the parameters, is done first, leaving almost nothing to
+    hide its 630 MB behind.  The training plans therefore hand their parameter gradients over layer by layer
+    (`grad.emit`, called the moment a layer's weight / bias / norm gradients are final and un-scaled): this reducer
+    collects them into buckets of `bucket_bytes` and all-reduces (mean) every full bucket IN PLACE on a communication
+    stream while the compute stream walks the remaining layers.  At the end of each Function's backward
+    (`function_done`) the compute stream waits for the buckets still in flight, because autograd's AccumulateGrad reads
+    the returned tensors next; what stays exposed per Function is the tail of its last bucket only.
+
+        reducer = InBackwardGradientReducer(dist, world)
+        with reducer:                       # installs itself as grad._grad_sink
+            loss.backward()
+        reducer.reduce_rest(other_params)   # parameters outside the plans (hyper-latent density, discriminator)
+
+    Every rank walks the same plans in the same order, so buckets line up across ranks without negotiation.
+    Backend-agnostic: NCCL (coalesced in-place ncclAvg on a side stream) or gloo (CPU tests: flatten, sum, divide)."""
+
+    def __init__(self, dist=None, world=None, bucket_bytes=32 << 20):
+        if dist is None:
+            import torch.distributed as dist
+        self.dist = dist
+        self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.bucket_bytes = int(bucket_bytes)
+        self.pending, self.pending_bytes = [], 0
+        self.inflight = []                  # gloo: (work, flat, grads)
+        self._comm, self._done = None, None
+        self.bytes_reduced, self.buckets_launched, self.ids = 0, 0, set()
+
+    # -- sink protocol (hific_b200.grad) ---------------------------------------------------------------------------
+    def submit(self, tensors):
+        if self.world == 1:
+            return
+        for t in tensors:
+            self.pending.append(t)
+            self.pending_bytes += t.numel() * t.element_size()
+            self.ids.add(t.data_ptr())
+        if self.pending_bytes >= self.bucket_bytes:
+            self._launch()
+
+    def function_done(self):
+        """End of one Function's backward: launch the partial bucket and make the compute stream wait for this Function's
+        reductions (the tensors are about to be accumulated into .grad)."""
+        if self.world == 1:
+            return
+        self._launch()
+        if self._done is not None:
+            torch.cuda.current_stream().wait_event(self._done)
+            self._done = None
+        for work, flat, grads in self.inflight:
+            work.wait()
+            flat.div_(self.world)
+            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(f)
+        self.inflight = []
+
+    def _launch(self):
+        grads, self.pending, self.pending_bytes = self.pending, [], 0
+        if not grads:
+            return
+        dist = self.dist
+        self.bytes_reduced += sum(g.numel() * g.element_size() for g in grads)
+        self.buckets_launched += 1
+        if grads[0].is_cuda:
+            dev = grads[0].device
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(device=dev)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(dev))            # the gradients of this bucket are final
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(ready)
+                with dist._coalescing_manager(device=dev):
+                    for g in grads:
+                        dist.all_reduce(g, op=dist.ReduceOp.AVG)
+                self._done = torch.cuda.Event()
+                self._done.record(self._comm)
+                for g in grads:
+                    g.record_stream(self._comm)
+        else:
+            flat = torch._utils._flatten_dense_tensors(grads)
+            self.inflight.append((dist.all_reduce(flat, async_op=True), flat, grads))
+
+    # -- user side -------------------------------------------------------------------------------------------------
+    def __enter__(self):
+        from . import grad
+        self._prev, grad._grad_sink = grad._grad_sink, self
+        self.bytes_reduced, self.buckets_launched, self.ids = 0, 0, set()
+        return self
+
+    def __exit__(self, *exc):
+        from . import grad
+        grad._grad_sink = self._prev
+        self.function_done()
+        return False
+
+    def reduce_rest(self, params):
+        """Plain all-reduce of the gradients no plan emitted (parameters of modules that are not training plans)."""
+        return allreduce_gradients(list(params), self.dist, self.world)

@@ -112,11 +112,11 @@ class GeneratorPlan:
         self.res_convs = [(Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows960),
                            Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows960))
                           for _ in range(n_residual_blocks)]
-        # HFC_FUSE_RESNORM=1: every residual conv runs fused with the ChannelNorm (+ReLU / + residual adds) behind it
+        # default (HFC_FUSE_RESNORM=0 restores the two-launch plan): every residual conv runs fused with the ChannelNorm (+ReLU / + residual adds) behind it
         # (hfc_conv_forward_widenorm: the 960-channel row of a pixel is normalised across a 4-CTA cluster), which removes
         # the stand-alone ChannelNorm launch and the fp32 round trip of the conv output.  Opt-in: not yet run on hardware.
         self.fused = None
-        if os.environ.get("HFC_FUSE_RESNORM") == "1" and n_residual_blocks > 0:
+        if os.environ.get("HFC_FUSE_RESNORM", "1") == "1" and n_residual_blocks > 0:
             fused = []
             for i in range(n_residual_blocks):
                 last = i == n_residual_blocks - 1
@@ -298,6 +298,10 @@ class DiscriminatorPlan:
         self.flops = self.c_ctx.flops + sum(c.flops for c in self.convs) + self.c_out.flops
 
     def run(self, mod, x, y):
+        # the training plan (train_plan.DiscriminatorTrainPlan) reads these buffers in its backward: any run() that is
+        # not the one a pending backward belongs to bumps the generation so that backward fails loudly instead of
+        # differentiating through the wrong activations
+        self._generation = getattr(self, "_generation", 0) + 1
         ops.nchw_to_act(y, self.g_y, reflect=True, out=self.y_act)
         self.c_ctx(self.y_act, mod.context_conv.weight, mod.context_conv.bias, out=self.ctx_act)
         ops.disc_input(x, self.ctx_act, self.g_ctx, self.g_in, self.scale, out=self.in_act)

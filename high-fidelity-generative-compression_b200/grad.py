@@ -40,6 +40,19 @@ _K_ACT = 2 if GRAD_BF16 else 0     #                           fp16 act buffer -
 
 # calibration only: device scalars max|operand| of every gradient operand written while a GradScale calibrates
 _amax_log = None
+# 1 / S of the GradScale whose backward is running: folded into every PARAMETER gradient where it is produced (the
+# permute of the weight gradient, the bias column sums, the ChannelNorm parameter sums), so that parameter gradients are
+# final -- and can be handed to a gradient all-reduce -- the moment their layer is done
+_inv_scale = 1.0
+# where finished parameter gradients go while a backward Function is still walking its layers (multi-GPU: the
+# in-backward gradient reducer of hific_b200.dist); None = nowhere
+_grad_sink = None
+
+
+def emit(*tensors):
+    """Called by the training plans when the gradients of a layer are final."""
+    if _grad_sink is not None:
+        _grad_sink.submit([t for t in tensors if t is not None])
 
 
 def _log_operand(buf):
@@ -50,8 +63,8 @@ def _log_operand(buf):
 class GradScale:
     """Power-of-two loss scale of ONE backward Function (fp16 gradient operands; a no-op with HFC_GRAD_FMT=bf16).
 
-    `run(plan_backward, dout)` multiplies the incoming gradient by S, calls `plan_backward(scaled)` -> (dx, grads) and
-    divides every result by S (exact).  S is calibrated on the first call and then every HFC_GRAD_RECAL calls (default
+    `run(plan_backward, dout)` multiplies the incoming gradient by S, calls `plan_backward(scaled)` -> (dx, grads) with
+    1 / S folded into every parameter gradient where it is produced (`_inv_scale`) and divides dx by S (all exact).  S is calibrated on the first call and then every HFC_GRAD_RECAL calls (default
     200) from the largest operand magnitude seen anywhere in that backward chain (one device->host read per
     calibration, none in between): it is placed near 2^PEAK_LOG2, i.e. 5 binades below fp16's saturation and 24
     above its smallest normal.  Between calibrations the conversions saturate, so a gradient that grew > 32 x clips."""
@@ -67,20 +80,30 @@ class GradScale:
         return 2.0 ** math.floor(math.log2(v))
 
     def run(self, plan_backward, dout):
-        global _amax_log
+        global _amax_log, _inv_scale, _grad_sink
         if GRAD_BF16:
             return plan_backward(dout)
         self.calls += 1
+
+        def scaled(s):
+            global _inv_scale
+            _inv_scale = 1.0 / s
+            try:
+                return plan_backward(dout * s)
+            finally:
+                _inv_scale = 1.0
         if self.scale is None or (self.RECAL > 0 and self.calls % self.RECAL == 0):
             amax_in = float(dout.detach().abs().amax())
             if not (amax_in > 0.0) or amax_in == float("inf"):
                 return plan_backward(dout)                  # all-zero (or broken) upstream gradient: nothing to place
             s = self.scale if self.scale is not None else self._pow2_at_most(1.0 / amax_in)
             res = None
-            for _ in range(4):
+            sink, _grad_sink = _grad_sink, None             # a calibration pass may repeat: its gradients are handed
+            try:                                            # over in one piece afterwards
+              for _ in range(4):
                 _amax_log = []
                 try:
-                    res = plan_backward(dout * s)
+                    res = scaled(s)
                     peak = float(torch.stack(_amax_log).max()) if _amax_log else 0.0
                 finally:
                     _amax_log = None
@@ -92,16 +115,16 @@ class GradScale:
                     break
                 # saturated: the true peak is unknown, step down far; else move the measured peak onto the target
                 s = s / 4096.0 if peak >= 65504.0 else s * self._pow2_at_most(want / peak)
+            finally:
+                _grad_sink = sink
+            emit(*res[1])
+            s = self.scale
         else:
             s = self.scale
-            res = plan_backward(dout * s)
+            res = scaled(s)
         dx, grads = res
-        inv = 1.0 / s
-        live = [g for g in grads if g is not None]
-        if live:
-            torch._foreach_mul_(live, inv)
         if dx is not None:
-            dx = dx * inv
+            dx = dx * (1.0 / s)
         return dx, grads
 
 
@@ -321,14 +344,14 @@ class ConvGrad:
             # C is [ci][(slot, co)] but dW is [co][ci][ky][kx]: permute into a temporary and transpose the leading dims
             tmp = torch.empty((self.cin, self.cout, k, k), dtype=torch.float32, device=dev)
             check(lib.hfc_permute_wgrad(_ptr(cbuf), ncols, self.wg_m, self.wg_c2, self.wg_c2_rows, k, k, len(self.wg_taps),
-                                        ky, kx, float(scale), 0, _ptr(tmp), _stream()), "permute_wgrad")
+                                        ky, kx, float(scale) * _inv_scale, 0, _ptr(tmp), _stream()), "permute_wgrad")
             if accumulate:
                 dw_out += tmp.transpose(0, 1)
             else:
                 dw_out.copy_(tmp.transpose(0, 1))
             return dw_out
         check(lib.hfc_permute_wgrad(_ptr(cbuf), ncols, self.wg_m, self.wg_c2, self.wg_c2_rows, k, k, len(self.wg_taps), ky, kx,
-                                    float(scale), int(accumulate), _ptr(dw_out), _stream()), "permute_wgrad")
+                                    float(scale) * _inv_scale, int(accumulate), _ptr(dw_out), _stream()), "permute_wgrad")
         return dw_out
 
     def weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, scale=1.0, dy_act=None):
@@ -390,15 +413,15 @@ class ConvGrad:
         if self.swap:
             # C is [ci][(tap, co)] but dW is [co][ci][ky][kx]: permute into a temporary and transpose the two leading dims
             tmp = torch.empty((self.cin, self.cout, k, k), dtype=torch.float32, device=dev)
-            check(lib.hfc_permute_wgrad(_ptr(cbuf), cbuf.shape[1], m, c2, c2_rows, k, k, len(self.taps), ky, kx, float(scale),
-                                        0, _ptr(tmp), _stream()), "permute_wgrad")
+            check(lib.hfc_permute_wgrad(_ptr(cbuf), cbuf.shape[1], m, c2, c2_rows, k, k, len(self.taps), ky, kx,
+                                        float(scale) * _inv_scale, 0, _ptr(tmp), _stream()), "permute_wgrad")
             if accumulate:
                 dw_out += tmp.transpose(0, 1)
             else:
                 dw_out.copy_(tmp.transpose(0, 1))
             return dw_out
-        check(lib.hfc_permute_wgrad(_ptr(cbuf), cbuf.shape[1], m, c2, c2_rows, k, k, len(self.taps), ky, kx, float(scale),
-                                    int(accumulate), _ptr(dw_out), _stream()), "permute_wgrad")
+        check(lib.hfc_permute_wgrad(_ptr(cbuf), cbuf.shape[1], m, c2, c2_rows, k, k, len(self.taps), ky, kx,
+                                    float(scale) * _inv_scale, int(accumulate), _ptr(dw_out), _stream()), "permute_wgrad")
         return dw_out
 
     def bias_grad(self, dy_rows, db_out=None, accumulate=False, scale=1.0):
@@ -406,6 +429,6 @@ class ConvGrad:
             db_out = torch.zeros(self.cout, dtype=torch.float32, device=dy_rows.device)
         elif not accumulate:
             db_out.zero_()
-        check(lib.hfc_col_sums(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, float(scale), _ptr(db_out),
+        check(lib.hfc_col_sums(_ptr(dy_rows), dy_rows.shape[-1], self.p_out, self.cout, float(scale) * _inv_scale, _ptr(db_out),
                                _stream()), "col_sums")
         return db_out

@@ -27,10 +27,16 @@ def weighted_rate_loss(config, total_nbpp, total_qbpp, step_counter, ignore_sche
 
 
 def gan_loss(gan_loss_type, disc_out, mode='generator_loss'):
-    """losses.py:52-66.  The non-saturating losses come from one fused reduction over the logits
-    (`hfc_gan_sums`); the least-squares variant is a non-default option and is not built."""
+    """losses.py:52-66.  The non-saturating losses (the HiFIC default) come from one fused reduction over the logits
+    (`hfc_gan_sums`, backward `hfc_gan_grad`); the least-squares variant (losses.py:43-50, a non-default option on
+    B*256 sigmoid outputs) is three torch reductions with torch autograd."""
+    if gan_loss_type == 'least_squares':
+        D_real, D_gen = disc_out.D_real, disc_out.D_gen
+        if mode == 'generator_loss':
+            return 0.5 * torch.mean(torch.square(D_gen - 1.0))
+        return 0.5 * (torch.mean(torch.square(D_real - 1.0)) + torch.mean(torch.square(D_gen)))
     if gan_loss_type != 'non_saturating':
-        raise NotImplementedError("only gan_loss_type='non_saturating' (the HiFIC default) is built")
+        raise ValueError('Invalid GAN loss')
     if torch.is_grad_enabled() and (disc_out.D_real_logits.requires_grad or disc_out.D_gen_logits.requires_grad):
         return ops.GanLossFn.apply(disc_out.D_real_logits, disc_out.D_gen_logits, 0 if mode == 'generator_loss' else 1)
     logits = torch.cat([disc_out.D_real_logits.reshape(-1), disc_out.D_gen_logits.reshape(-1)])

@@ -27,6 +27,17 @@ def _find_lin_weights():
     return None
 
 
+def _synthetic_or_raise(what):
+    """The reference always loads pretrained weights (pretrained_networks.py:59, networks_basic.py weights/v0.1/alex.pth).
+    Training against a random trunk silently optimises k_P * noise, so a missing checkpoint is an ERROR unless the caller
+    opts in to the seeded stand-in (tests, bench and smoke on the network-less GPU box do: HFC_LPIPS_SYNTHETIC=1)."""
+    if os.environ.get("HFC_LPIPS_SYNTHETIC") != "1":
+        raise RuntimeError(f"PerceptualLoss: {what}.  Provide the checkpoint, pass trunk= / lin_weights=, or set "
+                           "HFC_LPIPS_SYNTHETIC=1 to accept a seeded random stand-in (parity tests / benchmarks only).")
+    import warnings
+    warnings.warn(f"PerceptualLoss: {what}; using the seeded synthetic stand-in (HFC_LPIPS_SYNTHETIC=1)", stacklevel=3)
+
+
 class PerceptualLoss(nn.Module):
     def __init__(self, model='net-lin', net='alex', colorspace='rgb', spatial=False, use_gpu=True, gpu_ids=[0],
                  version='0.1', trunk=None, lin_weights=None):
@@ -39,6 +50,9 @@ class PerceptualLoss(nn.Module):
             if os.path.exists(cached):   # ImageNet weights only if already cached: never touch the network
                 trunk = torchvision.models.alexnet(weights="IMAGENET1K_V1").features
             else:                        # offline stand-in (same seed as oracle/ref_shim.py)
+                _synthetic_or_raise("the ImageNet AlexNet checkpoint (alexnet-owt-7be5be79.pth) is not in the torch hub cache "
+                                    f"({cached}): a randomly initialised trunk is NOT LPIPS")
+                self._synthetic_trunk = True
                 state = torch.random.get_rng_state()
                 torch.manual_seed(1234)
                 trunk = torchvision.models.alexnet(weights=None).features
@@ -68,11 +82,13 @@ class PerceptualLoss(nn.Module):
             if key in sd:
                 w = sd[key].reshape(-1).float()
             else:   # deterministic non-negative stand-in when the vendored file is not reachable
+                _synthetic_or_raise(f"LPIPS 'lin' weights ({key}) not found")
                 g = torch.Generator().manual_seed(100 + k)
                 w = torch.rand(c, generator=g) * 0.02
             lins.append(nn.Parameter(w.clone(), requires_grad=False))
         self.lins = nn.ParameterList(lins)
         self.lin_source = path or ("provided" if lin_weights else "synthetic")
+        self.trunk_source = "provided / ImageNet checkpoint" if not getattr(self, "_synthetic_trunk", False) else "synthetic"
 
     def features(self, x):
         h = (x - self.shift) / self.scale                      # ScalingLayer, networks_basic.py:91-98
@@ -84,9 +100,11 @@ class PerceptualLoss(nn.Module):
         return outs
 
     def native_trunk(self):
-        """HFC_LPIPS_TRUNK=native runs the AlexNet trunk on the tcgen05 conv kernel (loss/lpips_trunk.py) instead of
-        cuDNN.  Opt-in until its GPU parity tests have run on hardware (written without GPU time left in round 1)."""
-        return os.environ.get("HFC_LPIPS_TRUNK", "cudnn") == "native"
+        """The AlexNet trunk runs on the tcgen05 conv kernel (loss/lpips_trunk.py) by default -- 27.2 vs 29.2 ms per c2
+        training step on the B200 (round 2, gpurun_out/c2_bench_full.json), gradients as close to the fp32 trunk as
+        cuDNN's own TF32 path (tests/test_gpu_zzlpips_trunk.py).  HFC_LPIPS_TRUNK=cudnn selects torchvision's module
+        executed by cuDNN + torch autograd."""
+        return os.environ.get("HFC_LPIPS_TRUNK", "native") == "native"
 
     def _native(self, pred, target, normalize):
         from .. import engine

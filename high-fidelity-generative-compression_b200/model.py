@@ -45,6 +45,8 @@ class Model(nn.Module):
         self.log_interval = args.log_interval
         self.storage_train, self.storage_test = storage_train, storage_test
         self.step_counter = 0
+        if getattr(args, "use_latent_mixture_model", False) is True:                   # src/model.py:53-54
+            self.args.latent_channels = self.args.latent_channels_DLMM
         if not hasattr(ModelTypes, self.model_type.upper()):
             raise ValueError("Invalid model_type: [{}]".format(self.model_type))
         if not hasattr(ModelModes, self.model_mode.upper()):

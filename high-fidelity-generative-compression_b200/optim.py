@@ -36,6 +36,7 @@ class Adam(torch.optim.Optimizer):
             if not ps[0].is_cuda:
                 raise RuntimeError("hific_b200.optim.Adam has no CPU path")
             by_step = {}            # parameters that skipped steps (no gradient) carry their own bias correction
+            keep = []               # contiguous copies of strided gradients must outlive the launch that reads them
             for p in ps:
                 if p.grad.is_sparse or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("hific_b200.optim.Adam: dense contiguous float32 parameters only")
@@ -45,7 +46,10 @@ class Adam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                g = p.grad
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                    keep.append(g)
                 by_step.setdefault(int(st["step"]), []).append(
                     (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()))
             b1, b2 = group["betas"]
@@ -62,4 +66,7 @@ class Adam(torch.optim.Optimizer):
             # saved-tensor checks and the packed-weight caches (ops.Conv.packed_weights) see the update
             for p in ps:
                 torch.autograd.graph.increment_version(p)
+            for g in keep:          # the caching allocator must not hand the copies out before the kernel has read them
+                g.record_stream(torch.cuda.current_stream(dev))
+            del keep
         return loss

@@ -55,6 +55,8 @@ def norm_bwd(z, g, gamma, beta, act, as_operand=True):
                                   _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _ptr(dz_act), cpad, int(GRAD_BF16), _stream()), "channelnorm_bwd")
     if as_operand:
         _grad._log_operand(dz)
+    if _grad._inv_scale != 1.0:
+        dgb.mul_(_grad._inv_scale)           # parameter gradients leave the layer un-scaled (grad.GradScale); dz keeps S
     return dz, dgb[0].view_as(gamma), dgb[1].view_as(beta), dgb[2]
 
 
@@ -157,10 +159,12 @@ class EncoderTrainPlan:
     def backward(self, dy, p):
         grads = [None] * 22
         g, grads[20], grads[21] = self.out.backward(nchw_to_rows(dy), p[20])
+        _grad.emit(grads[20], grads[21])
         for i in range(4, -1, -1):
             w, b, gm, bt = p[4 * i:4 * i + 4]
             dz, grads[4 * i + 2], grads[4 * i + 3], db = norm_bwd(self.z[i], g, gm, bt, ACT_RELU)
             g, grads[4 * i], grads[4 * i + 1] = self.layers[i].backward(dz, w, need_dx=i > 0, db=db)
+            _grad.emit(*grads[4 * i:4 * i + 4])
         return grads
 
     def release(self):
@@ -232,10 +236,12 @@ class GeneratorTrainPlan:
         o = 6 + 8 * R
         grads = [None] * len(p)
         g, grads[o + 16], grads[o + 17] = self.out.backward(nchw_to_rows(dxhat), p[o + 16])
+        _grad.emit(grads[o + 16], grads[o + 17])
         for i in range(3, -1, -1):
             w, b, gm, bt = p[o + 4 * i:o + 4 * i + 4]
             dz, grads[o + 4 * i + 2], grads[o + 4 * i + 3], db = norm_bwd(self.zu[i], g, gm, bt, ACT_RELU)
             g, grads[o + 4 * i], grads[o + 4 * i + 1] = self.ups[i].backward(dz, w, db=db)
+            _grad.emit(*grads[o + 4 * i:o + 4 * i + 4])
         # g = gradient w.r.t. the trunk output x_R (+ head): identity paths carry it to every block input and to head
         g_head = g.clone() if R else g
         for m in range(R - 1, -1, -1):
@@ -244,14 +250,17 @@ class GeneratorTrainPlan:
             z1, z2 = self.zr[m]
             dz2, grads[6 + 8 * m + 6], grads[6 + 8 * m + 7], db2 = norm_bwd(z2, g, g2, be2, ACT_NONE)
             ga1, grads[6 + 8 * m + 2], grads[6 + 8 * m + 3] = c2.backward(dz2, w2, db=db2)
+            _grad.emit(grads[6 + 8 * m + 2], grads[6 + 8 * m + 3], grads[6 + 8 * m + 6], grads[6 + 8 * m + 7])
             dz1, grads[6 + 8 * m + 4], grads[6 + 8 * m + 5], db1 = norm_bwd(z1, ga1, g1, be1, ACT_RELU)
             gx, grads[6 + 8 * m], grads[6 + 8 * m + 1] = c1.backward(dz1, w1, db=db1)
+            _grad.emit(grads[6 + 8 * m], grads[6 + 8 * m + 1], grads[6 + 8 * m + 4], grads[6 + 8 * m + 5])
             g = g + gx                                  # identity_map + residual branch (generator.py:44)
         if R:
             g_head = g_head + g                         # block 0 consumed head; the final `x += head` added it again
         dz0, grads[4], grads[5], db0 = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE)
         ga0, grads[2], grads[3] = self.init.backward(dz0, p[2], db=db0)
         dy_rows, grads[0], grads[1], _ = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE, as_operand=False)
+        _grad.emit(*grads[0:6])
         return rows_to_nchw(dy_rows, self.n, self.C, self.h, self.w), grads
 
     def release(self):
@@ -282,10 +291,13 @@ class HyperAnalysisTrainPlan:
     def backward(self, dz, p):
         grads = [None] * 6
         g, grads[4], grads[5] = self.l3.backward(nchw_to_rows(dz), p[4])
+        _grad.emit(grads[4], grads[5])
         g = relu_mask(g, self.a2, self.g2)
         g, grads[2], grads[3] = self.l2.backward(g, p[2])
+        _grad.emit(grads[2], grads[3])
         g = relu_mask(g, self.a1, self.g1)
         g, grads[0], grads[1] = self.l1.backward(g, p[0])
+        _grad.emit(grads[0], grads[1])
         return rows_to_nchw(g, self.n, self.C, self.h, self.w), grads
 
     def release(self):
@@ -311,10 +323,13 @@ class HyperSynthesisTrainPlan:
     def backward(self, dout, p):
         grads = [None] * 6
         g, grads[4], grads[5] = self.l3.backward(nchw_to_rows(dout), p[4])
+        _grad.emit(grads[4], grads[5])
         g = relu_mask(g, self.a2, self.g2)
         g, grads[2], grads[3] = self.l2.backward(g, p[2])
+        _grad.emit(grads[2], grads[3])
         g = relu_mask(g, self.a1, self.g1)
         g, grads[0], grads[1] = self.l1.backward(g, p[0])
+        _grad.emit(grads[0], grads[1])
         return rows_to_nchw(g, self.n, self.N, self.h, self.w), grads
 
     def release(self):
@@ -348,10 +363,13 @@ class HyperSynthesisDLMMTrainPlan:
         grads = [None] * 8
         g, grads[6], grads[7] = self.l4.backward(nchw_to_rows(dout), p[6])
         g, grads[4], grads[5] = self.l3.backward(g, p[4])                      # linear layer: no mask
+        _grad.emit(grads[4], grads[5], grads[6], grads[7])
         g = relu_mask(g, self.a2, self.g2)
         g, grads[2], grads[3] = self.l2.backward(g, p[2])
+        _grad.emit(grads[2], grads[3])
         g = relu_mask(g, self.a1, self.g1)
         g, grads[0], grads[1] = self.l1.backward(g, p[0])
+        _grad.emit(grads[0], grads[1])
         return rows_to_nchw(g, self.n, self.N, self.h, self.w), grads
 
     def release(self):
@@ -429,18 +447,39 @@ class DiscriminatorTrainPlan:
         return dx, dw, db
 
 
+def _stamp(plan):
+    """Saved activations live on the (cached, shared) plan, not on the autograd ctx: every forward stamps the plan with a
+    new generation and its backward refuses to run against a plan that another forward has overwritten since (two
+    forwards of the same shape before one backward -- micro-batch accumulation with a summed loss -- or a no-grad
+    Discriminator forward in between, which shares the plan's buffers)."""
+    plan._generation = getattr(plan, "_generation", 0) + 1
+    return plan._generation
+
+
+def _check_stamp(plan, generation, who):
+    if getattr(plan, "_generation", None) != generation:
+        raise RuntimeError(f"{who}: the plan's saved activations were overwritten by a later forward of the same shape "
+                           "before this backward ran (hific_b200 keeps ONE set of saved tensors per input shape: call "
+                           "backward() before the next forward of that shape, or accumulate gradients step by step)")
+
+
 class DiscriminatorFunction(torch.autograd.Function):
     """forward(plan, module, x, y, *params) -> logits; y gets no gradient (the reference detaches the latents)."""
 
     @staticmethod
     def forward(ctx, plan, mod, x, y, *params):
         ctx.plan, ctx.params, ctx.needs_dx = plan, params, x.requires_grad
+        ctx.generation = _stamp(plan)
         with torch.no_grad():
-            return plan.forward(mod, x.contiguous(), y.contiguous())
+            out = plan.forward(mod, x.contiguous(), y.contiguous())
+        ctx.generation_f = plan.f._generation                      # the inference plan owns the shared buffers
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
         plan = ctx.plan
+        _check_stamp(plan, ctx.generation, "Discriminator backward")
+        _check_stamp(plan.f, ctx.generation_f, "Discriminator backward")
         if not hasattr(plan, "grad_scale"):
             plan.grad_scale = GradScale()
         with torch.no_grad():
@@ -462,12 +501,14 @@ class PlanFunction(torch.autograd.Function):
         ctx.plan = plan
         ctx.params = params
         ctx.needs_dx = x.requires_grad
+        ctx.generation = _stamp(plan)
         with torch.no_grad():
             return plan.forward(x.contiguous(), [q.detach() for q in params])
 
     @staticmethod
     def backward(ctx, dout):
         plan = ctx.plan
+        _check_stamp(plan, ctx.generation, type(plan).__name__ + " backward")
         if not hasattr(plan, "grad_scale"):
             plan.grad_scale = GradScale()
 
@@ -478,6 +519,8 @@ class PlanFunction(torch.autograd.Function):
             params = [q.detach() for q in ctx.params]
             dx, grads = plan.grad_scale.run(walk, dout)
             plan.release()
+            if _grad._grad_sink is not None:
+                _grad._grad_sink.function_done()           # autograd reads the returned tensors next: reductions must be in
         grads = [g.reshape(q.shape) if g is not None else None for g, q in zip(grads, ctx.params)]
         return (None, dx if ctx.needs_dx else None, *grads)
 

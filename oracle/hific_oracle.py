@@ -337,8 +337,8 @@ def lpips_forward(trunk_features, lin_weights, pred, target, normalize=True):
     Returns (N,1,1,1) like PerceptualLoss.forward(pred, target, normalize)."""
     if normalize:
         target, pred = 2 * target - 1, 2 * pred - 1
-    shift = torch.tensor([-.030, -.088, -.188]).view(1, 3, 1, 1)
-    scale = torch.tensor([.458, .448, .450]).view(1, 3, 1, 1)
+    shift = torch.tensor([-.030, -.088, -.188], device=pred.device).view(1, 3, 1, 1)
+    scale = torch.tensor([.458, .448, .450], device=pred.device).view(1, 3, 1, 1)
 
     def feats(x):
         h = (x - shift) / scale

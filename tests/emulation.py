@@ -576,7 +576,7 @@ def convgrad_weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, sc
     with torch.enable_grad():
         w = torch.zeros(shape, requires_grad=True)
         _convgrad_apply(self, x, w).backward(dy)
-    dw = w.grad * scale
+    dw = w.grad * (scale * _grad._inv_scale)
     if dw_out is None:
         return dw
     if accumulate:
@@ -587,7 +587,7 @@ def convgrad_weight_grad(self, x_act, dy_rows, dw_out=None, accumulate=False, sc
 
 
 def convgrad_bias_grad(self, dy_rows, db_out=None, accumulate=False, scale=1.0):
-    db = dy_rows[:, :self.cout].sum(0) * scale
+    db = dy_rows[:, :self.cout].sum(0) * (scale * _grad._inv_scale)
     if db_out is None:
         return db
     if accumulate:
@@ -658,7 +658,8 @@ def norm_bwd(z, g, gamma, beta, act, as_operand=True):
         y.backward(g[:, :c])
     dz = torch.zeros((z.shape[0], (c + 3) // 4 * 4))
     dz[:, :c] = zz.grad
-    return dz, gm.grad.view_as(gamma), bt.grad.view_as(beta), zz.grad.sum(0)
+    inv = _grad._inv_scale
+    return dz, (gm.grad * inv).view_as(gamma), (bt.grad * inv).view_as(beta), zz.grad.sum(0) * inv
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -731,3 +732,38 @@ def dropin_cpu_emulation():
             yield
         finally:
             _discriminator.Discriminator.forward = old
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The MIRROR's whole COMPRESSION_GAN training iteration on the CPU (tests/test_train_ddp.py): on top of the drop-in
+# stand-ins, the mirror's own loss modules -- LPIPS (fused per-layer kernels + cuDNN trunk on the GPU) and the fused GAN
+# loss -- are replaced by the oracle's torch formulas.
+# ----------------------------------------------------------------------------------------------------------------------
+from hific_b200.loss import perceptual as _perceptual
+
+
+def perceptual_forward(self, pred, target, normalize=False):
+    return O.lpips_forward(self.trunk, [w for w in self.lins], pred, target, normalize=normalize)
+
+
+def gan_loss_fn(logits_real, logits_gen, mode):
+    d_loss, g_loss = O.gan_losses_non_saturating(logits_real, logits_gen)
+    return d_loss if mode == 1 else g_loss
+
+
+@contextlib.contextmanager
+def gan_model_cpu_emulation():
+    saved = []
+
+    def patch(obj, name, value):
+        saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, value)
+
+    with dropin_cpu_emulation():
+        patch(_perceptual.PerceptualLoss, "forward", perceptual_forward)
+        patch(ops.GanLossFn, "apply", staticmethod(gan_loss_fn))
+        try:
+            yield
+        finally:
+            for obj, name, value in reversed(saved):
+                setattr(obj, name, value)

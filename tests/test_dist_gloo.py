@@ -133,3 +133,83 @@ def test_overlapped_gradient_reducer_world2():
             assert nbytes == sum(g.numel() for g in grads[:-1]) * 4
             for g, r in zip(grads[:-1], ref[:-1]):
                 assert torch.allclose(g, r, rtol=1e-5, atol=1e-7)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# In-backward reducer on the REAL training plans (kernels emulated on the CPU): the gradients of every layer are handed to
+# the reducer from inside the network Functions, bucketed, all-reduced while the backward is still walking
+# ----------------------------------------------------------------------------------------------------------------------
+def _plan_worker(rank, world, port, out):
+    import logging
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.dirname(here)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from emulation import train_step_cpu_emulation
+    from hific_b200 import synth
+    from hific_b200.config import mse_lpips_args
+    from hific_b200.dist import InBackwardGradientReducer
+    from hific_b200.model import Model
+    from oracle.ref_shim import NoiseFeeder
+    if world > 1:
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        cfg = mse_lpips_args()
+        cfg.n_residual_blocks = 1
+        m = Model(cfg, logging.getLogger(f"rank{rank}"))
+        m.load_state_dict(synth.synth_state_dict(0, n_residual_blocks=1), strict=True)
+        m.train()
+        n_total = 4
+        x = synth.synth_image(n_total, 128, 128, 0)
+        nz, ny = synth.synth_noise((n_total, 320, 2, 2), "zd", 0), synth.synth_noise((n_total, 220, 8, 8), "yd", 0)
+        lo, hi = shard_range(n_total, rank, world)
+        reducer = InBackwardGradientReducer(dist, world, bucket_bytes=4 << 20)
+        with train_step_cpu_emulation():
+            for step in range(2):     # step 0 calibrates the loss scales (its gradients are handed over per Function),
+                for p in m.parameters():      # step 1 is the steady state: layer by layer from inside the Functions
+                    p.grad = None
+                with NoiseFeeder([nz[lo:hi], ny[lo:hi]]):
+                    inter, info = m.compression_forward(x[lo:hi])
+                loss = 2.0 * inter.n_bpp + cfg.k_M * m.distortion_loss(inter.reconstruction, inter.input_image)
+                with reducer:
+                    loss.backward()
+        density = list(m.Hyperprior.hyperlatent_likelihood.parameters())
+        reducer.reduce_rest(density)
+        grads = {k: p.grad.numpy().copy() for k, p in m.named_parameters() if p.grad is not None}   # plain arrays: no fd passing
+        emitted = sum(p.numel() * 4 for k, p in m.named_parameters() if "hyperlatent_likelihood" not in k)
+        out.put((rank, grads, reducer.bytes_reduced, reducer.buckets_launched, emitted))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def test_in_backward_reducer_on_training_plans_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs.append(ctx.Process(target=_plan_worker, args=(0, 1, 0, out)))       # the full batch on one process
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=600) for _ in range(3)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single = [r for r in res if r[3] == 0]
+    multi = sorted([r for r in res if r[3] > 0], key=lambda t: t[0])
+    assert len(single) == 1 and len(multi) == 2
+    ref = single[0][1]
+    for rank, grads, nbytes, buckets, emitted in multi:
+        assert nbytes == emitted                          # every plan parameter went through the in-backward path, once
+        assert buckets >= 8                               # several buckets per network, not one per network
+        assert set(grads) == set(ref)
+        for k in ref:
+            a, b = torch.from_numpy(grads[k]).double(), torch.from_numpy(ref[k]).double()
+            # identical on both ranks; equal to the single-process full-batch gradient up to the fp16 operand rounding
+            # (each rank scales / rounds its own half) -- the density parameters went through reduce_rest
+            assert (grads[k] == multi[0][1][k]).all(), k
+            assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 2e-2, k

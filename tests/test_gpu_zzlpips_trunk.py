@@ -21,7 +21,9 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 GRAD_TOL = 1e-1            # vs the fp32 trunk: dominated by ReLU / arg-max flips of the fp16-feature forward (measured
                            # 3-5.3e-2 on the B200 in round 1 / 2; the report line carries cuDNN-TF32's own figure)
-GRAD_TOL_MATCHED = 2e-2    # vs the operand-matched trunk: what the native BACKWARD arithmetic adds
+GRAD_TOL_MATCHED = 4e-2    # vs the operand-matched trunk (no forward flips between the two): measured 1.3 / 1.6 / 2.2e-2 on
+                           # the B200 (gpurun_out/lpips_trunk_errors.txt, round 2) -- the remaining flips are those of
+                           # the accumulation order; cuDNN's own TF32 path sits at 1.5 / 4.8 / 3.0e-2 from its fp32 path
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "lpips_trunk_errors.txt")
 
 

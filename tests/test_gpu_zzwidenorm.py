@@ -64,6 +64,7 @@ def test_generator_plan_fused_equals_default(monkeypatch):
     gen.cuda().eval()
     g = torch.Generator().manual_seed(1)
     y_hat = torch.round(torch.randn((4, 220, 16, 16), generator=g) * 2).cuda()
+    monkeypatch.setenv("HFC_FUSE_RESNORM", "0")
     with torch.no_grad():
         want = gen(y_hat)
     monkeypatch.setenv("HFC_FUSE_RESNORM", "1")
@@ -83,7 +84,7 @@ def test_generator_plan_fused_equals_default(monkeypatch):
     e_mut = ((got - want).norm() / want.norm()).item()
     print(f"generator rel-L2 vs oracle: default plan {e_def:.3e}, fused-norm plan {e_fus:.3e}; mutual {e_mut:.3e}")
     assert e_def < 1e-3 and e_fus < 1e-3 and e_mut < 1e-3
-    monkeypatch.delenv("HFC_FUSE_RESNORM")
+    monkeypatch.setenv("HFC_FUSE_RESNORM", "0")
     gen._plans.clear()
     with torch.no_grad():
         l0 = ops.launch_count()

@@ -108,3 +108,44 @@ def test_whole_training_step_on_cpu():
     assert worst(m.Hyperprior, "Hyperprior.")[1] < 0.1
     assert worst(m.Encoder, "Encoder.")[1] < 0.3
     assert worst(m.Generator, "Generator.")[1] < 0.3
+
+
+def test_backward_arithmetic_at_the_products_own_forward_state_cpu():
+    """CPU twin (kernel emulation) of tests/test_gpu_train.py::test_backward_arithmetic_at_the_products_own_forward_state:
+    with the oracle teacher-forced onto the product's forward state the emulated fp16-operand backward agrees with fp32
+    autograd to < 2e-3 per tensor (bf16 operands: < 1.5e-2) -- the bound the GPU test holds the real kernels to."""
+    import logging
+    from emulation import train_step_cpu_emulation
+    from hific_b200.config import mse_lpips_args
+    from hific_b200.grad import GRAD_BF16
+    from hific_b200.model import Model
+    from tools import grad_precision as GP
+    tol = 1.5e-2 if GRAD_BF16 else 2e-3
+    n_res = 1
+    cfg = mse_lpips_args()
+    cfg.n_residual_blocks = n_res
+    sd2 = synth.synth_state_dict(0, n_residual_blocks=n_res)
+    m = Model(cfg, logging.getLogger("forced-cpu"))
+    m.load_state_dict(sd2, strict=True)
+    m.train()
+    g = torch.Generator().manual_seed(11)
+    yh = torch.round(2 * torch.randn(1, 220, 8, 8, generator=g))
+    upx = torch.randn(1, 3, 128, 128, generator=g)
+    with train_step_cpu_emulation():
+        def gen():
+            yc = yh.clone().requires_grad_(True)
+            xh = m.Generator(yc)
+            plan = m.Generator._train_plans.get(yc)
+            zs = {"init": GP.rows_to_nchw(plan.z_init, 1, 8, 8, 960)}
+            for k, (z1, z2) in enumerate(plan.zr):
+                zs[("r", k, 0)], zs[("r", k, 1)] = GP.rows_to_nchw(z1, 1, 8, 8, 960), GP.rows_to_nchw(z2, 1, 8, 8, 960)
+            for i, (z, lay) in enumerate(zip(plan.zu, plan.ups)):
+                zs[("u", i + 1)] = GP.rows_to_nchw(z, 1, lay.oh, lay.ow, lay.cout)
+            (xh * upx).sum().backward()
+            return xh.detach(), yc.grad, zs
+        r = GP.study("Generator", m.Generator, "Generator.", sd2, gen,
+                     lambda s, t, rr: O.generator_forward(s, t, n_residual_blocks=n_res, rnd=rr), [yh], upx,
+                     forced=lambda s, t, zs, rr: GP.forced_generator(s, t, n_res, zs, rr))
+    f = r["forced"]
+    assert f["forward_rel_l2"] < 1e-4 and f["worst_tensor_rel_l2"] < tol and f["input_grad_rel_l2"] < tol, f
+    assert r["fp32"]["worst_tensor_rel_l2"] > 3 * f["worst_tensor_rel_l2"]      # the flips, not the arithmetic, dominate

@@ -12,7 +12,9 @@ KEEP = ("Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dra
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
         "launch__cluster_size", "launch__shared_mem_per_block_dynamic", "sm__inst_executed_pipe_lsu.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu.sum", "smsp__cycles_active.avg")
+        "l1tex__data_bank_conflicts_pipe_lsu.sum", "smsp__cycles_active.avg",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed")
 
 
 def main():
