@@ -33,6 +33,12 @@ static constexpr int kBlockK = 64;                       // 64 x 16-bit = one 12
 static constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
 static constexpr int kEpiThreads = 256;                  // 8 epilogue warps (2 per TMEM lane quadrant)
 static constexpr int kThreads = 64 + kEpiThreads;        // + TMA producer warp + MMA issuer warp
+// "thin" instantiation (narrow N, big maps: the layers whose time is the epilogue): 16 epilogue warps = 4 groups of 4, one
+// group per accumulator stage, 4 stages of 128 TMEM columns
+static constexpr int kThinEpiThreads = 512;
+static constexpr int kThinThreads = 64 + kThinEpiThreads;
+static constexpr int kThinAccStages = 4;
+static constexpr int kThinAccStride = 128;
 static constexpr int kMaxTaps = 64;
 static constexpr int kAccStride = 256;                   // TMEM columns per accumulator stage
 static constexpr int kTmemCols = 512;
@@ -40,7 +46,7 @@ static constexpr int kMaxStages = 8;
 static constexpr int kParamStride = 256;                 // floats per epilogue parameter row (>= block_n)
 static constexpr int kTailBytes = 256 + 2 * 3 * kParamStride * 4 + 2 * 512 * 4;  // barriers + parameter rows + stats exchange
 static constexpr int kTapnLd = 33;                       // padded row pitch (floats) of the tap-in-N staging tile
-static constexpr int kTapnBytes = 2 * kBlockM * kTapnLd * 4;  // double-buffered [128][33] fp32
+static constexpr int kTapnBytes = 2 * kBlockM * kTapnLd * 4;  // double-buffered [128][33] fp32 (thin: one per group, x2)
 
 struct ConvKernelParams {
   int32_t tw, th, tn;                 // tile extents, tw*th*tn <= 128 (rows past the product are idle)
@@ -58,6 +64,7 @@ struct ConvKernelParams {
   int32_t a_split_n;                  // A slice split: 1 = along the batch dim of the box, 0 = along rows
   int32_t tapn, w_step;               // 'tap-in-N' mode (tiny cout): N = kw*cout, shifted sum in the epilogue;
                                       // tiles advance by w_step = 128-kw+1 output pixels
+  int32_t thin;                       // host only: launch the thin instantiation (16 epilogue warps, 4 accumulator stages)
   int32_t dbg;                        // debugging bits (env HFC_DBG): 1 skip stores, 2 skip norm stats, 4 skip epilogue body
   int32_t wide_boff;                  // debugging: set the descriptor base-offset field for shifted starts
   int32_t winflat;                    // window packing served from a PLAIN pixel segment (un-swizzled descriptor with
@@ -117,7 +124,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // cross-warp exchange, no named barrier) and frees the TMEM stage right after the load -- for the big-map 60-channel layers
 // whose tiles are epilogue-latency-bound (E1 355 us, G.up4 384 us against ~50 us of HBM time).  Own instantiation.
 template <bool kPair, int kNsub, bool kWideNorm = false, bool kThin = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThin ? kThinThreads : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ ConvKernelParams p) {
@@ -133,11 +140,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_res + w_res_bytes);
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + kMaxStages;       // [stages]
-  uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint64_t* wfull_bar = tempty_bar + 2;          // [1] resident weights landed (wide mode)
-  uint64_t* xchg_bar = bars + 24;                // [1] statistics of the peer CTA landed (norm == 2)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [4] (2 used outside the thin instantiation)
+  uint64_t* tempty_bar = tfull_bar + 4;          // [4]
+  uint64_t* wfull_bar = tempty_bar + 4;          // [1] resident weights landed (wide mode)
+  uint64_t* xchg_bar = bars + 25;                // [1] statistics of the peer CTA landed (norm == 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   float* s_par = reinterpret_cast<float*>(bars + 32);  // [2][3][kParamStride] bias / gamma / beta
   float* s_red = s_par + 2 * 3 * kParamStride;         // [2 acc stages][2 (sum, ssq)][2 warps][128 rows]
   float* s_tapn = s_red + 2 * 512;                     // [2 acc stages][128][kTapnLd] (tap-in-N mode only)
@@ -166,9 +173,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // arrivals that free a stage: one commit per CTA (pair: per pair leader) that reads what lands here
       mbar_init(&empty_bar[s], static_cast<uint32_t>(kPair ? p.cn : p.cm + p.cn - 1));
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < (kThin ? kThinAccStages : 2); ++s) {
       mbar_init(&tfull_bar[s], 1);
-      // pair mode: the leader's MMA warp waits for the epilogue warps of BOTH CTAs
+      // pair mode: the leader's MMA warp waits for the epilogue warps of BOTH CTAs; thin: the 4 warps of the stage's group
       mbar_init(&tempty_bar[s], kThin ? 4u : (kPair ? 2 : 1) * (kEpiThreads / 32));
     }
     mbar_init(wfull_bar, 1);
@@ -323,7 +330,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int ct = cid; ct < total_ctiles; ct += ncl) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * kAccStride;
+      const uint32_t d_tmem = tmem_base + as * (kThin ? kThinAccStride : kAccStride);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
@@ -362,7 +369,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == (kThin ? kThinAccStages : 2)) { as = 0; aph ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -370,22 +377,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // chunks, so every scheduler has two epilogue warps to interleave (a lone warp issues one dependent
     // instruction every ~5 cycles, which made the 128-wide epilogues the bottleneck of the big-map layers).
     if constexpr (kThin) {
+      // Thin epilogue: 16 warps = 4 groups x 4 TMEM lane quadrants.  Group g owns accumulator stage g and the work items
+      // it % 4 == g, so FOUR tiles are in their epilogue at any time (the generic epilogue below puts all its warps on
+      // one tile: ~1 200 dependent instructions per warp and tile at two warps per scheduler made E1 / G.up4 / G3
+      // 3.5 us per tile, profiles/r02_ncu_bigmap_layers.json).  Thread == pixel; the ChannelNorm statistics are an
+      // in-thread one-pass shifted sum over the row in TMEM, the second pass re-reads TMEM, normalises and stores: no
+      // cross-warp exchange, no CTA-wide barrier.  Per-channel parameters come from shared memory as ld.shared.v4.
       const int q = warp & 3;            // TMEM lane quadrant this warp may access
-      const int grp = (warp - 2) >> 2;   // epilogue group == the accumulator stage it serves (items alternate stages)
+      const int grp = (warp - 2) >> 2;   // epilogue group == accumulator stage
       const int m = q * 32 + lane;
       const int et = threadIdx.x - 64;
       float* s_bias_raw = s_par + 3 * kParamStride;            // tap-in-N: bias per output channel (cout <= 32 there)
-      for (int i = et; i < p.block_n; i += kEpiThreads) {     // one N tile: parameters staged once
+      for (int i = et; i < p.block_n; i += kThinEpiThreads) {  // one N tile: parameters staged once
         const bool real = i < p.cout;
         s_bias_raw[i] = (real && p.bias) ? __ldg(p.bias + i) : 0.f;
         s_par[i] = (real && p.bias && !p.tapn) ? __ldg(p.bias + i) : 0.f;
         s_par[kParamStride + i] = (real && p.norm) ? __ldg(p.gamma + i) : 0.f;
         s_par[2 * kParamStride + i] = (real && p.norm) ? __ldg(p.beta + i) : 0.f;
       }
-      asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-      const float* s_bias = s_par;
-      const float* s_gamma = s_par + kParamStride;
-      const float* s_beta = s_par + 2 * kParamStride;
+      asm volatile("bar.sync 1, %0;\n" ::"n"(kThinEpiThreads) : "memory");
+      const uint32_t sp_bias = smem_u32(s_par), sp_gamma = sp_bias + kParamStride * 4, sp_beta = sp_bias + 2 * kParamStride * 4;
+      auto lds4 = [](uint32_t addr) {
+        float4 r;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+        return r;
+      };
       const int twi_in = m % p.tw;
       const int thi_in = (m / p.tw) % p.th;
       const int tni_in = m / (p.tw * p.th);
@@ -394,8 +410,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const float inv_c = 1.f / static_cast<float>(p.cout);
       int it = 0;
       for (int ct = cid; ct < total_ctiles; ct += ncl, ++it) {
-        if ((it & 1) != grp) continue;
-        const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+        if ((it & (kThinAccStages - 1)) != grp) continue;
+        const uint32_t aph = static_cast<uint32_t>(it / kThinAccStages) & 1u;
         int mt = (ct / n_groups) * p.cm + m_idx;
         const int twi = mt % p.tiles_w;
         mt /= p.tiles_w;
@@ -410,19 +426,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                            (ow < p.out_w) && (!p.tapn || m < p.w_step);
         mbar_wait(&tfull_bar[grp], aph);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + grp * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-        uint32_t v[4][16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (16 * c < p.block_n) tmem_ld16(t_row + 16 * c, v[c]);
-        tmem_ld_wait();
-        tc_fence_before();                 // the row is in registers: hand the accumulator stage back to the MMA warp
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+        const uint32_t t_row = tmem_base + grp * kThinAccStride + (static_cast<uint32_t>(q * 32) << 16);
         if (p.tapn) {
           // 'tap-in-N' (7x7 60 -> 3 head): column t*cout + co of pixel row m is the partial product of filter column t;
-          // out[w][co] = bias[co] + sum_t D[w + t][t*cout + co].  The group stages its tile in ITS half of s_tapn and
-          // synchronises on its own named barrier, so the two groups work on two tiles at the same time.
+          // out[w][co] = bias[co] + sum_t D[w + t][t*cout + co].  The group stages its tile in ITS quarter of s_tapn and
+          // synchronises on its own named barrier; the accumulator stage is free as soon as the row is in registers.
+          uint32_t v[2][16];
+          tmem_ld16(t_row, v[0]);
+          if (p.block_n > 16) tmem_ld16(t_row + 16, v[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[grp]);
           float* st = s_tapn + grp * (kBlockM * kTapnLd);
 #pragma unroll
           for (int c = 0; c < 2; ++c)
@@ -430,53 +445,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
               for (int j = 0; j < 16; ++j) st[m * kTapnLd + 16 * c + j] = __uint_as_float(v[c][j]);
             }
-          if (grp == 0) asm volatile("bar.sync 3, 128;\n" ::: "memory");
-          else asm volatile("bar.sync 4, 128;\n" ::: "memory");
+          asm volatile("bar.sync %0, 128;\n" ::"r"(3 + grp) : "memory");
           if (valid) {
             float* dst = reinterpret_cast<float*>(p.out);
             const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
             for (int co = 0; co < p.cout; ++co) {
-              float acc = p.bias ? s_bias_raw[co] : 0.f;
+              float acc = s_bias_raw[co];
               for (int t = 0; t < p.kw; ++t) acc += st[(m + t) * kTapnLd + t * p.cout + co];
               dst[(static_cast<size_t>(n) * p.cout + co) * plane + static_cast<size_t>(oh) * p.out_w + ow] =
                   apply_act(acc, p.act);
             }
           }
           // the next tile of this group overwrites the staging buffer: everyone must be done reading it
-          if (grp == 0) asm volatile("bar.sync 3, 128;\n" ::: "memory");
-          else asm volatile("bar.sync 4, 128;\n" ::: "memory");
+          asm volatile("bar.sync %0, 128;\n" ::"r"(3 + grp) : "memory");
           continue;
         }
-        // in place: v holds the bit patterns of x = acc + bias, then of the normalised values
-#define HFC_X(c, j) __uint_as_float(v[c][j])
+        // ---- pass 1: ChannelNorm statistics, one pass with shifted sums (shift = the row's first channel), the padding
+        // columns (acc = bias = 0, d = -shift) removed analytically
+        float mean = 0.f, rstd = 1.f;
+        if (p.norm) {
+          uint32_t va[16];
+          tmem_ld16(t_row, va);
+          tmem_ld_wait();
+          const float shift = __uint_as_float(va[0]) + lds4(sp_bias).x;
+          float sd0 = 0.f, sd1 = 0.f, sq0 = 0.f, sq1 = 0.f;
+          for (int c0 = 0; c0 < p.block_n; c0 += 16) {        // (the other three warps of this scheduler hide the TMEM latency)
+            if (c0) {
+              tmem_ld16(t_row + c0, va);
+              tmem_ld_wait();
+            }
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[c][j] = (16 * c < p.block_n) ? __float_as_uint(HFC_X(c, j) + s_bias[16 * c + j]) : 0u;
-        if (p.norm) {                      // two-pass mean / unbiased variance over the real channels, all in registers
-          float sum = 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (16 * c + j < p.cout) sum += HFC_X(c, j);
-          const float mean = sum * inv_c;
-          float ssq = 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (16 * c + j < p.cout) { const float dlt = HFC_X(c, j) - mean; ssq = fmaf(dlt, dlt, ssq); }
-          const float rstd = rsqrtf(ssq / static_cast<float>(p.cout - 1) + p.eps);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (16 * c < p.block_n)   // padding columns: gamma = beta = 0 -> exactly 0
-                v[c][j] = __float_as_uint(fmaf(s_gamma[16 * c + j] * rstd, HFC_X(c, j) - mean, s_beta[16 * c + j]));
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = lds4(sp_bias + 4 * (c0 + 4 * j4));
+              const float d0 = (__uint_as_float(va[4 * j4 + 0]) + b4.x) - shift;
+              const float d1 = (__uint_as_float(va[4 * j4 + 1]) + b4.y) - shift;
+              const float d2 = (__uint_as_float(va[4 * j4 + 2]) + b4.z) - shift;
+              const float d3 = (__uint_as_float(va[4 * j4 + 3]) + b4.w) - shift;
+              sd0 += d0; sd1 += d1; sd0 += d2; sd1 += d3;
+              sq0 = fmaf(d0, d0, sq0); sq1 = fmaf(d1, d1, sq1); sq0 = fmaf(d2, d2, sq0); sq1 = fmaf(d3, d3, sq1);
+            }
+          }
+          const float npad = static_cast<float>(p.block_n - p.cout);
+          const float sd = (sd0 + sd1) + npad * shift;
+          const float sq = (sq0 + sq1) - npad * shift * shift;
+          const float mean_d = sd * inv_c;
+          mean = shift + mean_d;
+          rstd = rsqrtf(fmaxf(sq - sd * mean_d, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
         }
-        if (!valid) continue;
+        // ---- pass 2: re-read the row, normalise, activate, store (NHWC fp16, with the reflected border of the next conv)
         int rows[3], cols[3];
         int nr = 0, nc = 0;
         rows[nr++] = oh + p.out_pt;
@@ -487,29 +503,62 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (ow >= 1 && ow <= p.out_pl) cols[nc++] = p.out_pl - ow;
           if (ow <= p.out_w - 2 && ow >= p.out_w - 1 - p.out_pr) cols[nc++] = p.out_pl + 2 * (p.out_w - 1) - ow;
         }
-        for (int ri = 0; ri < nr; ++ri)
-          for (int ci = 0; ci < nc; ++ci) {
-            __half* dst = reinterpret_cast<__half*>(p.out) +
-                          ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) * p.out_cpad;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              if (16 * c >= p.block_n || 16 * c >= p.out_cpad) continue;
-              uint4 lo, hi;
-              lo.x = pack_half2(apply_act(HFC_X(c, 0), p.act), apply_act(HFC_X(c, 1), p.act));
-              lo.y = pack_half2(apply_act(HFC_X(c, 2), p.act), apply_act(HFC_X(c, 3), p.act));
-              lo.z = pack_half2(apply_act(HFC_X(c, 4), p.act), apply_act(HFC_X(c, 5), p.act));
-              lo.w = pack_half2(apply_act(HFC_X(c, 6), p.act), apply_act(HFC_X(c, 7), p.act));
-              hi.x = pack_half2(apply_act(HFC_X(c, 8), p.act), apply_act(HFC_X(c, 9), p.act));
-              hi.y = pack_half2(apply_act(HFC_X(c, 10), p.act), apply_act(HFC_X(c, 11), p.act));
-              hi.z = pack_half2(apply_act(HFC_X(c, 12), p.act), apply_act(HFC_X(c, 13), p.act));
-              hi.w = pack_half2(apply_act(HFC_X(c, 14), p.act), apply_act(HFC_X(c, 15), p.act));
-              reinterpret_cast<uint4*>(dst + 16 * c)[0] = lo;
-              if (16 * c + 8 < p.out_cpad) reinterpret_cast<uint4*>(dst + 16 * c)[1] = hi;
+        if (!valid) nr = 0;
+        __half* dst0 = reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + rows[0]) * Wp + cols[0]) * p.out_cpad;
+        const bool interior = nr == 1 && nc == 1;
+        {
+          uint32_t v[16];
+          for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+            tmem_ld16(t_row + c0, v);
+            tmem_ld_wait();
+            if (c0 + 16 >= p.block_n) {      // the last chunk is in registers: hand the accumulator stage back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[grp]);
             }
-            for (int c = p.block_n; c < p.out_cpad; c += 8)      // channel padding the N tile does not cover
-              *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+            float f[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = lds4(sp_bias + 4 * (c0 + 4 * j4));
+              float x0 = __uint_as_float(v[4 * j4 + 0]) + b4.x, x1 = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+              float x2 = __uint_as_float(v[4 * j4 + 2]) + b4.z, x3 = __uint_as_float(v[4 * j4 + 3]) + b4.w;
+              if (p.norm) {
+                const float4 g4 = lds4(sp_gamma + 4 * (c0 + 4 * j4));
+                const float4 e4 = lds4(sp_beta + 4 * (c0 + 4 * j4));
+                x0 = fmaf(g4.x * rstd, x0 - mean, e4.x); x1 = fmaf(g4.y * rstd, x1 - mean, e4.y);
+                x2 = fmaf(g4.z * rstd, x2 - mean, e4.z); x3 = fmaf(g4.w * rstd, x3 - mean, e4.w);
+              }
+              f[4 * j4 + 0] = apply_act(x0, p.act); f[4 * j4 + 1] = apply_act(x1, p.act);
+              f[4 * j4 + 2] = apply_act(x2, p.act); f[4 * j4 + 3] = apply_act(x3, p.act);
+            }
+            if (nr == 0 || c0 >= p.out_cpad) continue;
+            uint4 lo, hi;
+            lo.x = pack_half2(f[0], f[1]);   lo.y = pack_half2(f[2], f[3]);
+            lo.z = pack_half2(f[4], f[5]);   lo.w = pack_half2(f[6], f[7]);
+            hi.x = pack_half2(f[8], f[9]);   hi.y = pack_half2(f[10], f[11]);
+            hi.z = pack_half2(f[12], f[13]); hi.w = pack_half2(f[14], f[15]);
+            const bool two = c0 + 8 < p.out_cpad;
+            if (interior) {
+              reinterpret_cast<uint4*>(dst0 + c0)[0] = lo;
+              if (two) reinterpret_cast<uint4*>(dst0 + c0)[1] = hi;
+            } else {
+              for (int ri = 0; ri < nr; ++ri)
+                for (int ci = 0; ci < nc; ++ci) {
+                  __half* dst = reinterpret_cast<__half*>(p.out) +
+                                ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) * p.out_cpad + c0;
+                  reinterpret_cast<uint4*>(dst)[0] = lo;
+                  if (two) reinterpret_cast<uint4*>(dst)[1] = hi;
+                }
+            }
           }
-#undef HFC_X
+        }
+        if (nr)
+          for (int c = p.block_n; c < p.out_cpad; c += 8)        // channel padding the N tile does not cover
+            for (int ri = 0; ri < nr; ++ri)
+              for (int ci = 0; ci < nc; ++ci)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) +
+                                          ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) * p.out_cpad + c) =
+                    make_uint4(0, 0, 0, 0);
       }
     } else {
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
@@ -1311,12 +1360,24 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
     kp->tx_short = kp->winflat ? kABytes - (kBlockM + 7) * 16 : 0;
     free_tile = false;
   }
+  // Thin instantiation (conv_igemm_kernel<false, 1, false, true>): one N tile of <= 64 columns (tap-in-N: <= 32) on a
+  // map big enough that the launch is a long stream of tiny tiles -- the epilogue-bound layers E1, G.up4, G3.  Single
+  // CTAs (no pair / cluster: the K loops are short), 4 accumulator stages.  HFC_THIN_EPILOGUE=0 disables it,
+  // HFC_THIN_EPILOGUE=2 also takes one-N-tile layers up to 128 columns (E2, G.up3).
+  static const int env_thin = getenv("HFC_THIN_EPILOGUE") ? atoi(getenv("HFC_THIN_EPILOGUE")) : 1;
+  {
+    const long long px = static_cast<long long>(batch) * ph.grid_h * ph.grid_w;
+    const int n_max = env_thin >= 2 ? 128 : 64;
+    kp->thin = (env_thin >= 1 && !widenorm && !kp->wide && pl.n_tiles == 1 && px >= 148LL * 128 * 16 &&
+                (pl.tapn ? (d->out_mode == HFC_OUT_NCHW_F32 && pl.block_n <= 32)
+                         : (d->out_mode == HFC_OUT_NHWC_F16 && pl.block_n <= n_max && d->norm != 2))) ? 1 : 0;
+  }
   kp->tiles_w = pl.tapn ? (ph.grid_w + (kBlockM - d->kw + 1) - 1) / (kBlockM - d->kw + 1)
                         : (ph.grid_w + kp->tw - 1) / kp->tw;
   kp->tiles_h = (ph.grid_h + kp->th - 1) / kp->th;
   kp->tiles_n = (batch + kp->tn - 1) / kp->tn;
   int stage_bytes = kABytes + pl.block_n * kBlockK * 2;
-  int budget = 226 * 1024 - 1024 - kTailBytes - (pl.tapn ? kTapnBytes : 0);
+  int budget = 226 * 1024 - 1024 - kTailBytes - (pl.tapn ? (kp->thin ? 2 : 1) * kTapnBytes : 0);
   if (kp->wide) {
     kp->a_region = ((kBlockM + d->kw - 1) * kBlockK * 2 + 1023) / 1024 * 1024;
     stage_bytes = kp->a_region;
@@ -1337,7 +1398,7 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
     cm = (cm == 0) ? ((big && tiles_m % 2 == 0) ? 2 : 1) : cm;
   }
   if (cm < 1 || cm > 2 || cn < 1 || cn > 2) return -1;
-  if (kp->wide || pl.tapn || kp->winflat) cm = cn = 1;
+  if (kp->wide || pl.tapn || kp->winflat || kp->thin) cm = cn = 1;
   if (free_tile) cn = 1;                 // the multicast A slices assume a full 128-row tile
   if ((pl.block_n / cm) % 8 != 0 || pl.block_n % cm != 0) cm = 1;
   kp->a_split_n = 0;
@@ -1632,7 +1693,7 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     const int max_clusters = csize == 4 ? (sm_count * 132 / 148) / 4 : sm_count / csize;
     const int grid = std::min(ctiles, std::max(1, max_clusters)) * csize;
     const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 /*align*/ + kTailBytes +
-                        (kp.tapn ? kTapnBytes : 0) + (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
+                        (kp.tapn ? (kp.thin ? 2 : 1) * kTapnBytes : 0) + (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, 1>,
@@ -1656,7 +1717,7 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kp.thin ? kThinThreads : kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1666,11 +1727,8 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    // thin epilogue (opt-in, HFC_THIN_EPILOGUE=1): single-CTA MMA, one N tile of <= 64 columns, NHWC fp16 output
-    static const bool env_thin = getenv("HFC_THIN_EPILOGUE") != nullptr && getenv("HFC_THIN_EPILOGUE")[0] == '1';
-    const bool thin = env_thin && !wn && !kp.pair && kp.cn == 1 && kp.n_tiles == 1 && kp.block_n <= 64 && !kp.wide &&
-                      kp.k_splits == 1 &&
-                      (kp.tapn ? (d->out_mode == HFC_OUT_NCHW_F32 && kp.block_n <= 32) : d->out_mode == HFC_OUT_NHWC_F16);
+    const bool thin = kp.thin && !wn && !kp.pair && kp.cn == 1 && kp.cm == 1 && kp.k_splits == 1;
+    if (kp.thin && !thin) return set_error(HFC_ERR_INVALID, "conv: internal: thin plan with a pair / cluster launch");
     cudaError_t e = thin ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1, false, true>, tmA, tmB, kp)
                     : wn ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, 2, true>, tmA, tmB, kp)
                     : !kp.pair ? cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, 1>, tmA, tmB, kp)

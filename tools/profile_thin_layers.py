@@ -31,9 +31,10 @@ def timed(name, fn, reps=int(os.environ.get('HFC_REPS', 5))):
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
-    print(f"{name}: {sorted(ts)[len(ts) // 2]:.1f} us (thin epilogue {'on' if os.environ.get('HFC_THIN_EPILOGUE') == '1' else 'off'})")
+    print(f"{name}: {sorted(ts)[len(ts) // 2]:.1f} us (HFC_THIN_EPILOGUE={os.environ.get('HFC_THIN_EPILOGUE', '1 (default)')})")
 
 
+THIN = os.environ.get("HFC_THIN_EPILOGUE", "1 (default)")
 enc = EncoderPlan(B, 256, 256, 3, 220, dev)
 x_act = (torch.rand(enc.g_in.shape, device=dev) - 0.5).half()
 w1 = torch.randn(60, 3, 7, 7, device=dev) * 0.05
@@ -51,3 +52,14 @@ a5 = (torch.randn(gen.conv_out.in_geom.shape, device=dev) * 0.5).half()
 w5 = torch.randn(3, 60, 7, 7, device=dev) * 0.02
 b5 = torch.randn(3, device=dev)
 timed("G3   7x7 60->3 (tap-in-N)", lambda: gen.conv_out(a5, w5, b5))
+
+# the two N = 128 layers of the same kind (one N tile, big maps): thin only with HFC_THIN_EPILOGUE=2
+a1 = (torch.randn(enc.convs[1].in_geom.shape, device=dev) * 0.5).half()
+w2 = torch.randn(120, 60, 3, 3, device=dev) * 0.04
+b2, g2, be2 = torch.randn(120, device=dev), torch.rand(120, device=dev) + 0.5, torch.randn(120, device=dev)
+timed("E2   3x3 s2 60->120 +CN+ReLU", lambda: enc.convs[1](a1, w2, b2, g2, be2, out=enc.bufs[1]))
+conv3, _, out3, _ = gen.ups[2]
+a3 = (torch.randn(conv3.in_geom.shape, device=dev) * 0.5).half()
+w3 = torch.randn(240, 120, 3, 3, device=dev) * 0.02
+b3, g3, be3 = torch.randn(120, device=dev), torch.rand(120, device=dev) + 0.5, torch.randn(120, device=dev)
+timed("G.up3 convT 240->120 +CN+ReLU (4 phases)", lambda: conv3(a3, w3, b3, g3, be3, out=out3))
