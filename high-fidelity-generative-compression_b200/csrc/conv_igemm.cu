@@ -44,7 +44,8 @@ static constexpr int kAccStride = 256;                   // TMEM columns per acc
 static constexpr int kTmemCols = 512;
 static constexpr int kMaxStages = 8;
 static constexpr int kParamStride = 256;                 // floats per epilogue parameter row (>= block_n)
-static constexpr int kTailBytes = 256 + 2 * 3 * kParamStride * 4 + 2 * 512 * 4;  // barriers + parameter rows + stats exchange
+static constexpr int kMaxKb = 512;                       // K blocks per tile the producer's coordinate table holds
+static constexpr int kTailBytes = 256 + 2 * 3 * kParamStride * 4 + 2 * 512 * 4 + kMaxKb * 4;  // barriers + parameter rows + stats exchange + K-block table
 static constexpr int kTapnLd = 33;                       // padded row pitch (floats) of the tap-in-N staging tile
 static constexpr int kTapnBytes = 2 * kBlockM * kTapnLd * 4;  // double-buffered [128][33] fp32 (thin: one per group, x2)
 
@@ -65,6 +66,8 @@ struct ConvKernelParams {
   int32_t tapn, w_step;               // 'tap-in-N' mode (tiny cout): N = kw*cout, shifted sum in the epilogue;
                                       // tiles advance by w_step = 128-kw+1 output pixels
   int32_t thin;                       // host only: launch the thin instantiation (16 epilogue warps, 4 accumulator stages)
+  int32_t b_res;                      // thin: ALL weight K blocks of the (single) N tile stay resident in smem (loaded once
+                                      // per CTA); the ring then carries A tiles only -- one TMA per K block instead of two
   int32_t dbg;                        // debugging bits (env HFC_DBG): 1 skip stores, 2 skip norm stats, 4 skip epilogue body
   int32_t wide_boff;                  // debugging: set the descriptor base-offset field for shifted starts
   int32_t winflat;                    // window packing served from a PLAIN pixel segment (un-swizzled descriptor with
@@ -133,10 +136,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int b_bytes = p.b_rows * kBlockK * 2;
-  const int stage_bytes = p.wide ? p.a_region : kABytes + kNsub * b_bytes;
-  // wide mode: every weight sub-tile (num_kb * kw of them) stays resident behind the A ring
+  const int stage_bytes = p.wide ? p.a_region : (p.b_res ? kABytes : kABytes + kNsub * b_bytes);
+  // wide mode: every weight sub-tile (num_kb * kw of them) stays resident behind the A ring; b_res: every K block
   uint8_t* w_res = smem + p.stages * stage_bytes;
-  const int w_res_bytes = p.wide ? p.num_kb * p.kw * b_bytes : 0;
+  const int w_res_bytes = p.wide ? p.num_kb * p.kw * b_bytes : (p.b_res ? p.num_kb * b_bytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_res + w_res_bytes);
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + kMaxStages;       // [stages]
@@ -147,7 +150,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   float* s_par = reinterpret_cast<float*>(bars + 32);  // [2][3][kParamStride] bias / gamma / beta
   float* s_red = s_par + 2 * 3 * kParamStride;         // [2 acc stages][2 (sum, ssq)][2 warps][128 rows]
-  float* s_tapn = s_red + 2 * 512;                     // [2 acc stages][128][kTapnLd] (tap-in-N mode only)
+  uint32_t* s_kbt = reinterpret_cast<uint32_t*>(s_red + 2 * 512);   // [num_kb] producer table: chunk | dw << 16 | dh << 24
+  float* s_tapn = s_red + 2 * 512 + kMaxKb;           // [2 acc stages][128][kTapnLd] (tap-in-N mode only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -231,7 +235,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
-      } else
+      }
+    }
+    if (!p.wide) {
+      // The whole warp walks the loop (warp-uniform control flow and operands; one elected lane issues).  The first version
+      // ran it on lane 0 alone with the tap / chunk bookkeeping and two constant-bank table look-ups per K block: ~130
+      // dependent single-thread instructions = ~0.45 us per K BLOCK (ncu, profiles/r02_ncu_bigmap_thin.json: the
+      // epilogue warps of E1 sat in the accumulator-full wait 62 % of the time) -- 3.3 us per tile for the 7-block tiles
+      // of E1 / G3 and as long as the MMAs of one K block of the 960-channel residual convolution.  Now the per-K-block
+      // coordinates come from a table built once per CTA.
+      if (!p.gemm)
+        for (int kb = lane; kb < p.num_kb; kb += 32) {
+          const int tap = kb / p.c_chunks, chunk = kb - tap * p.c_chunks;
+          s_kbt[kb] = static_cast<uint32_t>(chunk) | (static_cast<uint32_t>(static_cast<uint8_t>(p.tap_dw[tap])) << 16) |
+                      (static_cast<uint32_t>(static_cast<uint8_t>(p.tap_dh[tap])) << 24);
+        }
+      __syncwarp();
+      if (p.b_res && elect_one()) {            // (n_tiles == 1, no cluster: checked on the host)
+        mbar_arrive_expect_tx(wfull_bar, static_cast<uint32_t>(w_res_bytes));
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(w_res + kb * b_bytes, &tmap_b, wfull_bar, kb * kBlockK, 0);
+      }
+      __syncwarp();
+      int s = 0;
+      uint32_t ph = 0;
+      const int a_slice_bytes = kABytes / p.cn;
+      const int b_slice_rows = p.block_n / p.cm;
+      const uint32_t tx_bytes = static_cast<uint32_t>(kPair ? 2 * (stage_bytes - p.tx_short) : stage_bytes - p.tx_short);
+      const uint32_t kbt_addr = smem_u32(s_kbt);
+      const bool use_table = !p.gemm;
       for (int ct = cid; ct < total_ctiles; ct += ncl) {
         const int ks = ct % p.k_splits;          // K split (gemm mode), else 0
         const int ctile = ct / p.k_splits;
@@ -245,40 +276,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // my slice of the shared A tile: rows [n_idx*128/cn, (n_idx+1)*128/cn)
         const int h_base = (thi * p.th + (p.a_split_n ? 0 : n_idx * (p.th / p.cn))) * p.sh + p.ih0;
         const int n_base = tni * p.tn + (p.a_split_n ? n_idx * (p.tn / p.cn) : 0);
-        int tap = 0, chunk = ks * p.kb_per_split;   // split-K only exists with a single tap (gemm mode)
-        const int kb0 = ks * p.kb_per_split;
+        const int kb0 = ks * p.kb_per_split;     // split-K only exists with a single tap (gemm mode)
+        const int b_row = kPair ? nt * p.block_n + m_idx * p.b_rows : nt * p.block_n;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
+          int c0 = (kb0 + kb) * kBlockK, cw = w_base, chh = h_base;
+          if (use_table) {
+            uint32_t e;
+            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(e) : "r"(kbt_addr + 4u * static_cast<uint32_t>(kb)));
+            c0 = static_cast<int>(e & 0xffffu) * kBlockK;
+            cw += static_cast<int8_t>(e >> 16);
+            chh += static_cast<int8_t>(e >> 24);
+          }
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + kABytes;
-          if constexpr (kPair) {
-            // both CTAs of the pair fill their own stage; all bytes are accounted on the LEADER's barrier
-            if (m_idx == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * (stage_bytes - p.tx_short)));
-            if (p.cn > 1)
-              tma_load_4d_pair_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], chunk * kBlockK,
-                                  w_base + p.tap_dw[tap], h_base + p.tap_dh[tap], n_base, mask_a);
-            else
-              tma_load_4d_pair(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
-                               h_base + p.tap_dh[tap], n_base);
-            for (int j = 0; j < kNsub; ++j)
-              tma_load_2d_pair(sb + j * b_bytes, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK,
-                               (nt + j) * p.block_n + m_idx * p.b_rows);
-            if (p.gemm) ++chunk; else if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
-            if (++s == p.stages) { s = 0; ph ^= 1; }
-            continue;
+          if (elect_one()) {
+            if constexpr (kPair) {
+              // both CTAs of the pair fill their own stage; all bytes are accounted on the LEADER's barrier
+              if (m_idx == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+              if (p.cn > 1)
+                tma_load_4d_pair_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], c0, cw, chh, n_base, mask_a);
+              else
+                tma_load_4d_pair(sa, &tmap_a, &full_bar[s], c0, cw, chh, n_base);
+#pragma unroll
+              for (int j = 0; j < kNsub; ++j)
+                tma_load_2d_pair(sb + j * b_bytes, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, b_row + j * p.block_n);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+              if (csize > 1) {
+                tma_load_4d_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], c0, cw, chh, n_base, mask_a);
+                tma_load_2d_mc(sb + m_idx * b_slice_rows * (kBlockK * 2), &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK,
+                               nt * p.block_n + m_idx * b_slice_rows, mask_b);
+              } else {
+                tma_load_4d(sa, &tmap_a, &full_bar[s], c0, cw, chh, n_base);
+                if (!p.b_res) tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, b_row);
+              }
+            }
           }
-          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes - p.tx_short));
-          if (csize > 1) {
-            tma_load_4d_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], chunk * kBlockK,
-                           w_base + p.tap_dw[tap], h_base + p.tap_dh[tap], n_base, mask_a);
-            tma_load_2d_mc(sb + m_idx * b_slice_rows * (kBlockK * 2), &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK,
-                           nt * p.block_n + m_idx * b_slice_rows, mask_b);
-          } else {
-            tma_load_4d(sa, &tmap_a, &full_bar[s], chunk * kBlockK, w_base + p.tap_dw[tap],
-                        h_base + p.tap_dh[tap], n_base);
-            tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, nt * p.block_n);
-          }
-          if (p.gemm) ++chunk; else if (++chunk == p.c_chunks) { chunk = 0; ++tap; }
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -326,7 +361,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
-    if (p.wide) mbar_wait(wfull_bar, 0);
+    if (p.wide || p.b_res) mbar_wait(wfull_bar, 0);
     for (int ct = cid; ct < total_ctiles; ct += ncl) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
@@ -356,7 +391,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // winflat: K = 16 covers two pixels of the window -> the start moves by 2 x 16 B per step, as it does (by
           // 32 B) inside the 128 B swizzle row of the regular layout
           const uint64_t a_desc = p.winflat ? make_nosw_window_desc(a_addr) : make_sw128_kmajor_desc(a_addr);
-          const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
+          const uint64_t b_desc = make_sw128_kmajor_desc(p.b_res ? smem_u32(w_res) + static_cast<uint32_t>(kb * b_bytes)
+                                                                   : a_addr + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4)
@@ -1366,9 +1402,11 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   // HFC_THIN_EPILOGUE=2 also takes one-N-tile layers up to 128 columns (E2, G.up3).
   static const int env_thin = getenv("HFC_THIN_EPILOGUE") ? atoi(getenv("HFC_THIN_EPILOGUE")) : 1;
   {
-    const long long px = static_cast<long long>(batch) * ph.grid_h * ph.grid_w;
+    // the choice depends on the map size of ONE image only, never on the batch: a sample's result must not depend on
+    // its batch neighbours bit for bit (tests/test_gpu_parity.py), and the two epilogues sum the statistics in a
+    // different order
     const int n_max = env_thin >= 2 ? 128 : 64;
-    kp->thin = (env_thin >= 1 && !widenorm && !kp->wide && pl.n_tiles == 1 && px >= 148LL * 128 * 16 &&
+    kp->thin = (env_thin >= 1 && !widenorm && !kp->wide && pl.n_tiles == 1 && ph.grid_h * ph.grid_w >= 4096 &&
                 (pl.tapn ? (d->out_mode == HFC_OUT_NCHW_F32 && pl.block_n <= 32)
                          : (d->out_mode == HFC_OUT_NHWC_F16 && pl.block_n <= n_max && d->norm != 2))) ? 1 : 0;
   }
@@ -1378,6 +1416,16 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   kp->tiles_n = (batch + kp->tn - 1) / kp->tn;
   int stage_bytes = kABytes + pl.block_n * kBlockK * 2;
   int budget = 226 * 1024 - 1024 - kTailBytes - (pl.tapn ? (kp->thin ? 2 : 1) * kTapnBytes : 0);
+  {
+    // thin layers: the whole weight matrix of the N tile (num_kb x block_n x 128 B) stays in smem when it fits in 72 KB
+    static const bool env_no_bres = getenv("HFC_NO_BRES") != nullptr;
+    const int w_all = ph.ntaps * pl.c_chunks * pl.block_n * kBlockK * 2;
+    kp->b_res = (kp->thin && !env_no_bres && w_all <= 72 * 1024) ? 1 : 0;
+    if (kp->b_res) {
+      stage_bytes = kABytes;
+      budget -= w_all;
+    }
+  }
   if (kp->wide) {
     kp->a_region = ((kBlockM + d->kw - 1) * kBlockK * 2 + 1023) / 1024 * 1024;
     stage_bytes = kp->a_region;
@@ -1612,6 +1660,9 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     kp.c_chunks = pl.c_chunks;
     kp.ntaps = ph.ntaps;
     kp.num_kb = kp.wide ? d->kh : ph.ntaps * pl.c_chunks;
+    if (kp.num_kb > kMaxKb)
+      return set_error(HFC_ERR_UNSUPPORTED, "conv: %d K blocks per tile (taps x 64-channel chunks) exceed the %d the producer's table holds",
+                       kp.num_kb, kMaxKb);
     kp.grid_h = ph.grid_h; kp.grid_w = ph.grid_w; kp.batch = ig.n;
     kp.sh = ph.sh; kp.sw = ph.sw;
     kp.ih0 = ig.pt; kp.iw0 = ig.pl;
@@ -1693,7 +1744,8 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     const int max_clusters = csize == 4 ? (sm_count * 132 / 148) / 4 : sm_count / csize;
     const int grid = std::min(ctiles, std::max(1, max_clusters)) * csize;
     const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + 1024 /*align*/ + kTailBytes +
-                        (kp.tapn ? (kp.thin ? 2 : 1) * kTapnBytes : 0) + (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
+                        (kp.tapn ? (kp.thin ? 2 : 1) * kTapnBytes : 0) +
+                        (kp.b_res ? static_cast<size_t>(kp.num_kb) * pl.block_n * kBlockK * 2 : 0) + (kp.wide ? static_cast<size_t>(kp.num_kb) * kp.kw * pl.block_n * kBlockK * 2 : 0);
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, 1>,

@@ -503,7 +503,7 @@ extern "C" int hfc_channelnorm(const float* x, int32_t ld, const hfc_act_geom* g
 
 static int likelihood_variant() {
   const char* v = getenv("HFC_LIKELIHOOD_V");
-  return (v && v[0] >= '1' && v[0] <= '3') ? v[0] - '0' : HFC_LIKELIHOOD_DEFAULT_VARIANT;
+  return (v && v[0] >= '1' && v[0] <= '4') ? v[0] - '0' : HFC_LIKELIHOOD_DEFAULT_VARIANT;
 }
 
 extern "C" int hfc_latent_likelihood(const float* y, const float* mean, const float* scale_raw,
@@ -521,9 +521,19 @@ extern "C" int hfc_latent_likelihood(const float* y, const float* mean, const fl
   // double-buffered loads) -- measured at c2 / c5 sizes with a cold L2 (profiles/r01_likelihood_ab.json): schedule 1
   // 20.5 / 49.2 us, schedule 2 16.4 / 36.9 us, schedule 3 14.3 / 35.8 us.  HFC_LIKELIHOOD_V=1|2|3 selects one explicitly.
   const int variant = likelihood_variant();
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(scale_raw) |
+                           reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(decoded)) & 15) == 0;
+  if (likelihood_type == 0 && variant == 4 && aligned16) {
+    rc = launch_latent_likelihood_bulk(y, mean, scale_raw, noise, count, scale_lower_bound, decoded, sums,
+                                       static_cast<cudaStream_t>(stream));
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "latent_likelihood (bulk) launch: %s", cudaGetErrorString(e2));
+    note_launch();
+    return rc;
+  }
   if (likelihood_type == 0 && variant >= 2) {
     rc = launch_latent_likelihood_v2(y, mean, scale_raw, noise, count, scale_lower_bound, decoded, sums, sms,
-                                     variant == 3, static_cast<cudaStream_t>(stream));
+                                     variant >= 3, static_cast<cudaStream_t>(stream));
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "latent_likelihood (v2) launch: %s", cudaGetErrorString(e2));
     note_launch();

@@ -23,5 +23,8 @@ void note_launch();
 int launch_latent_likelihood_v2(const float* y, const float* mean, const float* scale_raw, const float* noise,
                                 int64_t count, float lb, float* decoded, double* sums, int sms, bool prefetch,
                                 cudaStream_t st);
+// Schedule 4: inputs staged by cp.async.bulk (16-byte aligned pointers only).
+int launch_latent_likelihood_bulk(const float* y, const float* mean, const float* scale_raw, const float* noise,
+                                  int64_t count, float lb, float* decoded, double* sums, cudaStream_t st);
 
 }  // namespace hfc

@@ -61,7 +61,7 @@ def inputs(shape, seed, scale=2.0):
 
 @pytest.mark.parametrize("shape", [(4, 220, 16, 16), (32, 220, 16, 16), (1, 3, 5, 7), (1, 1, 1, 2), (3, 7, 11, 13)])
 @pytest.mark.parametrize("with_noise", [True, False])
-@pytest.mark.parametrize("schedule", [2, 3])
+@pytest.mark.parametrize("schedule", [2, 3, 4])
 def test_schedule2_matches_float64_and_schedule1(shape, with_noise, schedule):
     y, mu, sraw, noise = inputs(shape, seed=sum(shape))
     if not with_noise:
@@ -85,7 +85,7 @@ def test_schedule2_matches_float64_and_schedule1(shape, with_noise, schedule):
         assert sums2[0].item() == 0.0
 
 
-@pytest.mark.parametrize("schedule", [2, 3])
+@pytest.mark.parametrize("schedule", [2, 3, 4])
 def test_schedule2_far_tails_and_tiny_scales(schedule):
     """|y - mu| up to 1e4 at scale 0.11 (p underflows to the 1e-9 bound), large scales (p ~ 4e-3 from the difference of two values near 1), exact half-integers."""
     g = torch.Generator().manual_seed(3)
