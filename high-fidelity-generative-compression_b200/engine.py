@@ -98,38 +98,47 @@ class EncoderPlan:
 class GeneratorPlan:
     FILTERS = (960, 480, 240, 120, 60)
 
-    def __init__(self, n, h, w, C, n_residual_blocks, im_channels, device):
+    def __init__(self, n, h, w, C, n_residual_blocks, im_channels, device, noise_dim=0):
         f = self.FILTERS
         self.n_res = n_residual_blocks
+        # sample_noise (generator.py:105-107, 149-153): noise_dim channels of N(0, 1) noise are concatenated to the
+        # 960-channel head, and the residual trunk + the first transposed conv are F0 = 960 + noise_dim channels wide
+        self.noise_dim = noise_dim
+        F0 = f[0] + noise_dim
+        self.F0 = F0
+        F0p = round_up(F0, 64)
         b1 = (1, 1, 1, 1)
         self.g_in = Geom(n, h, w, C, round_up(C, 64), *b1)
         self.in_act = self.g_in.alloc(device)
         rows960 = Geom(n, h, w, 960, 960)
-        self.g_b1 = Geom(n, h, w, 960, 960, *b1)      # bordered (input of a 3x3 reflect conv)
-        self.g_flat = Geom(n, h, w, 960, 960)         # border-less (input of the first transposed conv)
+        rows_t = Geom(n, h, w, F0, F0)
+        self.g_head = Geom(n, h, w, 960, 960, *b1)
+        self.g_b1 = Geom(n, h, w, F0, F0p, *b1)       # bordered (input of a 3x3 reflect conv)
+        self.g_flat = Geom(n, h, w, F0, F0p)          # border-less (input of the first transposed conv)
         self.conv_init = Conv(self.g_in, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows960)
         # one Conv object per residual conv so each keeps its own packed weights
-        self.res_convs = [(Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows960),
-                           Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows960))
+        self.res_convs = [(Conv(self.g_b1, F0, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows_t),
+                           Conv(self.g_b1, F0, 3, pad_mode=PAD_REFLECT, pad=b1, out_mode=OUT_NHWC_F32, out_geom=rows_t))
                           for _ in range(n_residual_blocks)]
-        # default (HFC_FUSE_RESNORM=0 restores the two-launch plan): every residual conv runs fused with the ChannelNorm (+ReLU / + residual adds) behind it
-        # (hfc_conv_forward_widenorm: the 960-channel row of a pixel is normalised across a 4-CTA cluster), which removes
-        # the stand-alone ChannelNorm launch and the fp32 round trip of the conv output.  Opt-in: not yet run on hardware.
+        # default (HFC_FUSE_RESNORM=0 restores the two-launch plan): every residual conv runs fused with the ChannelNorm
+        # (+ReLU / + residual adds) behind it (hfc_conv_forward_widenorm: the 960-channel row of a pixel is normalised
+        # across a 4-CTA cluster), which removes the stand-alone ChannelNorm launch and the fp32 round trip of the conv
+        # output.  Geometries the fused kernel does not take (ragged maps, the 992-channel noise variant) use two launches.
         self.fused = None
-        if os.environ.get("HFC_FUSE_RESNORM", "1") == "1" and n_residual_blocks > 0:
+        if os.environ.get("HFC_FUSE_RESNORM", "1") == "1" and n_residual_blocks > 0 and F0 == F0p:
             fused = []
             for i in range(n_residual_blocks):
                 last = i == n_residual_blocks - 1
-                c1 = Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_geom=self.g_b1, out_reflect=True, act=ACT_RELU)
-                c2 = Conv(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1, out_geom=self.g_flat if last else self.g_b1,
+                c1 = Conv(self.g_b1, F0, 3, pad_mode=PAD_REFLECT, pad=b1, out_geom=self.g_b1, out_reflect=True, act=ACT_RELU)
+                c2 = Conv(self.g_b1, F0, 3, pad_mode=PAD_REFLECT, pad=b1, out_geom=self.g_flat if last else self.g_b1,
                           out_reflect=not last, act=ACT_NONE)
                 fused.append((c1, c2))
             if all(c.widenorm_supported() for pair in fused for c in pair):
                 self.fused = fused
         m = n * h * w
-        self.rows = torch.empty((m, 960), dtype=torch.float32, device=device)
-        self.head_f32 = torch.empty((m, 960), dtype=torch.float32, device=device)
-        self.x_f32 = [torch.empty((m, 960), dtype=torch.float32, device=device) for _ in range(2)]
+        self.rows = torch.empty((m, F0), dtype=torch.float32, device=device)
+        self.head_f32 = torch.empty((m, F0), dtype=torch.float32, device=device)
+        self.x_f32 = [torch.empty((m, F0), dtype=torch.float32, device=device) for _ in range(2)]
         self.act_a = self.g_b1.alloc(device)
         self.act_b = self.g_b1.alloc(device)
         self.act_flat = self.g_flat.alloc(device)
@@ -157,9 +166,21 @@ class GeneratorPlan:
         init = mod.conv_block_init
         ops.nchw_to_act(y_hat, self.g_in, reflect=True, norm=True, gamma=init[0].gamma, beta=init[0].beta,
                         out=self.in_act)
-        self.conv_init(self.in_act, init[2].weight, init[2].bias, out=self.rows)
-        ops.channelnorm(self.rows, self.g_b1, init[3].gamma, init[3].beta, act=ACT_NONE, reflect=True,
-                        want_f32=True, out_f32=self.head_f32, out_act=self.act_a)
+        if self.noise_dim == 0:
+            self.conv_init(self.in_act, init[2].weight, init[2].bias, out=self.rows)
+            ops.channelnorm(self.rows, self.g_b1, init[3].gamma, init[3].beta, act=ACT_NONE, reflect=True,
+                            want_f32=True, out_f32=self.head_f32, out_act=self.act_a)
+        else:
+            # head = cat(norm(conv(.)), z), z ~ N(0, 1) drawn with torch.randn as the reference does (generator.py:150-153):
+            # pure data movement on a (B, 992, 16, 16) tensor, done with torch ops
+            n, hh, ww = self.g_b1.n, self.g_b1.h, self.g_b1.w
+            rows960 = self.conv_init(self.in_act, init[2].weight, init[2].bias)
+            _, head960 = ops.channelnorm(rows960, self.g_head, init[3].gamma, init[3].beta, act=ACT_NONE, reflect=False,
+                                         want_f32=True, want_act=False)
+            z = torch.randn((n, self.noise_dim, hh, ww)).to(head960)
+            head = torch.cat((head960.view(n, hh, ww, 960).permute(0, 3, 1, 2), z), dim=1).contiguous()
+            self.head_f32.copy_(head.permute(0, 2, 3, 1).reshape(-1, self.F0))
+            ops.nchw_to_act(head, self.g_b1, reflect=True, out=self.act_a)
         x_f32, x_act = self.head_f32, self.act_a
         for m in range(self.n_res if self.fused is not None else 0):
             blk = getattr(mod, f"resblock_{m}")

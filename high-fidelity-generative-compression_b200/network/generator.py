@@ -9,7 +9,7 @@ from ..normalisation.channel import ChannelNorm2D
 
 
 class ResidualBlock(nn.Module):
-    """Parameter holder for one residual block (conv1, conv2, norm1, norm2 -- generator.py:9-44)."""
+    """One residual block (conv1, conv2, norm1, norm2 -- generator.py:9-44)."""
 
     def __init__(self, input_dims, kernel_size=3, stride=1, channel_norm=True, activation='relu'):
         super().__init__()
@@ -20,9 +20,23 @@ class ResidualBlock(nn.Module):
         self.conv2 = nn.Conv2d(c, c, kernel_size, stride=stride)
         self.norm1 = ChannelNorm2D(c)
         self.norm2 = ChannelNorm2D(c)
+        self._plans = engine.PlanCache(lambda x: train_plan.ResidualBlockTrainPlan(x.shape[0], x.shape[2], x.shape[3],
+                                                                                   x.shape[1], x.device))
+
+    def _apply(self, fn, *a, **k):
+        self._plans.clear()
+        return super()._apply(fn, *a, **k)
 
     def forward(self, x):
-        raise NotImplementedError("ResidualBlock runs fused inside hific_b200 Generator.forward")
+        """generator.py:33-44 for a stand-alone call (inside Generator.forward the blocks run in the Generator's plans)."""
+        engine._require_cuda(x, "ResidualBlock")
+        plan = self._plans.get(x)
+        if engine.wants_grad(self, x):
+            return train_plan.run_training(plan, x, list(self.parameters()))
+        with torch.no_grad():
+            out = plan.forward(x.contiguous(), [q.detach() for q in self.parameters()])
+            plan.release()
+        return out
 
 
 class Generator(nn.Module):
@@ -31,15 +45,17 @@ class Generator(nn.Module):
         super().__init__()
         if activation != 'relu' or channel_norm is not True:
             raise NotImplementedError("hific_b200.Generator implements the HiFIC default (ReLU + ChannelNorm)")
-        if sample_noise:
-            raise NotImplementedError("sample_noise=True is a non-default variant (SURVEY.md 8f) not built yet")
-        filters = engine.GeneratorPlan.FILTERS
+        filters = list(engine.GeneratorPlan.FILTERS)
         self.C, self.n_residual_blocks = C, n_residual_blocks
         self.sample_noise, self.noise_dim = sample_noise, noise_dim
+        trunk_noise = noise_dim if sample_noise else 0
         self.n_upsampling_layers = 4
         self.conv_block_init = nn.Sequential(ChannelNorm2D(C), nn.ReflectionPad2d(1),
                                              nn.Conv2d(C, filters[0], kernel_size=(3, 3), stride=1),
                                              ChannelNorm2D(filters[0]))
+        self._trunk_noise = trunk_noise
+        if sample_noise is True:
+            filters[0] += noise_dim                      # generator.py:105-107: the trunk carries the noise channels too
         for m in range(n_residual_blocks):
             self.add_module(f"resblock_{m}", ResidualBlock((batch_size, filters[0], 0, 0)))
         for i in range(1, 5):
@@ -48,11 +64,11 @@ class Generator(nn.Module):
         self.conv_block_out = nn.Sequential(nn.ReflectionPad2d(3), nn.Conv2d(filters[-1], 3, kernel_size=(7, 7), stride=1))
         self._plans = engine.PlanCache(self._make_plan)
         self._train_plans = engine.PlanCache(lambda y: train_plan.GeneratorTrainPlan(
-            y.shape[0], y.shape[2], y.shape[3], self.C, self.n_residual_blocks, 3, y.device))
+            y.shape[0], y.shape[2], y.shape[3], self.C, self.n_residual_blocks, 3, y.device, noise_dim=self._trunk_noise))
 
     def _make_plan(self, y):
         n, _, h, w = y.shape
-        return engine.GeneratorPlan(n, h, w, self.C, self.n_residual_blocks, 3, y.device)
+        return engine.GeneratorPlan(n, h, w, self.C, self.n_residual_blocks, 3, y.device, noise_dim=self._trunk_noise)
 
     def _apply(self, fn, *a, **k):
         self._plans.clear()

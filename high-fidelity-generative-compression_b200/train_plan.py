@@ -177,15 +177,19 @@ class EncoderTrainPlan:
 class GeneratorTrainPlan:
     FILTERS = (960, 480, 240, 120, 60)
 
-    def __init__(self, n, h, w, C, n_res, im_channels, device):
+    def __init__(self, n, h, w, C, n_res, im_channels, device, noise_dim=0):
         f = self.FILTERS
         self.n, self.h, self.w, self.C, self.n_res = n, h, w, C, n_res
+        # sample_noise (generator.py:105-107, 149-153): the trunk is F0 = 960 + noise_dim channels wide
+        self.noise_dim, self.F0 = noise_dim, f[0] + noise_dim
+        F0, F0p = self.F0, round_up(self.F0, 64)
         b1 = (1, 1, 1, 1)
         self.g_in = Geom(n, h, w, C, round_up(C, 64), *b1)
-        self.g_b1 = Geom(n, h, w, 960, 960, *b1)
-        self.g_flat = Geom(n, h, w, 960, 960)
+        self.g_head = Geom(n, h, w, 960, 960)
+        self.g_b1 = Geom(n, h, w, F0, F0p, *b1)
+        self.g_flat = Geom(n, h, w, F0, F0p)
         self.init = Layer(self.g_in, 960, 3, pad_mode=PAD_REFLECT, pad=b1)
-        self.res = [(Layer(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1), Layer(self.g_b1, 960, 3, pad_mode=PAD_REFLECT, pad=b1))
+        self.res = [(Layer(self.g_b1, F0, 3, pad_mode=PAD_REFLECT, pad=b1), Layer(self.g_b1, F0, 3, pad_mode=PAD_REFLECT, pad=b1))
                     for _ in range(n_res)]
         self.ups, self.up_geoms = [], []
         g = self.g_flat
@@ -206,7 +210,17 @@ class GeneratorTrainPlan:
         self.y_rows = nchw_to_rows(y_hat)
         a0, _ = norm_fwd(self.y_rows, self.g_in, p[0], p[1], ACT_NONE, True)
         self.z_init = self.init.forward(a0, p[2], p[3])
-        x_act, head = norm_fwd(self.z_init, self.g_b1 if R else self.g_flat, p[4], p[5], ACT_NONE, bool(R), want_f32=True)
+        if self.noise_dim == 0:
+            x_act, head = norm_fwd(self.z_init, self.g_b1 if R else self.g_flat, p[4], p[5], ACT_NONE, bool(R), want_f32=True)
+        else:
+            # head = cat(norm(conv(.)), z), z ~ N(0, 1) (generator.py:150-153): data movement with torch ops; the noise
+            # channels carry no gradient back
+            _, head960 = ops.channelnorm(self.z_init, self.g_head, p[4], p[5], act=ACT_NONE, reflect=False, want_f32=True,
+                                         want_act=False)
+            z = torch.randn((self.n, self.noise_dim, self.h, self.w)).to(head960)
+            hn = torch.cat((head960.view(self.n, self.h, self.w, 960).permute(0, 3, 1, 2), z), dim=1).contiguous()
+            head = hn.permute(0, 2, 3, 1).reshape(-1, self.F0).contiguous()
+            x_act = ops.nchw_to_act(hn, self.g_b1 if R else self.g_flat, reflect=bool(R))
         self.zr = []
         x_f32 = head
         for m in range(R):
@@ -257,6 +271,8 @@ class GeneratorTrainPlan:
             g = g + gx                                  # identity_map + residual branch (generator.py:44)
         if R:
             g_head = g_head + g                         # block 0 consumed head; the final `x += head` added it again
+        if self.noise_dim:
+            g_head = g_head[:, :960].contiguous()       # the noise channels of the head are constants
         dz0, grads[4], grads[5], db0 = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE)
         ga0, grads[2], grads[3] = self.init.backward(dz0, p[2], db=db0)
         dy_rows, grads[0], grads[1], _ = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE, as_operand=False)
@@ -265,6 +281,45 @@ class GeneratorTrainPlan:
 
     def release(self):
         self.zr = self.zu = self.z_init = self.y_rows = None
+
+
+class ResidualBlockTrainPlan:
+    """One ResidualBlock.forward (src/network/generator.py:33-44) called on its own: pad, conv, norm, ReLU, pad, conv,
+    norm, + identity.  Serves both the no-grad call and autograd (PlanFunction); inside Generator.forward the blocks run
+    as part of the Generator plans instead.  Parameter order: conv1 (w, b), conv2 (w, b), norm1 (g, b), norm2 (g, b)."""
+
+    def __init__(self, n, h, w, c, device):
+        self.n, self.h, self.w, self.c = n, h, w, c
+        b1 = (1, 1, 1, 1)
+        self.g_b1 = Geom(n, h, w, c, round_up(c, 64), *b1)
+        self.g_flat = Geom(n, h, w, c, round_up(c, 64))
+        self.c1 = Layer(self.g_b1, c, 3, pad_mode=PAD_REFLECT, pad=b1)
+        self.c2 = Layer(self.g_b1, c, 3, pad_mode=PAD_REFLECT, pad=b1)
+
+    def forward(self, x, p):
+        w1, bb1, w2, bb2, g1, be1, g2, be2 = p
+        x_rows = nchw_to_rows(x)
+        x_act = ops.nchw_to_act(x, self.g_b1, reflect=True)
+        self.z1 = self.c1.forward(x_act, w1, bb1)
+        a1, _ = norm_fwd(self.z1, self.g_b1, g1, be1, ACT_RELU, True)
+        self.z2 = self.c2.forward(a1, w2, bb2)
+        _, out = ops.channelnorm(self.z2, self.g_flat, g2, be2, act=ACT_NONE, reflect=False, res1=x_rows, want_f32=True,
+                                 want_act=False)
+        return rows_to_nchw(out, self.n, self.c, self.h, self.w)
+
+    def backward(self, dout, p):
+        w1, bb1, w2, bb2, g1, be1, g2, be2 = p
+        grads = [None] * 8
+        g = nchw_to_rows(dout)
+        dz2, grads[6], grads[7], db2 = norm_bwd(self.z2, g, g2, be2, ACT_NONE)
+        ga1, grads[2], grads[3] = self.c2.backward(dz2, w2, db=db2)
+        dz1, grads[4], grads[5], db1 = norm_bwd(self.z1, ga1, g1, be1, ACT_RELU)
+        gx, grads[0], grads[1] = self.c1.backward(dz1, w1, db=db1)
+        _grad.emit(*grads)
+        return rows_to_nchw(g[:, :self.c] + gx[:, :self.c], self.n, self.c, self.h, self.w), grads
+
+    def release(self):
+        self.z1 = self.z2 = None
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -93,7 +93,9 @@ def residual_block(sd, prefix, x, rnd=_ident):
     return res + x
 
 
-def generator_forward(sd, y_hat, n_residual_blocks=9, prefix="Generator.", rnd=_ident, taps=None):
+def generator_forward(sd, y_hat, n_residual_blocks=9, prefix="Generator.", rnd=_ident, taps=None, noise=None):
+    """`noise`: the (B, noise_dim, H, W) draw of the `sample_noise=True` variant (generator.py:149-153), concatenated to
+    the head; None = the default architecture."""
     p = prefix
     # conv_block_init: ChannelNorm, ReflectionPad2d(1), Conv 3x3, ChannelNorm    (generator.py:98-103)
     head = _cn(sd, p + "conv_block_init.0", y_hat)
@@ -101,6 +103,8 @@ def generator_forward(sd, y_hat, n_residual_blocks=9, prefix="Generator.", rnd=_
     head = _cn(sd, p + "conv_block_init.3", head)
     if taps is not None:
         taps["G0"] = head
+    if noise is not None:
+        head = torch.cat((head, noise.to(head)), dim=1)
     x = head
     for m in range(n_residual_blocks):                                           # generator.py:154-159
         x = residual_block(sd, p + f"resblock_{m}", x, rnd=rnd)

@@ -332,3 +332,35 @@ def test_compress_py_runs_unchanged_on_the_mirror(runs, monkeypatch):
                 a, b = read(out), read(own)
                 psnr = 10 * np.log10(255.0 ** 2 / max(np.mean((a - b) ** 2), 1e-12))
                 assert psnr > 40.0, (dec_name, stem, psnr)     # same symbols; generator arithmetic differs (fp16 operands)
+
+
+def test_sample_noise_generator_against_the_real_reference():
+    """`sample_noise=True` (src/network/generator.py:105-107, 149-161): the real reference Generator, the oracle's
+    restatement (pinned here: identical) and the mirror (kernel emulation: fp16 operands) on the same weights and the
+    same noise draw; identical state_dict keys / shapes."""
+    _reference()
+    import src.network.generator as ref_generator
+    from hific_b200.network import generator as mirror_generator
+    from oracle import hific_oracle as O
+    torch.manual_seed(9)
+    ref = ref_generator.Generator((220, 8, 8), 2, C=220, n_residual_blocks=2, sample_noise=True, noise_dim=32)
+    mir = mirror_generator.Generator((220, 8, 8), 2, C=220, n_residual_blocks=2, sample_noise=True, noise_dim=32)
+    assert [(k, tuple(v.shape)) for k, v in ref.state_dict().items()] == [(k, tuple(v.shape)) for k, v in mir.state_dict().items()]
+    mir.load_state_dict(ref.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(10)
+    y_hat = torch.round(torch.randn((2, 220, 8, 8), generator=g) * 2)
+    z = torch.randn((2, 32, 8, 8), generator=g)
+    orig = torch.randn
+    torch.randn = lambda *a, **k: z.clone()
+    try:
+        with torch.no_grad():
+            want = ref(y_hat)
+            with E.plan_cpu_emulation():
+                got = mir.eval()(y_hat)
+    finally:
+        torch.randn = orig
+    sd = {"Generator." + k: v for k, v in ref.state_dict().items()}
+    with torch.no_grad():
+        orc = O.generator_forward(sd, y_hat, n_residual_blocks=2, noise=z)
+    assert torch.equal(orc, want)                                   # the oracle's noise variant is the reference's
+    assert float((got - want).norm() / want.norm()) < 1e-3

@@ -141,3 +141,89 @@ def test_generator_plan_with_fused_residual_norms(sd, monkeypatch):
             plan = gen._plans.get(y_hat)
         assert (plan.fused is not None) == fused
         assert rel_l2(x_hat, O.generator_forward(sd, y_hat)) < REL
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Non-default generator variants: sample_noise=True (992-channel trunk) and a stand-alone ResidualBlock
+# ----------------------------------------------------------------------------------------------------------------------
+class _FixedRandn:
+    """The plans draw the generator noise with torch.randn as the reference does (generator.py:151): feed a known draw."""
+
+    def __init__(self, noise):
+        self.noise = noise
+
+    def __enter__(self):
+        self._orig = torch.randn
+        torch.randn = lambda *a, **k: self.noise.clone()
+        return self
+
+    def __exit__(self, *e):
+        torch.randn = self._orig
+
+
+def _noise_generator(n_res=2):
+    torch.manual_seed(21)
+    gen = generator.Generator((220, 8, 8), 2, C=220, n_residual_blocks=n_res, sample_noise=True, noise_dim=32)
+    with torch.no_grad():
+        for name, p in gen.named_parameters():           # away from the identity initialisation of the norms
+            if "gamma" in name:
+                p.add_(0.1 * torch.randn(p.shape))
+            elif "beta" in name or "bias" in name:
+                p.add_(0.1 * torch.randn(p.shape))
+    sdg = {"Generator." + k: v.detach().clone() for k, v in gen.state_dict().items()}
+    return gen, sdg
+
+
+def test_generator_with_sample_noise_inference_and_training_plans():
+    from emulation import training_cpu_emulation
+    gen, sdg = _noise_generator()
+    g = torch.Generator().manual_seed(3)
+    y_hat = torch.round(torch.randn((2, 220, 8, 8), generator=g) * 2)
+    z = torch.randn((2, 32, 8, 8), generator=g)
+    want = O.generator_forward(sdg, y_hat, n_residual_blocks=2, noise=z)
+    gen.eval()
+    with torch.no_grad(), plan_cpu_emulation(), _FixedRandn(z):
+        got = gen(y_hat)
+    assert gen._plans.get(y_hat).fused is None and gen._plans.get(y_hat).F0 == 992
+    assert rel_l2(got, want) < REL
+    # training plan: every parameter gradient and the input gradient against autograd of the oracle
+    gen.train()
+    up = torch.randn(want.shape, generator=g)
+    yc = y_hat.clone().requires_grad_(True)
+    with training_cpu_emulation(), _FixedRandn(z):
+        out = gen(yc)
+        (out * up).sum().backward()
+    sd2 = {k: v.clone().requires_grad_(True) for k, v in sdg.items()}
+    yo = y_hat.clone().requires_grad_(True)
+    (O.generator_forward(sd2, yo, n_residual_blocks=2, noise=z) * up).sum().backward()
+    assert rel_l2(out.detach(), want) < REL
+    worst = max(rel_l2(p.grad, sd2["Generator." + k].grad) for k, p in gen.named_parameters())
+    assert worst < 5e-2 and rel_l2(yc.grad, yo.grad) < 5e-2, worst
+    assert gen.resblock_0.conv1.weight.shape == (992, 992, 3, 3) and gen.upconv_block1[0].weight.shape[0] == 992
+
+
+def test_residual_block_called_on_its_own():
+    from emulation import training_cpu_emulation
+    torch.manual_seed(5)
+    blk = generator.ResidualBlock((2, 128, 8, 8))
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(0.05 * torch.randn(p.shape))
+    sdb = {"b." + k: v.detach().clone() for k, v in blk.state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((2, 128, 8, 8), generator=g)
+    want = O.residual_block(sdb, "b", x)
+    with torch.no_grad(), plan_cpu_emulation():
+        blk.eval()
+        got = blk(x)
+    assert rel_l2(got, want) < REL
+    up = torch.randn(want.shape, generator=g)
+    xc = x.clone().requires_grad_(True)
+    blk.train()
+    with training_cpu_emulation():
+        (blk(xc) * up).sum().backward()
+    sd2 = {k: v.clone().requires_grad_(True) for k, v in sdb.items()}
+    xo = x.clone().requires_grad_(True)
+    (O.residual_block(sd2, "b", xo) * up).sum().backward()
+    assert max(rel_l2(p.grad, sd2["b." + k].grad) for k, p in blk.named_parameters()) < 3e-2
+    assert rel_l2(xc.grad, xo.grad) < 3e-2
