@@ -336,9 +336,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-            const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+          // operands are warp-uniform and computed by the whole warp; ONE elected lane issues.  (Inside `if (lane == 0)` the
+          // compiler cannot prove uniformity and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST retry loop: ~100
+          // cycles per MMA, i.e. as long as the MMAs of a K block themselves.)
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+          if (elect_one()) {
+#pragma unroll
             for (int j = 0; j < kNsub; ++j) {
               const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes + j * b_bytes);
 #pragma unroll
@@ -386,13 +390,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           umma_commit(&empty_bar[s]);
           if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);
-        } else if (lane == 0) {
+        } else if (!p.wide) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           // winflat: K = 16 covers two pixels of the window -> the start moves by 2 x 16 B per step, as it does (by
           // 32 B) inside the 128 B swizzle row of the regular layout
           const uint64_t a_desc = p.winflat ? make_nosw_window_desc(a_addr) : make_sw128_kmajor_desc(a_addr);
           const uint64_t b_desc = make_sw128_kmajor_desc(p.b_res ? smem_u32(w_res) + static_cast<uint32_t>(kb * b_bytes)
                                                                    : a_addr + kABytes);
+          if (elect_one()) {               // warp-uniform operands, one issuing lane (see the pair issuer)
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4)
@@ -401,6 +406,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (csize > 1) umma_commit_mc(&empty_bar[s], mask_e);
           else umma_commit(&empty_bar[s]);
           if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1; }

@@ -123,7 +123,12 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
   const int ncta = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // The whole warp walks the loop with warp-uniform operands and ONE elected lane issues (the first version ran it on lane
+    // 0 alone: three integer divisions per K block for the pixel-block coordinates and a divergent context in which every
+    // TMA operand went through an ELECT / R2UR.BROADCAST sequence -- ~1 000 cycles per K block against ~500-1 000 cycles
+    // of MMA work; same finding as in conv_igemm.cu, profiles/r02_ncu_bigmap_thin.json).  Coordinates advance
+    // incrementally.
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int it = cta0; it < total_items; it += ncta) {
@@ -134,34 +139,38 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
         const int mt = r / p.ntaps;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        int twi = kb0 % p.tiles_w, thi = (kb0 / p.tiles_w) % p.tiles_h, tni = kb0 / (p.tiles_w * p.tiles_h);
+        const int dw = p.tap_dw[tap], dh = p.tap_dh[tap];
         for (int kb = kb0; kb < kb1; ++kb) {
-          int t = kb;
-          const int twi = t % p.tiles_w; t /= p.tiles_w;
-          const int thi = t % p.tiles_h;
-          const int tni = t / p.tiles_h;
           const int gw = twi * p.bw, gh = thi * p.bh, gn = tni * p.bn;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + 2 * kWgChunkBytes;
-          const int sw0 = gw * p.stride + p.s_w0 + p.tap_dw[tap];
-          const int sh0 = gh * p.stride + p.s_h0 + p.tap_dh[tap];
-          if constexpr (kPair) {
-            // both CTAs fill their own stage; every byte is accounted on the LEADER's barrier
-            if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
-            for (int j = 0; j < 2; ++j)
-              tma_load_4d_pair(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 4 + crank * 2 + j) * 64, gw + p.p_w0,
-                               gh + p.p_h0, gn);
-            for (int js = 0; js < kNsub; ++js)
-              for (int j = 0; j < s_chunks; ++j)
-                tma_load_4d_pair(sb + (js * s_chunks + j) * kWgChunkBytes, &tmap_s, &full_bar[s],
-                                 ((nt + js) * p.nch + crank * s_chunks + j) * 64, sw0, sh0, gn);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>((p.p_chunks + p.nch) * kWgChunkBytes));
-            for (int j = 0; j < p.p_chunks; ++j)
-              tma_load_4d(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 2 + j) * 64, gw + p.p_w0, gh + p.p_h0, gn);
-            for (int j = 0; j < p.nch; ++j)
-              tma_load_4d(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], (nt * p.nch + j) * 64, sw0, sh0, gn);
+          const int sw0 = gw * p.stride + p.s_w0 + dw;
+          const int sh0 = gh * p.stride + p.s_h0 + dh;
+          if (elect_one()) {
+            if constexpr (kPair) {
+              // both CTAs fill their own stage; every byte is accounted on the LEADER's barrier
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(2 * stage_bytes));
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                tma_load_4d_pair(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 4 + crank * 2 + j) * 64, gw + p.p_w0,
+                                 gh + p.p_h0, gn);
+#pragma unroll
+              for (int js = 0; js < kNsub; ++js)
+                for (int j = 0; j < s_chunks; ++j)
+                  tma_load_4d_pair(sb + (js * s_chunks + j) * kWgChunkBytes, &tmap_s, &full_bar[s],
+                                   ((nt + js) * p.nch + crank * s_chunks + j) * 64, sw0, sh0, gn);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>((p.p_chunks + p.nch) * kWgChunkBytes));
+              for (int j = 0; j < p.p_chunks; ++j)
+                tma_load_4d(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 2 + j) * 64, gw + p.p_w0, gh + p.p_h0, gn);
+              for (int j = 0; j < p.nch; ++j)
+                tma_load_4d(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], (nt * p.nch + j) * 64, sw0, sh0, gn);
+            }
           }
+          __syncwarp();
+          if (++twi == p.tiles_w) { twi = 0; if (++thi == p.tiles_h) { thi = 0; ++tni; } }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -180,9 +189,9 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + 2 * kWgChunkBytes;
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);      // warp-uniform operands, one elected issuer
+        const uint32_t b_addr = a_addr + 2 * kWgChunkBytes;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // K = 16 pixels = 16 rows of 128 B = two 1024 B swizzle atoms per step
