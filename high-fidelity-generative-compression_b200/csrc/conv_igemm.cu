@@ -70,6 +70,9 @@ struct ConvKernelParams {
                                       // per CTA); the ring then carries A tiles only -- one TMA per K block instead of two
   int32_t dbg;                        // debugging bits (env HFC_DBG): 1 skip stores, 2 skip norm stats, 4 skip epilogue body
   int32_t wide_boff;                  // debugging: set the descriptor base-offset field for shifted starts
+  const uint8_t* a_base;              // winflat: the NHWC8 input buffer (bulk copies of contiguous pixel segments)
+  long long a_total_bytes;            // winflat: size of that buffer (copies are clamped to it)
+  int32_t a_wp, a_hp;                 // winflat: padded width / height of the input buffer
   int32_t winflat;                    // window packing served from a PLAIN pixel segment (un-swizzled descriptor with
                                       // overlapping rows) instead of an 8x inflated window tile; tile = 128 px of a row
   int32_t wide, kw;                   // 'wide' mode: row-resident A halo (128+kw-1 pixels), resident weights
@@ -307,6 +310,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tma_load_4d_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], c0, cw, chh, n_base, mask_a);
                 tma_load_2d_mc(sb + m_idx * b_slice_rows * (kBlockK * 2), &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK,
                                nt * p.block_n + m_idx * b_slice_rows, mask_b);
+              } else if (p.winflat) {
+                // one filter row of the tile = (128 + 7) CONTIGUOUS pixels of the NHWC8 image (16 B each): a 1-D bulk
+                // copy instead of a tensor-map box of 135 rows of 16 B (the TMA unit spends ~5 cycles per box row
+                // whatever its length: 0.39 us per K block of E1, profiles/r02_ncu_bigmap_v3.json).  The segment of the
+                // last tile of a row may run past the row (values feed masked pixels only); it is clamped to the buffer.
+                const long long off = ((static_cast<long long>(n_base) * p.a_hp + chh) * p.a_wp + cw) * 16;
+                // (the expected-transaction count was armed with the full segment: top up what the clamp removes)
+                long long nbytes = (kBlockM + 7) * 16;
+                if (off + nbytes > p.a_total_bytes) nbytes = p.a_total_bytes > off ? p.a_total_bytes - off : 0;
+                if (nbytes > 0) bulk_g2s(sa, p.a_base + off, static_cast<uint32_t>(nbytes), &full_bar[s]);
+                if (nbytes < (kBlockM + 7) * 16)
+                  asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full_bar[s])),
+                               "r"(static_cast<uint32_t>((kBlockM + 7) * 16 - nbytes)) : "memory");
+                if (!p.b_res) tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, b_row);
               } else {
                 tma_load_4d(sa, &tmap_a, &full_bar[s], c0, cw, chh, n_base);
                 if (!p.b_res) tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, b_row);
@@ -1686,6 +1703,9 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     kp.fmt_b = d->b_bf16 ? 1u : 0u;
     kp.bias = bias; kp.gamma = gamma; kp.beta = beta;
     kp.out = out;
+    kp.a_base = static_cast<const uint8_t*>(in);
+    kp.a_wp = Wp; kp.a_hp = Hp;
+    kp.a_total_bytes = static_cast<long long>(ig.n) * Hp * Wp * ig.cpad * 2;
     if (wn) {
       kp.norm = 2;
       kp.res1 = wn->res1; kp.res2 = wn->res2; kp.ld_res = wn->ld_res;

@@ -208,13 +208,6 @@ latent_likelihood_v2_kernel(const float* __restrict__ y, const float* __restrict
 // 5.5 us of traffic at peak).  One chunk of kBulkVec float4 per array and block; non-persistent grid.
 constexpr int kBulkVec = 768;                       // float4 per array per block: 12 KB x 4 arrays = 48 KB of smem
 
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 template <bool HAS_NOISE>
 __global__ void __launch_bounds__(256, 4)
 latent_likelihood_bulk_kernel(const float* __restrict__ y, const float* __restrict__ mean,

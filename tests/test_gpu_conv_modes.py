@@ -101,3 +101,65 @@ def test_cta_pair_two_n_tiles_per_item():
     # odd number of N-tile pairs is impossible (n_tiles must be even); 480 = 2 x 240 -> one group
     run_conv_case(32, 960, 16, 16, 480, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F32,
                   expect=dict(pair=1))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Non-default generator variants on the kernels: sample_noise=True (992-channel trunk: 1 024-pitch act
+# buffers, four N tiles of 248, the two-launch conv + ChannelNorm plan) and a stand-alone ResidualBlock
+# ----------------------------------------------------------------------------------------------------------------------
+def test_generator_with_sample_noise_and_standalone_residual_block():
+    from hific_b200.network import generator
+    from oracle import hific_oracle as O
+
+    def rel(a, b):
+        return float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm())
+    torch.manual_seed(21)
+    gen = generator.Generator((220, 8, 8), 2, C=220, n_residual_blocks=2, sample_noise=True, noise_dim=32)
+    with torch.no_grad():
+        for name, p in gen.named_parameters():
+            if "gamma" in name or "beta" in name or "bias" in name:
+                p.add_(0.1 * torch.randn(p.shape))
+    sdg = {"Generator." + k: v.detach().clone() for k, v in gen.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    y_hat = torch.round(torch.randn((2, 220, 8, 8), generator=g) * 2)
+    z = torch.randn((2, 32, 8, 8), generator=g)
+    up = torch.randn((2, 3, 128, 128), generator=g)
+    sd2 = {k: v.clone().requires_grad_(True) for k, v in sdg.items()}
+    yo = y_hat.clone().requires_grad_(True)
+    want = O.generator_forward(sd2, yo, n_residual_blocks=2, noise=z)
+    (want * up).sum().backward()
+    orig = torch.randn
+    torch.randn = lambda *a, **k: z.clone()
+    try:
+        gen.cuda().eval()
+        with torch.no_grad():
+            got = gen(y_hat.cuda())
+        assert rel(got, want.detach()) < 1.5e-3
+        gen.train()
+        yc = y_hat.cuda().requires_grad_(True)
+        out = gen(yc)
+        (out * up.cuda()).sum().backward()
+    finally:
+        torch.randn = orig
+    assert rel(out.detach(), want.detach()) < 1.5e-3
+    worst = max(rel(p.grad, sd2["Generator." + k].grad) for k, p in gen.named_parameters())
+    assert worst < 5e-2 and rel(yc.grad, yo.grad) < 5e-2, worst
+    # stand-alone block (generator.py:33-44), no-grad and autograd
+    blk = generator.ResidualBlock((2, 128, 8, 8))
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(0.05 * torch.randn(p.shape))
+    sdb = {"b." + k: v.detach().clone().requires_grad_(True) for k, v in blk.state_dict().items()}
+    x = torch.randn((2, 128, 8, 8), generator=g)
+    upb = torch.randn((2, 128, 8, 8), generator=g)
+    xo = x.clone().requires_grad_(True)
+    wb = O.residual_block(sdb, "b", xo)
+    (wb * upb).sum().backward()
+    blk.cuda().eval()
+    with torch.no_grad():
+        assert rel(blk(x.cuda()), wb.detach()) < 1.5e-3
+    blk.train()
+    xc = x.cuda().requires_grad_(True)
+    (blk(xc) * upb.cuda()).sum().backward()
+    assert max(rel(p.grad, sdb["b." + k].grad) for k, p in blk.named_parameters()) < 3e-2
+    assert rel(xc.grad, xo.grad) < 3e-2
