@@ -1,7 +1,8 @@
 """Multi-GPU plumbing of the training step (one process per GPU, torch.distributed): the HiFIC path is purely
 data-parallel (ChannelNorm is per pixel, no batch statistics), so ranks only exchange GRADIENTS -- one coalesced
-all-reduce of the stepped parameter group after backward (train.py has no DDP wrapper; north_star asks for "NCCL
-allreduce over NVLink for gradients only").  Backend-agnostic: NCCL on the GPUs, gloo in the CPU tests."""
+all-reduce of the stepped parameter group after backward (`allreduce_gradients`), or bucketed all-reduces issued from
+inside the backward (`InBackwardGradientReducer`; train.py has no DDP wrapper; north_star asks for "NCCL allreduce over
+NVLink for gradients only").  Backend-agnostic: NCCL on the GPUs, gloo in the CPU tests."""
 import torch
 
 
@@ -49,102 +50,10 @@ def max_over_ranks(value, device, dist=None):
     return t.item()
 
 
-class OverlappedGradientReducer:
-    """Gradient all-reduce overlapped with the rest of the backward pass ("bucketed, overlapped with
-    backward, issued from grad-ready hooks in reverse layer order").
-
-    The parameters are given as BUCKETS in the order their gradients complete (the networks of the hot path are one
-    autograd Function each, so a bucket per network: Generator first -- 157 M of the 181 M parameters --, then the
-    hyperprior, then the Encoder).  A post-accumulate-grad hook per parameter counts arrivals; when a bucket is
-    complete its gradients are flattened and all-reduced (mean) asynchronously on a communication stream while the
-    autograd engine keeps walking the remaining networks on the compute stream.  `finish()` -- called after
-    `backward()`, before the optimizer step -- launches whatever bucket did not complete (parameters the pass never
-    touched), waits for the collectives and scatters the averaged values back into the `.grad` tensors.
-
-    Every rank must build the reducer over the same buckets; the collectives are issued in bucket-completion order,
-    which is the same on every rank because every rank walks the same autograd graph.  Backend-agnostic: NCCL on the
-    GPUs (side stream + events), gloo in the CPU test (no streams)."""
-
-    def __init__(self, buckets, dist=None, world=None):
-        if dist is None:
-            import torch.distributed as dist
-        self.dist = dist
-        self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
-        self.buckets = [[p for p in b if p.requires_grad] for b in buckets]
-        self.buckets = [b for b in self.buckets if b]
-        self.bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
-        assert len(self.bucket_of) == sum(len(b) for b in self.buckets), "a parameter appears in two buckets"
-        self.remaining = [len(b) for b in self.buckets]
-        self.launched = [False] * len(self.buckets)
-        self.inflight = []                 # (work, flat, grads)
-        self.bytes_reduced = 0
-        self.enabled = True
-        self._comm = None
-        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for b in self.buckets for p in b]
-
-    def remove(self):
-        for h in self._handles:
-            h.remove()
-        self._handles = []
-
-    def _on_grad(self, p):
-        if not self.enabled or self.world == 1:
-            return
-        i = self.bucket_of[id(p)]
-        self.remaining[i] -= 1
-        if self.remaining[i] == 0 and not self.launched[i]:
-            self._launch(i)
-
-    def _launch(self, i):
-        self.launched[i] = True
-        grads = [p.grad for p in self.buckets[i] if p.grad is not None]
-        if not grads:
-            return
-        dist = self.dist
-        self.bytes_reduced += sum(g.numel() * g.element_size() for g in grads)
-        if grads[0].is_cuda:
-            dev = grads[0].device
-            if self._comm is None:
-                self._comm = torch.cuda.Stream(device=dev)
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(self._comm):
-                self._comm.wait_event(ready)                      # the gradients of this bucket are final
-                flat = torch._utils._flatten_dense_tensors(grads)
-                op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
-                work = dist.all_reduce(flat, op=op, async_op=True)
-            self.inflight.append((work, flat, grads, op != dist.ReduceOp.SUM))
-        else:
-            flat = torch._utils._flatten_dense_tensors(grads)
-            work = dist.all_reduce(flat, async_op=True)
-            self.inflight.append((work, flat, grads, False))
-
-    def finish(self):
-        """Complete the reduction of this backward pass; returns the number of gradient bytes reduced."""
-        if self.world > 1 and self.enabled:
-            for i in range(len(self.buckets)):
-                if not self.launched[i]:
-                    self._launch(i)                                # buckets with parameters the pass did not reach
-            for work, flat, grads, averaged in self.inflight:
-                work.wait()                                        # CUDA: the current stream waits for the collective
-                if flat.is_cuda:
-                    flat.record_stream(torch.cuda.current_stream(flat.device))
-                if not averaged:
-                    flat.div_(self.world)
-                for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                    g.copy_(f)
-        nbytes = self.bytes_reduced
-        self.inflight = []
-        self.remaining = [len(b) for b in self.buckets]
-        self.launched = [False] * len(self.buckets)
-        self.bytes_reduced = 0
-        return nbytes
-
-
 class InBackwardGradientReducer:
     """Gradient all-reduce issued from INSIDE the backward of the network Functions.
 
-    Each network of the hot path is ONE autograd Function, so grad-ready hooks (`OverlappedGradientReducer`) only fire
+    Each network of the hot path is ONE autograd Function, so grad-ready hooks (round 1's reducer) only fire
     when a whole network is done -- and the Generator, 87 % of the parameters, is done first, leaving almost nothing to
     hide its 630 MB behind.  The training plans therefore hand their parameter gradients over layer by layer
     (`grad.emit`, called the moment a layer's weight / bias / norm gradients are final and un-scaled): this reducer

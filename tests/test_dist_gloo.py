@@ -7,7 +7,7 @@ import socket
 import torch
 import torch.multiprocessing as mp
 
-from hific_b200.dist import OverlappedGradientReducer, allreduce_gradients, max_over_ranks, shard_range
+from hific_b200.dist import allreduce_gradients, max_over_ranks, shard_range
 
 
 def _free_port():
@@ -74,65 +74,6 @@ def test_gradient_allreduce_world2():
         assert nbytes == sum(g.numel() for g in grads[:-1]) * 4    # one flat fp32 buffer
         for g, r in zip(grads[:-1], ref[:-1]):
             assert torch.allclose(g, r, rtol=1e-5, atol=1e-7)
-
-
-def _overlap_worker(rank, world, port, out):
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        torch.manual_seed(11)
-        x = torch.randn(8, 3, 6, 6)
-        lo, hi = shard_range(x.shape[0], rank, world)
-        m = _model()
-        params = list(m.parameters())
-        params[-1].requires_grad_(False)                  # a frozen parameter never enters a bucket
-        # buckets in gradient-completion order: last layer first (its bias is frozen), then the first layer
-        reducer = OverlappedGradientReducer([[params[2], params[3]], [params[0], params[1]]], dist, world)
-        launched_during_backward = []
-        orig = reducer._launch
-        reducer._launch = lambda i: (launched_during_backward.append(i), orig(i))[1]
-        grads_per_step = []
-        for step in range(2):                             # two passes: the counters must re-arm
-            for p in params:
-                p.grad = None
-            m(x[lo:hi] * (1 + step)).square().mean().backward()
-            order = list(launched_during_backward)
-            nbytes = reducer.finish()
-            grads_per_step.append(([None if p.grad is None else p.grad.clone() for p in params], nbytes, order))
-            launched_during_backward.clear()
-        reducer.remove()
-        out.put((rank, grads_per_step))
-    finally:
-        dist.destroy_process_group()
-
-
-def test_overlapped_gradient_reducer_world2():
-    """Bucketed all-reduce issued from grad-ready hooks while backward is still running: same averaged gradients as the
-    full-batch reference, both buckets launched from inside backward in completion order, counters re-arm per pass."""
-    world, port = 2, _free_port()
-    ctx = mp.get_context("spawn")
-    out = ctx.Queue()
-    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, out)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = sorted([out.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    torch.manual_seed(11)
-    x = torch.randn(8, 3, 6, 6)
-    for step in range(2):
-        m = _model()
-        m(x * (1 + step)).square().mean().backward()
-        ref = [p.grad for p in m.parameters()]
-        for rank, per_step in results:
-            grads, nbytes, order = per_step[step]
-            assert order == [0, 1]                                     # launched by the hooks, last layer first
-            assert grads[-1] is None
-            assert nbytes == sum(g.numel() for g in grads[:-1]) * 4
-            for g, r in zip(grads[:-1], ref[:-1]):
-                assert torch.allclose(g, r, rtol=1e-5, atol=1e-7)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
