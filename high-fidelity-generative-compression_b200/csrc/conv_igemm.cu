@@ -70,9 +70,6 @@ struct ConvKernelParams {
                                       // per CTA); the ring then carries A tiles only -- one TMA per K block instead of two
   int32_t dbg;                        // debugging bits (env HFC_DBG): 1 skip stores, 2 skip norm stats, 4 skip epilogue body
   int32_t wide_boff;                  // debugging: set the descriptor base-offset field for shifted starts
-  const uint8_t* a_base;              // winflat: the NHWC8 input buffer (bulk copies of contiguous pixel segments)
-  long long a_total_bytes;            // winflat: size of that buffer (copies are clamped to it)
-  int32_t a_wp, a_hp;                 // winflat: padded width / height of the input buffer
   int32_t winflat;                    // window packing served from a PLAIN pixel segment (un-swizzled descriptor with
                                       // overlapping rows) instead of an 8x inflated window tile; tile = 128 px of a row
   int32_t wide, kw;                   // 'wide' mode: row-resident A halo (128+kw-1 pixels), resident weights
@@ -111,6 +108,39 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == HFC_ACT_RELU) return fmaxf(v, 0.f);
   if (act == HFC_ACT_LEAKY02) return v > 0.f ? v : 0.2f * v;
   return v;
+}
+
+// Rows / columns of the bordered NHWC output that receive pixel (oh, ow): itself plus its mirror images in the reflected
+// border (ReflectionPad2d of the NEXT conv, materialised by the producer).  Scalars with -1 = none, never an indexed local
+// array: with ~220 KB of dynamic shared memory there is next to no L1, so every local-memory access of the old
+// `int rows[3], cols[3]` was an L2 round trip -- several per tile, on the critical path of every fused epilogue.
+struct BorderDst { int r0, r1, r2, c0, c1, c2; };
+__device__ __forceinline__ BorderDst border_dst(const ConvKernelParams& p, int oh, int ow) {
+  BorderDst b;
+  b.r0 = oh + p.out_pt; b.c0 = ow + p.out_pl;
+  b.r1 = b.r2 = b.c1 = b.c2 = -1;
+  if (p.out_reflect) {
+    if (oh >= 1 && oh <= p.out_pt) b.r1 = p.out_pt - oh;
+    if (oh <= p.out_h - 2 && oh >= p.out_h - 1 - p.out_pb) b.r2 = p.out_pt + 2 * (p.out_h - 1) - oh;
+    if (ow >= 1 && ow <= p.out_pl) b.c1 = p.out_pl - ow;
+    if (ow <= p.out_w - 2 && ow >= p.out_w - 1 - p.out_pr) b.c2 = p.out_pl + 2 * (p.out_w - 1) - ow;
+  }
+  return b;
+}
+// body(row, col) for every target of b (fully unrolled: the selects are on compile-time indices)
+template <typename F>
+__device__ __forceinline__ void for_each_dst(const BorderDst& b, F&& body) {
+#pragma unroll
+  for (int ri = 0; ri < 3; ++ri) {
+    const int rr = ri == 0 ? b.r0 : (ri == 1 ? b.r1 : b.r2);
+    if (rr < 0) continue;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      const int cc = ci == 0 ? b.c0 : (ci == 1 ? b.c1 : b.c2);
+      if (cc < 0) continue;
+      body(rr, cc);
+    }
+  }
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -310,20 +340,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tma_load_4d_mc(sa + n_idx * a_slice_bytes, &tmap_a, &full_bar[s], c0, cw, chh, n_base, mask_a);
                 tma_load_2d_mc(sb + m_idx * b_slice_rows * (kBlockK * 2), &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK,
                                nt * p.block_n + m_idx * b_slice_rows, mask_b);
-              } else if (p.winflat) {
-                // one filter row of the tile = (128 + 7) CONTIGUOUS pixels of the NHWC8 image (16 B each): a 1-D bulk
-                // copy instead of a tensor-map box of 135 rows of 16 B (the TMA unit spends ~5 cycles per box row
-                // whatever its length: 0.39 us per K block of E1, profiles/r02_ncu_bigmap_v3.json).  The segment of the
-                // last tile of a row may run past the row (values feed masked pixels only); it is clamped to the buffer.
-                const long long off = ((static_cast<long long>(n_base) * p.a_hp + chh) * p.a_wp + cw) * 16;
-                // (the expected-transaction count was armed with the full segment: top up what the clamp removes)
-                long long nbytes = (kBlockM + 7) * 16;
-                if (off + nbytes > p.a_total_bytes) nbytes = p.a_total_bytes > off ? p.a_total_bytes - off : 0;
-                if (nbytes > 0) bulk_g2s(sa, p.a_base + off, static_cast<uint32_t>(nbytes), &full_bar[s]);
-                if (nbytes < (kBlockM + 7) * 16)
-                  asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full_bar[s])),
-                               "r"(static_cast<uint32_t>((kBlockM + 7) * 16 - nbytes)) : "memory");
-                if (!p.b_res) tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, b_row);
               } else {
                 tma_load_4d(sa, &tmap_a, &full_bar[s], c0, cw, chh, n_base);
                 if (!p.b_res) tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * kBlockK, b_row);
@@ -552,19 +568,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           rstd = rsqrtf(fmaxf(sq - sd * mean_d, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
         }
         // ---- pass 2: re-read the row, normalise, activate, store (NHWC fp16, with the reflected border of the next conv)
-        int rows[3], cols[3];
-        int nr = 0, nc = 0;
-        rows[nr++] = oh + p.out_pt;
-        cols[nc++] = ow + p.out_pl;
-        if (p.out_reflect) {
-          if (oh >= 1 && oh <= p.out_pt) rows[nr++] = p.out_pt - oh;
-          if (oh <= p.out_h - 2 && oh >= p.out_h - 1 - p.out_pb) rows[nr++] = p.out_pt + 2 * (p.out_h - 1) - oh;
-          if (ow >= 1 && ow <= p.out_pl) cols[nc++] = p.out_pl - ow;
-          if (ow <= p.out_w - 2 && ow >= p.out_w - 1 - p.out_pr) cols[nc++] = p.out_pl + 2 * (p.out_w - 1) - ow;
-        }
-        if (!valid) nr = 0;
-        __half* dst0 = reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + rows[0]) * Wp + cols[0]) * p.out_cpad;
-        const bool interior = nr == 1 && nc == 1;
+        BorderDst bd = border_dst(p, oh, ow);
+        const int nr = valid ? 1 : 0;
+        __half* dst0 = reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + bd.r0) * Wp + bd.c0) * p.out_cpad;
+        const bool interior = (bd.r1 & bd.r2 & bd.c1 & bd.c2) < 0 && bd.r1 < 0 && bd.r2 < 0 && bd.c1 < 0 && bd.c2 < 0;
         {
           uint32_t v[16];
           for (int c0 = 0; c0 < p.block_n; c0 += 16) {
@@ -601,23 +608,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               reinterpret_cast<uint4*>(dst0 + c0)[0] = lo;
               if (two) reinterpret_cast<uint4*>(dst0 + c0)[1] = hi;
             } else {
-              for (int ri = 0; ri < nr; ++ri)
-                for (int ci = 0; ci < nc; ++ci) {
-                  __half* dst = reinterpret_cast<__half*>(p.out) +
-                                ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) * p.out_cpad + c0;
-                  reinterpret_cast<uint4*>(dst)[0] = lo;
-                  if (two) reinterpret_cast<uint4*>(dst)[1] = hi;
-                }
+              for_each_dst(bd, [&](int rr, int cc) {
+                __half* dst = reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + rr) * Wp + cc) * p.out_cpad + c0;
+                reinterpret_cast<uint4*>(dst)[0] = lo;
+                if (two) reinterpret_cast<uint4*>(dst)[1] = hi;
+              });
             }
           }
         }
         if (nr)
           for (int c = p.block_n; c < p.out_cpad; c += 8)        // channel padding the N tile does not cover
-            for (int ri = 0; ri < nr; ++ri)
-              for (int ci = 0; ci < nc; ++ci)
-                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) +
-                                          ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) * p.out_cpad + c) =
-                    make_uint4(0, 0, 0, 0);
+            for_each_dst(bd, [&](int rr, int cc) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + rr) * Wp + cc) * p.out_cpad + c) =
+                  make_uint4(0, 0, 0, 0);
+            });
       }
     } else {
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
@@ -757,16 +761,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const float m2 = m2_a + m2_b + dl * dl * (cnt_a * cnt_b / ctot);
           const float rstd = rsqrtf(fmaxf(m2, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
           // ---- phase 2: normalise, activate, add the residual streams, write fp32 rows and / or the fp16 buffer
-          int rows[3], cols[3];
-          int nr = 0, nc = 0;
-          rows[nr++] = oh + p.out_pt;
-          cols[nc++] = ow + p.out_pl;
-          if (p.out_reflect) {
-            if (oh >= 1 && oh <= p.out_pt) rows[nr++] = p.out_pt - oh;
-            if (oh <= p.out_h - 2 && oh >= p.out_h - 1 - p.out_pb) rows[nr++] = p.out_pt + 2 * (p.out_h - 1) - oh;
-            if (ow >= 1 && ow <= p.out_pl) cols[nc++] = p.out_pl - ow;
-            if (ow <= p.out_w - 2 && ow >= p.out_w - 1 - p.out_pr) cols[nc++] = p.out_pl + 2 * (p.out_w - 1) - ow;
-          }
           const int Hp = p.out_h + p.out_pt + p.out_pb;
           const int Wp = p.out_w + p.out_pl + p.out_pr;
           const size_t pix = (static_cast<size_t>(n) * p.out_h + oh) * p.out_w + ow;
@@ -814,13 +808,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 lo.z = pack_half2(f[4], f[5]);   lo.w = pack_half2(f[6], f[7]);
                 hi.x = pack_half2(f[8], f[9]);   hi.y = pack_half2(f[10], f[11]);
                 hi.z = pack_half2(f[12], f[13]); hi.w = pack_half2(f[14], f[15]);
-                for (int ri = 0; ri < nr; ++ri)
-                  for (int ci = 0; ci < nc; ++ci) {
-                    __half* dst = reinterpret_cast<__half*>(p.out) +
-                                  ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) * p.out_cpad + cc;
-                    reinterpret_cast<uint4*>(dst)[0] = lo;
-                    reinterpret_cast<uint4*>(dst)[1] = hi;
-                  }
+                const BorderDst bd = border_dst(p, oh, ow);     // recomputed here: a few integer ops, no long live range
+                for_each_dst(bd, [&](int rr, int c2) {
+                  __half* dst = reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + rr) * Wp + c2) * p.out_cpad + cc;
+                  reinterpret_cast<uint4*>(dst)[0] = lo;
+                  reinterpret_cast<uint4*>(dst)[1] = hi;
+                });
               }
             });
           }
@@ -917,20 +910,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
 
       // target rows / cols of the (bordered) NHWC fp16 buffer
-      int rows[3], cols[3];
-      int nr = 0, nc = 0;
-      if (p.out_mode == HFC_OUT_NHWC_F16) {
-        rows[nr++] = oh + p.out_pt;
-        cols[nc++] = ow + p.out_pl;
-        if (p.out_reflect) {
-          if (oh >= 1 && oh <= p.out_pt) rows[nr++] = p.out_pt - oh;
-          if (oh <= p.out_h - 2 && oh >= p.out_h - 1 - p.out_pb)
-            rows[nr++] = p.out_pt + 2 * (p.out_h - 1) - oh;
-          if (ow >= 1 && ow <= p.out_pl) cols[nc++] = p.out_pl - ow;
-          if (ow <= p.out_w - 2 && ow >= p.out_w - 1 - p.out_pr)
-            cols[nc++] = p.out_pl + 2 * (p.out_w - 1) - ow;
-        }
-      }
       const int Hp = p.out_h + p.out_pt + p.out_pb;
       const int Wp = p.out_w + p.out_pl + p.out_pr;
 
@@ -967,15 +946,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             lo.z = pack_half2(f[4], f[5]);   lo.w = pack_half2(f[6], f[7]);
             hi.x = pack_half2(f[8], f[9]);   hi.y = pack_half2(f[10], f[11]);
             hi.z = pack_half2(f[12], f[13]); hi.w = pack_half2(f[14], f[15]);
-            for (int ri = 0; ri < nr; ++ri) {
-              for (int ci = 0; ci < nc; ++ci) {
-                __half* dst = reinterpret_cast<__half*>(p.out) +
-                              ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) *
-                                  p.out_cpad + cc;
-                reinterpret_cast<uint4*>(dst)[0] = lo;
-                if (cc + 8 < p.out_cpad) reinterpret_cast<uint4*>(dst)[1] = hi;
-              }
-            }
+            const BorderDst bd = border_dst(p, oh, ow);       // recomputed at the store site: no long live range
+            for_each_dst(bd, [&](int rr, int c2) {
+              __half* dst = reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + rr) * Wp + c2) * p.out_cpad + cc;
+              reinterpret_cast<uint4*>(dst)[0] = lo;
+              if (cc + 8 < p.out_cpad) reinterpret_cast<uint4*>(dst)[1] = hi;
+            });
           }
         } else if (p.out_mode == HFC_OUT_NHWC_F32) {
           if (cc < p.out_cpad) {
@@ -1025,15 +1001,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (valid && last_nt && hsel == 0 && !p.tapn && !p.out_atomic && p.out_mode != HFC_OUT_NCHW_F32) {
         const int c_end = p.n_tiles * p.block_n;
         if (p.out_mode == HFC_OUT_NHWC_F16) {
-          for (int c = c_end; c < p.out_cpad; c += 8) {
-            for (int ri = 0; ri < nr; ++ri)
-              for (int ci = 0; ci < nc; ++ci) {
-                __half* dst = reinterpret_cast<__half*>(p.out) +
-                              ((static_cast<size_t>(n) * Hp + rows[ri]) * Wp + cols[ci]) *
-                                  p.out_cpad + c;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-              }
-          }
+          const BorderDst bd = border_dst(p, oh, ow);
+          for (int c = c_end; c < p.out_cpad; c += 8)
+            for_each_dst(bd, [&](int rr, int c2) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + rr) * Wp + c2) * p.out_cpad + c) =
+                  make_uint4(0, 0, 0, 0);
+            });
         } else {
           float* dst = reinterpret_cast<float*>(p.out) +
                        ((static_cast<size_t>(n) * p.out_h + oh) * p.out_w + ow) * p.out_cpad;
@@ -1421,9 +1394,10 @@ static int tile_and_stages(const hfc_conv_desc* d, const Plan& pl, const Phase& 
   }
   // Thin instantiation (conv_igemm_kernel<false, 1, false, true>): one N tile of <= 64 columns (tap-in-N: <= 32) on a
   // map big enough that the launch is a long stream of tiny tiles -- the epilogue-bound layers E1, G.up4, G3.  Single
-  // CTAs (no pair / cluster: the K loops are short), 4 accumulator stages.  HFC_THIN_EPILOGUE=0 disables it,
-  // HFC_THIN_EPILOGUE=2 also takes one-N-tile layers up to 128 columns (E2, G.up3).
-  static const int env_thin = getenv("HFC_THIN_EPILOGUE") ? atoi(getenv("HFC_THIN_EPILOGUE")) : 1;
+  // CTAs (no pair / cluster: the K loops are short), 4 accumulator stages.  Default level 2: one-N-tile layers of up to
+  // 128 columns as well (E2 164 -> 130 us, G.up3 190 -> 165 us); HFC_THIN_EPILOGUE=1 restricts it to <= 64 columns, 0
+  // disables it.
+  static const int env_thin = getenv("HFC_THIN_EPILOGUE") ? atoi(getenv("HFC_THIN_EPILOGUE")) : 2;
   {
     // the choice depends on the map size of ONE image only, never on the batch: a sample's result must not depend on
     // its batch neighbours bit for bit (tests/test_gpu_parity.py), and the two epilogues sum the statistics in a
@@ -1703,9 +1677,6 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     kp.fmt_b = d->b_bf16 ? 1u : 0u;
     kp.bias = bias; kp.gamma = gamma; kp.beta = beta;
     kp.out = out;
-    kp.a_base = static_cast<const uint8_t*>(in);
-    kp.a_wp = Wp; kp.a_hp = Hp;
-    kp.a_total_bytes = static_cast<long long>(ig.n) * Hp * Wp * ig.cpad * 2;
     if (wn) {
       kp.norm = 2;
       kp.res1 = wn->res1; kp.res2 = wn->res2; kp.ld_res = wn->ld_res;

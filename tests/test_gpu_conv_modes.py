@@ -19,9 +19,12 @@ def test_cluster_multicast_resblock_shape(cluster):
 
 
 def test_cluster_auto_on_big_layer():
-    # 8 x 64x64 -> 256 M tiles, 1 N tile: auto picks 2x1 (weights shared by two pixel tiles)
-    run_conv_case(8, 64, 64, 64, 120, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F16,
+    # 32 x 32x32 -> 256 M tiles, 1 N tile: auto picks 2x1 (weights shared by two pixel tiles).  (Maps of >= 4 096 pixels
+    # per image with one N tile of <= 128 columns take the thin instantiation instead: single CTAs, no cluster.)
+    run_conv_case(32, 64, 32, 32, 120, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F16,
                   out_border=(1, 0, 0, 1), norm=True, act=ACT_RELU, expect=dict(cluster_m=2, cluster_n=1))
+    run_conv_case(8, 64, 64, 64, 120, 3, pad=(1, 1, 1, 1), pad_mode=PAD_REFLECT, out_mode=OUT_NHWC_F16,
+                  out_border=(1, 0, 0, 1), norm=True, act=ACT_RELU, expect=dict(cluster_m=1, cluster_n=1))
 
 
 def test_cluster_with_padding_tiles():
