@@ -3,6 +3,8 @@ data-parallel (ChannelNorm is per pixel, no batch statistics), so ranks only exc
 all-reduce of the stepped parameter group after backward (`allreduce_gradients`), or bucketed all-reduces issued from
 inside the backward (`InBackwardGradientReducer`; train.py has no DDP wrapper; north_star asks for "NCCL allreduce over
 NVLink for gradients only").  Backend-agnostic: NCCL on the GPUs, gloo in the CPU tests."""
+import os
+
 import torch
 
 
@@ -80,6 +82,7 @@ class InBackwardGradientReducer:
         self.inflight = []                  # gloo: (work, flat, grads)
         self._comm, self._done = None, None
         self.bytes_reduced, self.buckets_launched, self.ids = 0, 0, set()
+        self.debug_sync = os.environ.get("HFC_REDUCER_SYNC") == "1"      # diagnostics: host-synchronise after every bucket
 
     # -- sink protocol (hific_b200.grad) ---------------------------------------------------------------------------
     def submit(self, tensors):
@@ -130,6 +133,8 @@ class InBackwardGradientReducer:
                 self._done.record(self._comm)
                 for g in grads:
                     g.record_stream(self._comm)
+            if self.debug_sync:
+                self._comm.synchronize()
         else:
             flat = torch._utils._flatten_dense_tensors(grads)
             self.inflight.append((dist.all_reduce(flat, async_op=True), flat, grads))

@@ -13,6 +13,8 @@ import logging
 
 import torch
 
+os.environ.setdefault("HFC_LPIPS_SYNTHETIC", "1")   # no checkpoints on the boxes: seeded stand-in, as the tests do
+
 from hific_b200 import synth
 from hific_b200.config import ModelModes, ModelTypes, mse_lpips_args
 from hific_b200.model import Model

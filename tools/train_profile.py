@@ -10,6 +10,8 @@ import sys
 
 import torch
 
+os.environ.setdefault("HFC_LPIPS_SYNTHETIC", "1")   # no checkpoints on the boxes: seeded stand-in, as the tests do
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hific_b200  # noqa: E402,F401
 from hific_b200 import synth  # noqa: E402
