@@ -216,7 +216,7 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
                 grads_once(True)                                    # calibrates the loss scales (per-Function hand-over)
                 ref, got = grads_once(False), grads_once(True)
                 ok = all(torch.allclose(a, b, rtol=2e-2, atol=1e-3 * float(a.abs().max()) + 1e-12)
-                         for a, b in zip(ref, got)) and reducer.buckets_launched >= 20
+                         for a, b in zip(ref, got)) and reducer.buckets_launched >= 8
             except Exception:                        # every rank must still reach the agreement collective below
                 ok = False
             flag = torch.tensor([1.0 if ok else 0.0], device=dev)
