@@ -146,3 +146,33 @@ def test_kernel_element_code_on_the_host(host_kernels, kind, shape):
         want_dx, want_dp = E.dlmm_likelihood_bwd(x, params, noise, dd, torch.tensor([upstream]), kind)
         assert ((dx - want_dx).norm() / want_dx.norm()).item() < 1e-5
         assert ((dp - want_dp).norm() / want_dp.norm()).item() < 1e-5
+
+
+def test_model_level_lmm_uses_the_dlmm_channel_count():
+    """`Model(use_latent_mixture_model=True)` (`train.py -LMM`): the reference overrides `args.latent_channels` with
+    `args.latent_channels_DLMM` before building ANY sub-network (src/model.py:53-54); without the override the shipped
+    config (220 channels) trips `HyperpriorDLMM`'s `bottleneck_capacity <= 128` assertion.  Construct, run a
+    training-mode forward + backward and an eval forward through the emulated entry points."""
+    import logging
+    from hific_b200.config import mse_lpips_args
+    from hific_b200.model import Model
+    cfg = mse_lpips_args()
+    cfg.use_latent_mixture_model, cfg.latent_channels_DLMM, cfg.n_residual_blocks = True, 8, 1
+    cfg.image_dims, cfg.latent_dims, cfg.batch_size = (3, 128, 128), (8, 8, 8), 1
+    torch.manual_seed(0)
+    m = Model(cfg, logging.getLogger("lmm"))
+    assert m.args.latent_channels == 8
+    assert m.Encoder.conv_block_out[1].weight.shape[0] == 8 and m.Generator.conv_block_init[2].weight.shape[1] == 8
+    assert type(m.Hyperprior).__name__ == "HyperpriorDLMM" and m.Hyperprior.bottleneck_capacity == 8
+    x = torch.rand((1, 3, 128, 128))
+    with E.train_step_cpu_emulation():
+        m.train()
+        inter, info = m.compression_forward(x)
+        assert inter.reconstruction.shape == x.shape and torch.isfinite(inter.n_bpp) and torch.isfinite(inter.q_bpp)
+        (inter.n_bpp + m.distortion_loss(inter.reconstruction, inter.input_image) * 1e-3).backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.Encoder.parameters())
+        assert all(p.grad is not None for p in m.Hyperprior.synthesis_DLMM_params.parameters())
+        m.eval()
+        with torch.no_grad():
+            inter2, _ = m.compression_forward(x)
+        assert inter2.reconstruction.shape == x.shape and float(inter2.q_bpp) > 0

@@ -149,3 +149,28 @@ def test_backward_arithmetic_at_the_products_own_forward_state_cpu():
     f = r["forced"]
     assert f["forward_rel_l2"] < 1e-4 and f["worst_tensor_rel_l2"] < tol and f["input_grad_rel_l2"] < tol, f
     assert r["fp32"]["worst_tensor_rel_l2"] > 3 * f["worst_tensor_rel_l2"]      # the flips, not the arithmetic, dominate
+
+
+def test_backward_against_an_overwritten_plan_raises():
+    """Saved activations live on the cached plan of an input shape: a second forward of the same shape before
+    the first one's backward must make that backward FAIL, not differentiate through the wrong activations."""
+    import pytest
+    from emulation import training_cpu_emulation
+    from hific_b200.network import hyper
+    torch.manual_seed(0)
+    net = hyper.HyperpriorAnalysis(C=220, N=320).train()
+    g = torch.Generator().manual_seed(1)
+    y1 = torch.randn((1, 220, 8, 8), generator=g).requires_grad_(True)
+    y2 = torch.randn((1, 220, 8, 8), generator=g).requires_grad_(True)
+    with training_cpu_emulation():
+        z1 = net(y1)
+        z2 = net(y2)                       # overwrites the plan's saved tensors
+        z2.sum().backward()                # the latest forward is fine
+        with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+            z1.sum().backward()
+        # step by step is fine
+        for p in net.parameters():
+            p.grad = None
+        net(y1).sum().backward()
+        net(y2).sum().backward()
+        assert all(p.grad is not None for p in net.parameters())
