@@ -110,6 +110,21 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Division of a tile index by a runtime constant (tile counts, < 2^11) as a 64-bit multiply + shift: exact for n * d < 2^40.
+// The per-tile decode (work item -> K split, N group, tile column / row / image) is 7 integer divisions; as plain `/` and
+// `%` by runtime values that is ~300 dependent instructions per tile in the one-warp TMA producer -- ~0.8 us, more than
+// the whole K loop of a short-K tile (G.up4: t_tile = 1.5 us + 0.25 us x K blocks before this).
+struct FastDiv { unsigned long long m; int d; };
+__device__ __forceinline__ FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  f.m = d > 1 ? ((1ull << 40) + static_cast<unsigned long long>(d) - 1ull) / static_cast<unsigned long long>(d) : 0ull;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return f.d == 1 ? n : static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(n)) * f.m) >> 40);
+}
+
 // Rows / columns of the bordered NHWC output that receive pixel (oh, ow): itself plus its mirror images in the reflected
 // border (ReflectionPad2d of the NEXT conv, materialised by the producer).  Scalars with -1 = none, never an indexed local
 // array: with ~220 KB of dynamic shared memory there is next to no L1, so every local-memory access of the old
@@ -238,6 +253,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int m_groups = (tiles_m + p.cm - 1) / p.cm;
   const int n_groups = (p.n_tiles + p.cn * kNsub - 1) / (p.cn * kNsub);
   const int total_ctiles = m_groups * n_groups * p.k_splits;   // work items per cluster (x K splits in gemm mode)
+  const FastDiv fd_ks = make_fastdiv(p.k_splits), fd_ng = make_fastdiv(n_groups), fd_tw = make_fastdiv(p.tiles_w),
+                fd_th = make_fastdiv(p.tiles_h);
   const int cid = blockIdx.x / csize;
   const int ncl = gridDim.x / csize;
 
@@ -297,14 +314,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t kbt_addr = smem_u32(s_kbt);
       const bool use_table = !p.gemm;
       for (int ct = cid; ct < total_ctiles; ct += ncl) {
-        const int ks = ct % p.k_splits;          // K split (gemm mode), else 0
-        const int ctile = ct / p.k_splits;
-        const int nt = ((ctile % n_groups) * p.cn + n_idx) * kNsub;
-        int mt = (ctile / n_groups) * p.cm + m_idx;
-        const int twi = mt % p.tiles_w;
-        mt /= p.tiles_w;
-        const int thi = mt % p.tiles_h;
-        const int tni = mt / p.tiles_h;   // >= tiles_n for padding tiles: every row is out of bounds (zero fill)
+        const int ctile = fdiv(ct, fd_ks);
+        const int ks = ct - ctile * p.k_splits;  // K split (gemm mode), else 0
+        const int cg = fdiv(ctile, fd_ng);
+        const int nt = ((ctile - cg * n_groups) * p.cn + n_idx) * kNsub;
+        const int mt0 = cg * p.cm + m_idx;
+        const int mt1 = fdiv(mt0, fd_tw);
+        const int twi = mt0 - mt1 * p.tiles_w;
+        const int tni = fdiv(mt1, fd_th);        // >= tiles_n for padding tiles: every row is out of bounds (zero fill)
+        const int thi = mt1 - tni * p.tiles_h;
         const int w_base = (p.tapn ? twi * p.w_step : twi * p.tw * p.sw) + p.iw0;
         // my slice of the shared A tile: rows [n_idx*128/cn, (n_idx+1)*128/cn)
         const int h_base = (thi * p.th + (p.a_split_n ? 0 : n_idx * (p.th / p.cn))) * p.sh + p.ih0;
@@ -487,11 +505,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int ct = cid; ct < total_ctiles; ct += ncl, ++it) {
         if ((it & (kThinAccStages - 1)) != grp) continue;
         const uint32_t aph = static_cast<uint32_t>(it / kThinAccStages) & 1u;
-        int mt = (ct / n_groups) * p.cm + m_idx;
-        const int twi = mt % p.tiles_w;
-        mt /= p.tiles_w;
-        const int thi = mt % p.tiles_h;
-        const int tni = mt / p.tiles_h;
+        const int mt0 = fdiv(ct, fd_ng) * p.cm + m_idx;
+        const int mt1 = fdiv(mt0, fd_tw);
+        const int twi = mt0 - mt1 * p.tiles_w;
+        const int tni = fdiv(mt1, fd_th);
+        const int thi = mt1 - tni * p.tiles_h;
         const int gw = (p.tapn ? twi * p.w_step : twi * p.tw) + twi_in;
         const int gh = thi * p.th + thi_in;
         const int n = tni * p.tn + tni_in;
@@ -638,13 +656,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int cur_nt = -1, pbuf = 1;
     [[maybe_unused]] uint32_t xph = 0; // phase of xchg_bar == index of the exchange buffer (norm == 2)
     for (int ct = cid; ct < total_ctiles; ct += ncl) {
-      const int ctile = ct / p.k_splits;
-      const int nt0 = ((ctile % n_groups) * p.cn + n_idx) * kNsub;
-      int mt = (ctile / n_groups) * p.cm + m_idx;
-      const int twi = mt % p.tiles_w;
-      mt /= p.tiles_w;
-      const int thi = mt % p.tiles_h;
-      const int tni = mt / p.tiles_h;
+      const int ctile = fdiv(ct, fd_ks);
+      const int cg = fdiv(ctile, fd_ng);
+      const int nt0 = ((ctile - cg * n_groups) * p.cn + n_idx) * kNsub;
+      const int mt0 = cg * p.cm + m_idx;
+      const int mt1 = fdiv(mt0, fd_tw);
+      const int twi = mt0 - mt1 * p.tiles_w;
+      const int tni = fdiv(mt1, fd_th);
+      const int thi = mt1 - tni * p.tiles_h;
       const int gw = (p.tapn ? twi * p.w_step : twi * p.tw) + twi_in;
       const int gh = thi * p.th + thi_in;
       const int n = tni * p.tn + tni_in;
