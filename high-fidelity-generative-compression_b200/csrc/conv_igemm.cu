@@ -22,6 +22,7 @@
 #include "hfc_ptx.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -554,14 +555,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           continue;
         }
         // ---- pass 1: ChannelNorm statistics, one pass with shifted sums (shift = the row's first channel), the padding
-        // columns (acc = bias = 0, d = -shift) removed analytically
+        // columns (acc = bias = 0, d = -shift) removed analytically.  Packed fp32 (two channels per instruction).
         float mean = 0.f, rstd = 1.f;
         if (p.norm) {
           uint32_t va[16];
           tmem_ld16(t_row, va);
           tmem_ld_wait();
           const float shift = __uint_as_float(va[0]) + lds4(sp_bias).x;
-          float sd0 = 0.f, sd1 = 0.f, sq0 = 0.f, sq1 = 0.f;
+          const f32x2 nshift = pk2(-shift, -shift);
+          f32x2 sd = pk2(0.f, 0.f), sq = pk2(0.f, 0.f);
           for (int c0 = 0; c0 < p.block_n; c0 += 16) {        // (the other three warps of this scheduler hide the TMEM latency)
             if (c0) {
               tmem_ld16(t_row + c0, va);
@@ -570,27 +572,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 b4 = lds4(sp_bias + 4 * (c0 + 4 * j4));
-              const float d0 = (__uint_as_float(va[4 * j4 + 0]) + b4.x) - shift;
-              const float d1 = (__uint_as_float(va[4 * j4 + 1]) + b4.y) - shift;
-              const float d2 = (__uint_as_float(va[4 * j4 + 2]) + b4.z) - shift;
-              const float d3 = (__uint_as_float(va[4 * j4 + 3]) + b4.w) - shift;
-              sd0 += d0; sd1 += d1; sd0 += d2; sd1 += d3;
-              sq0 = fmaf(d0, d0, sq0); sq1 = fmaf(d1, d1, sq1); sq0 = fmaf(d2, d2, sq0); sq1 = fmaf(d3, d3, sq1);
+              const f32x2 d01 = add2x(add2x(pk2(__uint_as_float(va[4 * j4 + 0]), __uint_as_float(va[4 * j4 + 1])), pk2(b4.x, b4.y)), nshift);
+              const f32x2 d23 = add2x(add2x(pk2(__uint_as_float(va[4 * j4 + 2]), __uint_as_float(va[4 * j4 + 3])), pk2(b4.z, b4.w)), nshift);
+              sd = add2x(sd, d01); sq = fma2x(d01, d01, sq);
+              sd = add2x(sd, d23); sq = fma2x(d23, d23, sq);
             }
           }
+          float sd0, sd1, sq0, sq1;
+          unpk2(sd, sd0, sd1);
+          unpk2(sq, sq0, sq1);
           const float npad = static_cast<float>(p.block_n - p.cout);
-          const float sd = (sd0 + sd1) + npad * shift;
-          const float sq = (sq0 + sq1) - npad * shift * shift;
-          const float mean_d = sd * inv_c;
+          const float sds = (sd0 + sd1) + npad * shift;
+          const float sqs = (sq0 + sq1) - npad * shift * shift;
+          const float mean_d = sds * inv_c;
           mean = shift + mean_d;
-          rstd = rsqrtf(fmaxf(sq - sd * mean_d, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
+          rstd = rsqrtf(fmaxf(sqs - sds * mean_d, 0.f) / static_cast<float>(p.cout - 1) + p.eps);
         }
         // ---- pass 2: re-read the row, normalise, activate, store (NHWC fp16, with the reflected border of the next conv)
         BorderDst bd = border_dst(p, oh, ow);
         const int nr = valid ? 1 : 0;
         __half* dst0 = reinterpret_cast<__half*>(p.out) + ((static_cast<size_t>(n) * Hp + bd.r0) * Wp + bd.c0) * p.out_cpad;
-        const bool interior = (bd.r1 & bd.r2 & bd.c1 & bd.c2) < 0 && bd.r1 < 0 && bd.r2 < 0 && bd.c1 < 0 && bd.c2 < 0;
-        {
+        const bool interior = bd.r1 < 0 && bd.r2 < 0 && bd.c1 < 0 && bd.c2 < 0;
+        // one instantiation per (norm, ReLU) combination: no runtime switch inside the element loops
+        auto pass2 = [&](auto norm_tag, auto relu_tag) {
+          constexpr bool kNorm = decltype(norm_tag)::value, kRelu = decltype(relu_tag)::value;
+          const f32x2 nmean = pk2(-mean, -mean), rs2 = pk2(rstd, rstd);
           uint32_t v[16];
           for (int c0 = 0; c0 < p.block_n; c0 += 16) {
             tmem_ld16(t_row + c0, v);
@@ -600,27 +606,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty_bar[grp]);
             }
-            float f[16];
+            uint32_t h[8];
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 b4 = lds4(sp_bias + 4 * (c0 + 4 * j4));
-              float x0 = __uint_as_float(v[4 * j4 + 0]) + b4.x, x1 = __uint_as_float(v[4 * j4 + 1]) + b4.y;
-              float x2 = __uint_as_float(v[4 * j4 + 2]) + b4.z, x3 = __uint_as_float(v[4 * j4 + 3]) + b4.w;
-              if (p.norm) {
+              f32x2 x01 = add2x(pk2(__uint_as_float(v[4 * j4 + 0]), __uint_as_float(v[4 * j4 + 1])), pk2(b4.x, b4.y));
+              f32x2 x23 = add2x(pk2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), pk2(b4.z, b4.w));
+              if constexpr (kNorm) {
                 const float4 g4 = lds4(sp_gamma + 4 * (c0 + 4 * j4));
                 const float4 e4 = lds4(sp_beta + 4 * (c0 + 4 * j4));
-                x0 = fmaf(g4.x * rstd, x0 - mean, e4.x); x1 = fmaf(g4.y * rstd, x1 - mean, e4.y);
-                x2 = fmaf(g4.z * rstd, x2 - mean, e4.z); x3 = fmaf(g4.w * rstd, x3 - mean, e4.w);
+                x01 = fma2x(mul2x(pk2(g4.x, g4.y), rs2), add2x(x01, nmean), pk2(e4.x, e4.y));
+                x23 = fma2x(mul2x(pk2(g4.z, g4.w), rs2), add2x(x23, nmean), pk2(e4.z, e4.w));
               }
-              f[4 * j4 + 0] = apply_act(x0, p.act); f[4 * j4 + 1] = apply_act(x1, p.act);
-              f[4 * j4 + 2] = apply_act(x2, p.act); f[4 * j4 + 3] = apply_act(x3, p.act);
+              float y0, y1, y2, y3;
+              unpk2(x01, y0, y1);
+              unpk2(x23, y2, y3);
+              if constexpr (kRelu) {
+                y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f);
+              } else {
+                y0 = apply_act(y0, p.act); y1 = apply_act(y1, p.act); y2 = apply_act(y2, p.act); y3 = apply_act(y3, p.act);
+              }
+              h[2 * j4] = pack_half2(y0, y1);
+              h[2 * j4 + 1] = pack_half2(y2, y3);
             }
             if (nr == 0 || c0 >= p.out_cpad) continue;
-            uint4 lo, hi;
-            lo.x = pack_half2(f[0], f[1]);   lo.y = pack_half2(f[2], f[3]);
-            lo.z = pack_half2(f[4], f[5]);   lo.w = pack_half2(f[6], f[7]);
-            hi.x = pack_half2(f[8], f[9]);   hi.y = pack_half2(f[10], f[11]);
-            hi.z = pack_half2(f[12], f[13]); hi.w = pack_half2(f[14], f[15]);
+            const uint4 lo = make_uint4(h[0], h[1], h[2], h[3]), hi = make_uint4(h[4], h[5], h[6], h[7]);
             const bool two = c0 + 8 < p.out_cpad;
             if (interior) {
               reinterpret_cast<uint4*>(dst0 + c0)[0] = lo;
@@ -633,7 +643,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               });
             }
           }
-        }
+        };
+        if (p.norm && p.act == HFC_ACT_RELU) pass2(std::true_type{}, std::true_type{});
+        else if (p.norm) pass2(std::true_type{}, std::false_type{});
+        else pass2(std::false_type{}, std::false_type{});
         if (nr)
           for (int c = p.block_n; c < p.out_cpad; c += 8)        // channel padding the N tile does not cover
             for_each_dst(bd, [&](int rr, int cc) {

@@ -39,6 +39,11 @@ class PipelinedForward:
         if s.x_dev is None or s.x_dev.shape != x_host.shape:
             s.x_dev = torch.empty(x_host.shape, dtype=x_host.dtype, device=self.dev)
             s.recon_dev = s.recon_host = None
+            # The block comes from the MAIN stream's pool: it may be memory that kernels still queued on the main stream
+            # (temporaries of the previous submission, already freed on the host) have yet to write.  The copy stream
+            # must not touch it before they are done -- without this wait the second submission's input was overwritten
+            # by the tail of the first forward (intermittent in round 1, every time once the forward got faster).
+            self.h2d.wait_stream(main)
         with torch.cuda.stream(self.h2d):
             if s.used:
                 self.h2d.wait_event(s.ev_cmp)        # the kernels that read this slot's input have finished
