@@ -192,9 +192,9 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
     if dist is not None:
         reduce_mode = "after backward, one coalesced NCCL all-reduce"
     if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE", "1") == "1":
-        from hific_b200.dist import InBackwardGradientReducer
+        from hific_b200.dist import InBackwardGradientReducer, reducer_group
         try:
-            reducer = InBackwardGradientReducer(dist, world)
+            reducer = InBackwardGradientReducer(dist, world, group=reducer_group(dist))
             probe = [amort[0], amort[len(amort) // 2], amort[-1], hyper[0]]
 
             def grads_once(overlapped):
@@ -232,33 +232,62 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         for p in params:
             p.grad = None
 
-    def step():
+    def step(mark=None):
+        mark = mark or (lambda: None)
+        mark()
         losses = model(x, train_generator=True)
+        mark()
         if reducer is not None:
             with reducer:
                 losses['compression'].backward()
+            mark()
             reducer.reduce_rest(hyper)
         else:
             losses['compression'].backward()
+            mark()
             if dist is not None:
                 allreduce_gradients(params, dist, world)
+        mark()
         opt_a.step()
         opt_a.zero_grad()
         opt_h.step()
         opt_h.zero_grad()
+        mark()
 
+    phases = None
     try:
         for _ in range(3):
             step()
         steps = max(3, args.steps // 4)
         ms = timed(step, steps)
+        # where the step goes (3 extra untimed steps, events on the compute stream, median) and what the host needs to
+        # enqueue one step onto an idle GPU (a step whose enqueue time approaches its GPU time is launch-bound)
+        rows, host = [], []
+        for _ in range(3):
+            evs = []
+
+            def mark():
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append(e)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step(mark)
+            host.append((time.perf_counter() - t0) * 1e3)
+            torch.cuda.synchronize()
+            rows.append([evs[i].elapsed_time(evs[i + 1]) for i in range(4)])
+        med = [sorted(r[i] for r in rows)[1] for i in range(4)]
+        phases = {"forward_and_losses_ms": med[0], "backward_ms": med[1], "gradient_allreduce_after_backward_ms": med[2],
+                  "adam_ms": med[3], "host_enqueue_ms": sorted(host)[1],
+                  "note": "one step from an idle GPU, CUDA events on the compute stream; with the in-backward reducer the "
+                          "waits for the buckets are inside backward_ms"}
     except NotImplementedError as e:      # a piece of the backward is missing: report it, do not fake a number
         return {"unavailable": str(e)[:200]}
     finally:
         model.model_mode = ModelModes.EVALUATION
         model.eval()
     return {"ms_per_step": ms / steps, "images_per_s": world * B * steps / (ms * 1e-3), "steps": steps,
-            "per_gpu_batch": B, "n_gpus": world, "gradient_allreduce": reduce_mode,
+            "per_gpu_batch": B, "n_gpus": world, "gradient_allreduce": reduce_mode, "phases": phases,
             "lpips_trunk": os.environ.get("HFC_LPIPS_TRUNK", "native"),
             "dtype": ("bf16 x bf16 backward GEMMs (HFC_GRAD_FMT=bf16)" if os.environ.get("HFC_GRAD_FMT", "fp16").lower() == "bf16" else
                       "fp16 x fp16 backward GEMMs (10-bit mantissa as TF32; power-of-two loss scale per backward Function), "
@@ -297,8 +326,8 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed, batch=None, regim
 
     reducer = None
     if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE", "1") == "1":
-        from hific_b200.dist import InBackwardGradientReducer
-        reducer = InBackwardGradientReducer(dist, world)
+        from hific_b200.dist import InBackwardGradientReducer, reducer_group
+        reducer = InBackwardGradientReducer(dist, world, group=reducer_group(dist))
 
     def g_step():
         losses = model(x, train_generator=True)

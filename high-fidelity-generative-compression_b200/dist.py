@@ -72,12 +72,15 @@ class InBackwardGradientReducer:
     Every rank walks the same plans in the same order, so buckets line up across ranks without negotiation.
     Backend-agnostic: NCCL (coalesced in-place ncclAvg on a side stream) or gloo (CPU tests: flatten, sum, divide)."""
 
-    def __init__(self, dist=None, world=None, bucket_bytes=32 << 20):
+    def __init__(self, dist=None, world=None, bucket_bytes=None, group=None):
         if dist is None:
             import torch.distributed as dist
         self.dist = dist
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        if bucket_bytes is None:
+            bucket_bytes = int(os.environ.get("HFC_REDUCER_BUCKET_MB", "32")) << 20
         self.bucket_bytes = int(bucket_bytes)
+        self.group = group                  # None: the default process group; see reducer_group()
         self.pending, self.pending_bytes = [], 0
         self.inflight = []                  # gloo: (work, flat, grads)
         self._comm, self._done = None, None
@@ -126,9 +129,9 @@ class InBackwardGradientReducer:
             ready.record(torch.cuda.current_stream(dev))            # the gradients of this bucket are final
             with torch.cuda.stream(self._comm):
                 self._comm.wait_event(ready)
-                with dist._coalescing_manager(device=dev):
+                with dist._coalescing_manager(group=self.group, device=dev):
                     for g in grads:
-                        dist.all_reduce(g, op=dist.ReduceOp.AVG)
+                        dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
                 self._done = torch.cuda.Event()
                 self._done.record(self._comm)
                 for g in grads:
@@ -137,7 +140,7 @@ class InBackwardGradientReducer:
                 self._comm.synchronize()
         else:
             flat = torch._utils._flatten_dense_tensors(grads)
-            self.inflight.append((dist.all_reduce(flat, async_op=True), flat, grads))
+            self.inflight.append((dist.all_reduce(flat, async_op=True, group=self.group), flat, grads))
 
     # -- user side -------------------------------------------------------------------------------------------------
     def __enter__(self):
@@ -155,3 +158,28 @@ class InBackwardGradientReducer:
     def reduce_rest(self, params):
         """Plain all-reduce of the gradients no plan emitted (parameters of modules that are not training plans)."""
         return allreduce_gradients(list(params), self.dist, self.world)
+
+
+_reducer_group = None
+
+
+def reducer_group(dist=None):
+    """A process group of its own for the in-backward reducer (NCCL only; None = use the default group).  The bucket
+    all-reduces run WHILE the backward kernels do: an NCCL kernel that spreads over many SMs takes them away from conv
+    grids sized to fill the machine, so the communicator can be capped (HFC_REDUCER_MAX_CTAS, NCCL's `max_ctas`) and its
+    stream raised in priority (HFC_REDUCER_HIGH_PRIORITY=1) so that the few CTAs it does use are scheduled at once."""
+    global _reducer_group
+    if dist is None:
+        import torch.distributed as dist
+    if _reducer_group is not None:
+        return _reducer_group
+    max_ctas = int(os.environ.get("HFC_REDUCER_MAX_CTAS", "0"))
+    high = os.environ.get("HFC_REDUCER_HIGH_PRIORITY", "0") == "1"
+    if not dist.is_initialized() or dist.get_backend() != "nccl" or (max_ctas <= 0 and not high):
+        return None
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=high)
+    if max_ctas > 0:
+        opts.config.max_ctas = max_ctas
+        opts.config.min_ctas = min(max_ctas, 1)
+    _reducer_group = dist.new_group(backend="nccl", pg_options=opts)
+    return _reducer_group

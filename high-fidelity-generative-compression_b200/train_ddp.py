@@ -116,7 +116,7 @@ def train(args, model, batches, device, logger, optimizers, dist=None, rank=0, w
     disc_opt = optimizers.get('disc')
     density = list(model.Hyperprior.hyperlatent_likelihood.parameters())
     disc_params = list(model.Discriminator.parameters()) if model.use_discriminator is True else []
-    reducer = hdist.InBackwardGradientReducer(dist, world) if (world > 1 and overlap) else None
+    reducer = hdist.InBackwardGradientReducer(dist, world, group=hdist.reducer_group(dist)) if (world > 1 and overlap) else None
     if world > 1 and reducer is None:
         amort_params = [p for am in model.amortization_models for p in am.parameters()]
 
