@@ -93,6 +93,11 @@ SIGNATURES = {
     "hfc_pad_fold": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _i32, _vp]),
     "hfc_channelnorm_bwd": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _f32, _i32, _vp, _i32, _vp, _vp, _vp, _vp,
                                           _i32, _i32, _vp]),
+    "hfc_instancenorm_ws_bytes": (ctypes.c_int64, [_i32, _i32]),
+    "hfc_instancenorm": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _i64,
+                                       _vp]),
+    "hfc_instancenorm_bwd": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _i32, _vp, _vp, _vp,
+                                           _vp, _i32, _i32, _vp, _i64, _vp]),
     "hfc_relu_mask": (ctypes.c_int, [_vp, _i32, _vp, ctypes.POINTER(ActGeom), _f32, _vp, _i32, _vp]),
     "hfc_rows_to_act_geom": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ActGeom), _i32, _vp, _vp]),
     "hfc_adam_chunk": (ctypes.c_int32, []),

@@ -98,6 +98,39 @@ def channelnorm(x_rows, geom, gamma, beta, act=ACT_NONE, reflect=False, res1=Non
     return out_act, out_f32
 
 
+IN_EPS = 1e-5           # torch.nn.InstanceNorm2d default (src/normalisation/instance.py:12-14 does not override it)
+_in_ws_cache = {}
+
+
+def instancenorm_ws(n, c, device):
+    """Scratch of hfc_instancenorm / hfc_instancenorm_bwd (double accumulators + per-(n, c) statistics); one buffer per
+    device, grown on demand -- the launches that use it are ordered on the current stream."""
+    need = int(lib.hfc_instancenorm_ws_bytes(int(n), int(c)))
+    buf = _in_ws_cache.get(device)
+    if buf is None or buf.numel() * 8 < need:
+        buf = _in_ws_cache[device] = torch.empty((need + 7) // 8, dtype=torch.float64, device=device)
+    return buf, buf.numel() * 8
+
+
+def instancenorm(x_rows, geom, gamma, beta, act=ACT_NONE, reflect=False, res1=None, res2=None,
+                 want_f32=False, want_act=True, out_act=None, out_f32=None):
+    """InstanceNorm2d(affine) over NHWC fp32 rows (use_channel_norm=False variant; src/normalisation/instance.py:7-15):
+    the drop-in of `channelnorm` with per-(image, channel) statistics."""
+    assert x_rows.dtype == torch.float32 and x_rows.is_contiguous()
+    ld = x_rows.shape[-1]
+    if want_act and out_act is None:
+        out_act = geom.alloc(x_rows.device)
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((geom.n * geom.h * geom.w, geom.c), dtype=torch.float32, device=x_rows.device)
+    g = geom.c_struct()
+    ws, ws_bytes = instancenorm_ws(geom.n, geom.c, x_rows.device)
+    check(lib.hfc_instancenorm(_ptr(x_rows), ld, ctypes.byref(g), int(reflect), _ptr(gamma.reshape(-1)),
+                               _ptr(beta.reshape(-1)), IN_EPS, act, _ptr(res1), _ptr(res2),
+                               _ptr(out_f32 if want_f32 else None), _ptr(out_act if want_act else None),
+                               _ptr(ws), ws_bytes, _stream()), "instancenorm")
+    return out_act, out_f32
+
+
 class Conv:
     """One convolution / transposed convolution of the hot path bound to fixed geometry.
 

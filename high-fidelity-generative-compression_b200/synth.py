@@ -145,3 +145,18 @@ def synth_image(n, h, w, seed=0, channels=3):
 def synth_noise(shape, tag, seed=0):
     """U(-1/2, 1/2) quantisation noise (the reference draws it with torch.nn.init.uniform_, hyperprior.py:65)."""
     return torch.rand(shape, generator=_gen("noise" + tag, seed)) - 0.5
+
+
+def instance_norm_variant(sd):
+    """The same synthetic parameters for the use_channel_norm = False architecture: torch.nn.InstanceNorm2d keeps its
+    affine pair as `weight` / `bias` of shape (c,) where ChannelNorm2D has `gamma` / `beta` of shape (1, c, 1, 1)
+    (src/normalisation/instance.py:7-15 vs channel.py:29-46)."""
+    out = {}
+    for k, v in sd.items():
+        if k.endswith(".gamma"):
+            out[k[:-len(".gamma")] + ".weight"] = v.reshape(-1).clone()
+        elif k.endswith(".beta"):
+            out[k[:-len(".beta")] + ".bias"] = v.reshape(-1).clone()
+        else:
+            out[k] = v
+    return out

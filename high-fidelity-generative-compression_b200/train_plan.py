@@ -35,8 +35,8 @@ def rows_to_nchw(r, n, c, h, w):
     return r.view(n, h, w, -1)[..., :c].permute(0, 3, 1, 2).contiguous()
 
 
-def norm_bwd(z, g, gamma, beta, act, as_operand=True):
-    """ChannelNorm(+ReLU) backward on fp32 rows.  Returns (dz, dgamma, dbeta, dbias) with dbias = column sums of dz
+def norm_bwd(z, g, gamma, beta, act, as_operand=True, kind="channel", n=None):
+    """ChannelNorm / InstanceNorm (+ReLU) backward on fp32 rows (kind "instance": n = images, the rows are n * hw).  Returns (dz, dgamma, dbeta, dbias) with dbias = column sums of dz
     (the gradient of the bias of the convolution that produced z).  as_operand: dz is written directly as the bf16
     NHWC operand of the two backward GEMMs of that convolution (pitch round_up(c, 64), shared workspace -- consume it
     before the next norm_bwd); otherwise as fp32 rows."""
@@ -50,9 +50,17 @@ def norm_bwd(z, g, gamma, beta, act, as_operand=True):
     else:
         dz = torch.empty((npix, round_up(c, 4)), dtype=torch.float32, device=z.device)
         dz_f32, dz_act, ld, cpad = dz, None, dz.shape[1], 0
-    check(lib.hfc_channelnorm_bwd(_ptr(z), z.shape[1], _ptr(g), g.shape[1], _ptr(gamma.detach().reshape(-1)),
-                                  _ptr(beta.detach().reshape(-1)), c, npix, CN_EPS, act, _ptr(dz_f32), ld,
-                                  _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _ptr(dz_act), cpad, int(GRAD_BF16), _stream()), "channelnorm_bwd")
+    if kind == "instance":
+        ws, ws_bytes = ops.instancenorm_ws(n, c, z.device)
+        check(lib.hfc_instancenorm_bwd(_ptr(z), z.shape[1], _ptr(g), g.shape[1], _ptr(gamma.detach().reshape(-1)),
+                                       _ptr(beta.detach().reshape(-1)), c, n, npix // n, ops.IN_EPS, act, _ptr(dz_f32), ld,
+                                       _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _ptr(dz_act), cpad, int(GRAD_BF16),
+                                       _ptr(ws), ws_bytes, _stream()), "instancenorm_bwd")
+    else:
+        check(lib.hfc_channelnorm_bwd(_ptr(z), z.shape[1], _ptr(g), g.shape[1], _ptr(gamma.detach().reshape(-1)),
+                                      _ptr(beta.detach().reshape(-1)), c, npix, CN_EPS, act, _ptr(dz_f32), ld,
+                                      _ptr(dgb[0]), _ptr(dgb[1]), _ptr(dgb[2]), _ptr(dz_act), cpad, int(GRAD_BF16), _stream()),
+              "channelnorm_bwd")
     if as_operand:
         _grad._log_operand(dz)
     if _grad._inv_scale != 1.0:
@@ -118,8 +126,10 @@ class Layer:
         return dx, dw, db
 
 
-def norm_fwd(z, geom, gamma, beta, act, reflect, res1=None, res2=None, want_f32=False):
-    return ops.channelnorm(z, geom, gamma, beta, act=act, reflect=reflect, res1=res1, res2=res2, want_f32=want_f32)
+def norm_fwd(z, geom, gamma, beta, act, reflect, res1=None, res2=None, want_f32=False, want_act=True, kind="channel"):
+    """The inter-layer normalisation of the plan: ChannelNorm2D (default) or InstanceNorm2d (use_channel_norm=False)."""
+    fn = ops.instancenorm if kind == "instance" else ops.channelnorm
+    return fn(z, geom, gamma, beta, act=act, reflect=reflect, res1=res1, res2=res2, want_f32=want_f32, want_act=want_act)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -128,9 +138,10 @@ def norm_fwd(z, geom, gamma, beta, act, reflect, res1=None, res2=None, want_f32=
 class EncoderTrainPlan:
     FILTERS = (60, 120, 240, 480, 960)
 
-    def __init__(self, n, h, w, im_channels, C, device):
+    def __init__(self, n, h, w, im_channels, C, device, norm_kind="channel"):
         f = self.FILTERS
         self.n = n
+        self.kind = norm_kind
         self.g_in = Geom(n, h, w, im_channels, 8, 3, 3, 3, 4)
         asym = (1, 0, 0, 1)
         self.layers, self.geoms = [], []
@@ -153,7 +164,7 @@ class EncoderTrainPlan:
             w, b, gm, bt = p[4 * i:4 * i + 4]
             z = lay.forward(h, w, b)
             self.z.append(z)
-            h, _ = norm_fwd(z, self.geoms[i], gm, bt, ACT_RELU, True)
+            h, _ = norm_fwd(z, self.geoms[i], gm, bt, ACT_RELU, True, kind=self.kind)
         return self.out.forward(h, p[20], p[21])
 
     def backward(self, dy, p):
@@ -162,7 +173,7 @@ class EncoderTrainPlan:
         _grad.emit(grads[20], grads[21])
         for i in range(4, -1, -1):
             w, b, gm, bt = p[4 * i:4 * i + 4]
-            dz, grads[4 * i + 2], grads[4 * i + 3], db = norm_bwd(self.z[i], g, gm, bt, ACT_RELU)
+            dz, grads[4 * i + 2], grads[4 * i + 3], db = norm_bwd(self.z[i], g, gm, bt, ACT_RELU, kind=self.kind, n=self.n)
             g, grads[4 * i], grads[4 * i + 1] = self.layers[i].backward(dz, w, need_dx=i > 0, db=db)
             _grad.emit(*grads[4 * i:4 * i + 4])
         return grads
@@ -177,9 +188,10 @@ class EncoderTrainPlan:
 class GeneratorTrainPlan:
     FILTERS = (960, 480, 240, 120, 60)
 
-    def __init__(self, n, h, w, C, n_res, im_channels, device, noise_dim=0):
+    def __init__(self, n, h, w, C, n_res, im_channels, device, noise_dim=0, norm_kind="channel"):
         f = self.FILTERS
         self.n, self.h, self.w, self.C, self.n_res = n, h, w, C, n_res
+        self.kind = norm_kind
         # sample_noise (generator.py:105-107, 149-153): the trunk is F0 = 960 + noise_dim channels wide
         self.noise_dim, self.F0 = noise_dim, f[0] + noise_dim
         F0, F0p = self.F0, round_up(self.F0, 64)
@@ -208,15 +220,15 @@ class GeneratorTrainPlan:
     def forward(self, y_hat, p):
         R = self.n_res
         self.y_rows = nchw_to_rows(y_hat)
-        a0, _ = norm_fwd(self.y_rows, self.g_in, p[0], p[1], ACT_NONE, True)
+        k = dict(kind=self.kind)
+        a0, _ = norm_fwd(self.y_rows, self.g_in, p[0], p[1], ACT_NONE, True, **k)
         self.z_init = self.init.forward(a0, p[2], p[3])
         if self.noise_dim == 0:
-            x_act, head = norm_fwd(self.z_init, self.g_b1 if R else self.g_flat, p[4], p[5], ACT_NONE, bool(R), want_f32=True)
+            x_act, head = norm_fwd(self.z_init, self.g_b1 if R else self.g_flat, p[4], p[5], ACT_NONE, bool(R), want_f32=True, **k)
         else:
             # head = cat(norm(conv(.)), z), z ~ N(0, 1) (generator.py:150-153): data movement with torch ops; the noise
             # channels carry no gradient back
-            _, head960 = ops.channelnorm(self.z_init, self.g_head, p[4], p[5], act=ACT_NONE, reflect=False, want_f32=True,
-                                         want_act=False)
+            _, head960 = norm_fwd(self.z_init, self.g_head, p[4], p[5], ACT_NONE, False, want_f32=True, want_act=False, **k)
             z = torch.randn((self.n, self.noise_dim, self.h, self.w)).to(head960)
             hn = torch.cat((head960.view(self.n, self.h, self.w, 960).permute(0, 3, 1, 2), z), dim=1).contiguous()
             head = hn.permute(0, 2, 3, 1).reshape(-1, self.F0).contiguous()
@@ -227,11 +239,11 @@ class GeneratorTrainPlan:
             w1, bb1, w2, bb2, g1, be1, g2, be2 = p[6 + 8 * m:14 + 8 * m]
             c1, c2 = self.res[m]
             z1 = c1.forward(x_act, w1, bb1)
-            a1, _ = norm_fwd(z1, self.g_b1, g1, be1, ACT_RELU, True)
+            a1, _ = norm_fwd(z1, self.g_b1, g1, be1, ACT_RELU, True, **k)
             z2 = c2.forward(a1, w2, bb2)
             last = m == R - 1
             x_act, x_new = norm_fwd(z2, self.g_flat if last else self.g_b1, g2, be2, ACT_NONE, not last, res1=x_f32,
-                                    res2=head if last else None, want_f32=not last)
+                                    res2=head if last else None, want_f32=not last, **k)
             self.zr.append((z1, z2))
             x_f32 = x_new
         self.zu = []
@@ -242,18 +254,19 @@ class GeneratorTrainPlan:
             z = lay.forward(h, w, b)
             self.zu.append(z)
             gg = self.up_geoms[i]
-            h, _ = norm_fwd(z, gg, gm, bt, ACT_RELU, any((gg.pt, gg.pl, gg.pb, gg.pr)))
+            h, _ = norm_fwd(z, gg, gm, bt, ACT_RELU, any((gg.pt, gg.pl, gg.pb, gg.pr)), **k)
         return self.out.forward(h, p[o + 16], p[o + 17])
 
     def backward(self, dxhat, p):
         R = self.n_res
         o = 6 + 8 * R
         grads = [None] * len(p)
+        k = dict(kind=self.kind, n=self.n)
         g, grads[o + 16], grads[o + 17] = self.out.backward(nchw_to_rows(dxhat), p[o + 16])
         _grad.emit(grads[o + 16], grads[o + 17])
         for i in range(3, -1, -1):
             w, b, gm, bt = p[o + 4 * i:o + 4 * i + 4]
-            dz, grads[o + 4 * i + 2], grads[o + 4 * i + 3], db = norm_bwd(self.zu[i], g, gm, bt, ACT_RELU)
+            dz, grads[o + 4 * i + 2], grads[o + 4 * i + 3], db = norm_bwd(self.zu[i], g, gm, bt, ACT_RELU, **k)
             g, grads[o + 4 * i], grads[o + 4 * i + 1] = self.ups[i].backward(dz, w, db=db)
             _grad.emit(*grads[o + 4 * i:o + 4 * i + 4])
         # g = gradient w.r.t. the trunk output x_R (+ head): identity paths carry it to every block input and to head
@@ -262,10 +275,10 @@ class GeneratorTrainPlan:
             w1, bb1, w2, bb2, g1, be1, g2, be2 = p[6 + 8 * m:14 + 8 * m]
             c1, c2 = self.res[m]
             z1, z2 = self.zr[m]
-            dz2, grads[6 + 8 * m + 6], grads[6 + 8 * m + 7], db2 = norm_bwd(z2, g, g2, be2, ACT_NONE)
+            dz2, grads[6 + 8 * m + 6], grads[6 + 8 * m + 7], db2 = norm_bwd(z2, g, g2, be2, ACT_NONE, **k)
             ga1, grads[6 + 8 * m + 2], grads[6 + 8 * m + 3] = c2.backward(dz2, w2, db=db2)
             _grad.emit(grads[6 + 8 * m + 2], grads[6 + 8 * m + 3], grads[6 + 8 * m + 6], grads[6 + 8 * m + 7])
-            dz1, grads[6 + 8 * m + 4], grads[6 + 8 * m + 5], db1 = norm_bwd(z1, ga1, g1, be1, ACT_RELU)
+            dz1, grads[6 + 8 * m + 4], grads[6 + 8 * m + 5], db1 = norm_bwd(z1, ga1, g1, be1, ACT_RELU, **k)
             gx, grads[6 + 8 * m], grads[6 + 8 * m + 1] = c1.backward(dz1, w1, db=db1)
             _grad.emit(grads[6 + 8 * m], grads[6 + 8 * m + 1], grads[6 + 8 * m + 4], grads[6 + 8 * m + 5])
             g = g + gx                                  # identity_map + residual branch (generator.py:44)
@@ -273,9 +286,9 @@ class GeneratorTrainPlan:
             g_head = g_head + g                         # block 0 consumed head; the final `x += head` added it again
         if self.noise_dim:
             g_head = g_head[:, :960].contiguous()       # the noise channels of the head are constants
-        dz0, grads[4], grads[5], db0 = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE)
+        dz0, grads[4], grads[5], db0 = norm_bwd(self.z_init, g_head, p[4], p[5], ACT_NONE, **k)
         ga0, grads[2], grads[3] = self.init.backward(dz0, p[2], db=db0)
-        dy_rows, grads[0], grads[1], _ = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE, as_operand=False)
+        dy_rows, grads[0], grads[1], _ = norm_bwd(self.y_rows, ga0, p[0], p[1], ACT_NONE, as_operand=False, **k)
         _grad.emit(*grads[0:6])
         return rows_to_nchw(dy_rows, self.n, self.C, self.h, self.w), grads
 
@@ -288,8 +301,9 @@ class ResidualBlockTrainPlan:
     norm, + identity.  Serves both the no-grad call and autograd (PlanFunction); inside Generator.forward the blocks run
     as part of the Generator plans instead.  Parameter order: conv1 (w, b), conv2 (w, b), norm1 (g, b), norm2 (g, b)."""
 
-    def __init__(self, n, h, w, c, device):
+    def __init__(self, n, h, w, c, device, norm_kind="channel"):
         self.n, self.h, self.w, self.c = n, h, w, c
+        self.kind = norm_kind
         b1 = (1, 1, 1, 1)
         self.g_b1 = Geom(n, h, w, c, round_up(c, 64), *b1)
         self.g_flat = Geom(n, h, w, c, round_up(c, 64))
@@ -301,19 +315,20 @@ class ResidualBlockTrainPlan:
         x_rows = nchw_to_rows(x)
         x_act = ops.nchw_to_act(x, self.g_b1, reflect=True)
         self.z1 = self.c1.forward(x_act, w1, bb1)
-        a1, _ = norm_fwd(self.z1, self.g_b1, g1, be1, ACT_RELU, True)
+        a1, _ = norm_fwd(self.z1, self.g_b1, g1, be1, ACT_RELU, True, kind=self.kind)
         self.z2 = self.c2.forward(a1, w2, bb2)
-        _, out = ops.channelnorm(self.z2, self.g_flat, g2, be2, act=ACT_NONE, reflect=False, res1=x_rows, want_f32=True,
-                                 want_act=False)
+        _, out = norm_fwd(self.z2, self.g_flat, g2, be2, ACT_NONE, False, res1=x_rows, want_f32=True, want_act=False,
+                          kind=self.kind)
         return rows_to_nchw(out, self.n, self.c, self.h, self.w)
 
     def backward(self, dout, p):
         w1, bb1, w2, bb2, g1, be1, g2, be2 = p
         grads = [None] * 8
         g = nchw_to_rows(dout)
-        dz2, grads[6], grads[7], db2 = norm_bwd(self.z2, g, g2, be2, ACT_NONE)
+        k = dict(kind=self.kind, n=self.n)
+        dz2, grads[6], grads[7], db2 = norm_bwd(self.z2, g, g2, be2, ACT_NONE, **k)
         ga1, grads[2], grads[3] = self.c2.backward(dz2, w2, db=db2)
-        dz1, grads[4], grads[5], db1 = norm_bwd(self.z1, ga1, g1, be1, ACT_RELU)
+        dz1, grads[4], grads[5], db1 = norm_bwd(self.z1, ga1, g1, be1, ACT_RELU, **k)
         gx, grads[0], grads[1] = self.c1.backward(dz1, w1, db=db1)
         _grad.emit(*grads)
         return rows_to_nchw(g[:, :self.c] + gx[:, :self.c], self.n, self.c, self.h, self.w), grads
@@ -582,3 +597,13 @@ class PlanFunction(torch.autograd.Function):
 
 def run_training(plan, x, params):
     return PlanFunction.apply(plan, x, *params)
+
+
+def run_inference(plan, x, params):
+    """The plan's forward without autograd (variants that have no fused inference plan: InstanceNorm, a stand-alone
+    ResidualBlock): the layer-by-layer forward, saved tensors dropped at once."""
+    _stamp(plan)                      # a backward still pending on this plan must fail loudly, not read these buffers
+    with torch.no_grad():
+        out = plan.forward(x.contiguous(), [q.detach() for q in params])
+        plan.release()
+    return out

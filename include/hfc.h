@@ -304,6 +304,26 @@ int hfc_channelnorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld
                         const float* beta, int32_t c, int64_t npix, float eps, int32_t act, float* dz, int32_t ld_dz,
                         float* dgamma, float* dbeta, float* dbias, void* dz_act, int32_t act_cpad, int32_t act_bf16,
                         void* stream);
+/*
+ * InstanceNorm2d variant of the inter-layer normalisation (use_channel_norm = False: src/normalisation/instance.py:7-15 ->
+ * torch.nn.InstanceNorm2d(affine=True, track_running_stats=False), selected in src/network/encoder.py:41-44 and
+ * src/network/generator.py:21-24, 81-84).  Same contract as hfc_channelnorm, but the statistics are per (image, channel)
+ * over the h*w pixels (biased variance):  y = act(gamma * (x - mean_nc) * rsqrt(var_nc + eps) + beta) [+ res1] [+ res2],
+ * written as fp32 rows (out_f32, pitch c, optional) and as the bordered act buffer `g` (out_act, optional).
+ * ws: device scratch of at least hfc_instancenorm_ws_bytes(n, c) bytes (8-byte aligned; contents are overwritten).
+ */
+int64_t hfc_instancenorm_ws_bytes(int32_t n, int32_t c);
+int hfc_instancenorm(const float* x, int32_t ld, const hfc_act_geom* g, int32_t reflect, const float* gamma,
+                     const float* beta, float eps, int32_t act, const float* res1, const float* res2, float* out_f32,
+                     void* out_act, void* ws, int64_t ws_bytes, void* stream);
+/* Autograd of hfc_instancenorm (torch.nn.InstanceNorm2d + ReLU as encoder.py:56-61 / generator.py:33-44 chain them):
+ * z [n*hw][ld_z] = the saved norm input, g [n*hw][ld_g] = the gradient of the norm output.  dz as fp32 rows and / or
+ * as the 16-bit operand of the backward GEMMs (dz_act, pitch act_cpad, bf16 if act_bf16 else saturating fp16); dgamma /
+ * dbeta / dbias (optional; = column sums of dz) are ACCUMULATED into the caller's (zeroed) buffers. */
+int hfc_instancenorm_bwd(const float* z, int32_t ld_z, const float* g, int32_t ld_g, const float* gamma, const float* beta,
+                         int32_t c, int32_t n, int32_t hw, float eps, int32_t act, float* dz, int32_t ld_dz, float* dgamma,
+                         float* dbeta, float* dbias, void* dz_act, int32_t act_cpad, int32_t act_bf16, void* ws,
+                         int64_t ws_bytes, void* stream);
 /* out = g * (y > 0 ? 1 : slope): backward of the fused bias + ReLU (slope 0) / LeakyReLU (slope 0.2) epilogue; y_act
  * is that layer's (bordered) NHWC fp16 output */
 int hfc_relu_mask(const float* g, int32_t ld_g, const void* y_act, const hfc_act_geom* geom, float slope, float* out,

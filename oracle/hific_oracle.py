@@ -53,8 +53,16 @@ def _convT(sd, prefix, x, stride, padding, output_padding, rnd=_ident):
                               padding=padding, output_padding=output_padding)
 
 
+IN_EPS = 1e-5
+
+
 def _cn(sd, prefix, x):
-    return channel_norm(x, sd[prefix + ".gamma"], sd[prefix + ".beta"])
+    """The inter-layer normalisation: ChannelNorm2D (gamma / beta in the state dict), or -- use_channel_norm = False --
+    torch.nn.InstanceNorm2d(affine=True, track_running_stats=False) (weight / bias; src/normalisation/instance.py:7-15,
+    encoder.py:41-44, generator.py:21-24, 81-84)."""
+    if prefix + ".gamma" in sd:
+        return channel_norm(x, sd[prefix + ".gamma"], sd[prefix + ".beta"])
+    return F.instance_norm(x, weight=sd[prefix + ".weight"], bias=sd[prefix + ".bias"], eps=IN_EPS)
 
 
 def _reflect(x, pad):

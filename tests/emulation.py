@@ -380,6 +380,27 @@ def channelnorm(x_rows, geom, gamma, beta, act=ACT_NONE, reflect=False, res1=Non
     return out_act, out_f32
 
 
+def instancenorm(x_rows, geom, gamma, beta, act=ACT_NONE, reflect=False, res1=None, res2=None, want_f32=False,
+                 want_act=True, out_act=None, out_f32=None):
+    """ops.instancenorm: torch.nn.functional.instance_norm on the NCHW view of the rows (eps 1e-5, biased variance)."""
+    n, h, w, c = geom.n, geom.h, geom.w, geom.c
+    y = x_rows.view(n * h * w, -1)[:, :c].reshape(n, h, w, c).permute(0, 3, 1, 2)
+    y = F.instance_norm(y, weight=gamma.detach().float().reshape(-1), bias=beta.detach().float().reshape(-1), eps=ops.IN_EPS)
+    y = _apply_act(y, act)
+    for r in (res1, res2):
+        if r is not None:
+            y = y + r.view(n, h, w, -1)[..., :c].permute(0, 3, 1, 2)
+    if want_f32:
+        if out_f32 is None:
+            out_f32 = torch.empty((n * h * w, c), dtype=torch.float32)
+        out_f32.copy_(y.permute(0, 2, 3, 1).reshape(n * h * w, c))
+    if want_act:
+        if out_act is None:
+            out_act = geom.alloc(x_rows.device)
+        _write_act(y, geom, out_act, reflect)
+    return out_act, out_f32
+
+
 @contextlib.contextmanager
 def plan_cpu_emulation():
     saved = []
@@ -392,6 +413,7 @@ def plan_cpu_emulation():
     patch(ops.Conv, "call_widenorm", conv_call_widenorm)
     patch(ops, "nchw_to_act", nchw_to_act)
     patch(ops, "channelnorm", channelnorm)
+    patch(ops, "instancenorm", instancenorm)
     patch(engine, "_require_cuda", lambda x, who: None)
     try:
         yield
@@ -644,17 +666,22 @@ def training_cpu_emulation():
                 setattr(obj, name, value)
 
 
-def norm_bwd(z, g, gamma, beta, act, as_operand=True):
-    """train_plan.norm_bwd through torch autograd of ChannelNorm(+ReLU) on fp32 rows; always returns fp32 rows (the
-    emulated ConvGrad works from rows, so the bf16 operand form of the real kernel is not modelled)."""
+def norm_bwd(z, g, gamma, beta, act, as_operand=True, kind="channel", n=None):
+    """train_plan.norm_bwd through torch autograd of ChannelNorm / InstanceNorm (+ReLU) on fp32 rows; always returns fp32
+    rows (the emulated ConvGrad works from rows, so the 16-bit operand form of the real kernels is not modelled)."""
     c = gamma.numel()
     with torch.enable_grad():
         zz = z[:, :c].detach().clone().requires_grad_(True)
         gm = gamma.detach().reshape(-1).clone().requires_grad_(True)
         bt = beta.detach().reshape(-1).clone().requires_grad_(True)
-        mean = zz.mean(dim=1, keepdim=True)
-        var = zz.var(dim=1, keepdim=True)
-        y = _apply_act(gm * (zz - mean) * torch.rsqrt(var + CN_EPS) + bt, act)
+        if kind == "instance":
+            img = zz.view(n, -1, c).permute(0, 2, 1)                     # (n, c, hw)
+            y = F.instance_norm(img, weight=gm, bias=bt, eps=ops.IN_EPS).permute(0, 2, 1).reshape(-1, c)
+            y = _apply_act(y, act)
+        else:
+            mean = zz.mean(dim=1, keepdim=True)
+            var = zz.var(dim=1, keepdim=True)
+            y = _apply_act(gm * (zz - mean) * torch.rsqrt(var + CN_EPS) + bt, act)
         y.backward(g[:, :c])
     dz = torch.zeros((z.shape[0], (c + 3) // 4 * 4))
     dz[:, :c] = zz.grad
