@@ -232,16 +232,16 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         for p in params:
             p.grad = None
 
-    def step(mark=None):
+    def step(mark=None, red=None):
         mark = mark or (lambda: None)
         mark()
         losses = model(x, train_generator=True)
         mark()
-        if reducer is not None:
-            with reducer:
+        if red is not None:
+            with red:
                 losses['compression'].backward()
             mark()
-            reducer.reduce_rest(hyper)
+            red.reduce_rest(hyper)
         else:
             losses['compression'].backward()
             mark()
@@ -254,12 +254,11 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         opt_h.zero_grad()
         mark()
 
-    phases = None
-    try:
+    def measure(red):
         for _ in range(3):
-            step()
+            step(red=red)
         steps = max(3, args.steps // 4)
-        ms = timed(step, steps)
+        ms = timed(lambda: step(red=red), steps)
         # where the step goes (3 extra untimed steps, events on the compute stream, median) and what the host needs to
         # enqueue one step onto an idle GPU (a step whose enqueue time approaches its GPU time is launch-bound)
         rows, host = [], []
@@ -272,7 +271,7 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
                 evs.append(e)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            step(mark)
+            step(mark, red)
             host.append((time.perf_counter() - t0) * 1e3)
             torch.cuda.synchronize()
             rows.append([evs[i].elapsed_time(evs[i + 1]) for i in range(4)])
@@ -281,6 +280,22 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
                   "adam_ms": med[3], "host_enqueue_ms": sorted(host)[1],
                   "note": "one step from an idle GPU, CUDA events on the compute stream; with the in-backward reducer the "
                           "waits for the buckets are inside backward_ms"}
+        return ms, steps, phases
+
+    other = None
+    try:
+        ms, steps, phases = measure(reducer)
+        if reducer is not None:
+            # the same step with the plain after-backward all-reduce: NCCL's kernels take SMs from conv grids sized to
+            # fill the machine, so hiding the collective behind the backward is not free -- both
+            # are timed at every N, the faster one is the headline, the other is reported beside it
+            ms_p, steps_p, phases_p = measure(None)
+            plain_mode = "after backward, one coalesced NCCL all-reduce"
+            alt = {"ms_per_step": ms_p / steps_p, "gradient_allreduce": plain_mode, "phases": phases_p}
+            if ms_p / steps_p < ms / steps:
+                alt = {"ms_per_step": ms / steps, "gradient_allreduce": reduce_mode, "phases": phases}
+                ms, steps, phases, reduce_mode = ms_p, steps_p, phases_p, plain_mode + " (faster than the in-backward reducer at this N)"
+            other = alt
     except NotImplementedError as e:      # a piece of the backward is missing: report it, do not fake a number
         return {"unavailable": str(e)[:200]}
     finally:
@@ -288,6 +303,7 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         model.eval()
     return {"ms_per_step": ms / steps, "images_per_s": world * B * steps / (ms * 1e-3), "steps": steps,
             "per_gpu_batch": B, "n_gpus": world, "gradient_allreduce": reduce_mode, "phases": phases,
+            "other_allreduce_mode": other,
             "lpips_trunk": os.environ.get("HFC_LPIPS_TRUNK", "native"),
             "dtype": ("bf16 x bf16 backward GEMMs (HFC_GRAD_FMT=bf16)" if os.environ.get("HFC_GRAD_FMT", "fp16").lower() == "bf16" else
                       "fp16 x fp16 backward GEMMs (10-bit mantissa as TF32; power-of-two loss scale per backward Function), "
