@@ -1655,6 +1655,48 @@ struct WideNormArgs {
   int32_t ld_f32;
 };
 
+// The s*s sub-pixel phases of a transposed convolution write disjoint output pixels and read the same input: they are
+// independent launches.  On one stream they run back to back, each with its own ramp-up and tail (on the 4x4 ... 16x16
+// maps of the hyper-synthesis networks a phase is a dozen CTAs); forked onto helper streams they overlap and share the
+// input tiles in L2.  Fork / join is two event edges per helper stream, valid in eager mode and under stream capture
+// (the helper streams join the capture through the event and are joined back before the call returns).
+struct PhaseFork {
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  int device = -1;
+  bool ok = false;
+};
+
+static PhaseFork* phase_fork(cudaStream_t st) {
+  static PhaseFork pools[16];
+  static const bool enabled = [] {
+    const char* e = getenv("HFC_PHASE_STREAMS");
+    return !(e && e[0] == '0');
+  }();
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  PhaseFork& pf = pools[dev];
+  if (!pf.ok) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;                      // never create streams / events inside a capture: this call stays serial
+    }
+    bool good = cudaEventCreateWithFlags(&pf.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && good; ++i)
+      good = cudaStreamCreateWithFlags(&pf.aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&pf.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    pf.device = dev;
+    pf.ok = true;
+  }
+  return &pf;
+}
+
 static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void* packed, const float* bias,
                              const float* gamma, const float* beta, void* out, void* stream, const WideNormArgs* wn) {
   Plan pl;
@@ -1674,7 +1716,15 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
   const int Hp = ig.h + ig.pt + ig.pb;
   const int Wp = ig.w + ig.pl + ig.pr;
 
-  for (int i = 0; i < pl.nphases; ++i) {
+  PhaseFork* pf = (pl.nphases > 1 && pl.nphases <= 4) ? phase_fork(st) : nullptr;
+  if (pf) {
+    cudaError_t e = cudaEventRecord(pf->fork, st);
+    for (int i = 1; i < pl.nphases && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(pf->aux[i - 1], pf->fork, 0);
+    if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "conv: phase fork: %s", cudaGetErrorString(e));
+  }
+  const cudaStream_t st_main = st;
+  auto launch_phase = [&](int i) -> int {
+    st = (pf && i > 0) ? pf->aux[i - 1] : st_main;
     const Phase& ph = pl.ph[i];
     ConvKernelParams kp;
     memset(&kp, 0, sizeof(kp));
@@ -1818,8 +1868,19 @@ static int conv_forward_impl(const hfc_conv_desc* d, const void* in, const void*
     if (e != cudaSuccess)
       return set_error(HFC_ERR_LAUNCH, "conv_igemm launch: %s", cudaGetErrorString(e));
     note_launch();
+    return HFC_OK;
+  };
+  int rc_phase = HFC_OK;
+  for (int i = 0; i < pl.nphases && rc_phase == HFC_OK; ++i) rc_phase = launch_phase(i);
+  if (pf) {                                // join (also after an error: a capture must not be left with unjoined streams)
+    cudaError_t e = cudaSuccess;
+    for (int i = 1; i < pl.nphases && e == cudaSuccess; ++i) {
+      e = cudaEventRecord(pf->join[i - 1], pf->aux[i - 1]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st_main, pf->join[i - 1], 0);
+    }
+    if (e != cudaSuccess && rc_phase == HFC_OK) return set_error(HFC_ERR_LAUNCH, "conv: phase join: %s", cudaGetErrorString(e));
   }
-  return HFC_OK;
+  return rc_phase;
 }
 
 extern "C" int hfc_conv_forward(const hfc_conv_desc* d, const void* in, const void* packed,
