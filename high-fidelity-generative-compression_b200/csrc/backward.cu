@@ -178,9 +178,13 @@ struct PermuteParams {
 // One block per GEMM row m: the row C[m][ntaps * c2_rows] is read with consecutive threads on consecutive addresses,
 // transposed through shared memory and written as the contiguous torch slab dW[m][:][:][:] (c2 * kh * kw floats).
 // (A thread-per-output-element gather reads with a stride of c2_rows floats: one 32 B sector per element.)
+// VEC (odd kh*kw, so T == kh*kw and the shared row IS the torch slab in its final order; c2, c2_rows, ldc multiples of 4,
+// 16-byte aligned pointers): float4 reads of the GEMM row and float4 writes of the slab -- the scalar version ran the
+// 960 x 960 x 3 x 3 gradients at ~2 TB/s (34 dependent 4-byte accesses per thread and phase, latency-bound).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 permute_wgrad_kernel(const float* __restrict__ c, float* __restrict__ dw, const __grid_constant__ PermuteParams p) {
-  extern __shared__ float s_row[];                 // [c2][T], T = kh*kw | 1
+  extern __shared__ __align__(16) float s_row[];   // [c2][T], T = kh*kw | 1
   const int m = blockIdx.x;
   const int khkw = p.kh * p.kw;
   const int T = khkw | 1;
@@ -188,15 +192,35 @@ permute_wgrad_kernel(const float* __restrict__ c, float* __restrict__ dw, const 
   for (int tap = 0; tap < p.ntaps; ++tap) {
     if (p.ky[tap] < 0) continue;                   // unused column slot (window packing: 8 slots per filter row)
     const int t = p.ky[tap] * p.kw + p.kx[tap];
-    for (int c2 = threadIdx.x; c2 < p.c2; c2 += blockDim.x) s_row[c2 * T + t] = crow[tap * p.c2_rows + c2];
+    if constexpr (VEC) {
+      const float4* src4 = reinterpret_cast<const float4*>(crow + static_cast<size_t>(tap) * p.c2_rows);
+      for (int q = threadIdx.x; q < (p.c2 >> 2); q += blockDim.x) {
+        const float4 v = __ldg(src4 + q);
+        float* d = s_row + (4 * q) * T + t;
+        d[0] = v.x; d[T] = v.y; d[2 * T] = v.z; d[3 * T] = v.w;
+      }
+    } else {
+      for (int c2 = threadIdx.x; c2 < p.c2; c2 += blockDim.x) s_row[c2 * T + t] = crow[tap * p.c2_rows + c2];
+    }
   }
   __syncthreads();
   float* drow = dw + static_cast<size_t>(m) * p.c2 * khkw;
   const int total = p.c2 * khkw;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int c2 = e / khkw, t = e - c2 * khkw;
-    const float v = s_row[c2 * T + t] * p.scale;
-    drow[e] = p.accumulate ? drow[e] + v : v;
+  if constexpr (VEC) {                             // T == khkw: s_row[e] is element e of the slab
+    float4* d4 = reinterpret_cast<float4*>(drow);
+    const float4* s4 = reinterpret_cast<const float4*>(s_row);
+    for (int q = threadIdx.x; q < (total >> 2); q += blockDim.x) {
+      float4 v = s4[q];
+      v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
+      if (p.accumulate) { const float4 o = d4[q]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      d4[q] = v;
+    }
+  } else {
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int c2 = e / khkw, t = e - c2 * khkw;
+      const float v = s_row[c2 * T + t] * p.scale;
+      drow[e] = p.accumulate ? drow[e] + v : v;
+    }
   }
 }
 
@@ -337,10 +361,15 @@ extern "C" int hfc_permute_wgrad(const float* c, int32_t ldc, int32_t m, int32_t
   if (smem > 96 * 1024) return set_error(HFC_ERR_UNSUPPORTED, "permute_wgrad: c2 * kh * kw too large for the row buffer");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(permute_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(permute_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(permute_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set = true;
   }
-  permute_wgrad_kernel<<<m, 256, smem, static_cast<cudaStream_t>(stream)>>>(c, dw, p);
+  static const bool vec_on = [] { const char* e = getenv("HFC_PERMUTE_VEC"); return !(e && e[0] == '0'); }();
+  const bool vec = vec_on && ((kh * kw) & 1) && c2 % 4 == 0 && c2_rows % 4 == 0 && ldc % 4 == 0 &&
+                   reinterpret_cast<uintptr_t>(c) % 16 == 0 && reinterpret_cast<uintptr_t>(dw) % 16 == 0;
+  if (vec) permute_wgrad_kernel<true><<<m, 256, smem, static_cast<cudaStream_t>(stream)>>>(c, dw, p);
+  else permute_wgrad_kernel<false><<<m, 256, smem, static_cast<cudaStream_t>(stream)>>>(c, dw, p);
   HFC_CHECK_LAUNCH("permute_wgrad launch");
   return HFC_OK;
 }

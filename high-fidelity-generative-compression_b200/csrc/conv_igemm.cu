@@ -1152,12 +1152,23 @@ struct PackRowParams {
   int8_t kx[kMaxTaps];
 };
 
-// KHKW: kh*kw as a compile-time constant (the index split is then a multiply-shift), 0 = runtime value
-template <int KHKW>
+__device__ __forceinline__ uint16_t pack_cvt(float v, uint32_t fmt) {
+  if (fmt == 0) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// KHKW: kh*kw as a compile-time constant (the index split is then a multiply-shift), 0 = runtime value.
+// VEC (odd KHKW only, so that T == KHKW and the shared row is simply the converted source slab in source order): 16-byte
+// global accesses on both sides -- float4 reads of a contiguous conv2d filter slab (4 independent scalar loads per thread
+// for the kh*kw-float runs of a conv_transpose2d / dgrad filter) and one 16-byte store per 8 output channels.  The scalar
+// version ran the 960 x 960 x 3 x 3 filters at ~2 TB/s: 34 dependent 4-byte loads per thread with every block of the grid
+// resident at once, i.e. latency-bound, not bandwidth-bound.
+template <int KHKW, bool VEC>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ w, const float* __restrict__ scale, uint16_t* __restrict__ out,
                  const __grid_constant__ PackRowParams pp) {
-  extern __shared__ uint16_t s_pack[];               // [cin][T], T odd: conflict-free transposed reads
+  extern __shared__ __align__(16) uint16_t s_pack[];  // [cin][T], T odd: conflict-free transposed reads
   const float mul = scale ? *scale : 1.f;
   const int r = blockIdx.x;
   const int khkw = KHKW ? KHKW : pp.kh * pp.kw;
@@ -1167,27 +1178,75 @@ pack_rows_kernel(const float* __restrict__ w, const float* __restrict__ scale, u
     const int total = pp.cin * khkw;
     const float* src_row = w + static_cast<size_t>(r) * (pp.strided ? khkw : total);
     const size_t c_stride = pp.strided ? static_cast<size_t>(pp.rows_real) * khkw : static_cast<size_t>(khkw);
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-      const int c = e / khkw, t = e - c * khkw;
-      const float val = src_row[c * c_stride + t] * mul;
-      uint16_t bits;
-      if (pp.fmt == 0) { __half h = __float2half_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
-      else { __nv_bfloat16 h = __float2bfloat16_rn(val); bits = *reinterpret_cast<uint16_t*>(&h); }
-      s_pack[c * T + t] = bits;
+    if constexpr (VEC) {
+      static_assert(KHKW % 2 == 1, "the vector path needs T == KHKW");
+      if (!pp.strided) {                   // contiguous slab: s_pack[e] = cvt(src[e])   (host checked total % 4, alignment)
+        const float4* src4 = reinterpret_cast<const float4*>(src_row);
+        for (int q = threadIdx.x; q < (total >> 2); q += blockDim.x) {
+          const float4 v = __ldg(src4 + q);
+          uint2 pk;
+          pk.x = static_cast<uint32_t>(pack_cvt(v.x * mul, pp.fmt)) | (static_cast<uint32_t>(pack_cvt(v.y * mul, pp.fmt)) << 16);
+          pk.y = static_cast<uint32_t>(pack_cvt(v.z * mul, pp.fmt)) | (static_cast<uint32_t>(pack_cvt(v.w * mul, pp.fmt)) << 16);
+          *reinterpret_cast<uint2*>(s_pack + 4 * q) = pk;
+        }
+      } else {
+        for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j * blockDim.x;
+            v[j] = 0.f;
+            if (e < total) {
+              const int c = e / khkw, t = e - c * khkw;
+              v[j] = __ldg(src_row + c * c_stride + t);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j * blockDim.x;
+            if (e < total) s_pack[e] = pack_cvt(v[j] * mul, pp.fmt);     // c * T + t == e
+          }
+        }
+      }
+    } else {
+      for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int c = e / khkw, t = e - c * khkw;
+        s_pack[c * T + t] = pack_cvt(src_row[c * c_stride + t] * mul, pp.fmt);
+      }
     }
   }
   __syncthreads();
-  uint32_t* orow = reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r) * pp.ktot);   // cin_pad is even: 2 channels / thread
-  const int half = pp.cin_pad >> 1;
-  for (int tap = 0; tap < pp.ntaps; ++tap) {
-    int ky = pp.ky[tap], kx = pp.kx[tap];
-    if (pp.flip) { ky = pp.kh - 1 - ky; kx = pp.kw - 1 - kx; }
-    const int t = ky * pp.kw + kx;
-    for (int c2 = threadIdx.x; c2 < half; c2 += blockDim.x) {
-      const int c = 2 * c2;
-      const uint32_t lo = (real && c < pp.cin) ? s_pack[c * T + t] : 0u;
-      const uint32_t hi = (real && c + 1 < pp.cin) ? s_pack[(c + 1) * T + t] : 0u;
-      orow[tap * half + c2] = lo | (hi << 16);
+  if constexpr (VEC) {
+    const int octs = pp.cin_pad >> 3;                                    // 8 channels = one 16-byte store
+    uint4* orow4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * pp.ktot);
+    for (int item = threadIdx.x; item < pp.ntaps * octs; item += blockDim.x) {
+      const int tap = item / octs, q = item - tap * octs;
+      int ky = pp.ky[tap], kx = pp.kx[tap];
+      if (pp.flip) { ky = pp.kh - 1 - ky; kx = pp.kw - 1 - kx; }
+      const int t = ky * pp.kw + kx;
+      uint32_t wd[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = 8 * q + 2 * j;
+        const uint32_t lo = (real && c < pp.cin) ? s_pack[c * T + t] : 0u;
+        const uint32_t hi = (real && c + 1 < pp.cin) ? s_pack[(c + 1) * T + t] : 0u;
+        wd[j] = lo | (hi << 16);
+      }
+      orow4[item] = make_uint4(wd[0], wd[1], wd[2], wd[3]);              // item == tap * octs + q
+    }
+  } else {
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r) * pp.ktot);   // cin_pad is even: 2 channels / thread
+    const int half = pp.cin_pad >> 1;
+    for (int tap = 0; tap < pp.ntaps; ++tap) {
+      int ky = pp.ky[tap], kx = pp.kx[tap];
+      if (pp.flip) { ky = pp.kh - 1 - ky; kx = pp.kw - 1 - kx; }
+      const int t = ky * pp.kw + kx;
+      for (int c2 = threadIdx.x; c2 < half; c2 += blockDim.x) {
+        const int c = 2 * c2;
+        const uint32_t lo = (real && c < pp.cin) ? s_pack[c * T + t] : 0u;
+        const uint32_t hi = (real && c + 1 < pp.cin) ? s_pack[(c + 1) * T + t] : 0u;
+        orow[tap * half + c2] = lo | (hi << 16);
+      }
     }
   }
 }
@@ -1623,13 +1682,28 @@ static int pack_weights_impl(const hfc_conv_desc* d, const float* w, const float
       memcpy(pr.ky, ph.ky, sizeof(pr.ky));
       memcpy(pr.kx, ph.kx, sizeof(pr.kx));
       uint16_t* dst = reinterpret_cast<uint16_t*>(packed) + ph.w_offset;
-      switch (d->kh * d->kw) {
-        case 1: pack_rows_kernel<1><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
-        case 9: pack_rows_kernel<9><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
-        case 16: pack_rows_kernel<16><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
-        case 25: pack_rows_kernel<25><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
-        case 49: pack_rows_kernel<49><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
-        default: pack_rows_kernel<0><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+      static const bool vec_on = [] { const char* e = getenv("HFC_PACK_VEC"); return !(e && e[0] == '0'); }();
+      const int khkw = d->kh * d->kw;
+      const bool vec = vec_on && (khkw & 1) && d->in.cpad % 8 == 0 && ph.ktot % 8 == 0 && ph.w_offset % 8 == 0 &&
+                       reinterpret_cast<uintptr_t>(packed) % 16 == 0 &&
+                       (pr.strided || ((static_cast<long long>(d->in.c) * khkw) % 4 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0));
+      if (vec) {
+        switch (khkw) {
+          case 1: pack_rows_kernel<1, true><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          case 9: pack_rows_kernel<9, true><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          case 25: pack_rows_kernel<25, true><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          case 49: pack_rows_kernel<49, true><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          default: pack_rows_kernel<0, false><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+        }
+      } else {
+        switch (khkw) {
+          case 1: pack_rows_kernel<1, false><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          case 9: pack_rows_kernel<9, false><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          case 16: pack_rows_kernel<16, false><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          case 25: pack_rows_kernel<25, false><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          case 49: pack_rows_kernel<49, false><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+          default: pack_rows_kernel<0, false><<<pl.rows, 256, row_smem, st>>>(w, scale, dst, pr); break;
+        }
       }
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return set_error(HFC_ERR_LAUNCH, "pack_rows launch: %s", cudaGetErrorString(e));

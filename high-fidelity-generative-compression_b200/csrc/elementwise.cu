@@ -152,7 +152,10 @@ __device__ __forceinline__ float group_sum(float v) {
 
 // GROUP lanes per pixel, VEC float4 per lane (capacity GROUP * VEC * 4 channels): narrow layers put several pixels
 // in a warp so that every lane carries data and enough bytes are in flight per SM to cover the HBM latency.
-template <int VEC, int GROUP>
+// ITER: pixel groups per warp slot, all loaded before the first is reduced (ITER x 16 B in flight per lane).  With one
+// group per slot the 60-channel 256 x 256 x 32 layers of the training forward ran 131 072 blocks of one load each at
+// ~2 TB/s; the wide variants (VEC > 1) already carry enough bytes per lane and keep ITER = 1.
+template <int VEC, int GROUP, int ITER>
 __global__ void __launch_bounds__(256)
 channelnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ res1,
@@ -162,79 +165,87 @@ channelnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gl = lane % GROUP;
   const size_t npix = static_cast<size_t>(p.n) * p.h * p.w;
-  const size_t pix = (static_cast<size_t>(blockIdx.x) * 8 + warp) * kPix + lane / GROUP;
-  const bool live = pix < npix;
-  const float* row = x + pix * p.ld;
-  float4 v[VEC];
-  float s = 0.f;
+  float4 v[ITER][VEC];
+  size_t pixs[ITER];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int c = (i * GROUP + gl) * 4;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live && c < p.c) {
-      v[i] = *reinterpret_cast<const float4*>(row + c);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int it = 0; it < ITER; ++it) {
+    const size_t pix = ((static_cast<size_t>(blockIdx.x) * ITER + it) * 8 + warp) * kPix + lane / GROUP;
+    pixs[it] = pix;
+    const float* row = x + pix * p.ld;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = (i * GROUP + gl) * 4;
+      v[it][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pix < npix && c < p.c) v[it][i] = *reinterpret_cast<const float4*>(row + c);
     }
   }
-  s = group_sum<GROUP>(s);
-  const float mean = s / static_cast<float>(p.c);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int c = (i * GROUP + gl) * 4;
-    if (c < p.c) {
-      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (cc * cc + d * d);
-    }
-  }
-  q = group_sum<GROUP>(q);
-  if (!live) return;
-  const float rstd = rsqrtf(q / static_cast<float>(p.c - 1) + p.eps);
-
-  // 32-bit pixel decode (n*h*w < 2^31 is checked by the launcher): 64-bit div / mod cost more than the rest of the
-  // thread's work on the narrow layers
-  const unsigned pix32 = static_cast<unsigned>(pix);
-  const unsigned row32 = pix32 / static_cast<unsigned>(p.w);
-  const int ww = static_cast<int>(pix32 - row32 * static_cast<unsigned>(p.w));
-  const int nn = static_cast<int>(row32 / static_cast<unsigned>(p.h));
-  const int hh = static_cast<int>(row32 - static_cast<unsigned>(nn) * static_cast<unsigned>(p.h));
-  int rows[3], cols[3];
-  const int nr = mirror_targets(hh, p.h, p.pt, p.pb, p.reflect != 0, rows);
-  const int nc = mirror_targets(ww, p.w, p.pl, p.pr, p.reflect != 0, cols);
   const int Hp = p.h + p.pt + p.pb, Wp = p.w + p.pl + p.pr;
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const size_t pix = pixs[it];
+    const bool live = pix < npix;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += (v[it][i].x + v[it][i].y) + (v[it][i].z + v[it][i].w);   // lanes past c hold zeros
+    s = group_sum<GROUP>(s);
+    const float mean = s / static_cast<float>(p.c);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c = (i * GROUP + gl) * 4;
+      if (c < p.c) {
+        const float a = v[it][i].x - mean, b = v[it][i].y - mean, cc = v[it][i].z - mean, d = v[it][i].w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    q = group_sum<GROUP>(q);
+    if (!live) continue;                           // after the shuffles: every lane of the warp takes part in them
+    const float rstd = rsqrtf(q / static_cast<float>(p.c - 1) + p.eps);
+
+    // 32-bit pixel decode (n*h*w < 2^31 is checked by the launcher): 64-bit div / mod cost more than the rest of the
+    // thread's work on the narrow layers
+    const unsigned pix32 = static_cast<unsigned>(pix);
+    const unsigned row32 = pix32 / static_cast<unsigned>(p.w);
+    const int ww = static_cast<int>(pix32 - row32 * static_cast<unsigned>(p.w));
+    const int nn = static_cast<int>(row32 / static_cast<unsigned>(p.h));
+    const int hh = static_cast<int>(row32 - static_cast<unsigned>(nn) * static_cast<unsigned>(p.h));
+    int rows[3], cols[3];
+    const int nr = mirror_targets(hh, p.h, p.pt, p.pb, p.reflect != 0, rows);
+    const int nc = mirror_targets(ww, p.w, p.pl, p.pr, p.reflect != 0, cols);
 
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int c = (i * GROUP + gl) * 4;
-    if (c >= p.cpad && c >= p.c) continue;
-    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < p.c) {
-      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-      const float4 b = *reinterpret_cast<const float4*>(beta + c);
-      y.x = act_apply(g.x * ((v[i].x - mean) * rstd) + b.x, p.act);
-      y.y = act_apply(g.y * ((v[i].y - mean) * rstd) + b.y, p.act);
-      y.z = act_apply(g.z * ((v[i].z - mean) * rstd) + b.z, p.act);
-      y.w = act_apply(g.w * ((v[i].w - mean) * rstd) + b.w, p.act);
-      if (res1) {
-        const float4 r = *reinterpret_cast<const float4*>(res1 + pix * p.c + c);
-        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
-      }
-      if (res2) {
-        const float4 r = *reinterpret_cast<const float4*>(res2 + pix * p.c + c);
-        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
-      }
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + pix * p.c + c) = y;
-    }
-    if (out_act && c < p.cpad) {
-      __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<uint32_t*>(&h1);
-      for (int ri = 0; ri < nr; ++ri)
-        for (int ci = 0; ci < nc; ++ci) {
-          __half* dst = out_act + ((static_cast<size_t>(nn) * Hp + rows[ri]) * Wp + cols[ci]) * p.cpad + c;
-          *reinterpret_cast<uint2*>(dst) = pk;
+    for (int i = 0; i < VEC; ++i) {
+      const int c = (i * GROUP + gl) * 4;
+      if (c >= p.cpad && c >= p.c) continue;
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < p.c) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+        const float4 b = *reinterpret_cast<const float4*>(beta + c);
+        y.x = act_apply(g.x * ((v[it][i].x - mean) * rstd) + b.x, p.act);
+        y.y = act_apply(g.y * ((v[it][i].y - mean) * rstd) + b.y, p.act);
+        y.z = act_apply(g.z * ((v[it][i].z - mean) * rstd) + b.z, p.act);
+        y.w = act_apply(g.w * ((v[it][i].w - mean) * rstd) + b.w, p.act);
+        if (res1) {
+          const float4 r = *reinterpret_cast<const float4*>(res1 + pix * p.c + c);
+          y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
         }
+        if (res2) {
+          const float4 r = *reinterpret_cast<const float4*>(res2 + pix * p.c + c);
+          y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+        }
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + pix * p.c + c) = y;
+      }
+      if (out_act && c < p.cpad) {
+        __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        for (int ri = 0; ri < nr; ++ri)
+          for (int ci = 0; ci < nc; ++ci) {
+            __half* dst = out_act + ((static_cast<size_t>(nn) * Hp + rows[ri]) * Wp + cols[ci]) * p.cpad + c;
+            *reinterpret_cast<uint2*>(dst) = pk;
+          }
+      }
     }
   }
 }
@@ -245,7 +256,14 @@ static void launch_channelnorm(const float* x, const float* gamma, const float* 
                                cudaStream_t st) {
   const long long npix = static_cast<long long>(p.n) * p.h * p.w;
   const long long per_block = 8LL * (32 / GROUP);
-  channelnorm_kernel<VEC, GROUP><<<static_cast<unsigned>((npix + per_block - 1) / per_block), 256, 0, st>>>(
+  static const bool iter_on = [] { const char* e = getenv("HFC_CN_ITER"); return !(e && e[0] == '0'); }();
+  if (VEC == 1 && iter_on && npix >= (1LL << 18)) {
+    constexpr int kIter = VEC == 1 ? 4 : 1;
+    channelnorm_kernel<VEC, GROUP, kIter><<<static_cast<unsigned>((npix + per_block * kIter - 1) / (per_block * kIter)), 256, 0, st>>>(
+        x, gamma, beta, res1, res2, out_f32, out_act, p);
+    return;
+  }
+  channelnorm_kernel<VEC, GROUP, 1><<<static_cast<unsigned>((npix + per_block - 1) / per_block), 256, 0, st>>>(
       x, gamma, beta, res1, res2, out_f32, out_act, p);
 }
 

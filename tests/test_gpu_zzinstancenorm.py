@@ -114,21 +114,29 @@ def test_networks_with_instance_norm_against_oracle():
     n_res = 2
     sd, enc, gen = _modules(n_res)
     g = torch.Generator().manual_seed(21)
-    x = synth.synth_image(2, 128, 96, 5)
-    y_hat = torch.round(torch.randn((2, 220, 8, 6), generator=g) * 2)
-    w_enc = torch.randn((2, 220, 8, 6), generator=g)
-    w_gen = torch.randn((2, 3, 128, 96), generator=g)
-    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(("Encoder.", "Generator."))}
-    y_o = O.encoder_forward(sdg, x)
-    (y_o * w_enc).sum().backward()
-    yo = y_hat.clone().requires_grad_(True)
-    x_o = O.generator_forward(sdg, yo, n_residual_blocks=n_res)
-    (x_o * w_gen).sum().backward()
+    x = synth.synth_image(2, 192, 160, 5)
+    y_hat = torch.round(torch.randn((2, 220, 12, 10), generator=g) * 2)
+    w_enc = torch.randn((2, 220, 12, 10), generator=g)
+    w_gen = torch.randn((2, 3, 192, 160), generator=g)
+
+    def oracle(rnd):
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(("Encoder.", "Generator."))}
+        y_o = O.encoder_forward(sdg, x, rnd=rnd)
+        (y_o * w_enc).sum().backward()
+        yo = y_hat.clone().requires_grad_(True)
+        x_o = O.generator_forward(sdg, yo, n_residual_blocks=n_res, rnd=rnd)
+        (x_o * w_gen).sum().backward()
+        return sdg, y_o.detach(), x_o.detach(), yo.grad
+
+    # fp32 oracle (the reference's arithmetic) and the operand-matched oracle (conv operands rounded to fp16 in the forward,
+    # as the kernels do: the same ReLU masks up to rounding, so what remains is the backward's own arithmetic -- DESIGN 3.13)
+    sdg, y_o, x_o, dy_o = oracle(O._ident)
+    sdm, _, _, dy_m = oracle(O.round_fp16)
     # inference (no autograd): the same layer-by-layer plan
     enc.eval(), gen.eval()
     with torch.no_grad():
-        assert rel(enc(x.to(DEV)).cpu(), y_o.detach()) < 5e-3
-        assert rel(gen(y_hat.to(DEV)).cpu(), x_o.detach()) < 5e-3
+        assert rel(enc(x.to(DEV)).cpu(), y_o) < 5e-3
+        assert rel(gen(y_hat.to(DEV)).cpu(), x_o) < 5e-3
     # training: forward + every gradient
     enc.train(), gen.train()
     yp = y_hat.to(DEV).requires_grad_(True)
@@ -136,9 +144,9 @@ def test_networks_with_instance_norm_against_oracle():
     (y_p * w_enc.to(DEV)).sum().backward()
     x_p = gen(yp)
     (x_p * w_gen.to(DEV)).sum().backward()
-    assert rel(y_p.detach().cpu(), y_o.detach()) < 5e-3 and rel(x_p.detach().cpu(), x_o.detach()) < 5e-3
-    assert rel(yp.grad.cpu(), yo.grad) < 5e-2
-    worst = ("", 0.0)
+    assert rel(y_p.detach().cpu(), y_o) < 5e-3 and rel(x_p.detach().cpu(), x_o) < 5e-3
+    assert rel(yp.grad.cpu(), dy_m) < 5e-2 and rel(yp.grad.cpu(), dy_o) < 1e-1
+    worst_m, worst_o = ("", 0.0), ("", 0.0)
     for prefix, mod in (("Encoder.", enc), ("Generator.", gen)):
         for name, p in mod.named_parameters():
             want = sdg[prefix + name].grad
@@ -146,9 +154,11 @@ def test_networks_with_instance_norm_against_oracle():
                 # conv bias in front of an InstanceNorm: mathematically zero gradient, rounding noise on both sides
                 assert p.grad.abs().max().item() < 2e-2 * sdg[prefix + name[:-5] + ".weight"].grad.abs().max().item(), name
                 continue
-            r = rel(p.grad.cpu(), want)
-            worst = max(worst, (prefix + name, r), key=lambda t: t[1])
-    assert worst[1] < 5e-2, worst
+            worst_m = max(worst_m, (prefix + name, rel(p.grad.cpu(), sdm[prefix + name].grad)), key=lambda t: t[1])
+            worst_o = max(worst_o, (prefix + name, rel(p.grad.cpu(), want)), key=lambda t: t[1])
+    print(f"instance-norm networks, worst parameter gradient: vs operand-matched oracle {worst_m}, vs fp32 oracle {worst_o}")
+    assert worst_m[1] < 5e-2, worst_m
+    assert worst_o[1] < 1e-1, worst_o
 
 
 def test_model_level_use_channel_norm_false():
