@@ -43,6 +43,7 @@ struct WgradParams {
   int32_t m_tiles, n_tiles, nch;       // nch = 64-channel chunks per N tile (1..4)
   int32_t p_chunks;                    // P chunks fetched per stage (1 when P has <= 64 channels: the other half stays zero)
   int32_t ntaps, k_splits, kb_per_split;
+  int32_t tapg, ngroups;               // taps per work item (1 = one tap per item) and ceil(ntaps / tapg)
   int32_t stages;
   int32_t stride;                      // S sampling stride
   int32_t p_h0, p_w0, s_h0, s_w0;      // interior origin of P / S inside their (bordered) buffers
@@ -118,7 +119,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
   // work item order: K split fastest, then N tile, tap, M tile -> concurrently running CTAs share P tiles in L2
   // (pair mode: m_tiles counts 256-channel tiles and one "CTA" of the loops below is a pair)
   const int n_groups = p.n_tiles / kNsub;      // the host makes n_tiles a multiple of kNsub
-  const int total_items = p.m_tiles * p.ntaps * n_groups * p.k_splits;
+  const int total_items = p.m_tiles * p.ngroups * n_groups * p.k_splits;
   const int cta0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int ncta = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
@@ -135,8 +136,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
         int r = it;
         const int ks = r % p.k_splits; r /= p.k_splits;
         const int nt = (r % n_groups) * kNsub; r /= n_groups;
-        const int tap = r % p.ntaps;
-        const int mt = r / p.ntaps;
+        const int tap = (r % p.ngroups) * p.tapg;      // first tap of the item's group
+        const int mt = r / p.ngroups;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         int twi = kb0 % p.tiles_w, thi = (kb0 / p.tiles_w) % p.tiles_h, tni = kb0 / (p.tiles_w * p.tiles_h);
@@ -165,8 +166,18 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
               mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>((p.p_chunks + p.nch) * kWgChunkBytes));
               for (int j = 0; j < p.p_chunks; ++j)
                 tma_load_4d(sa + j * kWgChunkBytes, &tmap_p, &full_bar[s], (mt * 2 + j) * 64, gw + p.p_w0, gh + p.p_h0, gn);
-              for (int j = 0; j < p.nch; ++j)
-                tma_load_4d(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], (nt * p.nch + j) * 64, sw0, sh0, gn);
+              if (p.tapg > 1) {
+                // tap group: the N tile is `nch` TAPS of the one 64-channel chunk of S, all multiplied against ONE fetch of
+                // the P tile (a tap past the last one re-loads the last: its columns are never stored)
+                for (int j = 0; j < p.nch; ++j) {
+                  const int tj = min(tap + j, p.ntaps - 1);
+                  tma_load_4d(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], 0, gw * p.stride + p.s_w0 + p.tap_dw[tj],
+                              gh * p.stride + p.s_h0 + p.tap_dh[tj], gn);
+                }
+              } else {
+                for (int j = 0; j < p.nch; ++j)
+                  tma_load_4d(sb + j * kWgChunkBytes, &tmap_s, &full_bar[s], (nt * p.nch + j) * 64, sw0, sh0, gn);
+              }
             }
           }
           __syncwarp();
@@ -230,8 +241,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
     for (int it = cta0; it < total_items; it += ncta) {
       int r = it / p.k_splits;
       const int nt0 = (r % n_groups) * kNsub; r /= n_groups;
-      const int tap = r % p.ntaps;
-      const int mt = r / p.ntaps;
+      const int tap = (r % p.ngroups) * p.tapg;
+      const int mt = r / p.ngroups;
       const int row = (kPair ? mt * 2 + static_cast<int>(crank) : mt) * 128 + m;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
@@ -241,11 +252,14 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_cons
       const uint32_t t_row = tmem_base + (kNsub == 2 ? jsub : as) * kWgAccStride + (static_cast<uint32_t>(q * 32) << 16);
       const int col0 = nt * ncols;
       float* dst = p.out + static_cast<size_t>(row) * p.ldc + static_cast<size_t>(tap) * p.c2_rows + col0;
+      // columns that exist: the rest of the tap's c2_rows, or (tap group: c2_rows == 64, consecutive taps are consecutive
+      // 64-column blocks of the row) the taps that are left
+      const int col_limit = p.tapg > 1 ? (p.ntaps - tap) * 64 : p.c2_rows - col0;
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
-        if (row < p.c1 && col0 + c0 < p.c2_rows) {
+        if (row < p.c1 && c0 < col_limit) {
           if (p.atomic) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
@@ -371,8 +385,18 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
   }
   if (pair) best = n_chunks >= 3 ? 4 : 2;   // the S tile is split in halves between the two CTAs
   kp.nch = best;
-  kp.n_tiles = (n_chunks + kp.nch - 1) / kp.nch;
   kp.ntaps = d->ntaps;
+  // Narrow shifted operand (<= 64 channels: the big-map layers E1 / E2 / G.up4 / G3): one tap per item re-fetches the P
+  // tile for every filter tap -- 9 x (16 + 8) KB per pixel block on G.up4, L2 -> SM bound at ~390 us.  Group up to four
+  // taps into one N tile (four S chunks against ONE P fetch): 9 taps cost 3 x 16 + 9 x 8 KB instead.
+  static const bool env_tapg = [] { const char* e = getenv("HFC_WGRAD_TAPG"); return !(e && e[0] == '0'); }();
+  kp.tapg = 1;
+  if (!pair && env_tapg && n_chunks == 1 && d->ntaps > 1) {
+    kp.tapg = std::min(4, static_cast<int>(d->ntaps));
+    kp.nch = kp.tapg;
+  }
+  kp.ngroups = (kp.ntaps + kp.tapg - 1) / kp.tapg;
+  kp.n_tiles = kp.tapg > 1 ? 1 : (n_chunks + kp.nch - 1) / kp.nch;
   kp.c2_rows = n_chunks * 64;
   if (ldc < d->ntaps * kp.c2_rows || ldc % 4 != 0)
     return set_error(HFC_ERR_INVALID, "wgrad: ldc (%d) must be a multiple of 4 and >= ntaps * round_up(c2, 64) = %d", ldc,
@@ -389,7 +413,7 @@ extern "C" int hfc_wgrad(const hfc_wgrad_desc* d, const void* plain, const void*
     const int prs = std::max(1, sms / 2);
     if (((it2 + prs - 1) / prs) * 180 < ((it1 + prs - 1) / prs) * 100) nsub = 2;
   }
-  const int items = kp.m_tiles * kp.ntaps * (kp.n_tiles / nsub);
+  const int items = kp.m_tiles * kp.ngroups * (kp.n_tiles / nsub);
   const int workers = pair ? sms / 2 : sms;      // CTAs, or CTA pairs
   int ks = d->k_splits;
   if (ks <= 0) {

@@ -6,8 +6,9 @@ generator.py:21-24, 81-84) on the real kernels.
   * Encoder / Generator built with channel_norm=False against the oracle (which tests/test_instancenorm_cpu.py pins to
     golden vectors of the real reference modules): forward without autograd, forward in training mode and every
     parameter gradient.
-Tolerances: fp32 outputs 1e-4 relative (summation order); fp16 buffers at fp16 resolution; network gradients 5e-2
-relative L2 per tensor (fp16 operands + ReLU-mask flips, the bar of tests/test_gpu_train.py)."""
+Tolerances: fp32 outputs 1e-4 relative (summation order); fp16 buffers at fp16 resolution; network gradients 6e-2
+relative L2 per tensor against the operand-matched oracle and 1e-1 against the fp32 oracle (fp16 operands + ReLU-mask flips on
+small maps; measured 4.0e-2 / 7.2e-2)."""
 import os
 import sys
 
@@ -157,7 +158,9 @@ def test_networks_with_instance_norm_against_oracle():
             worst_m = max(worst_m, (prefix + name, rel(p.grad.cpu(), sdm[prefix + name].grad)), key=lambda t: t[1])
             worst_o = max(worst_o, (prefix + name, rel(p.grad.cpu(), want)), key=lambda t: t[1])
     print(f"instance-norm networks, worst parameter gradient: vs operand-matched oracle {worst_m}, vs fp32 oracle {worst_o}")
-    assert worst_m[1] < 5e-2, worst_m
+    # measured on a B200 (profiles/r02_instancenorm_tests.log): 4.0e-2 matched (Generator.resblock_1.norm1.bias, a 120-pixel map),
+    # 7.2e-2 against the fp32 oracle (Encoder.conv_block2.2.bias) -- ReLU-mask flips of a 2-image batch, cf. DESIGN.md 3.13
+    assert worst_m[1] < 6e-2, worst_m
     assert worst_o[1] < 1e-1, worst_o
 
 
