@@ -794,32 +794,53 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         plan = model.Generator._plans.get(torch.empty((B, 220, 16, 16), device=dev))
-        conv = plan.res_convs[0][0]
         blk = model.Generator.resblock_0
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        reps, tot = 20, 0.0
-        for _ in range(3):
-            conv(plan.act_a, blk.conv1.weight, blk.conv1.bias, out=plan.rows)
-        for _ in range(reps):
-            flush.zero_()                                   # evict weights/activations: cold-L2 launch, as in the step
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            conv(plan.act_a, blk.conv1.weight, blk.conv1.bias, out=plan.rows)
-            e1.record()
-            torch.cuda.synchronize()
-            tot += e0.elapsed_time(e1)
-        k_ms = tot / reps
+        plain = plan.res_convs[0][0]
+        fused = plan.fused[0][0] if plan.fused is not None else None
+
+        def run_plain():
+            plain(plan.act_a, blk.conv1.weight, blk.conv1.bias, out=plan.rows)
+
+        def run_fused():       # what the step launches 18 x: conv + ChannelNorm + ReLU + reflected border in one kernel
+            fused.call_widenorm(plan.act_a, blk.conv1.weight, blk.conv1.bias, blk.norm1.gamma, blk.norm1.beta, out_act=plan.act_b)
+
+        def time_alone(fn, reps=20):
+            for _ in range(3):
+                fn()
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()                               # evict weights/activations: cold-L2 launch, as in the step
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / reps
+
         flops = RES_FLOPS_PER_IMAGE * B
+        ms_plain = time_alone(run_plain)
+        ms_fused = time_alone(run_fused) if fused is not None else None
+        k_ms = ms_fused if fused is not None else ms_plain
         achieved = flops / (k_ms * 1e-3) / 1e12
-        roof = {"kernel": "conv_igemm_kernel (Generator residual conv 960->960 3x3, M=%d N=960 K=8640)" % (B * 256),
+        ncu_file, ncu_kernel = (("r02_ncu_resconv_widenorm.json", "conv_igemm_kernel<1, 2, 1, 0>") if fused is not None
+                                else ("r01_ncu_resconv_v9.json", "conv_igemm_kernel<1, 2>"))
+        roof = {"kernel": ("conv_igemm_kernel<pair, 2 N tiles, widenorm> (Generator residual conv 960->960 3x3 fused with its 960-channel "
+                           "ChannelNorm + ReLU + reflected border: the launch the step issues 18 x; M=%d N=960 K=8640)" % (B * 256))
+                if fused is not None else
+                "conv_igemm_kernel (Generator residual conv 960->960 3x3, M=%d N=960 K=8640)" % (B * 256),
                 "bound": "tensor", "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["burst"],
-                "traffic": ncu_dram_traffic("r01_ncu_resconv_v9.json", "conv_igemm_kernel<1, 2>"),
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_resconv_v9.json "
+                "traffic": ncu_dram_traffic(ncu_file, ncu_kernel),
+                "traffic_source": f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/{ncu_file} "
                                   "(ncu --set full; the operands of this GEMM are L2-resident re-reads, DRAM sees the weights once)",
                 "ms_per_launch": k_ms,
                 "algorithmic_flops_per_launch": flops, "peak_source": peaks["source"] + ", bf16 burst",
                 "l2": "flushed (256 MiB memset) before every timed launch",
+                "conv_alone": {"what": "the same GEMM without the fused norm epilogue (fp32 rows out; round 1's dominant kernel, "
+                                       "still the training forward's)", "ms_per_launch": ms_plain,
+                               "frac": flops / (ms_plain * 1e-3) / 1e12 / peaks["burst"]},
                 "step_tensor_frac": (E_H_G_FLOPS_PER_IMAGE * B / (ms / args.steps * 1e-3) / 1e12) / peaks["sustained"]}
 
     # --- training step (config c2: compression model, fwd + bwd + Adam), second half of BASELINE.json's metric ---
