@@ -340,8 +340,10 @@ def run_gan_steps(args, dev, dist, rank, world, x_host, timed, batch=None, regim
         if dist is not None:
             allreduce_gradients(params, dist, world)
 
+    # plain after-backward all-reduce by default: the in-backward reducer measured slower at every N tried (train_step times
+    # both modes and says so); HFC_OVERLAP_ALLREDUCE=1 selects it here
     reducer = None
-    if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE", "1") == "1":
+    if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE", "") == "1":
         from hific_b200.dist import InBackwardGradientReducer, reducer_group
         reducer = InBackwardGradientReducer(dist, world, group=reducer_group(dist))
 

@@ -11,9 +11,11 @@ alternating generator / discriminator iterations, `optimize_compression_loss` / 
   * identical initial weights on every rank (same seed before `Model(...)`), rank-offset seeds for data and noise;
   * `args.gpu = LOCAL_RANK` before the model is built, so `PerceptualLoss(gpu_ids=[args.gpu])` and every plan live on the
     rank's own device (SURVEY.md 8e(iv));
-  * generator iterations: the Encoder / Hyperprior / Generator gradients are all-reduced (mean) FROM INSIDE their backward
-    (`dist.InBackwardGradientReducer`, buckets of 32 MB overlapped with the remaining layers), the 14 080 density
-    parameters afterwards; discriminator iterations: one coalesced all-reduce of the discriminator's gradients;
+  * generator iterations: the Encoder / Hyperprior / Generator gradients are all-reduced (mean) in one coalesced in-place
+    NCCL call after the backward; `--overlap` hands them over layer by layer FROM INSIDE the backward instead
+    (`dist.InBackwardGradientReducer`, buckets of 32 MB on a side stream) -- equal results, measured slower on B200s
+    because NCCL's kernels take SMs from the backward; discriminator iterations: one coalesced
+    all-reduce of the discriminator's gradients;
   * the reference's stale-gradient quirk is kept: on generator iterations autograd also fills the discriminator's
     `.grad` (its parameters require grad), nobody zeroes it (`train.py:54-59` only zeroes the stepped optimizers), and the
     next discriminator iteration ACCUMULATES onto it.  The sum is all-reduced on that discriminator iteration, so N ranks
@@ -110,7 +112,7 @@ def save_model(model, optimizers, epoch, args, logger, rank=0):
     return path
 
 
-def train(args, model, batches, device, logger, optimizers, dist=None, rank=0, world=1, overlap=True):
+def train(args, model, batches, device, logger, optimizers, dist=None, rank=0, world=1, overlap=False):
     """The reference's loop body (train.py:114-141, 175-193) over an iterable of (B, 3, H, W) batches in [0, 1]."""
     amortization_opt, hyperlatent_likelihood_opt = optimizers['amort'], optimizers['hyper']
     disc_opt = optimizers.get('disc')
@@ -212,7 +214,10 @@ def main(argv=None):
     ap.add_argument('--save', default='experiments/ddp')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--warmstart_ckpt', default=None, help='checkpoint (reference or hific_b200 format) to start from')
-    ap.add_argument('--no_overlap', action='store_true', help='one all-reduce after backward instead of in-backward buckets')
+    ap.add_argument('--overlap', action='store_true',
+                    help='all-reduce 32 MB gradient buckets from inside the backward (dist.InBackwardGradientReducer) instead of one '
+                         'coalesced all-reduce after it; measured slower on B200s over NCCL, whose kernels take SMs from the '
+                         'backward (DESIGN.md section 4)')
     a = ap.parse_args(argv)
     rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('LOCAL_RANK', 0), ('WORLD_SIZE', 1)))
     if not torch.cuda.is_available():
@@ -246,7 +251,7 @@ def main(argv=None):
     batches = folder_batches(a.image_dir, n_batches, a.batch_size, a.crop_size, seed) if a.image_dir else \
         synthetic_batches(n_batches, a.batch_size, a.crop_size, seed)
     t0 = time.time()
-    model, ckpt, last = train(args, model, batches, device, logger, optimizers, dist, rank, world, overlap=not a.no_overlap)
+    model, ckpt, last = train(args, model, batches, device, logger, optimizers, dist, rank, world, overlap=a.overlap)
     torch.cuda.synchronize()
     if rank == 0:
         logger.info('Training complete. Time elapsed: %.3f s. Number of steps: %d. Global batch %d. Checkpoint: %s',

@@ -80,7 +80,7 @@ def _worker(rank, world, port, tmp, out):
         hdist.allreduce_gradients = recording_allreduce
         with gan_model_cpu_emulation(), NoiseFeeder(noise):
             model, ckpt, last = train_ddp.train(args, model, xs, torch.device("cpu"), logging.getLogger(f"r{rank}"), optimizers,
-                                                dist if world > 1 else None, rank, world)
+                                                dist if world > 1 else None, rank, world, overlap=True)
         ck_keys = sorted(torch.load(ckpt, weights_only=False).keys()) if ckpt else None
         out.put((world, rank, recorded, ckpt, ck_keys, model.step_counter,
                  str(next(model.perceptual_loss.parameters()).device), args.gpu))
