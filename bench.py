@@ -184,81 +184,115 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
     opt_h = Adam(hyper, lr=1e-4)
     x = x_host[:B].to(dev)
     params = amort + hyper
-    # multi-GPU: the training plans hand every layer's parameter gradients to an in-backward reducer
-    # (hific_b200.dist.InBackwardGradientReducer): 32 MB buckets all-reduced (ncclAvg, in place) on a side stream while the
-    # backward keeps walking; only the hyper-latent density parameters (14 080) go through the plain call afterwards.  A
-    # self-check against the plain after-backward all-reduce runs once before timing; on any mismatch the plain path is used.
-    reducer, reduce_mode = None, "none (single GPU)"
-    if dist is not None:
-        reduce_mode = "after backward, one coalesced NCCL all-reduce"
-    if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE", "1") == "1":
-        from hific_b200.dist import InBackwardGradientReducer, reducer_group
-        try:
-            reducer = InBackwardGradientReducer(dist, world, group=reducer_group(dist))
-            probe = [amort[0], amort[len(amort) // 2], amort[-1], hyper[0]]
+    # multi-GPU: three ways to get the gradients averaged and the step taken, all timed at every N > 1 (the fastest is the
+    # headline, the others are reported beside it -- DESIGN.md section 4):
+    #   plain      one coalesced in-place NCCL all-reduce after backward, then Adam
+    #   pipelined  the same collective cut in 64 MB buckets on a side stream, the Adam launch of bucket i waiting for
+    #              bucket i only (hific_b200.dist.allreduce_then_step): Adam runs underneath the rest of the collective
+    #   in-backward 32 MB buckets handed over layer by layer from inside the network Functions
+    #              (hific_b200.dist.InBackwardGradientReducer)
+    # The two non-plain modes are self-checked against the plain all-reduce once before timing; a mode that disagrees
+    # (or raises) is dropped on every rank.
+    PLAIN = "after backward, one coalesced NCCL all-reduce"
+    modes = {"plain": PLAIN} if dist is not None else {"single": "none (single GPU)"}
+    reducer = None
+    if dist is not None and os.environ.get("HFC_OVERLAP_ALLREDUCE", "1") != "0":
+        from hific_b200.dist import InBackwardGradientReducer, allreduce_then_step, reducer_group
+        probe = [amort[0], amort[len(amort) // 2], amort[-1], hyper[0]]
 
-            def grads_once(overlapped):
-                for p in params:
-                    p.grad = None
-                torch.manual_seed(1234)
-                loss = model(x, train_generator=True)['compression']
-                if overlapped:
-                    with reducer:
-                        loss.backward()
-                    reducer.reduce_rest(hyper)
-                else:
+        class _NoStep:                       # allreduce_then_step's communication half alone (gradients stay inspectable)
+            def __init__(self, ps):
+                self.param_groups = [{"params": ps}]
+
+            def step_subset(self, group, ps):
+                pass
+
+            def step(self):
+                pass
+
+        def grads_once(mode):
+            for p in params:
+                p.grad = None
+            torch.manual_seed(1234)
+            loss = model(x, train_generator=True)['compression']
+            if mode == "in-backward":
+                with reducer:
                     loss.backward()
-                    allreduce_gradients(params, dist, world)
-                torch.cuda.synchronize()
-                return [p.grad.detach().clone() for p in probe]
+                reducer.reduce_rest(hyper)
+            elif mode == "pipelined":
+                loss.backward()
+                allreduce_then_step(_NoStep(amort), dist, world)
+                allreduce_gradients(hyper, dist, world)
+            else:
+                loss.backward()
+                allreduce_gradients(params, dist, world)
+            torch.cuda.synchronize()
+            return [p.grad.detach().clone() for p in probe]
 
-            try:
-                grads_once(True)                                    # calibrates the loss scales (per-Function hand-over)
-                ref, got = grads_once(False), grads_once(True)
-                ok = all(torch.allclose(a, b, rtol=2e-2, atol=1e-3 * float(a.abs().max()) + 1e-12)
-                         for a, b in zip(ref, got)) and reducer.buckets_launched >= 8
-            except Exception:                        # every rank must still reach the agreement collective below
-                ok = False
+        def agree(ok):
             flag = torch.tensor([1.0 if ok else 0.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if flag.item() < 1.0:
-                raise RuntimeError("in-backward all-reduce disagrees with the plain one")
-            reduce_mode = (f"overlapped with backward: {reducer.buckets_launched} buckets of <= 32 MB handed over layer by layer from "
-                           "inside the network Functions, all-reduced (ncclAvg, in place) on a side stream (self-check against "
-                           "the plain all-reduce passed)")
-        except Exception as e:                       # keep the measurement alive on the proven path
-            reducer = None
-            reduce_mode += f" (overlap disabled: {repr(e)[:120]})"
+            return flag.item() >= 1.0
+
+        def close(ref, got):
+            return all(torch.allclose(a, b, rtol=2e-2, atol=1e-3 * float(a.abs().max()) + 1e-12) for a, b in zip(ref, got))
+
+        try:
+            reducer = InBackwardGradientReducer(dist, world, group=reducer_group(dist))
+            grads_once("in-backward")                              # calibrates the loss scales (per-Function hand-over)
+            ref = grads_once("plain")
+        except Exception:
+            reducer, ref = None, None
+        if agree(ref is not None):
+            for mode, label in (("in-backward", "overlapped with backward: {n} buckets of <= 32 MB handed over layer by layer from inside "
+                                                "the network Functions, all-reduced (ncclAvg, in place) on a side stream"),
+                                ("pipelined", "after backward, in 64 MB buckets on a side stream, the Adam launch of bucket i waiting for "
+                                              "bucket i only (allreduce_then_step)")):
+                try:
+                    ok = close(ref, grads_once(mode)) and (mode != "in-backward" or reducer.buckets_launched >= 8)
+                except Exception:                    # every rank must still reach the agreement collective below
+                    ok = False
+                if agree(ok):
+                    modes[mode] = label.format(n=reducer.buckets_launched if reducer is not None else 0) + \
+                        " (self-check against the plain all-reduce passed)"
         for p in params:
             p.grad = None
 
-    def step(mark=None, red=None):
+    def step(mark=None, mode="plain"):
         mark = mark or (lambda: None)
         mark()
         losses = model(x, train_generator=True)
         mark()
-        if red is not None:
-            with red:
+        if mode == "in-backward":
+            with reducer:
                 losses['compression'].backward()
             mark()
-            red.reduce_rest(hyper)
+            reducer.reduce_rest(hyper)
+            mark()
+            opt_a.step()
+        elif mode == "pipelined":
+            losses['compression'].backward()
+            mark()
+            mark()
+            allreduce_then_step(opt_a, dist, world)
+            allreduce_gradients(hyper, dist, world)
         else:
             losses['compression'].backward()
             mark()
             if dist is not None:
                 allreduce_gradients(params, dist, world)
-        mark()
-        opt_a.step()
+            mark()
+            opt_a.step()
         opt_a.zero_grad()
         opt_h.step()
         opt_h.zero_grad()
         mark()
 
-    def measure(red):
+    def measure(mode):
         for _ in range(3):
-            step(red=red)
+            step(mode=mode)
         steps = max(3, args.steps // 4)
-        ms = timed(lambda: step(red=red), steps)
+        ms = timed(lambda: step(mode=mode), steps)
         # where the step goes (3 extra untimed steps, events on the compute stream, median) and what the host needs to
         # enqueue one step onto an idle GPU (a step whose enqueue time approaches its GPU time is launch-bound)
         rows, host = [], []
@@ -271,31 +305,26 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
                 evs.append(e)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            step(mark, red)
+            step(mark, mode)
             host.append((time.perf_counter() - t0) * 1e3)
             torch.cuda.synchronize()
             rows.append([evs[i].elapsed_time(evs[i + 1]) for i in range(4)])
         med = [sorted(r[i] for r in rows)[1] for i in range(4)]
         phases = {"forward_and_losses_ms": med[0], "backward_ms": med[1], "gradient_allreduce_after_backward_ms": med[2],
                   "adam_ms": med[3], "host_enqueue_ms": sorted(host)[1],
-                  "note": "one step from an idle GPU, CUDA events on the compute stream; with the in-backward reducer the "
-                          "waits for the buckets are inside backward_ms"}
+                  "note": "one step from an idle GPU, CUDA events on the compute stream; in-backward: the waits for the buckets "
+                          "are inside backward_ms; pipelined: the collective and Adam are both inside adam_ms"}
         return ms, steps, phases
 
     other = None
     try:
-        ms, steps, phases = measure(reducer)
-        if reducer is not None:
-            # the same step with the plain after-backward all-reduce: NCCL's kernels take SMs from conv grids sized to
-            # fill the machine, so hiding the collective behind the backward is not free -- both
-            # are timed at every N, the faster one is the headline, the other is reported beside it
-            ms_p, steps_p, phases_p = measure(None)
-            plain_mode = "after backward, one coalesced NCCL all-reduce"
-            alt = {"ms_per_step": ms_p / steps_p, "gradient_allreduce": plain_mode, "phases": phases_p}
-            if ms_p / steps_p < ms / steps:
-                alt = {"ms_per_step": ms / steps, "gradient_allreduce": reduce_mode, "phases": phases}
-                ms, steps, phases, reduce_mode = ms_p, steps_p, phases_p, plain_mode + " (faster than the in-backward reducer at this N)"
-            other = alt
+        results = {m: measure(m) for m in modes}
+        best = min(results, key=lambda m: results[m][0] / results[m][1])
+        ms, steps, phases = results[best]
+        reduce_mode = modes[best]
+        if len(results) > 1:
+            reduce_mode += " (the fastest of the modes timed at this N)"
+            other = [{"ms_per_step": r[0] / r[1], "gradient_allreduce": modes[m], "phases": r[2]} for m, r in results.items() if m != best]
     except NotImplementedError as e:      # a piece of the backward is missing: report it, do not fake a number
         return {"unavailable": str(e)[:200]}
     finally:
@@ -303,7 +332,7 @@ def run_train_step(args, cfg, model, dev, dist, rank, world, x_host, timed):
         model.eval()
     return {"ms_per_step": ms / steps, "images_per_s": world * B * steps / (ms * 1e-3), "steps": steps,
             "per_gpu_batch": B, "n_gpus": world, "gradient_allreduce": reduce_mode, "phases": phases,
-            "other_allreduce_mode": other,
+            "other_allreduce_modes": other,
             "lpips_trunk": os.environ.get("HFC_LPIPS_TRUNK", "native"),
             "dtype": ("bf16 x bf16 backward GEMMs (HFC_GRAD_FMT=bf16)" if os.environ.get("HFC_GRAD_FMT", "fp16").lower() == "bf16" else
                       "fp16 x fp16 backward GEMMs (10-bit mantissa as TF32; power-of-two loss scale per backward Function), "

@@ -42,6 +42,60 @@ def allreduce_gradients(params, dist=None, world=None):
     return nbytes
 
 
+_step_comm = {}
+
+
+def allreduce_then_step(optimizer, dist=None, world=None, bucket_bytes=None):
+    """The plain after-backward gradient all-reduce PIPELINED with the optimizer: the stepped group's gradients are cut
+    into buckets (HFC_STEP_BUCKET_MB, default 64 MB), every bucket is one coalesced in-place ncclAvg on a communication
+    stream, and the Adam launch of bucket i (`hific_b200.optim.Adam.step_subset`, compute stream) waits for bucket i only --
+    so the 0.8 ms HBM-bound Adam pass runs underneath the NVLink-bound collective of the next buckets instead of after
+    all of it.  Unlike hiding the collective behind the BACKWARD (InBackwardGradientReducer), nothing here competes for
+    whole SMs: Adam is an elementwise grid that co-resides with NCCL's CTAs.  Same arithmetic per parameter as
+    `allreduce_gradients(params); optimizer.step()`.  Optimizers without `step_subset`, non-NCCL backends and world 1
+    take exactly that plain path."""
+    if dist is None:
+        import torch.distributed as dist
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    groups = [(g, [p for p in g["params"] if p.grad is not None]) for g in optimizer.param_groups]
+    params = [p for _, ps in groups for p in ps]
+    if (world == 1 or not params or not hasattr(optimizer, "step_subset") or dist.get_backend() != "nccl" or
+            not params[0].is_cuda):
+        allreduce_gradients(params, dist, world)
+        optimizer.step()
+        return 0
+    if bucket_bytes is None:
+        bucket_bytes = int(os.environ.get("HFC_STEP_BUCKET_MB", "64")) << 20
+    dev = params[0].device
+    comm = _step_comm.get(dev)
+    if comm is None:
+        comm = _step_comm[dev] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    comm.wait_stream(main)                                   # the gradients are final
+    plan = []                                                # (group, params, event)
+    for group, ps in groups:
+        bucket, nbytes = [], 0
+        for i, p in enumerate(ps):
+            bucket.append(p)
+            nbytes += p.grad.numel() * p.grad.element_size()
+            if nbytes >= bucket_bytes or i == len(ps) - 1:
+                with torch.cuda.stream(comm):
+                    with dist._coalescing_manager(device=dev):
+                        for q in bucket:
+                            dist.all_reduce(q.grad, op=dist.ReduceOp.AVG)
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
+                for q in bucket:
+                    q.grad.record_stream(comm)
+                plan.append((group, bucket, ev))
+                bucket, nbytes = [], 0
+    for group, bucket, ev in plan:
+        main.wait_event(ev)
+        optimizer.step_subset(group, bucket)
+    return len(plan)
+
+
 def max_over_ranks(value, device, dist=None):
     """The contract's timing rule: a step takes as long as its slowest rank."""
     if dist is None:
