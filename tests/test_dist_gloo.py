@@ -154,3 +154,53 @@ def test_in_backward_reducer_on_training_plans_world2():
             # (each rank scales / rounds its own half) -- the density parameters went through reduce_rest
             assert (grads[k] == multi[0][1][k]).all(), k
             assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 2e-2, k
+
+
+def _then_step_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from hific_b200.dist import allreduce_then_step
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(11)
+        x = torch.randn(8, 3, 6, 6)
+        lo, hi = shard_range(x.shape[0], rank, world)
+        m = _model()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-2)   # no step_subset: the helper must take the plain path
+        m(x[lo:hi]).square().mean().backward()
+        buckets = allreduce_then_step(opt, dist, world)
+        out.put((rank, buckets, [p.detach().numpy().copy() for p in m.parameters()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_then_step_falls_back_to_allreduce_plus_step():
+    """hific_b200.dist.allreduce_then_step with an optimizer that cannot step bucket by bucket (and on gloo): exactly
+    allreduce_gradients + optimizer.step() -- the parameters of both ranks equal one process stepping on the mean gradient
+    of the two shards.  (The bucketed NCCL path is self-checked by bench.py on the GPUs.)"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_then_step_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    torch.manual_seed(11)
+    x = torch.randn(8, 3, 6, 6)
+    m = _model()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    grads = []
+    for r in range(world):
+        lo, hi = shard_range(8, r, world)
+        m.zero_grad()
+        m(x[lo:hi]).square().mean().backward()
+        grads.append([p.grad.clone() for p in m.parameters()])
+    for p, g0, g1 in zip(m.parameters(), *grads):
+        p.grad = (g0 + g1) / world
+    opt.step()
+    for rank, buckets, params in results:
+        assert buckets == 0
+        for got, want in zip(params, m.parameters()):
+            assert torch.allclose(torch.from_numpy(got), want.detach(), rtol=1e-5, atol=1e-7)
