@@ -51,7 +51,10 @@ def optimize_compression_loss(model, compression_loss, amortization_opt, hyperla
         reducer.reduce_rest(density)
     else:
         compression_loss.backward()
-    amortization_opt.step()
+    if reducer is not None and hasattr(reducer, "then_step"):
+        reducer.then_step(amortization_opt)         # all-reduce in buckets, Adam of bucket i right behind bucket i
+    else:
+        amortization_opt.step()
     hyperlatent_likelihood_opt.step()
     amortization_opt.zero_grad()
     hyperlatent_likelihood_opt.zero_grad()
@@ -120,15 +123,17 @@ def train(args, model, batches, device, logger, optimizers, dist=None, rank=0, w
     disc_params = list(model.Discriminator.parameters()) if model.use_discriminator is True else []
     reducer = hdist.InBackwardGradientReducer(dist, world, group=hdist.reducer_group(dist)) if (world > 1 and overlap) else None
     if world > 1 and reducer is None:
-        amort_params = [p for am in model.amortization_models for p in am.parameters()]
-
-        class _Plain:                                  # same interface, one all-reduce after backward
+        class _Plain:                                  # same interface, the all-reduce after backward
             def __enter__(self):
                 return self
 
             def __exit__(self, *e):
-                hdist.allreduce_gradients(amort_params, dist, world)
                 return False
+
+            def then_step(self, opt):
+                # the amortization group: coalesced in-place all-reduce in 64 MB buckets on a side stream with the Adam launch
+                # of each bucket right behind it (plain all-reduce + opt.step() for optimizers that cannot step by bucket)
+                hdist.allreduce_then_step(opt, dist, world)
 
             def reduce_rest(self, params):
                 return hdist.allreduce_gradients(list(params), dist, world)

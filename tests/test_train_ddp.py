@@ -7,6 +7,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.multiprocessing as mp
 
@@ -17,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, tmp, out):
+def _worker(rank, world, port, tmp, out, overlap=True):
     import logging
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
@@ -80,7 +81,7 @@ def _worker(rank, world, port, tmp, out):
         hdist.allreduce_gradients = recording_allreduce
         with gan_model_cpu_emulation(), NoiseFeeder(noise):
             model, ckpt, last = train_ddp.train(args, model, xs, torch.device("cpu"), logging.getLogger(f"r{rank}"), optimizers,
-                                                dist if world > 1 else None, rank, world, overlap=True)
+                                                dist if world > 1 else None, rank, world, overlap=overlap)
         ck_keys = sorted(torch.load(ckpt, weights_only=False).keys()) if ckpt else None
         out.put((world, rank, recorded, ckpt, ck_keys, model.step_counter,
                  str(next(model.perceptual_loss.parameters()).device), args.gpu))
@@ -94,12 +95,13 @@ def _rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-def test_train_ddp_world2_matches_one_process_on_the_whole_batch(tmp_path):
+@pytest.mark.parametrize("overlap", [True, False], ids=["in-backward-reducer", "allreduce-then-step"])
+def test_train_ddp_world2_matches_one_process_on_the_whole_batch(tmp_path, overlap):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), out)) for r in range(2)]
-    procs.append(ctx.Process(target=_worker, args=(0, 1, 0, str(tmp_path), out)))
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), out, overlap)) for r in range(2)]
+    procs.append(ctx.Process(target=_worker, args=(0, 1, 0, str(tmp_path), out, overlap)))
     for p in procs:
         p.start()
     res = [out.get(timeout=300) for _ in range(3)]
