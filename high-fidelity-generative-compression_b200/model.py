@@ -2,7 +2,9 @@
 B200 kernels: `compression_forward`, `discriminator_forward`, `compression_loss`, `GAN_loss` and `forward` in all
 three model modes.  The compression model (Encoder / Hyperprior / Generator + distortion, LPIPS and rate losses) is
 differentiable end to end through hand-written backward kernels (hific_b200.train_plan / grad), so the reference's
-`optimize_compression_loss` (train.py:54-59) works on it; the Discriminator is forward-only so far.
+`optimize_compression_loss` (train.py:54-59) works on it; so is the Discriminator with the GAN losses
+(train_plan.DiscriminatorTrainPlan: spectral-norm reparametrisation, LeakyReLU masks, the upsample + concat input), i.e.
+`optimize_loss(disc_loss, disc_opt)` (train.py:49-52) and the generator's adversarial term through D into G.
 """
 from collections import defaultdict, namedtuple
 
