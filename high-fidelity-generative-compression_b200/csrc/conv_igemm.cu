@@ -1742,7 +1742,7 @@ struct PhaseFork {
 };
 
 static PhaseFork* phase_fork(cudaStream_t st) {
-  static PhaseFork pools[16];
+  static thread_local PhaseFork pools[16];     // per calling thread: the entry points stay thread-safe for distinct streams
   static const bool enabled = [] {
     const char* e = getenv("HFC_PHASE_STREAMS");
     return !(e && e[0] == '0');
