@@ -69,8 +69,10 @@ def test_hyper_training_plans(sd):
           lambda s, t: O.hyper_synthesis(s, t, "Hyperprior.synthesis_std."), torch.randn((2, 220, 8, 12), generator=g))
 
 
-def test_whole_training_step_on_cpu():
-    """CPU mirror of tests/test_gpu_train.py::test_full_training_step_vs_oracle: `Model.compression_forward` in training
+@pytest.mark.parametrize("channel_norm", [True, False], ids=["channel-norm", "instance-norm"])
+def test_whole_training_step_on_cpu(channel_norm):
+    """(instance-norm: the same step with `args.use_channel_norm = False`, src/model.py:69-72 -> InstanceNorm2d in both networks.)
+    CPU mirror of tests/test_gpu_train.py::test_full_training_step_vs_oracle: `Model.compression_forward` in training
     mode (noise fed as the reference draws it), rate + distortion loss, `backward()` through every training plan and
     autograd Function -- every parameter gradient against autograd of the oracle.  Same tolerances as on the GPU: the rate
     side strictly, the image side loosely (rounding flips of y_hat make the loss only piecewise smooth)."""
@@ -81,7 +83,10 @@ def test_whole_training_step_on_cpu():
     from oracle.ref_shim import NoiseFeeder
     cfg = mse_lpips_args()
     cfg.n_residual_blocks = 2
+    cfg.use_channel_norm = channel_norm
     sd2 = synth.synth_state_dict(0, n_residual_blocks=2)
+    if not channel_norm:
+        sd2 = synth.instance_norm_variant(sd2)
     m = Model(cfg, logging.getLogger("cpu-train"))
     m.load_state_dict(sd2, strict=True)
     m.train()
@@ -103,11 +108,19 @@ def test_whole_training_step_on_cpu():
         w = ("", 0.0)
         for name, p in module.named_parameters():
             assert p.grad is not None, prefix + name
-            w = max(w, (name, rel(p.grad, sdg[prefix + name].grad)), key=lambda t: t[1])
+            want = sdg[prefix + name].grad
+            if not channel_norm and name.endswith(".bias") and prefix + name[:-5] + ".weight" in sdg and \
+                    want.abs().max() < 1e-3 * sdg[prefix + name[:-5] + ".weight"].grad.abs().max():
+                continue     # conv bias in front of an InstanceNorm: mathematically zero gradient, rounding noise on both sides
+            w = max(w, (name, rel(p.grad, want)), key=lambda t: t[1])
         return w
     assert worst(m.Hyperprior, "Hyperprior.")[1] < 0.1
-    assert worst(m.Encoder, "Encoder.")[1] < 0.3
-    assert worst(m.Generator, "Generator.")[1] < 0.3
+    # image side: with these synthetic weights the instance-norm network is far more sensitive to y_hat rounding flips than
+    # the channel-norm one -- the ORACLE with fp16-rounded conv operands differs from its own fp32 run by 0.45 (Encoder,
+    # conv_block1.2.weight) where the channel-norm oracle differs by 0.08; the product sits at 0.41 / 0.49 (measured)
+    image_side = 0.3 if channel_norm else 0.6
+    assert worst(m.Encoder, "Encoder.")[1] < image_side
+    assert worst(m.Generator, "Generator.")[1] < image_side
 
 
 def test_backward_arithmetic_at_the_products_own_forward_state_cpu():
